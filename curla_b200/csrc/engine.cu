@@ -1,0 +1,746 @@
+// The agent engine: memory plan + launch sequence of one whole CurlSacAgent.update
+// (curl_sac.py:426-451) on one GPU, data-parallel over NCCL when world > 1.
+//
+// Host-side C++ only (no kernels here).  The caller (curla_b200/curl_sac.py) owns five
+// zero-initialised arenas; this file decides where every tensor lives in them, exposes
+// that table (curla_agent_tensor_info) and issues the kernels of gather.cu / conv.cu /
+// gemm.cu / small.cu / curl.cu / optim.cu in dependency order on one stream.
+//
+// Distinct-work schedule (numerically identical to the reference's 7 encoder forwards,
+// SURVEY.md 3.4): F1 conv_theta(next), F2 conv_target(next), F3 conv_theta(obs)+bwd,
+// F4 conv_theta'(obs) shared by the actor step, the critic-on-pi evaluation and the CURL
+// anchor, F7 conv_target'(pos).
+#include "common.cuh"
+#include "../../include/curla_b200.h"
+
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <type_traits>
+#include <vector>
+
+namespace curla {
+
+// ---------------------------------------------------------------- error plumbing
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+static thread_local long long g_launches = 0;
+int check_launch(const char* what) {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("%s: %s", what, cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F64 = 2, DT_I32 = 3, DT_U8 = 4 };
+static const int kDtSize[] = {4, 2, 8, 4, 1};
+
+struct TensorInfo {
+    std::string name;
+    int arena;
+    long long byte_off;
+    int ndim;
+    long long dims[4];
+    int dtype;
+};
+
+struct EncP { long long conv_w[4], conv_b[4], fc_w, fc_b, ln_w, ln_b; };      // float offsets
+struct MlpP { long long w0, b0, w1, b1, w2, b2; int in_real, out; };
+struct EncS { long long conv[4], fc; };                                        // bf16 offsets
+struct MlpS { long long w0, w1; };
+struct MlpBuf { bf16 *X, *H1, *H2; float* out; };
+struct TailBuf { float *fc_out, *z; };
+
+}  // namespace curla
+
+using namespace curla;
+
+struct curla_agent {
+    curla_agent_config cfg;
+    // geometry
+    int Hs, pitch, S, Ho[4], Wo[4], Kfc, CP1, PAD, fc_splits;
+    // parameter layout (float offsets into ARENA_PARAMS)
+    long long off_W, n_W, off_critic, n_critic, n_enc, off_actor, n_actor, off_target, n_params;
+    EncP enc_critic, enc_target, enc_actor;   // enc_actor.conv_* alias the critic's (tied)
+    MlpP q_critic[2], q_target[2], trunk_actor;
+    // shadows
+    EncS s_critic, s_target; long long s_actor_fc;
+    MlpS sq_critic[2], sq_target[2], s_trunk;
+    long long n_shadow;
+    std::vector<long long> pack_critic, pack_critic_enc, pack_actor, pack_target;   // 7 per seg
+    // grads / adam
+    long long g_critic, g_actor, g_cpc, n_cpc, n_grads;
+    long long a_m1, a_v1, a_m2, a_v2, a_m3, a_v3, n_adam;
+    std::vector<TensorInfo> tensors;
+    long long arena_bytes[CURLA_ARENA_COUNT];
+    // bound arenas
+    float* P; bf16* Sh; float* G; float* Ad; uint8_t* Wk;
+    bool bound;
+    // workspace pointers
+    bf16 *s2d_obs, *s2d_next, *s2d_pos, *actA[4], *actB[4], *dact[4];
+    long long act_sstride, s2d_sstride;
+    float *fc_partial, *wgrad_ws, *curl_ws, *ln_scratch;
+    TailBuf t_p1, t_p2, t_p3, t_p4, t_p5, t_p7;
+    MlpBuf m_p1, m_p2q[2], m_p3q[2], m_p4, m_p5q[2];
+    float *t_out1, *t_out4, *a_next, *logpi_next, *mu_scratch, *pi4, *logpi4, *ls4, *noise4, *ls1;
+    float *tq[2], *q3[2], *q5[2], *target_q, *dq[2], *dt4;
+    bf16 *dH2, *dH1;
+    float *dX[2], *dXa, *dz_curl, *dfc_f32; bf16* dfc_bf16;
+    float *z_pos_all, *act_b, *rew_b, *nd_b, *metrics, *glogpi;
+    double *log_alpha, *g_log_alpha, *alpha_state;
+    // optimizer step counters (host)
+    int t_critic, t_actor, t_alpha, t_cpc;
+    long long last_launches;
+    // NCCL (dlopen'ed)
+    void* nccl_lib; void* comm;
+};
+
+namespace {
+
+// ---------------------------------------------------------------- layout helpers
+struct Builder {
+    curla_agent* a;
+    long long cur[CURLA_ARENA_COUNT] = {0, 0, 0, 0, 0};
+    long long add(int arena, const char* name, int dtype, int ndim, const long long* dims,
+                  long long align_elems, long long front_pad_elems = 0, long long back_pad_elems = 0) {
+        long long n = 1;
+        for (int i = 0; i < ndim; ++i) n *= dims[i];
+        const int es = kDtSize[dtype];
+        long long off_bytes = cur[arena];
+        const long long al = align_elems * es;
+        off_bytes = (off_bytes + al - 1) / al * al;
+        off_bytes += front_pad_elems * es;
+        TensorInfo t;
+        t.name = name; t.arena = arena; t.byte_off = off_bytes; t.ndim = ndim; t.dtype = dtype;
+        for (int i = 0; i < 4; ++i) t.dims[i] = i < ndim ? dims[i] : 1;
+        a->tensors.push_back(t);
+        cur[arena] = off_bytes + (n + back_pad_elems) * es;
+        return off_bytes / es;
+    }
+    long long p(const std::string& name, std::vector<long long> dims) {   // fp32 parameter
+        return add(CURLA_ARENA_PARAMS, name.c_str(), DT_F32, (int)dims.size(), dims.data(), 4);
+    }
+    long long s(const std::string& name, std::vector<long long> dims) {   // bf16 shadow
+        return add(CURLA_ARENA_SHADOW, ("shadow." + name).c_str(), DT_BF16, (int)dims.size(), dims.data(), 64);
+    }
+    template <typename T>
+    T* w(const std::string& name, int dtype, std::vector<long long> dims, long long fp = 0, long long bp = 0) {
+        long long off = add(CURLA_ARENA_WORK, name.c_str(), dtype, (int)dims.size(), dims.data(),
+                            256 / kDtSize[dtype], fp, bp);
+        return reinterpret_cast<T*>(off * kDtSize[dtype]);   // offset now, rebased at bind
+    }
+};
+
+void layout_encoder(Builder& b, const std::string& pre, EncP& e, const curla_agent* a, const EncP* tie) {
+    const auto& c = a->cfg;
+    for (int i = 0; i < 4; ++i) {
+        if (tie) { e.conv_w[i] = tie->conv_w[i]; e.conv_b[i] = tie->conv_b[i]; continue; }
+        const long long cin = i == 0 ? c.C : c.num_filters;
+        e.conv_w[i] = b.p(pre + "convs." + std::to_string(i) + ".weight", {c.num_filters, cin, 3, 3});
+        e.conv_b[i] = b.p(pre + "convs." + std::to_string(i) + ".bias", {c.num_filters});
+    }
+    // canonical fc layout is the kernel layout: [feat][Ho4][pitch][F] (zero in pad columns)
+    e.fc_w = b.p(pre + "fc.weight_canon", {c.feature_dim, a->Ho[3], a->pitch, c.num_filters});
+    e.fc_b = b.p(pre + "fc.bias", {c.feature_dim});
+    e.ln_w = b.p(pre + "ln.weight", {c.feature_dim});
+    e.ln_b = b.p(pre + "ln.bias", {c.feature_dim});
+}
+void layout_mlp(Builder& b, const std::string& pre, MlpP& m, int in_real, int hid, int out) {
+    m.in_real = in_real; m.out = out;
+    m.w0 = b.p(pre + "0.weight", {hid, in_real}); m.b0 = b.p(pre + "0.bias", {hid});
+    m.w1 = b.p(pre + "2.weight", {hid, hid});     m.b1 = b.p(pre + "2.bias", {hid});
+    m.w2 = b.p(pre + "4.weight", {out, hid});     m.b2 = b.p(pre + "4.bias", {out});
+}
+void seg(std::vector<long long>& v, long long src, long long dst, int kind, int rows, int cols,
+         int rows_pad, int cols_pad) {
+    const long long r[7] = {src, dst, kind, rows, cols, rows_pad, cols_pad};
+    v.insert(v.end(), r, r + 7);
+}
+void shadow_encoder(Builder& b, const std::string& pre, const EncP& e, EncS& s, curla_agent* a,
+                    std::vector<long long>* packs[], int npacks, bool convs) {
+    const auto& c = a->cfg;
+    if (convs) {
+        s.conv[0] = b.s(pre + "convs.0", {4, c.num_filters, a->CP1});
+        for (int k = 0; k < npacks; ++k) seg(*packs[k], e.conv_w[0], s.conv[0], 2, c.num_filters, c.C, c.num_filters, a->CP1);
+        for (int i = 1; i < 4; ++i) {
+            s.conv[i] = b.s(pre + "convs." + std::to_string(i), {9, c.num_filters, c.num_filters});
+            for (int k = 0; k < npacks; ++k) seg(*packs[k], e.conv_w[i], s.conv[i], 1, c.num_filters, c.num_filters, c.num_filters, c.num_filters);
+        }
+    }
+    s.fc = b.s(pre + "fc", {64, a->Kfc});
+    for (int k = 0; k < npacks; ++k) seg(*packs[k], e.fc_w, s.fc, 0, c.feature_dim, a->Kfc, 64, a->Kfc);
+}
+void shadow_mlp(Builder& b, const std::string& pre, const MlpP& m, MlpS& s, int hid,
+                std::vector<long long>& pack) {
+    s.w0 = b.s(pre + "0", {hid, 64});
+    seg(pack, m.w0, s.w0, 0, hid, m.in_real, hid, 64);
+    s.w1 = b.s(pre + "2", {hid, hid});
+    seg(pack, m.w1, s.w1, 0, hid, hid, hid, hid);
+}
+
+}  // namespace
+
+extern "C" const char* curla_last_error(void) { return g_err; }
+extern "C" int curla_version(void) { return 100; }
+
+extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
+    const auto& c = *cfg;
+    if (c.num_filters != 32 || c.num_layers != 4) { set_last_error("agent: only num_filters=32, num_layers=4 are built"); return nullptr; }
+    if (c.feature_dim > 64 || c.feature_dim + c.action_dim > 64 || c.action_dim > 4 || (c.feature_dim & 1) || ((c.feature_dim + c.action_dim) & 1)) {
+        set_last_error("agent: need even feature_dim, feature_dim+action_dim <= 64, action_dim <= 4"); return nullptr; }
+    if (c.hidden_dim % 8 || c.hidden_dim < 8) { set_last_error("agent: hidden_dim must be a multiple of 8"); return nullptr; }
+    if (4 * c.C > 48) { set_last_error("agent: at most 12 input channels"); return nullptr; }
+    if (c.H < 11 || c.W < 11 || c.batch < 1 || c.global_batch != c.batch * c.world) { set_last_error("agent: bad shape/batch"); return nullptr; }
+    curla_agent* a = new curla_agent();
+    a->cfg = c;
+    a->Hs = (c.H + 1) / 2; a->pitch = (c.W + 1) / 2; a->S = a->Hs * a->pitch;
+    a->Ho[0] = (c.H - 3) / 2 + 1; a->Wo[0] = (c.W - 3) / 2 + 1;
+    for (int i = 1; i < 4; ++i) { a->Ho[i] = a->Ho[i - 1] - 2; a->Wo[i] = a->Wo[i - 1] - 2; }
+    a->Kfc = a->Ho[3] * a->pitch * 32;
+    a->CP1 = 48;
+    a->PAD = 128 + 2 * a->pitch + 2;
+    const int B = c.batch, Bg = c.global_batch, hid = c.hidden_dim, feat = c.feature_dim, A = c.action_dim;
+    Builder b; b.a = a;
+
+    // ---- parameters: [W][critic: enc Q1 Q2][actor-own: fc ln trunk][target: enc Q1 Q2]
+    a->off_W = b.p("CURL.W", {feat, feat});
+    a->off_critic = (b.cur[0] + 15) / 16 * 4;
+    a->n_W = a->off_critic - a->off_W;            // incl. alignment tail (zero grads there)
+    layout_encoder(b, "critic.encoder.", a->enc_critic, a, nullptr);
+    a->n_enc = (b.cur[0] + 15) / 16 * 4 - a->off_critic;
+    layout_mlp(b, "critic.Q1.trunk.", a->q_critic[0], feat + A, hid, 1);
+    layout_mlp(b, "critic.Q2.trunk.", a->q_critic[1], feat + A, hid, 1);
+    a->off_actor = (b.cur[0] + 15) / 16 * 4;
+    a->n_critic = a->off_actor - a->off_critic;
+    {   // actor-own: fc, ln (convs tied to the critic's: curl_sac.py:290)
+        EncP& e = a->enc_actor;
+        for (int i = 0; i < 4; ++i) { e.conv_w[i] = a->enc_critic.conv_w[i]; e.conv_b[i] = a->enc_critic.conv_b[i]; }
+        e.fc_w = b.p("actor.encoder.fc.weight_canon", {feat, a->Ho[3], a->pitch, 32});
+        e.fc_b = b.p("actor.encoder.fc.bias", {feat});
+        e.ln_w = b.p("actor.encoder.ln.weight", {feat});
+        e.ln_b = b.p("actor.encoder.ln.bias", {feat});
+    }
+    layout_mlp(b, "actor.trunk.", a->trunk_actor, feat, hid, 2 * A);
+    a->off_target = (b.cur[0] + 15) / 16 * 4;
+    a->n_actor = a->off_target - a->off_actor;
+    layout_encoder(b, "target.encoder.", a->enc_target, a, nullptr);
+    layout_mlp(b, "target.Q1.trunk.", a->q_target[0], feat + A, hid, 1);
+    layout_mlp(b, "target.Q2.trunk.", a->q_target[1], feat + A, hid, 1);
+    a->n_params = (b.cur[0] + 15) / 16 * 4;
+    if (a->n_params - a->off_target != a->n_critic) { set_last_error("agent: internal layout mismatch"); delete a; return nullptr; }
+    a->arena_bytes[CURLA_ARENA_PARAMS] = a->n_params * 4;
+
+    // ---- shadows + pack tables
+    {
+        std::vector<long long>* pc[] = {&a->pack_critic, &a->pack_critic_enc};
+        shadow_encoder(b, "critic.encoder.", a->enc_critic, a->s_critic, a, pc, 2, true);
+        shadow_mlp(b, "critic.Q1.", a->q_critic[0], a->sq_critic[0], hid, a->pack_critic);
+        shadow_mlp(b, "critic.Q2.", a->q_critic[1], a->sq_critic[1], hid, a->pack_critic);
+        std::vector<long long>* pa[] = {&a->pack_actor};
+        EncS tmp;
+        shadow_encoder(b, "actor.encoder.", a->enc_actor, tmp, a, pa, 1, false);
+        a->s_actor_fc = tmp.fc;
+        shadow_mlp(b, "actor.trunk.", a->trunk_actor, a->s_trunk, hid, a->pack_actor);
+        std::vector<long long>* pt[] = {&a->pack_target};
+        shadow_encoder(b, "target.encoder.", a->enc_target, a->s_target, a, pt, 1, true);
+        shadow_mlp(b, "target.Q1.", a->q_target[0], a->sq_target[0], hid, a->pack_target);
+        shadow_mlp(b, "target.Q2.", a->q_target[1], a->sq_target[1], hid, a->pack_target);
+        a->n_shadow = b.cur[1] / 2;
+        a->arena_bytes[CURLA_ARENA_SHADOW] = (b.cur[1] + 255) / 256 * 256;
+    }
+    // ---- grads: g_critic mirrors the critic segment, g_actor the actor-own segment,
+    //      g_cpc mirrors [W | critic.encoder]
+    a->g_critic = 0; a->g_actor = a->n_critic; a->g_cpc = a->n_critic + a->n_actor;
+    a->n_cpc = a->n_W + a->n_enc;
+    a->n_grads = a->g_cpc + a->n_cpc;
+    a->arena_bytes[CURLA_ARENA_GRADS] = a->n_grads * 4;
+    a->a_m1 = 0; a->a_v1 = a->n_critic;
+    a->a_m2 = 2 * a->n_critic; a->a_v2 = a->a_m2 + a->n_actor;
+    a->a_m3 = a->a_v2 + a->n_actor; a->a_v3 = a->a_m3 + a->n_cpc;
+    a->n_adam = a->a_v3 + a->n_cpc;
+    a->arena_bytes[CURLA_ARENA_ADAM] = a->n_adam * 4;
+    {   // expose the grad / adam sub-arenas as named tensors
+        const long long d1[1] = {a->n_critic}, d2[1] = {a->n_actor}, d3[1] = {a->n_cpc};
+        auto named = [&](int arena, const char* nm, long long off, const long long* d) {
+            TensorInfo t; t.name = nm; t.arena = arena; t.byte_off = off * 4; t.ndim = 1; t.dtype = DT_F32;
+            t.dims[0] = d[0]; t.dims[1] = t.dims[2] = t.dims[3] = 1; a->tensors.push_back(t);
+        };
+        named(CURLA_ARENA_GRADS, "grad.critic", a->g_critic, d1);
+        named(CURLA_ARENA_GRADS, "grad.actor", a->g_actor, d2);
+        named(CURLA_ARENA_GRADS, "grad.cpc", a->g_cpc, d3);
+        named(CURLA_ARENA_ADAM, "adam.critic.m", a->a_m1, d1); named(CURLA_ARENA_ADAM, "adam.critic.v", a->a_v1, d1);
+        named(CURLA_ARENA_ADAM, "adam.actor.m", a->a_m2, d2);  named(CURLA_ARENA_ADAM, "adam.actor.v", a->a_v2, d2);
+        named(CURLA_ARENA_ADAM, "adam.cpc.m", a->a_m3, d3);    named(CURLA_ARENA_ADAM, "adam.cpc.v", a->a_v3, d3);
+    }
+
+    // ---- workspace
+    const long long R = (long long)B * a->S, PADR = a->PAD;
+    a->act_sstride = (long long)a->S * 32; a->s2d_sstride = (long long)a->S * a->CP1;
+    a->s2d_obs = b.w<bf16>("s2d.obs", DT_BF16, {R, a->CP1}, PADR * a->CP1, PADR * a->CP1);
+    a->s2d_next = b.w<bf16>("s2d.next", DT_BF16, {R, a->CP1}, PADR * a->CP1, PADR * a->CP1);
+    a->s2d_pos = b.w<bf16>("s2d.pos", DT_BF16, {R, a->CP1}, PADR * a->CP1, PADR * a->CP1);
+    for (int i = 0; i < 4; ++i) {
+        a->actA[i] = b.w<bf16>("actA." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
+        a->actB[i] = b.w<bf16>("actB." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
+        a->dact[i] = b.w<bf16>("dact." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
+    }
+    {   // split-K for the fc forward: ~2 waves of 64x64 tiles
+        const int mt = cdiv(B, 64);
+        int sp = cdiv(2 * sm_count(), mt);
+        const int ktiles = cdiv(a->Kfc, 32);
+        if (sp > ktiles / 4) sp = ktiles / 4 > 0 ? ktiles / 4 : 1;
+        a->fc_splits = curla_gemm_effective_splits(a->Kfc, sp);
+    }
+    a->fc_partial = b.w<float>("fc_partial", DT_F32, {a->fc_splits, B, 64});
+    {
+        long long w1 = curla_conv_wgrad_workspace_floats(1), w2 = curla_conv_wgrad_workspace_floats(0);
+        a->wgrad_ws = b.w<float>("wgrad_ws", DT_F32, {w1 > w2 ? w1 : w2});
+    }
+    a->curl_ws = b.w<float>("curl_ws", DT_F32, {curla_curl_workspace_floats(B, Bg)});
+    a->ln_scratch = b.w<float>("ln_scratch", DT_F32, {2, B, 64});
+    auto tail = [&](const char* nm, TailBuf& t) {
+        t.fc_out = b.w<float>(std::string(nm) + ".fc_out", DT_F32, {B, 64});
+        t.z = b.w<float>(std::string(nm) + ".z", DT_F32, {B, 64});
+    };
+    auto mlp = [&](const char* nm, MlpBuf& m, int out) {
+        m.X = b.w<bf16>(std::string(nm) + ".X", DT_BF16, {B, 64});
+        m.H1 = b.w<bf16>(std::string(nm) + ".H1", DT_BF16, {B, hid});
+        m.H2 = b.w<bf16>(std::string(nm) + ".H2", DT_BF16, {B, hid});
+        m.out = b.w<float>(std::string(nm) + ".out", DT_F32, {B, out});
+    };
+    tail("p1", a->t_p1); tail("p2", a->t_p2); tail("p3", a->t_p3); tail("p4", a->t_p4);
+    tail("p5", a->t_p5); tail("p7", a->t_p7);
+    mlp("p1.trunk", a->m_p1, 2 * A);
+    mlp("p2.q1", a->m_p2q[0], 1); mlp("p2.q2", a->m_p2q[1], 1);
+    mlp("p3.q1", a->m_p3q[0], 1); mlp("p3.q2", a->m_p3q[1], 1);
+    mlp("p4.trunk", a->m_p4, 2 * A);
+    mlp("p5.q1", a->m_p5q[0], 1); mlp("p5.q2", a->m_p5q[1], 1);
+    a->t_out1 = a->m_p1.out; a->t_out4 = a->m_p4.out;
+    a->tq[0] = a->m_p2q[0].out; a->tq[1] = a->m_p2q[1].out;
+    a->q3[0] = a->m_p3q[0].out; a->q3[1] = a->m_p3q[1].out;
+    a->q5[0] = a->m_p5q[0].out; a->q5[1] = a->m_p5q[1].out;
+    a->a_next = b.w<float>("next_action", DT_F32, {B, A});
+    a->logpi_next = b.w<float>("next_log_pi", DT_F32, {B});
+    a->ls1 = b.w<float>("next_log_std", DT_F32, {B, A});
+    a->mu_scratch = b.w<float>("mu", DT_F32, {B, A});
+    a->pi4 = b.w<float>("pi", DT_F32, {B, A});
+    a->logpi4 = b.w<float>("log_pi", DT_F32, {B});
+    a->ls4 = b.w<float>("log_std", DT_F32, {B, A});
+    a->noise4 = b.w<float>("noise_used", DT_F32, {B, A});
+    a->target_q = b.w<float>("target_q", DT_F32, {B});
+    a->dq[0] = b.w<float>("dq1", DT_F32, {B}); a->dq[1] = b.w<float>("dq2", DT_F32, {B});
+    a->dt4 = b.w<float>("d_trunk_out", DT_F32, {B, 2 * A});
+    a->dH2 = b.w<bf16>("dH2", DT_BF16, {B, hid}); a->dH1 = b.w<bf16>("dH1", DT_BF16, {B, hid});
+    a->dX[0] = b.w<float>("dX1", DT_F32, {B, 64}); a->dX[1] = b.w<float>("dX2", DT_F32, {B, 64});
+    a->dXa = b.w<float>("dXa", DT_F32, {B, 64});
+    a->dz_curl = b.w<float>("dz_curl", DT_F32, {B, 64});
+    a->dfc_f32 = b.w<float>("dfc_f32", DT_F32, {B, 64});
+    a->dfc_bf16 = b.w<bf16>("dfc_bf16", DT_BF16, {B, 64});
+    a->z_pos_all = b.w<float>("z_pos_all", DT_F32, {Bg, 64});
+    a->act_b = b.w<float>("batch.action", DT_F32, {B, A});
+    a->rew_b = b.w<float>("batch.reward", DT_F32, {B});
+    a->nd_b = b.w<float>("batch.not_done", DT_F32, {B});
+    a->metrics = b.w<float>("metrics", DT_F32, {16});
+    a->glogpi = b.w<float>("glogpi", DT_F32, {4});
+    a->log_alpha = b.w<double>("log_alpha", DT_F64, {1});
+    a->g_log_alpha = b.w<double>("grad.log_alpha", DT_F64, {1});
+    a->alpha_state = b.w<double>("adam.log_alpha", DT_F64, {2});
+    a->arena_bytes[CURLA_ARENA_WORK] = (b.cur[4] + 255) / 256 * 256;
+    a->bound = false;
+    a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
+    a->last_launches = 0;
+    a->nccl_lib = nullptr; a->comm = nullptr;
+    return a;
+}
+
+extern "C" void curla_agent_destroy(curla_agent* a) { delete a; }
+extern "C" long long curla_agent_arena_bytes(const curla_agent* a, int which) {
+    return (which >= 0 && which < CURLA_ARENA_COUNT) ? a->arena_bytes[which] : -1;
+}
+extern "C" int curla_agent_num_tensors(const curla_agent* a) { return (int)a->tensors.size(); }
+extern "C" int curla_agent_tensor_info(const curla_agent* a, int i, char* name, int name_cap,
+                                       int* arena, long long* byte_offset, int* ndim,
+                                       long long* dims, int* dtype) {
+    if (i < 0 || i >= (int)a->tensors.size()) { set_last_error("tensor_info: index"); return -1; }
+    const TensorInfo& t = a->tensors[i];
+    snprintf(name, name_cap, "%s", t.name.c_str());
+    *arena = t.arena; *byte_offset = t.byte_off; *ndim = t.ndim; *dtype = t.dtype;
+    for (int k = 0; k < 4; ++k) dims[k] = t.dims[k];
+    return 0;
+}
+
+extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
+    for (int i = 0; i < CURLA_ARENA_COUNT; ++i)
+        CURLA_CHECK(arenas[i] != nullptr && ((uintptr_t)arenas[i] % 256) == 0, "bind: arena %d null or not 256-byte aligned", i);
+    CURLA_CHECK(!a->bound, "bind: already bound");
+    a->P = (float*)arenas[0]; a->Sh = (bf16*)arenas[1]; a->G = (float*)arenas[2];
+    a->Ad = (float*)arenas[3]; a->Wk = (uint8_t*)arenas[4];
+    const uintptr_t base = (uintptr_t)a->Wk;
+    auto rb = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(base + (uintptr_t)p); };
+    rb(a->s2d_obs); rb(a->s2d_next); rb(a->s2d_pos);
+    for (int i = 0; i < 4; ++i) { rb(a->actA[i]); rb(a->actB[i]); rb(a->dact[i]); }
+    rb(a->fc_partial); rb(a->wgrad_ws); rb(a->curl_ws); rb(a->ln_scratch);
+    TailBuf* tb[] = {&a->t_p1, &a->t_p2, &a->t_p3, &a->t_p4, &a->t_p5, &a->t_p7};
+    for (auto t : tb) { rb(t->fc_out); rb(t->z); }
+    MlpBuf* mb[] = {&a->m_p1, &a->m_p2q[0], &a->m_p2q[1], &a->m_p3q[0], &a->m_p3q[1], &a->m_p4, &a->m_p5q[0], &a->m_p5q[1]};
+    for (auto m : mb) { rb(m->X); rb(m->H1); rb(m->H2); rb(m->out); }
+    rb(a->t_out1); rb(a->t_out4); rb(a->tq[0]); rb(a->tq[1]); rb(a->q3[0]); rb(a->q3[1]); rb(a->q5[0]); rb(a->q5[1]);
+    rb(a->a_next); rb(a->logpi_next); rb(a->ls1); rb(a->mu_scratch); rb(a->pi4); rb(a->logpi4); rb(a->ls4); rb(a->noise4);
+    rb(a->target_q); rb(a->dq[0]); rb(a->dq[1]); rb(a->dt4); rb(a->dH2); rb(a->dH1);
+    rb(a->dX[0]); rb(a->dX[1]); rb(a->dXa); rb(a->dz_curl); rb(a->dfc_f32); rb(a->dfc_bf16);
+    rb(a->z_pos_all); rb(a->act_b); rb(a->rew_b); rb(a->nd_b); rb(a->metrics); rb(a->glogpi);
+    rb(a->log_alpha); rb(a->g_log_alpha); rb(a->alpha_state);
+    a->bound = true;
+    return 0;
+}
+
+// ================================================================== launch helpers
+namespace {
+
+struct Run {
+    curla_agent* a;
+    cudaStream_t st;
+    int rc = 0;
+    bool ok() const { return rc == 0; }
+    void chk(int r) { if (r && !rc) rc = r; }
+    float* P(long long off) const { return a->P + off; }
+    bf16* Sh(long long off) const { return a->Sh + off; }
+
+    void pack(const std::vector<long long>& segs) {
+        if (!ok()) return;
+        chk(curla_pack_shadows(a->P, a->Sh, segs.data(), (int)(segs.size() / 7), st));
+    }
+    // conv stack forward: s2d input -> acts[0..3]
+    void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4]) {
+        if (!ok()) return;
+        const int B = a->cfg.batch;
+        chk(curla_conv_fwd(s2d, a->s2d_sstride, Sh(s.conv[0]), P(e.conv_b[0]), 1.0f / 255.0f, acts[0],
+                           a->act_sstride, B, a->pitch, a->S, a->Ho[0], a->Wo[0], 1, st));
+        for (int i = 1; i < 4 && ok(); ++i)
+            chk(curla_conv_fwd(acts[i - 1], a->act_sstride, Sh(s.conv[i]), P(e.conv_b[i]), 1.0f, acts[i],
+                               a->act_sstride, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 0, st));
+    }
+    // fc (split-K) + bias + LayerNorm
+    void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0) {
+        if (!ok()) return;
+        chk(curla_gemm_bf16(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
+                            3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f, st));
+        if (!ok()) return;
+        chk(curla_ln_fwd(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
+                         a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, st));
+    }
+    void mlp_fwd(const float* z, const float* act, const MlpP& m, const MlpS& s, MlpBuf& buf, int B) {
+        if (!ok()) return;
+        const int hid = a->cfg.hidden_dim;
+        chk(curla_pack_x(z, act, B, a->cfg.feature_dim, a->cfg.action_dim, buf.X, st));
+        if (!ok()) return;
+        chk(curla_gemm_bf16(buf.X, 64, Sh(s.w0), 64, buf.H1, hid, B, hid, 64, 3, hid, 1, P(m.b0), 1, nullptr, 0, 1, 0, 1.f, st));
+        if (!ok()) return;
+        chk(curla_gemm_bf16(buf.H1, hid, Sh(s.w1), hid, buf.H2, hid, B, hid, hid, 3, hid, 1, P(m.b1), 1, nullptr, 0, 1, 0, 1.f, st));
+        if (!ok()) return;
+        chk(curla_head_fwd(buf.H2, hid, P(m.w2), P(m.b2), B, hid, m.out, buf.out, st));
+    }
+    // backward of one 3-layer MLP.  g = float offset of this MLP's w0 grad relative layout
+    // (same relative offsets as the params) or <0 for "input gradient only".
+    void mlp_bwd(const float* dOut, const MlpP& m, const MlpS& s, const MlpBuf& buf, float* gbase,
+                 long long pbase, float* dX) {
+        if (!ok()) return;
+        const int B = a->cfg.batch, hid = a->cfg.hidden_dim;
+        auto g = [&](long long poff) { return gbase + (poff - pbase); };
+        chk(curla_head_bwd(dOut, P(m.w2), buf.H2, B, hid, m.out, a->dH2, st));
+        if (gbase && ok()) chk(curla_head_wgrad(dOut, buf.H2, B, hid, m.out, g(m.w2), g(m.b2), st));
+        if (gbase && ok()) {
+            chk(curla_gemm_bf16(a->dH2, hid, buf.H1, hid, g(m.w1), hid, hid, hid, B, 0, hid, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+            if (ok()) chk(curla_colsum_bf16(a->dH2, B, hid, g(m.b1), st));
+        }
+        if (ok()) chk(curla_gemm_bf16(a->dH2, hid, Sh(s.w1), hid, a->dH1, hid, B, hid, hid, 1, hid, 1, nullptr, 0, buf.H1, hid, 1, 0, 1.f, st));
+        if (gbase && ok()) {
+            chk(curla_gemm_bf16(a->dH1, hid, buf.X, 64, g(m.w0), m.in_real, hid, 64, B, 0, m.in_real, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+            if (ok()) chk(curla_colsum_bf16(a->dH1, B, hid, g(m.b0), st));
+        }
+        if (dX && ok()) chk(curla_gemm_bf16(a->dH1, hid, Sh(s.w0), 64, dX, 64, B, 64, hid, 1, 64, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+    }
+    // LayerNorm + fc backward (+ conv stack backward when conv==true)
+    void enc_bwd(const float* dz_a, const float* dz_b, const TailBuf& t, const EncP& e, long long fc_shadow,
+                 const EncS* convs, bf16* const acts[4], const bf16* s2d, float* gbase, long long pbase, bool conv) {
+        if (!ok()) return;
+        const int B = a->cfg.batch, feat = a->cfg.feature_dim;
+        auto g = [&](long long poff) { return gbase + (poff - pbase); };
+        chk(curla_ln_bwd(dz_a, dz_b, t.fc_out, P(e.ln_w), B, feat, a->dfc_f32, a->dfc_bf16, a->ln_scratch,
+                         g(e.ln_w), g(e.ln_b), g(e.fc_b), st));
+        // dWfc[feat][Kfc] = dfc^T . act4
+        if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
+                                      a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+        if (!conv) return;
+        // d(act4) = relu'(act4) * dfc . Wfc
+        if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
+                                      a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f, st));
+        for (int i = 3; i >= 1 && ok(); --i) {
+            chk(curla_conv_wgrad(acts[i - 1], a->act_sstride, a->dact[i], a->act_sstride, a->wgrad_ws, g(e.conv_w[i]),
+                                 g(e.conv_b[i]), 1.f, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 32, 0, st));
+            if (ok()) chk(curla_conv_dgrad(a->dact[i], a->act_sstride, Sh(convs->conv[i]), acts[i - 1], a->dact[i - 1],
+                                           a->act_sstride, B, a->pitch, a->S, a->Ho[i - 1], a->Wo[i - 1], st));
+        }
+        if (ok()) chk(curla_conv_wgrad(s2d, a->s2d_sstride, a->dact[0], a->act_sstride, a->wgrad_ws, g(e.conv_w[0]),
+                                       g(e.conv_b[0]), 1.0f / 255.0f, B, a->pitch, a->S, a->Ho[0], a->Wo[0], a->cfg.C, 1, st));
+    }
+};
+
+// ---- NCCL via dlopen (no link-time dependency; CPU-only hosts can still load the .so)
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_getid_t)(void*);
+struct NcclApi {
+    void* lib = nullptr;
+    nccl_allreduce_t all_reduce = nullptr;
+    nccl_allgather_t all_gather = nullptr;
+    nccl_getid_t get_id = nullptr;
+    void* init_rank = nullptr;
+    const char* (*err_str)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    CURLA_CHECK(g_nccl.lib, "nccl: cannot dlopen libnccl.so.2 (%s)", dlerror());
+    g_nccl.all_reduce = (nccl_allreduce_t)dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.all_gather = (nccl_allgather_t)dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.get_id = (nccl_getid_t)dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.init_rank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.err_str = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    CURLA_CHECK(g_nccl.all_reduce && g_nccl.all_gather && g_nccl.get_id && g_nccl.init_rank, "nccl: missing symbols");
+    return 0;
+}
+enum { NCCL_F32 = 7, NCCL_F64 = 8, NCCL_SUM = 0 };
+int all_reduce(curla_agent* a, void* buf, size_t n, int dt, cudaStream_t st) {
+    if (a->cfg.world == 1) return 0;
+    CURLA_CHECK(a->comm, "update: world>1 but no communicator (curla_agent_init_comm)");
+    const int r = g_nccl.all_reduce(buf, buf, n, dt, NCCL_SUM, a->comm, st);
+    CURLA_CHECK(r == 0, "ncclAllReduce: %s", g_nccl.err_str ? g_nccl.err_str(r) : "error");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int curla_nccl_unique_id(void* out128) {
+    if (load_nccl()) return -1;
+    const int r = g_nccl.get_id(out128);
+    CURLA_CHECK(r == 0, "ncclGetUniqueId failed (%d)", r);
+    return 0;
+}
+extern "C" int curla_agent_init_comm(curla_agent* a, const void* id128) {
+    if (a->cfg.world == 1) return 0;
+    if (load_nccl()) return -1;
+    struct Id { char b[128]; } id;
+    memcpy(&id, id128, 128);
+    typedef int (*init_t)(void**, int, Id, int);
+    const int r = ((init_t)g_nccl.init_rank)(&a->comm, a->cfg.world, id, a->cfg.rank);
+    CURLA_CHECK(r == 0, "ncclCommInitRank: %s", g_nccl.err_str ? g_nccl.err_str(r) : "error");
+    return 0;
+}
+
+extern "C" int curla_agent_refresh_shadows(curla_agent* a, cudaStream_t stream) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    Run r{a, stream};
+    r.pack(a->pack_critic); r.pack(a->pack_actor); r.pack(a->pack_target);
+    return r.rc;
+}
+
+extern "C" int curla_agent_last_launches(const curla_agent* a) { return (int)a->last_launches; }
+
+// ================================================================== the update
+extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    const auto& c = a->cfg;
+    const int B = c.batch, A = c.action_dim, feat = c.feature_dim;
+    const float gs = 1.0f / (float)c.global_batch;
+    const long long launches0 = g_launches;
+    Run r{a, st};
+    const bool do_sac = !u->only_cpc;
+    const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0);
+    const bool do_ema = do_sac && (u->step % c.critic_target_update_freq == 0);
+    const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
+
+    // ---- sample: gather (+crop) straight into the conv stack's input layout
+    auto stage = [&](const float* f32, const uint8_t* frames, const int64_t* h1, const int64_t* w1, bf16* dst) {
+        if (!r.ok()) return;
+        if (f32) r.chk(curla_f32_to_s2d(f32, c.C, c.H, c.W, B, a->CP1, a->s2d_sstride, dst, st));
+        else r.chk(curla_gather_crop_s2d(frames, c.C, c.Hf, c.Wf, u->idxs, h1, w1, B, c.H, c.W, a->CP1, a->s2d_sstride, dst, st));
+    };
+    stage(u->obs_f32, u->obses, u->h1_obs, u->w1_obs, a->s2d_obs);
+    const bf16* s2d_pos = a->s2d_obs;
+    if (do_cpc && !u->pos_is_obs) { stage(u->pos_f32, u->obses, u->h1_pos, u->w1_pos, a->s2d_pos); s2d_pos = a->s2d_pos; }
+    if (do_sac) {
+        stage(u->next_f32, u->next_obses, u->h1_next, u->w1_next, a->s2d_next);
+        if (r.ok()) r.chk(curla_gather_rows_f32(u->actions, u->idxs, B, A, a->act_b, st));
+        if (r.ok()) r.chk(curla_gather_rows_f32(u->rewards, u->idxs, B, 1, a->rew_b, st));
+        if (r.ok()) r.chk(curla_gather_rows_f32(u->not_dones, u->idxs, B, 1, a->nd_b, st));
+    }
+
+    bool have_p5 = false;
+    if (do_sac) {
+        // ---------------- update_critic (curl_sac.py:349-371)
+        // F1: actor(next_obs) -> a', log_pi'
+        r.conv_stack(a->s2d_next, a->enc_critic, a->s_critic, a->actB);
+        r.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B);
+        r.mlp_fwd(a->t_p1.z, nullptr, a->trunk_actor, a->s_trunk, a->m_p1, B);
+        if (r.ok()) r.chk(curla_policy_fwd(a->t_out1, u->noise_next, u->seed, u->offset * 2, B, A, (float)c.log_std_min,
+                                           (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, st));
+        // F2: critic_target(next_obs, a')
+        r.conv_stack(a->s2d_next, a->enc_target, a->s_target, a->actB);
+        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p2, B);
+        for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p2.z, a->a_next, a->q_target[k], a->sq_target[k], a->m_p2q[k], B);
+        // F3: critic(obs, action)
+        r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
+        r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p3, B);
+        for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p3.z, a->act_b, a->q_critic[k], a->sq_critic[k], a->m_p3q[k], B);
+        if (r.ok()) r.chk(curla_critic_loss(a->tq[0], a->tq[1], a->logpi_next, a->rew_b, a->nd_b, a->log_alpha, (float)c.discount,
+                                            a->q3[0], a->q3[1], B, gs, a->target_q, a->dq[0], a->dq[1], a->metrics, st));
+        // backward
+        float* gC = a->G + a->g_critic;
+        for (int k = 0; k < 2; ++k) r.mlp_bwd(a->dq[k], a->q_critic[k], a->sq_critic[k], a->m_p3q[k], gC, a->off_critic, a->dX[k]);
+        r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
+                  a->off_critic, !c.detach_encoder);
+        if (r.ok()) r.chk(all_reduce(a, gC, (size_t)a->n_critic, NCCL_F32, st));
+        if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, a->n_critic, a->n_critic,
+                                         c.critic_lr, c.critic_beta, 0.999, 1e-8, ++a->t_critic, nullptr, st));
+        r.pack(a->pack_critic);
+
+        if (do_actor) {
+            // ---------------- update_actor_and_alpha (curl_sac.py:373-404)
+            // F4: conv_theta'(obs) shared by actor(obs), critic(obs, pi) and the CURL anchor
+            r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
+            r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B);
+            r.mlp_fwd(a->t_p4.z, nullptr, a->trunk_actor, a->s_trunk, a->m_p4, B);
+            if (r.ok()) r.chk(curla_policy_fwd(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, B, A, (float)c.log_std_min,
+                                               (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4, a->ls4, a->noise4, st));
+            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B);
+            have_p5 = true;
+            for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p5.z, a->pi4, a->q_critic[k], a->sq_critic[k], a->m_p5q[k], B);
+            if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
+                                               a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
+            for (int k = 0; k < 2; ++k) r.mlp_bwd(a->dq[k], a->q_critic[k], a->sq_critic[k], a->m_p5q[k], nullptr, 0, a->dX[k]);
+            if (r.ok()) r.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
+                                               (float)c.log_std_min, (float)c.log_std_max, a->dt4, st));
+            float* gA = a->G + a->g_actor;
+            r.mlp_bwd(a->dt4, a->trunk_actor, a->s_trunk, a->m_p4, gA, a->off_actor, a->dXa);
+            r.enc_bwd(a->dXa, nullptr, a->t_p4, a->enc_actor, a->s_actor_fc, nullptr, a->actA, nullptr, gA, a->off_actor, false);
+            if (r.ok()) r.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, st));
+            if (r.ok()) r.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, st));
+            if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_actor, gA, a->Ad + a->a_m2, a->Ad + a->a_v2, a->n_actor, a->n_actor,
+                                             c.actor_lr, c.actor_beta, 0.999, 1e-8, ++a->t_actor, nullptr, st));
+            r.pack(a->pack_actor);
+            if (r.ok()) r.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
+                                                    1e-8, ++a->t_alpha, nullptr, st));
+        }
+        if (do_ema) {
+            // soft_update_params x3 (curl_sac.py:442-445): encoder tau on [0,n_enc), critic tau on Q1,Q2
+            if (r.ok()) r.chk(curla_ema_f32(a->P + a->off_target, a->P + a->off_critic, a->n_critic, a->n_enc, c.encoder_tau,
+                                            c.critic_tau, st));
+            r.pack(a->pack_target);
+        }
+    }
+
+    if (do_cpc) {
+        // ---------------- update_cpc (curl_sac.py:406-423)
+        if (!have_p5) {   // F6: anchor through the current critic encoder
+            r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
+            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B);
+        }
+        // F7: keys through the (post-EMA) target encoder, no grad
+        r.conv_stack(s2d_pos, a->enc_target, a->s_target, a->actB);
+        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
+        const float* zpos = a->t_p7.z;
+        if (c.world > 1 && r.ok()) {
+            CURLA_CHECK(a->comm, "update: world>1 but no communicator");
+            const int rc = g_nccl.all_gather(a->t_p7.z, a->z_pos_all, (size_t)B * 64, NCCL_F32, a->comm, st);
+            CURLA_CHECK(rc == 0, "ncclAllGather failed (%d)", rc);
+            zpos = a->z_pos_all;
+        }
+        float* gK = a->G + a->g_cpc;
+        if (r.ok()) r.chk(curla_curl_fwd_bwd(a->t_p5.z, zpos, a->P + a->off_W, B, c.global_batch, feat, c.rank * B, gs, a->curl_ws,
+                                             a->metrics + 6, a->dz_curl, gK, nullptr, st));
+        // g_cpc mirrors [W | critic.encoder]: encoder grads start at n_W
+        r.enc_bwd(a->dz_curl, nullptr, a->t_p5, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs,
+                  gK + a->n_W, a->off_critic, true);
+        if (r.ok()) r.chk(all_reduce(a, gK, (size_t)a->n_cpc, NCCL_F32, st));
+        // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once
+        if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, a->n_cpc, a->n_W, c.encoder_lr, 0.9,
+                                         0.999, 1e-8, ++a->t_cpc, nullptr, st));
+        r.pack(a->pack_critic_enc);
+    }
+    a->last_launches = g_launches - launches0;
+    return r.rc;
+}
+
+// ================================================================== inference entry points
+extern "C" int curla_agent_encode(curla_agent* a, int net, const void* obs_s2d, int B,
+                                  int apply_tanh, float* z_out, cudaStream_t st) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    CURLA_CHECK(B >= 1 && B <= a->cfg.batch, "encode: B must be in [1, batch]");
+    Run r{a, st};
+    const EncP& e = net == 0 ? a->enc_actor : (net == 1 ? a->enc_critic : a->enc_target);
+    const EncS& s = net == 2 ? a->s_target : a->s_critic;
+    const long long fc = net == 0 ? a->s_actor_fc : (net == 1 ? a->s_critic.fc : a->s_target.fc);
+    // conv_stack uses cfg.batch tiles; run it on the first B samples only
+    const int saveB = a->cfg.batch;
+    a->cfg.batch = B;
+    r.conv_stack((const bf16*)obs_s2d, e, s, a->actB);
+    a->cfg.batch = saveB;
+    TailBuf t{a->t_p1.fc_out, z_out};
+    r.tail(a->actB[3], fc, e, t, B, apply_tanh);
+    return r.rc;
+}
+
+extern "C" int curla_agent_actor_head(curla_agent* a, const float* z, int B, const float* noise,
+                                      unsigned long long seed, unsigned long long offset,
+                                      int compute_pi, int compute_log_pi, float* mu, float* pi,
+                                      float* log_pi, float* log_std, cudaStream_t st) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    CURLA_CHECK(B >= 1 && B <= a->cfg.batch, "actor_head: B must be in [1, batch]");
+    Run r{a, st};
+    r.mlp_fwd(z, nullptr, a->trunk_actor, a->s_trunk, a->m_p1, B);
+    if (r.ok()) r.chk(curla_policy_fwd(a->t_out1, noise, seed, offset, B, a->cfg.action_dim, (float)a->cfg.log_std_min,
+                                       (float)a->cfg.log_std_max, compute_pi, compute_log_pi, mu, pi, log_pi, log_std, nullptr, st));
+    return r.rc;
+}
+
+extern "C" int curla_agent_q_heads(curla_agent* a, int net, const float* z, const float* action,
+                                   int B, float* q1, float* q2, cudaStream_t st) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    CURLA_CHECK(B >= 1 && B <= a->cfg.batch, "q_heads: B must be in [1, batch]");
+    Run r{a, st};
+    const MlpP* m = net == 2 ? a->q_target : a->q_critic;
+    const MlpS* s = net == 2 ? a->sq_target : a->sq_critic;
+    float* outs[2] = {q1, q2};
+    for (int k = 0; k < 2; ++k) {
+        MlpBuf buf = a->m_p2q[k];
+        buf.out = outs[k];
+        r.mlp_fwd(z, action, m[k], s[k], buf, B);
+    }
+    return r.rc;
+}

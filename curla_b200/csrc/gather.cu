@@ -1,0 +1,153 @@
+// K1: replay gather + random-crop kernels.
+//
+// Replaces, on device and without any host gather / PCIe upload:
+//   utils.py:147-166   ReplayBuffer.sample_cpc  (self.obses[idxs] fancy-index gather,
+//                                                torch.as_tensor(...).float())
+//   augmentations.py:47-75  RandomCrop.training_augmentation (view_as_windows crop)
+//   encoder.py:78      obs / 255.   (folded into the conv1 epilogue, see conv.cu)
+//
+// Two output formats:
+//   * NCHW float32  -- what sample_cpc() hands to user code (public API parity)
+//   * "s2d" bf16    -- what the conv stack consumes: space-to-depth by 2 so that the
+//                      stride-2 3x3 conv1 becomes a stride-1 2x2 "shifted GEMM" with the
+//                      same flattened-position indexing as conv2..4.
+//                      uint8 values are exact in bf16.
+#include "common.cuh"
+
+namespace curla {
+
+// ------------------------------------------------------------------ NCHW f32
+// one warp per output row (b, c, y); lanes stride over x.
+__global__ void __launch_bounds__(256)
+k_gather_crop_f32(const uint8_t* __restrict__ frames, int C, int Hf, int Wf,
+                  const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
+                  const int64_t* __restrict__ w1, int B, int H, int W,
+                  float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * C * H;
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (; row < rows; row += stride) {
+        const int y = (int)(row % H);
+        const long long bc = row / H;
+        const int c = (int)(bc % C);
+        const int b = (int)(bc / C);
+        const long long fi = idxs ? idxs[b] : b;
+        const int oy = h1 ? (int)h1[b] : 0;
+        const int ox = w1 ? (int)w1[b] : 0;
+        const uint8_t* src = frames + ((fi * C + c) * Hf + (oy + y)) * (long long)Wf + ox;
+        float* dst = out + row * W;
+        for (int x = lane; x < W; x += 32) dst[x] = (float)__ldg(src + x);
+    }
+}
+
+// ------------------------------------------------------------------ s2d bf16
+// One CTA per (sample b, s2d block-row yb).  Stage the 2*C source rows in shared memory
+// with coalesced loads, then emit Ws positions x CP channels with 16-byte stores.
+//   out[b][yb*Ws + xb][c*4 + sy*2 + sx] = frame[idx[b]][c][oy + 2yb+sy][ox + 2xb+sx]
+// zero where 2yb+sy >= H, 2xb+sx >= W or channel >= 4C.
+template <typename SrcT>
+__global__ void __launch_bounds__(128)
+k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
+             const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
+             const int64_t* __restrict__ w1, int H, int W, int Hs, int Ws, int CP,
+             long long out_sample_stride, bf16* __restrict__ out) {
+    extern __shared__ float s_rows[];   // [2*C][2*Ws] values (float holds u8 and f32 alike)
+    const int b = blockIdx.y, yb = blockIdx.x;
+    const long long fi = idxs ? idxs[b] : b;
+    const int oy = h1 ? (int)h1[b] : 0;
+    const int ox = w1 ? (int)w1[b] : 0;
+    const int W2 = 2 * Ws;
+    for (int i = threadIdx.x; i < 2 * C * W2; i += blockDim.x) {
+        const int x = i % W2;
+        const int r = i / W2;          // r = c*2 + sy
+        const int c = r >> 1, sy = r & 1;
+        const int y = 2 * yb + sy;
+        float v = 0.f;
+        if (y < H && x < W)
+            v = (float)frames[((fi * C + c) * Hf + (oy + y)) * (long long)Wf + ox + x];
+        s_rows[i] = v;
+    }
+    __syncthreads();
+    const int chunks = CP / 8;
+    bf16* orow = out + b * out_sample_stride + (long long)yb * Ws * CP;
+    for (int i = threadIdx.x; i < Ws * chunks; i += blockDim.x) {
+        const int j = i % chunks, xb = i / chunks;
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {          // two channels-of-s2d per 32-bit word
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ch = j * 8 + h * 2 + e;       // = c*4 + sy*2 + sx
+                const int c = ch >> 2, sy = (ch >> 1) & 1, sx = ch & 1;
+                v[e] = (c < C) ? s_rows[(c * 2 + sy) * W2 + 2 * xb + sx] : 0.f;
+            }
+            w[h] = pack_bf16x2(v[0], v[1]);
+        }
+        *reinterpret_cast<uint4*>(orow + (long long)xb * CP + j * 8) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ------------------------------------------------------------------ small row gather
+// out[b][k] = src[idx[b]][k]   (actions / rewards / not_dones: utils.py:163-165)
+__global__ void k_gather_rows_f32(const float* __restrict__ src, const int64_t* __restrict__ idxs,
+                                  int B, int K, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * K) {
+        const int b = i / K, k = i % K;
+        out[i] = src[idxs[b] * K + k];
+    }
+}
+
+}  // namespace curla
+
+using namespace curla;
+
+extern "C" int curla_gather_crop_f32(const uint8_t* frames, int C, int Hf, int Wf,
+                                     const int64_t* idxs, const int64_t* h1, const int64_t* w1,
+                                     int B, int H, int W, float* out, cudaStream_t stream) {
+    CURLA_CHECK(B > 0 && H > 0 && W > 0 && H <= Hf && W <= Wf, "gather_crop_f32: bad shape");
+    const long long rows = (long long)B * C * H;
+    const int wpb = 8;
+    int grid = (int)((rows + wpb - 1) / wpb);
+    const int cap = sm_count() * 32;
+    if (grid > cap) grid = cap;
+    k_gather_crop_f32<<<grid, wpb * 32, 0, stream>>>(frames, C, Hf, Wf, idxs, h1, w1, B, H, W, out);
+    return check_launch("gather_crop_f32");
+}
+
+template <typename SrcT>
+static int launch_s2d(const SrcT* frames, int C, int Hf, int Wf, const int64_t* idxs,
+                      const int64_t* h1, const int64_t* w1, int B, int H, int W, int CP,
+                      long long out_sample_stride, bf16* out, cudaStream_t stream) {
+    CURLA_CHECK(B > 0 && H <= Hf && W <= Wf && CP % 8 == 0 && CP >= 4 * C, "gather_s2d: bad shape");
+    const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
+    CURLA_CHECK(out_sample_stride >= (long long)Hs * Ws * CP, "gather_s2d: sample stride too small");
+    dim3 grid(Hs, B);
+    size_t smem = (size_t)2 * C * 2 * Ws * sizeof(float);
+    k_gather_s2d<SrcT><<<grid, 128, smem, stream>>>(frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
+                                                    CP, out_sample_stride, out);
+    return check_launch("gather_s2d");
+}
+
+extern "C" int curla_gather_crop_s2d(const uint8_t* frames, int C, int Hf, int Wf,
+                                     const int64_t* idxs, const int64_t* h1, const int64_t* w1,
+                                     int B, int H, int W, int CP, long long out_sample_stride,
+                                     void* out, cudaStream_t stream) {
+    return launch_s2d<uint8_t>(frames, C, Hf, Wf, idxs, h1, w1, B, H, W, CP, out_sample_stride,
+                               (bf16*)out, stream);
+}
+
+extern "C" int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
+                                long long out_sample_stride, void* out, cudaStream_t stream) {
+    return launch_s2d<float>(obs, C, H, W, nullptr, nullptr, nullptr, B, H, W, CP,
+                             out_sample_stride, (bf16*)out, stream);
+}
+
+extern "C" int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K,
+                                     float* out, cudaStream_t stream) {
+    k_gather_rows_f32<<<cdiv((long long)B * K, 256), 256, 0, stream>>>(src, idxs, B, K, out);
+    return check_launch("gather_rows_f32");
+}

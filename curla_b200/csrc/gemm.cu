@@ -1,0 +1,209 @@
+// K7/K9: one bf16 tensor-core GEMM for every dense layer on the path:
+//   encoder fc fwd (split-K) / dgrad / wgrad      encoder.py:98
+//   actor / Q-function trunk layers fwd / bwd      curl_sac.py:70-74,129-133
+//
+// C[M,N] = epilogue( A[M,K] . B[K,N] ) with either operand stored K-major or MN-major
+// (so forward, dgrad and wgrad all read the SAME bf16 buffers, no transposes in HBM):
+//   A_KMAJOR : A stored [M][lda] (k contiguous)     else stored [K][lda] (m contiguous)
+//   B_KMAJOR : B stored [N][ldb] (k contiguous)     else stored [K][ldb] (n contiguous)
+// "Row" extents (the slow index of a stored matrix) may be ragged; contiguous extents
+// must be multiples of 8 elements (16-byte cp.async chunks, zero padded buffers).
+// 64x64x32 CTA tile, 4 warps, 3-stage cp.async pipeline, mma.sync m16n8k16 bf16->fp32.
+#include "common.cuh"
+
+namespace curla {
+
+constexpr int BM = 64, BN = 64, BK = 32, STAGES = 3;
+
+struct GemmArgs {
+    const bf16* A; long long lda;
+    const bf16* B; long long ldb;
+    void* C; long long ldc;
+    int M, N, K;
+    int n_store;              // columns [0, n_store) are written
+    int out_bf16;             // 1: bf16 output, 0: fp32
+    const float* bias;        // per column, optional
+    int relu;
+    const bf16* mask; long long ldmask;   // optional: out = mask[m][n] > 0 ? v : 0
+    int k_per_split;          // multiple of BK; blockIdx.z selects the K range
+    long long split_stride;   // elements between split outputs (fp32 partials)
+    float alpha;
+};
+
+__device__ __forceinline__ uint32_t off64(int row, int chunk) {      // 64-byte rows
+    return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint32_t off128(int row, int chunk) {     // 128-byte rows
+    return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(128)
+k_gemm(GemmArgs p) {
+    __shared__ __align__(128) uint8_t smem[STAGES * (BM * BK * 2 + BN * BK * 2)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * p.k_per_split;
+    int kend = kbeg + p.k_per_split;
+    if (kend > p.K) kend = p.K;
+    const int nk = (kend - kbeg + BK - 1) / BK;
+    const uint32_t sA0 = smem_u32(smem), sB0 = sA0 + STAGES * BM * BK * 2;
+
+    auto load_stage = [&](int kt, int st) {
+        const int k0 = kbeg + kt * BK;
+        const uint32_t sA = sA0 + st * (BM * BK * 2), sB = sB0 + st * (BN * BK * 2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c = tid + i * 128;
+            if (A_KMAJOR) {
+                const int r = c >> 2, ch = c & 3;
+                const int m = m0 + r, k = k0 + ch * 8;
+                const bool ok = (m < p.M) && (k < kend);
+                cp_async16(sA + off64(r, ch), ok ? (const void*)(p.A + (long long)m * p.lda + k) : (const void*)p.A, ok ? 16 : 0);
+            } else {
+                const int r = c >> 3, ch = c & 7;
+                const int k = k0 + r, m = m0 + ch * 8;
+                const bool ok = (k < kend) && (m < p.M);
+                cp_async16(sA + off128(r, ch), ok ? (const void*)(p.A + (long long)k * p.lda + m) : (const void*)p.A, ok ? 16 : 0);
+            }
+            if (B_KMAJOR) {
+                const int r = c >> 2, ch = c & 3;
+                const int n = n0 + r, k = k0 + ch * 8;
+                const bool ok = (n < p.N) && (k < kend);
+                cp_async16(sB + off64(r, ch), ok ? (const void*)(p.B + (long long)n * p.ldb + k) : (const void*)p.B, ok ? 16 : 0);
+            } else {
+                const int r = c >> 3, ch = c & 7;
+                const int k = k0 + r, n = n0 + ch * 8;
+                const bool ok = (k < kend) && (n < p.N);
+                cp_async16(sB + off128(r, ch), ok ? (const void*)(p.B + (long long)k * p.ldb + n) : (const void*)p.B, ok ? 16 : 0);
+            }
+        }
+    };
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    const int l7 = lane & 7, j1 = (lane >> 3) & 1, j2 = lane >> 4;
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + STAGES - 1;
+        if (nxt < nk) load_stage(nxt, nxt % STAGES);
+        cp_async_commit();
+        const int st = kt % STAGES;
+        const uint32_t sA = sA0 + st * (BM * BK * 2), sB = sB0 + st * (BN * BK * 2);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[2][4], b[4][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (A_KMAJOR)
+                    ldmatrix_x4(sA + off64(wm * 32 + mt * 16 + j1 * 8 + l7, ks * 2 + j2),
+                                a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+                else
+                    ldmatrix_x4_trans(sA + off128(ks * 16 + j2 * 8 + l7, (wm * 32 + mt * 16) / 8 + j1),
+                                      a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
+            }
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                if (B_KMAJOR)
+                    ldmatrix_x4(sB + off64(wn * 32 + np * 16 + j2 * 8 + l7, ks * 2 + j1),
+                                b[np * 2][0], b[np * 2][1], b[np * 2 + 1][0], b[np * 2 + 1][1]);
+                else
+                    ldmatrix_x4_trans(sB + off128(ks * 16 + j1 * 8 + l7, (wn * 32 + np * 16) / 8 + j2),
+                                      b[np * 2][0], b[np * 2][1], b[np * 2 + 1][0], b[np * 2 + 1][1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma_bf16(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b[nt][0], b[nt][1]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue
+    const int gq = lane >> 2, q = lane & 3;
+    float* Cf = (float*)p.C + (long long)blockIdx.z * p.split_stride;
+    bf16* Cb = (bf16*)p.C;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + wm * 32 + mt * 16 + h * 8 + gq;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int n = n0 + wn * 32 + nt * 8 + q * 2;
+                if (n >= p.n_store) continue;
+                float v0 = acc[mt][nt][h * 2] * p.alpha, v1 = acc[mt][nt][h * 2 + 1] * p.alpha;
+                if (p.bias) { v0 += p.bias[n]; v1 += (n + 1 < p.n_store) ? p.bias[n + 1] : 0.f; }
+                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                if (p.mask) {
+                    const float2 mk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.mask + (long long)m * p.ldmask + n));
+                    v0 = mk.x > 0.f ? v0 : 0.f;
+                    v1 = mk.y > 0.f ? v1 : 0.f;
+                }
+                const long long o = (long long)m * p.ldc + n;
+                if (p.out_bf16) {
+                    *reinterpret_cast<uint32_t*>(Cb + o) = pack_bf16x2(v0, v1);
+                } else if (n + 1 < p.n_store) {
+                    *reinterpret_cast<float2*>(Cf + o) = make_float2(v0, v1);
+                } else {
+                    Cf[o] = v0;
+                }
+            }
+        }
+}
+
+}  // namespace curla
+
+using namespace curla;
+
+// Generic entry.  layout bits: 1 = A stored K-major ([M][lda]), 2 = B stored K-major ([N][ldb]).
+// splits > 1 writes fp32 partials C + z*split_stride (caller reduces); requires out fp32.
+extern "C" int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C,
+                               long long ldc, int M, int N, int K, int layout, int n_store,
+                               int out_bf16, const float* bias, int relu, const void* mask,
+                               long long ldmask, int splits, long long split_stride, float alpha,
+                               cudaStream_t stream) {
+    CURLA_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+    CURLA_CHECK(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8");
+    CURLA_CHECK((ldc % 2) == 0, "gemm: ldc must be even");
+    CURLA_CHECK(splits >= 1 && (splits == 1 || !out_bf16), "gemm: split-K needs fp32 output");
+    GemmArgs p;
+    p.A = (const bf16*)A; p.lda = lda; p.B = (const bf16*)B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.n_store = n_store > 0 ? n_store : N; p.out_bf16 = out_bf16;
+    p.bias = bias; p.relu = relu; p.mask = (const bf16*)mask; p.ldmask = ldmask;
+    const int kt = cdiv(K, BK);
+    p.k_per_split = cdiv(kt, splits) * BK;
+    const int zs = cdiv(K, p.k_per_split);
+    p.split_stride = split_stride; p.alpha = alpha;
+    dim3 grid(cdiv(N, BN), cdiv(M, BM), zs);
+    switch (layout & 3) {
+        case 3: k_gemm<true, true><<<grid, 128, 0, stream>>>(p); break;
+        case 1: k_gemm<true, false><<<grid, 128, 0, stream>>>(p); break;
+        case 2: k_gemm<false, true><<<grid, 128, 0, stream>>>(p); break;
+        default: k_gemm<false, false><<<grid, 128, 0, stream>>>(p); break;
+    }
+    return check_launch("gemm_bf16");
+}
+
+// number of K splits curla_gemm_bf16 will actually launch for (K, splits)
+extern "C" int curla_gemm_effective_splits(int K, int splits) {
+    const int kt = cdiv(K, BK);
+    const int kps = cdiv(kt, splits) * BK;
+    return cdiv(K, kps);
+}

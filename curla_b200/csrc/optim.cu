@@ -1,0 +1,188 @@
+// K13 fused Adam over flat parameter arenas, K14 EMA (soft target update) and the
+// fp32 -> bf16 "shadow" packers that lay weights out for the tensor-core kernels.
+//
+// Replaces torch.optim.Adam.step (curl_sac.py:299-313,368,392,404,419-420) and
+// utils.soft_update_params (utils.py:37-41; call sites curl_sac.py:443-445).
+// All tensors of one optimizer are contiguous in the arena, so one launch covers what
+// the reference does with ~4 tiny kernels per tensor.
+#include "common.cuh"
+#include <math.h>
+
+namespace curla {
+
+struct AdamHyper {
+    double lr, b1, b2, eps;
+};
+
+// torch._single_tensor_adam maths:
+//   m.lerp_(g, 1-b1); v = v*b2 + (1-b2)*g*g;
+//   denom = sqrt(v)/sqrt(1-b2^t) + eps;  p += -(lr/(1-b1^t)) * (m/denom)
+// Elements at index >= double_from receive the parameter step TWICE (sequentially, in
+// fp32) -- this reproduces encoder_optimizer.step(); cpc_optimizer.step() acting on the
+// critic encoder with identical optimizer states (curl_sac.py:419-420).
+__global__ void __launch_bounds__(256)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+       float* __restrict__ v, long long n, long long double_from, AdamHyper h, int t_host,
+       const int* __restrict__ t_dev) {
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {
+        const int t = t_dev ? *t_dev : t_host;
+        const double bc1 = 1.0 - pow(h.b1, (double)t);
+        const double bc2 = 1.0 - pow(h.b2, (double)t);
+        s_c[0] = (float)(-(h.lr / bc1));
+        s_c[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float neg_step = s_c[0], bc2_sqrt = s_c[1];
+    const float w1 = (float)(1.0 - h.b1), b2 = (float)h.b2, w2 = (float)(1.0 - h.b2);
+    const float eps = (float)h.eps;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        float mi = m[i], vi = v[i];
+        mi = __fadd_rn(mi, __fmul_rn(w1, __fsub_rn(gi, mi)));
+        vi = __fadd_rn(__fmul_rn(vi, b2), __fmul_rn(w2, __fmul_rn(gi, gi)));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+        const float u = __fmul_rn(neg_step, __fdiv_rn(mi, denom));
+        float pi = __fadd_rn(p[i], u);
+        if (i >= double_from) pi = __fadd_rn(pi, u);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+
+// log_alpha is a float64 0-dim tensor (curl_sac.py:292); state[0]=m, state[1]=v.
+__global__ void k_adam_f64_scalar(double* p, const double* g, double* state, AdamHyper h,
+                                  int t_host, const int* t_dev) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int t = t_dev ? *t_dev : t_host;
+    double m = state[0], v = state[1];
+    const double gi = *g;
+    m = m + (1.0 - h.b1) * (gi - m);
+    v = v * h.b2 + (1.0 - h.b2) * gi * gi;
+    const double bc1 = 1.0 - pow(h.b1, (double)t), bc2 = 1.0 - pow(h.b2, (double)t);
+    const double denom = sqrt(v) / sqrt(bc2) + h.eps;
+    *p = *p + (-(h.lr / bc1)) * (m / denom);
+    state[0] = m; state[1] = v;
+}
+
+// target = tau*p + (1-tau)*target  (two roundings of the products, one of the sum, as
+// the reference's three tensor ops); [0,split) uses tau_a, [split,n) tau_b.
+__global__ void __launch_bounds__(256)
+k_ema(float* __restrict__ tgt, const float* __restrict__ p, long long n, long long split,
+      float tau_a, float omt_a, float tau_b, float omt_b) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float tau = i < split ? tau_a : tau_b, omt = i < split ? omt_a : omt_b;
+        tgt[i] = __fadd_rn(__fmul_rn(tau, p[i]), __fmul_rn(omt, tgt[i]));
+    }
+}
+
+// ---------------------------------------------------------------- shadow packers
+enum { PACK_ROWS = 0, PACK_CONV = 1, PACK_CONV1_S2D = 2 };
+struct PackSeg {
+    long long src_off;   // floats into the fp32 arena
+    long long dst_off;   // bf16 elements into the shadow arena
+    int kind, rows, cols, rows_pad, cols_pad;   // conv: rows=F(out), cols=Cin, cols_pad=CP
+};
+#define CURLA_MAX_PACK 32
+struct PackTable {
+    int n;
+    PackSeg seg[CURLA_MAX_PACK];
+};
+
+__global__ void __launch_bounds__(256)
+k_pack(const float* __restrict__ src_arena, bf16* __restrict__ dst_arena, PackTable tbl) {
+    const PackSeg s = tbl.seg[blockIdx.y];
+    const float* src = src_arena + s.src_off;
+    bf16* dst = dst_arena + s.dst_off;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s.kind == PACK_ROWS) {
+        const long long n = (long long)s.rows_pad * s.cols_pad;
+        for (; i < n; i += stride) {
+            const int r = (int)(i / s.cols_pad), c = (int)(i % s.cols_pad);
+            dst[i] = __float2bfloat16((r < s.rows && c < s.cols) ? src[(long long)r * s.cols + c] : 0.f);
+        }
+    } else if (s.kind == PACK_CONV) {
+        // OIHW [F][Cin][3][3] -> [tap=ky*3+kx][F][cols_pad]
+        const long long n = 9LL * s.rows * s.cols_pad;
+        for (; i < n; i += stride) {
+            const int ci = (int)(i % s.cols_pad);
+            const int co = (int)((i / s.cols_pad) % s.rows);
+            const int t = (int)(i / ((long long)s.cols_pad * s.rows));
+            dst[i] = __float2bfloat16(ci < s.cols ? src[((long long)co * s.cols + ci) * 9 + t] : 0.f);
+        }
+    } else {
+        // stride-2 3x3 conv1 as a 2x2 conv on the space-to-depth input:
+        // [tap=by*2+bx][F][cp], cp = c*4 + sy*2 + sx  <->  (ky,kx) = (2by+sy, 2bx+sx)
+        const long long n = 4LL * s.rows * s.cols_pad;
+        for (; i < n; i += stride) {
+            const int cp = (int)(i % s.cols_pad);
+            const int co = (int)((i / s.cols_pad) % s.rows);
+            const int t = (int)(i / ((long long)s.cols_pad * s.rows));
+            const int c = cp >> 2, ky = 2 * (t >> 1) + ((cp >> 1) & 1), kx = 2 * (t & 1) + (cp & 1);
+            float val = 0.f;
+            if (c < s.cols && ky < 3 && kx < 3) val = src[((long long)co * s.cols + c) * 9 + ky * 3 + kx];
+            dst[i] = __float2bfloat16(val);
+        }
+    }
+}
+
+}  // namespace curla
+
+using namespace curla;
+
+static int ew_grid(long long n) {
+    long long g = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int curla_adam_f32(float* p, const float* g, float* m, float* v, long long n,
+                              long long double_from, double lr, double beta1, double beta2,
+                              double eps, int t_host, const int* t_dev, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    AdamHyper h{lr, beta1, beta2, eps};
+    k_adam<<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, double_from, h, t_host, t_dev);
+    return check_launch("adam_f32");
+}
+
+extern "C" int curla_adam_f64_scalar(double* p, const double* g, double* state, double lr,
+                                     double beta1, double beta2, double eps, int t_host,
+                                     const int* t_dev, cudaStream_t stream) {
+    AdamHyper h{lr, beta1, beta2, eps};
+    k_adam_f64_scalar<<<1, 32, 0, stream>>>(p, g, state, h, t_host, t_dev);
+    return check_launch("adam_f64_scalar");
+}
+
+extern "C" int curla_ema_f32(float* target, const float* p, long long n, long long split,
+                             double tau_a, double tau_b, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    k_ema<<<ew_grid(n), 256, 0, stream>>>(target, p, n, split, (float)tau_a, (float)(1.0 - tau_a),
+                                          (float)tau_b, (float)(1.0 - tau_b));
+    return check_launch("ema_f32");
+}
+
+// segs: n x 7 int64 rows {src_off, dst_off, kind, rows, cols, rows_pad, cols_pad}
+extern "C" int curla_pack_shadows(const float* src_arena, void* dst_arena, const long long* segs,
+                                  int n, cudaStream_t stream) {
+    for (int base = 0; base < n; base += CURLA_MAX_PACK) {
+        PackTable tbl;
+        tbl.n = (n - base < CURLA_MAX_PACK) ? n - base : CURLA_MAX_PACK;
+        long long maxn = 1;
+        for (int i = 0; i < tbl.n; ++i) {
+            const long long* r = segs + (long long)(base + i) * 7;
+            PackSeg& s = tbl.seg[i];
+            s.src_off = r[0]; s.dst_off = r[1]; s.kind = (int)r[2]; s.rows = (int)r[3];
+            s.cols = (int)r[4]; s.rows_pad = (int)r[5]; s.cols_pad = (int)r[6];
+            long long cnt = s.kind == PACK_ROWS ? (long long)s.rows_pad * s.cols_pad
+                          : (s.kind == PACK_CONV ? 9LL : 4LL) * s.rows * s.cols_pad;
+            if (cnt > maxn) maxn = cnt;
+        }
+        long long gx = (maxn + 255) / 256;
+        if (gx > 2048) gx = 2048;
+        k_pack<<<dim3((unsigned)gx, tbl.n), 256, 0, stream>>>(src_arena, (bf16*)dst_arena, tbl);
+        if (check_launch("pack_shadows")) return -1;
+    }
+    return 0;
+}

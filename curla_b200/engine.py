@@ -1,0 +1,98 @@
+"""Python handle on the C++ agent engine (curla_b200/csrc/engine.cu).
+
+Owns the five device arenas (plain torch allocations) and exposes every tensor of the
+engine's memory plan as a torch view, keyed by name.  All compute happens in the CUDA
+library; this file only moves pointers around.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DTYPES = {0: torch.float32, 1: torch.bfloat16, 2: torch.float64, 3: torch.int32, 4: torch.uint8}
+ARENA_NAMES = ('params', 'shadow', 'grads', 'adam', 'work')
+
+
+class Engine:
+    def __init__(self, device, **cfg):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.CurlaError('curla_b200 runs on CUDA devices only (no CPU fallback); got %s'
+                                  % self.device)
+        c = _lib.AgentConfig()
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise KeyError(k)
+            setattr(c, k, v)
+        self.cfg = c
+        with torch.cuda.device(self.device):
+            self.h = self.lib.curla_agent_create(C.byref(c))
+            if not self.h:
+                raise _lib.CurlaError('curla_agent_create: %s' % self.lib.curla_last_error().decode())
+            self.arenas = []
+            for i in range(5):
+                n = self.lib.curla_agent_arena_bytes(self.h, i)
+                self.arenas.append(torch.zeros(max(int(n), 256), dtype=torch.uint8, device=self.device))
+            ptrs = (C.c_void_p * 5)(*[a.data_ptr() for a in self.arenas])
+            _lib.check(self.lib.curla_agent_bind(self.h, ptrs), 'curla_agent_bind')
+        self.t = {}          # name -> torch view
+        self.info = {}       # name -> (arena, byte_offset, shape, dtype)
+        name = C.create_string_buffer(256)
+        arena, off, ndim, dt = C.c_int(), C.c_longlong(), C.c_int(), C.c_int()
+        dims = (C.c_longlong * 4)()
+        for i in range(self.lib.curla_agent_num_tensors(self.h)):
+            _lib.check(self.lib.curla_agent_tensor_info(self.h, i, name, 256, C.byref(arena), C.byref(off),
+                                                        C.byref(ndim), dims, C.byref(dt)), 'tensor_info')
+            shape = tuple(int(dims[k]) for k in range(ndim.value))
+            dtype = _DTYPES[dt.value]
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            view = self.arenas[arena.value][off.value:off.value + nbytes].view(dtype).view(shape)
+            key = name.value.decode()
+            self.t[key] = view
+            self.info[key] = (arena.value, off.value, shape, dtype)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.curla_agent_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def refresh_shadows(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.curla_agent_refresh_shadows(self.h, self.stream()), 'refresh_shadows')
+
+    def update(self, args):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.curla_agent_update(self.h, C.byref(args), self.stream()), 'curla_agent_update')
+
+    def last_launches(self):
+        return self.lib.curla_agent_last_launches(self.h)
+
+    # -- canonical <-> PyTorch layout of the encoder fc weight ---------------------
+    def fc_geometry(self):
+        feat, ho, pitch, f = self.t['critic.encoder.fc.weight_canon'].shape
+        wo = self._wo4()
+        return feat, ho, wo, pitch, f
+
+    def _wo4(self):
+        return (self.cfg.W - 3) // 2 + 1 - 6
+
+    def fc_to_torch(self, canon):
+        """[feat][Ho][pitch][F] -> PyTorch nn.Linear weight [feat][F*Ho*Wo] (NCHW flatten,
+        encoder.py:89)."""
+        feat, ho, wo, pitch, f = self.fc_geometry()
+        return canon[:, :, :wo, :].permute(0, 3, 1, 2).reshape(feat, f * ho * wo).contiguous()
+
+    def fc_from_torch(self, weight, canon_out):
+        feat, ho, wo, pitch, f = self.fc_geometry()
+        canon_out.zero_()
+        canon_out[:, :, :wo, :] = weight.reshape(feat, f, ho, wo).permute(0, 2, 3, 1).to(canon_out.dtype)

@@ -1,0 +1,207 @@
+/* curla_b200 -- C ABI of the B200-native CurlSacAgent.update hot path.
+ *
+ * The reference (paulvantieghem/curla) is pure Python/PyTorch and has no FFI; the
+ * boundary it exposes for this path is the Python API of curl_sac.py / encoder.py /
+ * utils.py / augmentations.py.  This header is the C ABI the Python host side
+ * (curla_b200/*.py, via ctypes) binds; every entry point cites the reference
+ * code it replaces (paths relative to the reference repo root).  INTEGRATION.md shows the
+ * ctypes stubs a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; device pointers unless stated; the caller owns
+ *    every buffer (PyTorch allocations); nothing returned by the library is freed by
+ *    the caller except handles via their *_destroy.
+ *  - every call is asynchronous on `stream` and never synchronises.
+ *  - return 0 on success, negative on error; curla_last_error() gives the message.
+ *  - bf16 buffers are passed as void*.
+ */
+#ifndef CURLA_B200_H
+#define CURLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* curla_stream_t; /* == cudaStream_t */
+
+const char* curla_last_error(void);
+int curla_version(void);
+
+/* ---- K1: replay gather + crop  (utils.py:147-166, augmentations.py:47-75) -------------
+ * frames: uint8 [capacity][C][Hf][Wf]; idxs/h1/w1: int64 [B] (h1,w1 may be NULL = 0,
+ * idxs may be NULL = arange).  out_f32: [B][C][H][W].                                   */
+int curla_gather_crop_f32(const uint8_t* frames, int C, int Hf, int Wf, const int64_t* idxs,
+                          const int64_t* h1, const int64_t* w1, int B, int H, int W,
+                          float* out, curla_stream_t stream);
+/* same gather, written as the bf16 space-to-depth rows the conv stack consumes:
+ * out[b][yb*Ws+xb][c*4+sy*2+sx], CP channels per row (>= 4C, multiple of 8).           */
+int curla_gather_crop_s2d(const uint8_t* frames, int C, int Hf, int Wf, const int64_t* idxs,
+                          const int64_t* h1, const int64_t* w1, int B, int H, int W, int CP,
+                          long long out_sample_stride, void* out, curla_stream_t stream);
+/* float NCHW observations (already augmented) -> s2d rows (encoder.py:77 input). */
+int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
+                     long long out_sample_stride, void* out, curla_stream_t stream);
+/* actions / rewards / not_dones rows (utils.py:163-165) */
+int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
+                          curla_stream_t stream);
+
+/* ---- K4-K6: conv stack as shifted GEMMs  (encoder.py:77-90 + autograd) ------------------ */
+int curla_conv_fwd(const void* in, long long in_sstride, const void* wts, const float* bias,
+                   float scale, void* out, long long out_sstride, int B, int pitch, int S,
+                   int Hv, int Wv, int first_layer, curla_stream_t stream);
+int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts, const void* x,
+                     void* dx, long long dx_sstride, int B, int pitch, int S, int Hv, int Wv,
+                     curla_stream_t stream);
+long long curla_conv_wgrad_workspace_floats(int first_layer);
+int curla_conv_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
+                     float* workspace, float* dW, float* db, float scale, int B, int pitch,
+                     int S, int Hv, int Wv, int Cin, int first_layer, curla_stream_t stream);
+
+/* ---- K7/K9: bf16 tensor-core GEMM  (encoder.py:98; curl_sac.py:70-74,129-133) ----------- */
+int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C,
+                    long long ldc, int M, int N, int K, int layout, int n_store, int out_bf16,
+                    const float* bias, int relu, const void* mask, long long ldmask, int splits,
+                    long long split_stride, float alpha, curla_stream_t stream);
+int curla_gemm_effective_splits(int K, int splits);
+
+/* ---- K8 LayerNorm, K10 policy head, K11 losses, MLP heads  (encoder.py:98-110;
+ *      curl_sac.py:20-35,79-110,349-404) ------------------------------------------------ */
+int curla_ln_fwd(const float* partial, int nsplit, long long split_stride, const float* bias,
+                 const float* gamma, const float* beta, int B, int feat, int apply_tanh,
+                 float* x_out, float* z_out, curla_stream_t stream);
+int curla_ln_bwd(const float* dz_a, const float* dz_b, const float* x_in, const float* gamma,
+                 int B, int feat, float* dx_f32, void* dx_bf16, float* scratch, float* dgamma,
+                 float* dbeta, float* dbias_fc, curla_stream_t stream);
+int curla_pack_x(const float* z, const float* act, int B, int feat, int A, void* X,
+                 curla_stream_t stream);
+int curla_head_fwd(const void* H, int ldh, const float* W, const float* bias, int B, int hid,
+                   int No, float* out, curla_stream_t stream);
+int curla_head_bwd(const float* dOut, const float* W, const void* H, int B, int hid, int No,
+                   void* dH, curla_stream_t stream);
+int curla_head_wgrad(const float* dOut, const void* H, int B, int hid, int No, float* dW,
+                     float* db, curla_stream_t stream);
+int curla_colsum_bf16(const void* dH, int B, int hid, float* db, curla_stream_t stream);
+int curla_policy_fwd(const float* t, const float* noise_in, unsigned long long seed,
+                     unsigned long long offset, int B, int A, float ls_min, float ls_max,
+                     int compute_pi, int compute_log_pi, float* mu, float* pi, float* log_pi,
+                     float* ls, float* noise_out, curla_stream_t stream);
+int curla_policy_bwd(const float* dx1, const float* dx2, int feat, const float* glogpi,
+                     const float* t, const float* noise, const float* pi, const float* ls, int B,
+                     int A, float ls_min, float ls_max, float* dt, curla_stream_t stream);
+int curla_critic_loss(const float* tq1, const float* tq2, const float* logpi_next,
+                      const float* reward, const float* not_done, const double* log_alpha,
+                      float discount, const float* q1, const float* q2, int B, float grad_scale,
+                      float* target_q, float* dq1, float* dq2, float* metrics,
+                      curla_stream_t stream);
+int curla_actor_loss(const float* log_pi, const float* q1, const float* q2, const float* ls, int B,
+                     int A, const double* log_alpha, float target_entropy, float grad_scale,
+                     float* dq1, float* dq2, float* glogpi, double* g_log_alpha, float* metrics,
+                     curla_stream_t stream);
+int curla_add2(const float* a, const float* b, long long n, float* out, curla_stream_t stream);
+
+/* ---- K12: CURL bilinear logits + cross-entropy fwd/bwd  (curl_sac.py:211-222,406-417) -- */
+long long curla_curl_workspace_floats(int B, int Bg);
+int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const float* W, int B, int Bg,
+                       int feat, int label0, float grad_scale, float* workspace, float* loss_out,
+                       float* dz_a, float* dW, float* logits_copy, curla_stream_t stream);
+
+/* ---- K13 Adam, K14 EMA, shadow packing  (curl_sac.py:299-313,368,392,404,419-420;
+ *      utils.py:37-41) ------------------------------------------------------------------- */
+int curla_adam_f32(float* p, const float* g, float* m, float* v, long long n,
+                   long long double_from, double lr, double beta1, double beta2, double eps,
+                   int t_host, const int* t_dev, curla_stream_t stream);
+int curla_adam_f64_scalar(double* p, const double* g, double* state, double lr, double beta1,
+                          double beta2, double eps, int t_host, const int* t_dev,
+                          curla_stream_t stream);
+int curla_ema_f32(float* target, const float* p, long long n, long long split, double tau_a,
+                  double tau_b, curla_stream_t stream);
+int curla_pack_shadows(const float* src_arena, void* dst_arena, const long long* segs, int n,
+                       curla_stream_t stream);
+
+/* ---- the agent engine: whole CurlSacAgent.update (curl_sac.py:426-451) ------------------ */
+typedef struct curla_agent curla_agent;
+
+typedef struct curla_agent_config {
+    int C, H, W;              /* encoder input (post-augmentation) shape, obs_shape      */
+    int Hf, Wf;               /* stored frame size in the replay buffer                  */
+    int feature_dim, hidden_dim, action_dim, num_filters, num_layers;
+    int batch;                /* local batch B                                            */
+    int global_batch;         /* B * world                                                */
+    int rank, world;
+    int detach_encoder, pixel_sac;
+    int actor_update_freq, critic_target_update_freq, cpc_update_freq;
+    double discount, critic_tau, encoder_tau;
+    double actor_lr, actor_beta, critic_lr, critic_beta, alpha_lr, alpha_beta, encoder_lr;
+    double log_std_min, log_std_max, target_entropy;
+} curla_agent_config;
+
+/* arenas the caller allocates (zero-initialised) and binds */
+enum {
+    CURLA_ARENA_PARAMS = 0,   /* fp32 master parameters (W | critic | actor-own | target)  */
+    CURLA_ARENA_SHADOW = 1,   /* bf16 kernel-layout copies                                 */
+    CURLA_ARENA_GRADS = 2,    /* fp32 [g_critic | g_actor | g_cpc]                         */
+    CURLA_ARENA_ADAM = 3,     /* fp32 m,v for the three fp32 optimizer states              */
+    CURLA_ARENA_WORK = 4,     /* activations / scratch (bytes)                             */
+    CURLA_ARENA_COUNT = 5
+};
+
+curla_agent* curla_agent_create(const curla_agent_config* cfg);
+void curla_agent_destroy(curla_agent* a);
+/* bytes needed for arena `which` */
+long long curla_agent_arena_bytes(const curla_agent* a, int which);
+int curla_agent_bind(curla_agent* a, void* const* arenas);
+/* tensor table: i in [0, curla_agent_num_tensors): name, arena, byte offset, dims (<=4) */
+int curla_agent_num_tensors(const curla_agent* a);
+int curla_agent_tensor_info(const curla_agent* a, int i, char* name, int name_cap, int* arena,
+                            long long* byte_offset, int* ndim, long long* dims, int* dtype);
+/* rebuild every bf16 shadow from the fp32 masters (after load_state_dict / init) */
+int curla_agent_refresh_shadows(curla_agent* a, curla_stream_t stream);
+
+typedef struct curla_update_args {
+    /* replay storage (device): utils.py:92-96 */
+    const uint8_t* obses; const uint8_t* next_obses;
+    const float* actions; const float* rewards; const float* not_dones;
+    /* sampled indices of the LOCAL shard (device int64[B]); h1/w1 NULL unless random_crop */
+    const int64_t* idxs;
+    const int64_t* h1_obs; const int64_t* w1_obs;
+    const int64_t* h1_next; const int64_t* w1_next;
+    const int64_t* h1_pos; const int64_t* w1_pos;
+    /* optional pre-augmented float observations [B][C][H][W] (colour-jiggle / noisy-cover);
+       when set they replace the uint8 gather for that stream */
+    const float* obs_f32; const float* next_f32; const float* pos_f32;
+    /* injected policy noise [B][A] (NULL => Philox with seed/offset) */
+    const float* noise_next; const float* noise_cur;
+    unsigned long long seed, offset;
+    int step;                 /* global env step (frequencies use it: curl_sac.py:439-449) */
+    int only_cpc;
+    int pos_is_obs;           /* identity branch: pos is a value-equal clone of obs      */
+} curla_update_args;
+
+/* One whole update.  metrics: device float[16]
+ * {batch_reward, critic_loss, actor_loss, entropy, alpha_loss, alpha, curl_loss, target_entropy} */
+int curla_agent_update(curla_agent* a, const curla_update_args* args, curla_stream_t stream);
+/* number of kernel launches issued by the last curla_agent_update */
+int curla_agent_last_launches(const curla_agent* a);
+
+/* inference entry points (sample_action / select_action / eval / latent extraction:
+ * curl_sac.py:330-347, plot_tsne/latent_data.py:63-104).  obs_s2d rows as produced by
+ * curla_gather_crop_s2d / curla_f32_to_s2d; net: 0 actor, 1 critic, 2 target.           */
+int curla_agent_encode(curla_agent* a, int net, const void* obs_s2d, int B, int apply_tanh,
+                       float* z_out /* [B][64] */, curla_stream_t stream);
+int curla_agent_actor_head(curla_agent* a, const float* z, int B, const float* noise,
+                           unsigned long long seed, unsigned long long offset, int compute_pi,
+                           int compute_log_pi, float* mu, float* pi, float* log_pi,
+                           float* log_std, curla_stream_t stream);
+int curla_agent_q_heads(curla_agent* a, int net, const float* z, const float* action, int B,
+                        float* q1, float* q2, curla_stream_t stream);
+
+/* data-parallel plumbing: NCCL communicator shared by all collectives of the update */
+int curla_nccl_unique_id(void* out128);
+int curla_agent_init_comm(curla_agent* a, const void* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURLA_B200_H */

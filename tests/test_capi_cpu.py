@@ -1,0 +1,87 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol declared in
+include/curla_b200.h; host-side layout logic of the engine; no compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from curla_b200 import build
+    build.build()
+    from curla_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from curla_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'curla_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = set(re.findall(r'\b(curla_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) > 40
+    for n in sorted(names):
+        assert hasattr(lib, n), 'missing export: ' + n
+        assert n in _lib.SIGNATURES, 'no ctypes signature for ' + n
+    assert set(_lib.SIGNATURES) <= names
+    assert lib.curla_version() >= 100
+
+
+def test_engine_layout_host_side(lib):
+    """curla_agent_create is pure host code: check the memory plan without a GPU."""
+    from curla_b200 import _lib
+    c = _lib.AgentConfig()
+    vals = dict(C=9, H=76, W=135, Hf=90, Wf=160, feature_dim=50, hidden_dim=1024, action_dim=2, num_filters=32,
+                num_layers=4, batch=512, global_batch=512, rank=0, world=1, actor_update_freq=2,
+                critic_target_update_freq=2, cpc_update_freq=1)
+    for k, v in vals.items():
+        setattr(c, k, v)
+    h = lib.curla_agent_create(C.byref(c))
+    assert h
+    info = {}
+    name = C.create_string_buffer(256)
+    arena, off, ndim, dt = C.c_int(), C.c_longlong(), C.c_int(), C.c_int()
+    dims = (C.c_longlong * 4)()
+    for i in range(lib.curla_agent_num_tensors(h)):
+        assert lib.curla_agent_tensor_info(h, i, name, 256, C.byref(arena), C.byref(off), C.byref(ndim), dims,
+                                           C.byref(dt)) == 0
+        info[name.value.decode()] = (arena.value, off.value, [dims[k] for k in range(ndim.value)], dt.value)
+    # fc_in 60,512 = 32*31*61 lives in a [50][31][68][32] canonical tensor
+    assert info['critic.encoder.fc.weight_canon'][2] == [50, 31, 68, 32]
+    assert info['critic.Q1.trunk.0.weight'][2] == [1024, 52]
+    assert info['actor.trunk.4.weight'][2] == [4, 1024]
+    # critic and target segments have identical structure (EMA runs flat over them)
+    c0, t0 = info['critic.encoder.convs.0.weight'][1], info['target.encoder.convs.0.weight'][1]
+    for k, v in info.items():
+        if k.startswith('critic.') and v[0] == 0:
+            assert info['target.' + k[len('critic.'):]][1] - t0 == v[1] - c0, k
+    # [W | critic.encoder] is contiguous: the CURL Adam covers it in one launch
+    assert info['CURL.W'][1] == 0 and c0 == 2500 * 4
+    n_crit = info['grad.critic'][2][0]
+    assert n_crit >= 5_265_912 and info['grad.actor'][2][0] >= 4_162_042 - 9248 * 3 - 2624
+    assert lib.curla_agent_arena_bytes(h, 4) > 512 * 2584 * 64 * 12
+    # bad configs fail loudly
+    c.num_filters = 16
+    assert not lib.curla_agent_create(C.byref(c))
+    assert b'num_filters' in lib.curla_last_error()
+    lib.curla_agent_destroy(h)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'curla_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert 'oracle' not in src.replace('CPU oracle', ''), f
+
+
+def test_no_cpu_fallback():
+    import torch
+    from curla_b200 import _lib, utils, augmentations
+    with pytest.raises(_lib.CurlaError):
+        utils.ReplayBuffer((9, 90, 160), (2,), 8, 4, torch.device('cpu'),
+                           augmentations.IdentityAugmentation((90, 160)))

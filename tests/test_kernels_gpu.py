@@ -1,0 +1,402 @@
+"""Per-kernel parity tests through the C ABI (run on the B200 box: pytest -m gpu).
+
+Integer / byte / index work must be bit exact.  Tensor-core kernels compute with bf16
+operands and fp32 accumulation: compared against fp32 torch references evaluated on the
+SAME bf16-rounded operands (tolerance 2e-3 relative L2: accumulation-order noise only),
+and against the un-rounded fp32 reference at 2e-2 (bf16 operand rounding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from curla_b200 import _lib
+from oracle import curla_oracle as O
+
+from helpers import DEV, Geom, bf16r, max_rel, pack_conv_w, rel_l2, stream
+
+pytestmark = pytest.mark.gpu
+
+
+def dv(a, dtype=None):
+    t = torch.as_tensor(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV).contiguous()
+
+
+# ------------------------------------------------------------------ K1 gather / crop
+@pytest.mark.parametrize('B,crop', [(5, True), (3, False), (33, True)])
+def test_gather_crop_bit_exact(B, crop):
+    rs = np.random.RandomState(0)
+    cap, Cc, Hf, Wf = 11, 9, 90, 160
+    frames = rs.randint(0, 256, size=(cap, Cc, Hf, Wf), dtype=np.uint8)
+    idxs = rs.randint(0, cap, size=B)
+    oh, ow = (76, 135) if crop else (Hf, Wf)
+    h1 = rs.randint(0, Hf - oh + 1, size=B)
+    w1 = rs.randint(0, Wf - ow + 1, size=B)
+    ref = O.gather_crop(frames, idxs, h1, w1, (oh, ow))
+    fr = dv(frames)
+    out = torch.empty((B, Cc, oh, ow), dtype=torch.float32, device=DEV)
+    _lib.call('curla_gather_crop_f32', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(dv(idxs)), _lib.ptr(dv(h1)),
+              _lib.ptr(dv(w1)), B, oh, ow, _lib.ptr(out), stream())
+    assert torch.equal(out.cpu(), torch.from_numpy(ref).float())
+    # space-to-depth bf16 variant: exact as well (uint8 is exact in bf16)
+    g = Geom(oh, ow, B)
+    full, view = g.alloc(g.CP1)
+    _lib.call('curla_gather_crop_s2d', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(dv(idxs)), _lib.ptr(dv(h1)),
+              _lib.ptr(dv(w1)), B, oh, ow, g.CP1, g.S * g.CP1, _lib.ptr(view), stream())
+    want = g.s2d_ref(torch.from_numpy(ref).to(DEV))
+    assert torch.equal(view.view(B, g.Hs, g.pitch, g.CP1).float(), want)
+    assert float(full[:g.PAD].abs().sum()) == 0 and float(full[g.PAD + B * g.S:].abs().sum()) == 0
+    # float-input variant
+    full2, view2 = g.alloc(g.CP1)
+    _lib.call('curla_f32_to_s2d', _lib.ptr(out), Cc, oh, ow, B, g.CP1, g.S * g.CP1, _lib.ptr(view2), stream())
+    assert torch.equal(view2, view)
+
+
+def test_gather_rows():
+    rs = np.random.RandomState(1)
+    src = rs.standard_normal((17, 2)).astype(np.float32)
+    idxs = rs.randint(0, 17, size=9)
+    out = torch.empty((9, 2), dtype=torch.float32, device=DEV)
+    _lib.call('curla_gather_rows_f32', _lib.ptr(dv(src)), _lib.ptr(dv(idxs)), 9, 2, _lib.ptr(out), stream())
+    assert np.array_equal(out.cpu().numpy(), src[idxs])
+
+
+# ------------------------------------------------------------------ conv stack
+def _conv_case(H, W, B, seed=0):
+    torch.manual_seed(seed)
+    g = Geom(H, W, B)
+    x = torch.randint(0, 256, (B, 9, H, W)).float()
+    ws = [torch.randn(32, 9, 3, 3) * (2.0 / 81) ** 0.5] + [torch.randn(32, 32, 3, 3) * (2.0 / 288) ** 0.5
+                                                            for _ in range(3)]
+    bs = [torch.randn(32) * 0.05 for _ in range(4)]
+    return g, x, ws, bs
+
+
+def _run_conv_stack(g, x, ws, bs):
+    """our kernels: returns per-layer logical views (bf16 pitch layout) + s2d buffer."""
+    full_s, s2d = g.alloc(g.CP1)
+    xd = x.to(DEV)
+    _lib.call('curla_f32_to_s2d', _lib.ptr(xd), 9, g.H, g.W, g.B, g.CP1, g.S * g.CP1, _lib.ptr(s2d), stream())
+    acts, keep = [], [full_s]
+    inp, stride = s2d, g.S * g.CP1
+    for l in range(4):
+        wsh = pack_conv_w(ws[l], l == 0)
+        full, out = g.alloc(32)
+        _lib.call('curla_conv_fwd', _lib.ptr(inp), stride, _lib.ptr(wsh), _lib.ptr(bs[l].to(DEV)),
+                  1.0 / 255.0 if l == 0 else 1.0, _lib.ptr(out), g.S * 32, g.B, g.pitch, g.S, g.Ho[l], g.Wo[l],
+                  1 if l == 0 else 0, stream())
+        acts.append(out)
+        keep += [full, wsh]
+        inp, stride = out, g.S * 32
+    return s2d, acts, keep
+
+
+@pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (64, 64, 5)])
+def test_conv_forward(H, W, B):
+    g, x, ws, bs = _conv_case(H, W, B)
+    s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
+    # reference on bf16-rounded operands, layer by layer (our activations are stored bf16)
+    cur = x.to(DEV) / 255.0
+    cur_exact = x.to(DEV) / 255.0
+    for l in range(4):
+        w, b = ws[l].to(DEV), bs[l].to(DEV)
+        st = 2 if l == 0 else 1
+        if l == 0:   # ours: integer input exact, weights bf16, scale applied in fp32
+            ref = torch.relu(F.conv2d(x.to(DEV), bf16r(w), None, stride=2) / 255.0 + b.view(1, -1, 1, 1))
+        else:
+            ref = torch.relu(F.conv2d(cur, bf16r(w), b, stride=st))
+        cur_exact = torch.relu(F.conv2d(cur_exact, w, b, stride=st))
+        ours = g.from_pitch(acts[l], g.Ho[l], g.Wo[l])
+        assert ref.shape == ours.shape
+        e = rel_l2(ours, ref)
+        assert e < 6e-3, (l, e)          # bf16 storage rounding of the output + accumulation order
+        assert rel_l2(ours, cur_exact) < 3e-2, l
+        # invalid positions are exact zeros
+        v = acts[l].view(B, g.Hs, g.pitch, 32).float()
+        assert float(v[:, g.Ho[l]:].abs().sum()) == 0 and float(v[:, :, g.Wo[l]:].abs().sum()) == 0
+        cur = bf16r(ours)                 # feed OUR stored activations to the next reference layer
+
+
+@pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2)])
+def test_conv_backward(H, W, B):
+    g, x, ws, bs = _conv_case(H, W, B, seed=1)
+    s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
+    torch.manual_seed(2)
+    # upstream gradient on the last layer's valid region
+    dy4 = torch.randn(B, 32, g.Ho[3], g.Wo[3], device=DEV) * (g.from_pitch(acts[3], g.Ho[3], g.Wo[3]) > 0)
+    # torch reference: autograd through convs evaluated on OUR stored activations
+    wref = [bf16r(w.to(DEV)).requires_grad_(True) for w in ws]
+    bref = [b.to(DEV).clone().requires_grad_(True) for b in bs]
+    a_in = [x.to(DEV) / 255.0] + [bf16r(g.from_pitch(acts[l], g.Ho[l], g.Wo[l])) for l in range(3)]
+    dfull, dview = g.to_pitch(bf16r(dy4), 3)
+    dcur = dview
+    ws_buf = torch.zeros(int(max(_lib.load().curla_conv_wgrad_workspace_floats(0),
+                                 _lib.load().curla_conv_wgrad_workspace_floats(1))), device=DEV)
+    dy_ref = bf16r(dy4)
+    for l in (3, 2, 1, 0):
+        # reference grads for layer l given dy_ref on its (post-ReLU-masked) output
+        xin = a_in[l].detach().requires_grad_(l > 0)
+        y = F.conv2d(xin, wref[l], bref[l], stride=2 if l == 0 else 1)
+        grads = torch.autograd.grad(y, ([xin] if l > 0 else []) + [wref[l], bref[l]], dy_ref)
+        dW = torch.zeros(ws[l].shape, device=DEV)
+        db = torch.zeros(32, device=DEV)
+        inp = acts[l - 1] if l > 0 else s2d
+        _lib.call('curla_conv_wgrad', _lib.ptr(inp), g.S * (32 if l > 0 else g.CP1), _lib.ptr(dcur), g.S * 32,
+                  _lib.ptr(ws_buf), _lib.ptr(dW), _lib.ptr(db), 1.0 / 255.0 if l == 0 else 1.0, B, g.pitch, g.S,
+                  g.Ho[l], g.Wo[l], ws[l].shape[1], 1 if l == 0 else 0, stream())
+        assert rel_l2(dW, grads[-2]) < 5e-3, ('dW', l, rel_l2(dW, grads[-2]))
+        assert rel_l2(db, grads[-1]) < 5e-3, ('db', l)
+        if l > 0:
+            full, dx = g.alloc(32)
+            _lib.call('curla_conv_dgrad', _lib.ptr(dcur), g.S * 32, _lib.ptr(pack_conv_w(ws[l], False)),
+                      _lib.ptr(acts[l - 1]), _lib.ptr(dx), g.S * 32, B, g.pitch, g.S, g.Ho[l - 1], g.Wo[l - 1],
+                      stream())
+            mask = (g.from_pitch(acts[l - 1], g.Ho[l - 1], g.Wo[l - 1]) > 0)
+            dx_ref = grads[0] * mask
+            ours = g.from_pitch(dx, g.Ho[l - 1], g.Wo[l - 1])
+            assert rel_l2(ours, dx_ref) < 6e-3, ('dx', l, rel_l2(ours, dx_ref))
+            v = dx.view(B, g.Hs, g.pitch, 32).float()
+            assert float(v[:, g.Ho[l - 1]:].abs().sum()) == 0 and float(v[:, :, g.Wo[l - 1]:].abs().sum()) == 0
+            keep.append(full)
+            dcur = dx
+            dy_ref = bf16r(ours)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize('layout', [3, 1, 2, 0])
+@pytest.mark.parametrize('M,N,K', [(70, 72, 96), (5, 64, 64), (130, 200, 40), (64, 64, 2048)])
+def test_gemm_layouts(layout, M, N, K):
+    torch.manual_seed(layout * 100 + M)
+    A = torch.randn(M, K, device=DEV)
+    Bm = torch.randn(K, N, device=DEV)
+    ref = bf16r(A) @ bf16r(Bm)
+    # contiguous extents must be multiples of 8: pad the leading dims
+    r8 = lambda n: (n + 7) // 8 * 8
+    if layout & 1:
+        a = torch.zeros(M, r8(K), device=DEV, dtype=torch.bfloat16); a[:, :K] = A
+    else:
+        a = torch.zeros(K, r8(M), device=DEV, dtype=torch.bfloat16); a[:, :M] = A.t()
+    if layout & 2:
+        b = torch.zeros(N, r8(K), device=DEV, dtype=torch.bfloat16); b[:, :K] = Bm.t()
+    else:
+        b = torch.zeros(K, r8(N), device=DEV, dtype=torch.bfloat16); b[:, :N] = Bm
+    out = torch.full((M, N + (N & 1)), 7.0, device=DEV)
+    _lib.call('curla_gemm_bf16', _lib.ptr(a), a.shape[1], _lib.ptr(b), b.shape[1], _lib.ptr(out), out.shape[1],
+              M, N, K, layout, N, 0, None, 0, None, 0, 1, 0, 1.0, stream())
+    assert rel_l2(out[:, :N], ref) < 2e-3, rel_l2(out[:, :N], ref)
+
+
+def test_gemm_epilogues_and_splitk():
+    torch.manual_seed(5)
+    M, N, K = 37, 64, 4096
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    W = torch.randn(N, K, device=DEV).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    ref = A.float() @ W.float().t()
+    # split-K partials
+    splits = _lib.load().curla_gemm_effective_splits(K, 7)
+    part = torch.zeros((splits, M, N), device=DEV)
+    _lib.call('curla_gemm_bf16', _lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(part), N, M, N, K, 3, N, 0, None, 0,
+              None, 0, splits, M * N, 1.0, stream())
+    assert rel_l2(part.sum(0), ref) < 2e-3
+    # bias + relu + bf16 out + mask + n_store
+    mask = (torch.randn(M, N, device=DEV) > 0).to(torch.bfloat16)
+    out = torch.zeros((M, N), device=DEV, dtype=torch.bfloat16)
+    _lib.call('curla_gemm_bf16', _lib.ptr(A), K, _lib.ptr(W), K, _lib.ptr(out), N, M, N, K, 3, 50, 1, _lib.ptr(bias),
+              1, _lib.ptr(mask), N, 1, 0, 0.5, stream())
+    want = torch.relu(ref * 0.5 + bias) * mask.float()
+    assert rel_l2(out[:, :50].float(), want[:, :50]) < 6e-3
+    assert float(out[:, 50:].abs().sum()) == 0
+
+
+# ------------------------------------------------------------------ LayerNorm / heads / policy / losses
+def test_layernorm_fwd_bwd():
+    torch.manual_seed(3)
+    B, feat = 19, 50
+    part = torch.zeros((3, B, 64), device=DEV); part[:, :, :feat] = torch.randn(3, B, feat, device=DEV)
+    bias, gamma, beta = [torch.randn(feat, device=DEV) for _ in range(3)]
+    x_out = torch.zeros((B, 64), device=DEV); z = torch.zeros((B, 64), device=DEV)
+    _lib.call('curla_ln_fwd', _lib.ptr(part), 3, B * 64, _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), B, feat,
+              0, _lib.ptr(x_out), _lib.ptr(z), stream())
+    x = (part.sum(0)[:, :feat] + bias).requires_grad_(True)
+    g = gamma.clone().requires_grad_(True); bt = beta.clone().requires_grad_(True)
+    zr = F.layer_norm(x, (feat,), g, bt, 1e-5)
+    assert max_rel(z[:, :feat], zr) < 1e-5 and float(z[:, feat:].abs().sum()) == 0
+    dz = torch.zeros((B, 64), device=DEV); dz[:, :feat] = torch.randn(B, feat, device=DEV)
+    dz2 = torch.zeros((B, 64), device=DEV); dz2[:, :feat] = torch.randn(B, feat, device=DEV)
+    zr.backward(dz[:, :feat] + dz2[:, :feat])
+    dx = torch.zeros((B, 64), device=DEV); dxb = torch.zeros((B, 64), device=DEV, dtype=torch.bfloat16)
+    scratch = torch.zeros((2, B, 64), device=DEV)
+    dg, dbt, dbias = [torch.zeros(feat, device=DEV) for _ in range(3)]
+    _lib.call('curla_ln_bwd', _lib.ptr(dz), _lib.ptr(dz2), _lib.ptr(x_out), _lib.ptr(gamma), B, feat, _lib.ptr(dx),
+              _lib.ptr(dxb), _lib.ptr(scratch), _lib.ptr(dg), _lib.ptr(dbt), _lib.ptr(dbias), stream())
+    assert max_rel(dx[:, :feat], x.grad) < 1e-4
+    assert max_rel(dg, g.grad) < 1e-4 and max_rel(dbt, bt.grad) < 1e-4
+    assert max_rel(dbias, x.grad.sum(0)) < 1e-4
+    assert rel_l2(dxb.float(), dx) < 4e-3
+
+
+def test_policy_head_fwd_bwd():
+    torch.manual_seed(4)
+    B, A = 21, 2
+    t = (torch.randn(B, 2 * A, device=DEV) * 1.5).requires_grad_(True)
+    noise = torch.randn(B, A, device=DEV)
+    mu, ls_raw = t.chunk(2, dim=-1)
+    ls = torch.tanh(ls_raw); ls = -10 + 0.5 * 12 * (ls + 1)
+    pi_pre = mu + noise * ls.exp()
+    lp = O.gaussian_logprob(noise, ls)
+    pi = torch.tanh(pi_pre)
+    lp = lp - torch.log(F.relu(1 - pi.pow(2)) + 1e-6).sum(-1, keepdim=True)
+    o = [torch.zeros((B, A), device=DEV) for _ in range(2)] + [torch.zeros(B, device=DEV)] + \
+        [torch.zeros((B, A), device=DEV) for _ in range(2)]
+    _lib.call('curla_policy_fwd', _lib.ptr(t.detach()), _lib.ptr(noise), 0, 0, B, A, -10.0, 2.0, 1, 1, _lib.ptr(o[0]),
+              _lib.ptr(o[1]), _lib.ptr(o[2]), _lib.ptr(o[3]), _lib.ptr(o[4]), stream())
+    assert max_rel(o[0], torch.tanh(mu)) < 1e-5 and max_rel(o[1], pi) < 1e-5
+    assert (o[2] - lp[:, 0]).abs().max() < 2e-3 * max(1.0, float(lp.abs().max()))
+    assert max_rel(o[3], ls) < 1e-5 and torch.equal(o[4], noise)
+    # backward: L = sum(gpi * pi) + glp * sum(log_pi)
+    gpi = torch.randn(B, A, device=DEV)
+    glp = 0.37
+    (gpi * pi).sum().add(glp * lp.sum()).backward()
+    dx1 = torch.zeros((B, 64), device=DEV); dx1[:, 50:52] = gpi * 0.25
+    dx2 = torch.zeros((B, 64), device=DEV); dx2[:, 50:52] = gpi * 0.75
+    dt = torch.zeros((B, 2 * A), device=DEV)
+    _lib.call('curla_policy_bwd', _lib.ptr(dx1), _lib.ptr(dx2), 50, _lib.ptr(torch.tensor([glp], device=DEV)),
+              _lib.ptr(t.detach()), _lib.ptr(noise), _lib.ptr(o[1]), _lib.ptr(o[3]), B, A, -10.0, 2.0, _lib.ptr(dt),
+              stream())
+    assert rel_l2(dt, t.grad) < 1e-3, rel_l2(dt, t.grad)
+    # built-in Philox noise: N(0,1) moments
+    Bn = 1 << 16
+    tt = torch.zeros((Bn, 2 * A), device=DEV)
+    nz = torch.zeros((Bn, A), device=DEV)
+    pi_o = torch.zeros((Bn, A), device=DEV); ls_o = torch.zeros((Bn, A), device=DEV)
+    _lib.call('curla_policy_fwd', _lib.ptr(tt), None, 1234, 5, Bn, A, -10.0, 2.0, 1, 0, None, _lib.ptr(pi_o), None,
+              _lib.ptr(ls_o), _lib.ptr(nz), stream())
+    assert abs(float(nz.mean())) < 0.02 and abs(float(nz.std()) - 1.0) < 0.02
+    assert abs(float((nz[:, 0] * nz[:, 1]).mean())) < 0.02
+
+
+def test_mlp_heads_and_losses():
+    torch.manual_seed(6)
+    B, hid, No = 13, 64, 4
+    H = torch.randn(B, hid, device=DEV).clamp_min(0).to(torch.bfloat16)
+    W = torch.randn(No, hid, device=DEV); b = torch.randn(No, device=DEV)
+    out = torch.zeros((B, No), device=DEV)
+    _lib.call('curla_head_fwd', _lib.ptr(H), hid, _lib.ptr(W), _lib.ptr(b), B, hid, No, _lib.ptr(out), stream())
+    assert max_rel(out, H.float() @ W.t() + b) < 1e-5
+    dO = torch.randn(B, No, device=DEV)
+    dH = torch.zeros((B, hid), device=DEV, dtype=torch.bfloat16)
+    _lib.call('curla_head_bwd', _lib.ptr(dO), _lib.ptr(W), _lib.ptr(H), B, hid, No, _lib.ptr(dH), stream())
+    assert rel_l2(dH.float(), (dO @ W) * (H.float() > 0)) < 4e-3
+    dW = torch.zeros((No, hid), device=DEV); db = torch.zeros(No, device=DEV)
+    _lib.call('curla_head_wgrad', _lib.ptr(dO), _lib.ptr(H), B, hid, No, _lib.ptr(dW), _lib.ptr(db), stream())
+    assert max_rel(dW, dO.t() @ H.float()) < 1e-5 and max_rel(db, dO.sum(0)) < 1e-5
+    cs = torch.zeros(hid, device=DEV)
+    _lib.call('curla_colsum_bf16', _lib.ptr(dH), B, hid, _lib.ptr(cs), stream())
+    assert max_rel(cs, dH.float().sum(0)) < 1e-5
+    # losses
+    tq1, tq2, lpn, rew, q1, q2 = [torch.randn(B, device=DEV) for _ in range(6)]
+    nd = (torch.rand(B, device=DEV) > 0.2).float()
+    la = torch.tensor([np.log(0.1)], device=DEV, dtype=torch.float64)
+    tq = torch.zeros(B, device=DEV); d1 = torch.zeros(B, device=DEV); d2 = torch.zeros(B, device=DEV)
+    m = torch.zeros(16, device=DEV)
+    _lib.call('curla_critic_loss', _lib.ptr(tq1), _lib.ptr(tq2), _lib.ptr(lpn), _lib.ptr(rew), _lib.ptr(nd),
+              _lib.ptr(la), 0.99, _lib.ptr(q1), _lib.ptr(q2), B, 1.0 / B, _lib.ptr(tq), _lib.ptr(d1), _lib.ptr(d2),
+              _lib.ptr(m), stream())
+    tref = rew + nd * 0.99 * (torch.min(tq1, tq2) - 0.1 * lpn)
+    assert max_rel(tq, tref) < 1e-5
+    assert abs(float(m[1]) - float(F.mse_loss(q1, tref) + F.mse_loss(q2, tref))) < 1e-4
+    assert max_rel(d1, 2 * (q1 - tref) / B) < 1e-5 and abs(float(m[0]) - float(rew.mean())) < 1e-5
+    ls = torch.randn(B, 2, device=DEV); glp = torch.zeros(4, device=DEV)
+    gla = torch.zeros(1, device=DEV, dtype=torch.float64)
+    _lib.call('curla_actor_loss', _lib.ptr(lpn), _lib.ptr(q1), _lib.ptr(q2), _lib.ptr(ls), B, 2, _lib.ptr(la), -2.0,
+              1.0 / B, _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(glp), _lib.ptr(gla), _lib.ptr(m), stream())
+    assert abs(float(m[2]) - float((0.1 * lpn - torch.min(q1, q2)).mean())) < 1e-5
+    assert abs(float(m[4]) - float((0.1 * (-lpn + 2.0)).mean())) < 1e-5
+    assert abs(float(gla) - 0.1 * float((-lpn + 2.0).mean())) < 1e-6
+    assert abs(float(glp[0]) - 0.1 / B) < 1e-8
+    assert torch.equal(d1 != 0, q1 <= q2)
+
+
+# ------------------------------------------------------------------ CURL
+@pytest.mark.parametrize('B,Bg,label0', [(12, 12, 0), (8, 24, 8), (70, 70, 0)])
+def test_curl_fwd_bwd(B, Bg, label0):
+    torch.manual_seed(7)
+    feat = 50
+    za = torch.zeros((B, 64), device=DEV); za[:, :feat] = torch.randn(B, feat, device=DEV)
+    zp = torch.zeros((Bg, 64), device=DEV); zp[:, :feat] = torch.randn(Bg, feat, device=DEV)
+    W = torch.rand(feat, feat, device=DEV)
+    zar = za[:, :feat].clone().requires_grad_(True); Wr = W.clone().requires_grad_(True)
+    logits = O.curl_logits(Wr, zar, zp[:, :feat])
+    labels = torch.arange(B, device=DEV) + label0
+    loss = F.cross_entropy(logits, labels, reduction='sum') / Bg
+    loss.backward()
+    ws = torch.zeros(int(_lib.load().curla_curl_workspace_floats(B, Bg)), device=DEV)
+    lo = torch.zeros(1, device=DEV); dza = torch.zeros((B, 64), device=DEV); dW = torch.zeros((feat, feat), device=DEV)
+    _lib.call('curla_curl_fwd_bwd', _lib.ptr(za), _lib.ptr(zp), _lib.ptr(W), B, Bg, feat, label0, 1.0 / Bg, _lib.ptr(ws),
+              _lib.ptr(lo), _lib.ptr(dza), _lib.ptr(dW), None, stream())
+    assert abs(float(lo) - float(F.cross_entropy(logits, labels))) < 1e-4 * max(1.0, abs(float(lo)))
+    assert rel_l2(dza[:, :feat], zar.grad) < 1e-4
+    assert rel_l2(dW, Wr.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ Adam / EMA / packers
+def test_adam_matches_oracle_adam():
+    torch.manual_seed(8)
+    n = 10007
+    p0 = torch.randn(n); lr, b1, b2 = 1e-3, 0.9, 0.999
+    q = p0.clone().requires_grad_(True)
+    opt = O.Adam([q], lr, (b1, b2))
+    p = p0.clone().to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    pd = p0.clone().to(DEV); md = torch.zeros(n, device=DEV); vd = torch.zeros(n, device=DEV)
+    for t in range(1, 6):
+        g = torch.randn(n) * (10.0 ** float(torch.randint(-4, 1, (1,))))
+        q.grad = g.clone(); opt.step()
+        gd = g.to(DEV)
+        _lib.call('curla_adam_f32', _lib.ptr(p), _lib.ptr(gd), _lib.ptr(m), _lib.ptr(v), n, n, lr, b1, b2, 1e-8, t,
+                  None, stream())
+        # double-step variant on the upper half
+        _lib.call('curla_adam_f32', _lib.ptr(pd), _lib.ptr(gd), _lib.ptr(md), _lib.ptr(vd), n, n // 2, lr, b1, b2, 1e-8,
+                  t, None, stream())
+        assert (p.cpu() - q.detach()).abs().max() < 2e-6, t
+    st = opt.state[id(q)]
+    assert max_rel(m.cpu(), st['m']) < 1e-5 and max_rel(v.cpu(), st['v']) < 1e-5
+    # doubled elements moved exactly twice as far in total (same m, v)
+    d1 = (p - p0.to(DEV)); d2 = (pd - p0.to(DEV))
+    assert torch.equal(d1[:n // 2], d2[:n // 2])
+    assert rel_l2(d2[n // 2:], 2 * d1[n // 2:]) < 1e-4
+    # float64 scalar
+    la = torch.tensor([np.log(0.1)], dtype=torch.float64, requires_grad=True)
+    o2 = O.Adam([la], 1e-4, (0.5, 0.999))
+    pa = la.detach().clone().to(DEV); sa = torch.zeros(2, dtype=torch.float64, device=DEV)
+    for t in range(1, 4):
+        gg = torch.tensor([0.3 * t - 0.5], dtype=torch.float64)
+        la.grad = gg.clone(); o2.step()
+        _lib.call('curla_adam_f64_scalar', _lib.ptr(pa), _lib.ptr(gg.to(DEV)), _lib.ptr(sa), 1e-4, 0.5, 0.999, 1e-8, t,
+                  None, stream())
+    assert abs(float(pa) - float(la)) < 1e-12
+
+
+def test_ema_bit_exact():
+    torch.manual_seed(9)
+    n = 5003
+    p, t = torch.randn(n), torch.randn(n)
+    want = t.clone()
+    want[:2000] = 0.05 * p[:2000] + (1 - 0.05) * t[:2000]
+    want[2000:] = 0.01 * p[2000:] + (1 - 0.01) * t[2000:]
+    td = t.to(DEV)
+    _lib.call('curla_ema_f32', _lib.ptr(td), _lib.ptr(p.to(DEV)), n, 2000, 0.05, 0.01, stream())
+    assert torch.equal(td.cpu(), want)
+
+
+def test_pack_rows():
+    src = torch.randn(50 * 52 + 3, device=DEV)
+    dst = torch.ones((64, 64), device=DEV, dtype=torch.bfloat16)
+    seg = np.array([3, 0, 0, 50, 52, 64, 64], dtype=np.int64)
+    _lib.call('curla_pack_shadows', _lib.ptr(src), _lib.ptr(dst), seg.ctypes.data_as(C.c_void_p), 1, stream())
+    want = torch.zeros((64, 64), device=DEV); want[:50, :52] = src[3:].view(50, 52)
+    assert torch.equal(dst, want.to(torch.bfloat16))
