@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the CurlSacAgent.update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload: BASELINE.json configs[1] -- CURL random-crop SAC update at train.py defaults
+(batch 512 per GPU, 9x90x160 stored frames cropped to 9x76x135, hidden 1024, feature 50,
+4x32 conv filters), synthetic replay buffer of 16,384 transitions (4.25 GB of uint8
+frames, far larger than the 126 MB L2) resident in HBM, random-init weights.  With N GPUs
+the update is data parallel: per-GPU batch stays 512 (weak scaling), the global batch
+512*N is what the CURL head sees (all-gathered keys), so N=8 is configs[3]'s batch 4096.
+`value` is observations/s through the update over all ranks (= global batch * updates/s;
+`updates_per_s` is printed beside it).
+
+One JSON line on stdout (rank 0).  --impl reference times the oracle port of the
+reference's CPU update on the host cores (the reference is pure Python; kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+FRAME = (9, 90, 160)
+ACTION = (2,)
+CAPACITY = 16384
+BATCH = 512
+# train.py defaults (train.py:62-104)
+HP = dict(hidden_dim=1024, discount=0.99, init_temperature=0.1, alpha_lr=1e-4, alpha_beta=0.5, actor_lr=1e-3,
+          actor_beta=0.9, actor_log_std_min=-10, actor_log_std_max=2, actor_update_freq=2, critic_lr=1e-3,
+          critic_beta=0.9, critic_tau=0.01, critic_target_update_freq=2, encoder_feature_dim=50,
+          encoder_lr=1e-3, encoder_tau=0.05, num_layers=4, num_filters=32, cpc_update_freq=1)
+
+
+class NullLogger:
+    def __init__(self):
+        self.last = {}
+
+    def log(self, key, value, step):
+        self.last[key] = float(value)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d.get('bf16_tflops_sustained', d['bf16_tflops']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v == 'Active':
+                    reasons.add(n)
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def fill_replay(rb, seed=1):
+    """SURVEY 8(d) synthetic fill, generated on the device in chunks (4.25 GB)."""
+    g = torch.Generator(device=rb.device).manual_seed(seed)
+    n = rb.capacity
+    for s in range(0, n, 1024):
+        e = min(n, s + 1024)
+        rb.obses[s:e] = torch.randint(0, 256, (e - s, *FRAME), device=rb.device, dtype=torch.uint8, generator=g)
+        rb.next_obses[s:e] = torch.randint(0, 256, (e - s, *FRAME), device=rb.device, dtype=torch.uint8, generator=g)
+    rb.actions.copy_(torch.rand((n, 2), device=rb.device, generator=g) * 2 - 1)
+    rb.rewards.copy_(torch.randn((n, 1), device=rb.device, generator=g))
+    rb.not_dones.copy_((torch.rand((n, 1), device=rb.device, generator=g) > 0.01).float())
+    rb.idx, rb.full = 0, True
+
+
+# ------------------------------------------------------------------ algorithmic work
+def conv_layer_work(B, layer):
+    """(flops, algorithmic bytes) of one forward launch of conv layer `layer` (1..3 = the
+    32->32 3x3 layers) at the 76x135 crop geometry: read the valid bf16 input once, write
+    the valid bf16 output once, weights once."""
+    ho = [37, 35, 33, 31]
+    wo = [67, 65, 63, 61]
+    hin, win, hout, wout = ho[layer - 1], wo[layer - 1], ho[layer], wo[layer]
+    flops = 2.0 * B * hout * wout * 32 * 288
+    byts = B * (hin * win + hout * wout) * 32 * 2 + 9 * 32 * 32 * 2
+    return flops, byts
+
+
+def run_ours(args, rank, world, device):
+    from curla_b200 import _lib, augmentations, curl_sac, utils
+    torch.cuda.set_device(device)
+    np.random.seed(12345)                    # identical global index stream on every rank
+    torch.manual_seed(0)
+    aug = augmentations.make_augmentor('random_crop', FRAME[1:])
+    Bg = args.batch * world
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        rb = utils.ReplayBuffer(FRAME, ACTION, CAPACITY, Bg, device, aug)
+    fill_replay(rb)
+    agent = curl_sac.CurlSacAgent((9, 76, 135), ACTION, device, aug, log_interval=10 ** 9, **HP)
+    L = NullLogger()
+    step0 = 0
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        agent.update(rb, L, step0 + i)
+    step0 += args.warmup
+    if step0 % 2:                             # start timed regions on an even step
+        agent.update(rb, L, step0)
+        step0 += 1
+
+    # ---- device-timed region: K updates, inputs resident in HBM
+    sampler = ClockSampler(device.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ev0.record()
+    for i in range(args.steps):
+        agent.update(rb, L, step0 + i)
+        launches += agent.engine.last_launches()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.finish() if sampler else None
+    step0 += args.steps
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(t) / args.steps
+
+    # ---- end to end through the public API with HOST buffers: every step ingests one
+    # transition from host numpy (ReplayBuffer.add: pinned staging + H2D), uploads the
+    # sampled indices, runs the update and reads the logged scalars back (D2H).
+    agent.log_interval = 1
+    host = np.random.RandomState(7)
+    h_obs = host.randint(0, 256, size=FRAME, dtype=np.uint8)
+    h_next = host.randint(0, 256, size=FRAME, dtype=np.uint8)
+    h_act = host.uniform(-1, 1, size=2).astype(np.float32)
+    for i in range(2):
+        rb.add(h_obs, h_act, 0.5, h_next, False)
+        agent.update(rb, L, step0 + i)
+    step0 += 2
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rb.add(h_obs, h_act, 0.5, h_next, False)
+        agent.update(rb, L, step0 + i)       # logs -> metrics D2H + sync every step
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    step0 += args.steps
+    agent.log_interval = 10 ** 9
+    t = torch.tensor([e2e_s], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_s = float(t)
+    h2d = 2 * int(np.prod(FRAME)) + 4 * 4 + 7 * Bg * 8
+    d2h = 16 * 4
+
+    # ---- live per-kernel times (CUDA events after every launch) for the roofline entry
+    prof = {}
+    if rank == 0 or world > 1:
+        lib = _lib.load()
+        lib.curla_profile_enable(1)
+        for i in range(args.prof_steps):
+            agent.update(rb, L, step0 + i)
+        torch.cuda.synchronize()
+        import ctypes as C
+        buf = C.create_string_buffer(1 << 16)
+        n = lib.curla_profile_read(buf, len(buf))
+        lib.curla_profile_enable(0)
+        for line in buf.raw[:max(n, 0)].decode().splitlines():
+            nm, cnt, tot = line.split()
+            prof[nm] = (int(cnt), float(tot))
+        step0 += args.prof_steps
+    return dict(ms_per_step=ms_per_step, launches=launches, clocks=clocks, e2e_s=e2e_s, h2d=h2d, d2h=d2h,
+                prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last)
+
+
+def cpu_reference_updates(batch, steps, warmup, threads):
+    """The oracle port of the reference's CPU update (torch fp32, oneDNN) on the host cores."""
+    from oracle import curla_oracle as O
+    torch.set_num_threads(threads)
+    rs = np.random.RandomState(1)
+    cap = 64
+    frames = rs.randint(0, 256, size=(2, cap, *FRAME), dtype=np.uint8)
+    actions = rs.uniform(-1, 1, size=(cap, 2)).astype(np.float32)
+    rewards = rs.standard_normal(size=(cap, 1)).astype(np.float32)
+    not_dones = (rs.uniform(size=(cap, 1)) > 0.01).astype(np.float32)
+    agent = O.OracleAgent((9, 76, 135), 2, hidden_dim=HP['hidden_dim'])
+    agent.init_random(0)
+    np.random.seed(0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        d = O.draw_sample_indices(cap, 0, True, batch, 'random_crop', FRAME[1:], (76, 135))
+        f = lambda a: torch.from_numpy(a).float()
+        obs = f(O.gather_crop(frames[0], d['idxs'], d['h1_obs'], d['w1_obs'], (76, 135)))
+        nxt = f(O.gather_crop(frames[1], d['idxs'], d['h1_next'], d['w1_next'], (76, 135)))
+        pos = f(O.gather_crop(frames[0], d['idxs'], d['h1_pos'], d['w1_pos'], (76, 135)))
+        noise = torch.randn(2, batch, 2)
+        agent.update(obs, torch.from_numpy(actions[d['idxs']]), torch.from_numpy(rewards[d['idxs']]), nxt,
+                     torch.from_numpy(not_dones[d['idxs']]), pos, i, noise[0], noise[1])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=4)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH, help='per-GPU batch (default: train.py default 512)')
+    ap.add_argument('--prof-steps', type=int, default=4)
+    ap.add_argument('--cpu-baseline-steps', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    cores = os.cpu_count()
+    config = {'workload': 'CURL random-crop SAC update, train.py defaults: per-GPU batch %d, frames 9x90x160 -> '
+                          'crop 9x76x135, hidden 1024, feature 50, 4x32 filters; synthetic replay of %d transitions '
+                          '(4.25 GB, > L2) resident in HBM' % (args.batch, CAPACITY),
+              'per_gpu_batch': args.batch, 'global_batch': args.batch * world,
+              'parallelism': 'dp%d (grad all-reduce + all-gathered CURL keys)' % world,
+              'l2': 'inputs larger than L2 (random replay rows from 4.25 GB; ~1.4 GB of activations per update)',
+              'precision': 'bf16 operands, fp32 accumulate, fp32 master weights/Adam/EMA/LN/losses'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        # bounded sample: a smaller batch of the same update, throughput in obs/s
+        sample_b = 128
+        sec = cpu_reference_updates(sample_b, args.steps if args.steps <= 8 else 8, 1, cores)
+        val = sample_b / sec
+        line = {'impl': 'reference', 'metric': 'sac_curl_update_obs_per_sec', 'value': val, 'unit': 'obs/s',
+                'updates_per_s': val / args.batch, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': sec * 1e3 * args.batch / sample_b, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': val, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
+                                 'sample': 'oracle port of the reference update (torch fp32 CPU, %d threads), batch %d '
+                                           'x %d updates of the same config; ms_per_step scaled to batch %d'
+                                           % (cores, sample_b, min(args.steps, 8), args.batch)},
+                'e2e': {'value': val, 'unit': 'obs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device: the hot path has no CPU fallback')
+    device = torch.device('cuda', local)
+    if world > 1:
+        torch.cuda.set_device(device)
+        torch.distributed.init_process_group('nccl', device_id=device)
+    r = run_ours(args, rank, world, device)
+    if world > 1:
+        torch.distributed.barrier()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    Bg = r['Bg']
+    ups = 1e3 / r['ms_per_step']
+    value = Bg * ups
+    hbm, tf, how = peaks()
+    # dominant kernel: the 32->32 3x3 conv forward (15 launches per update); per-launch
+    # duration from the live CUDA-event profile
+    roof = None
+    if 'conv_fwd' in r['prof']:
+        cnt, tot = r['prof']['conv_fwd']
+        # conv_fwd covers conv1 (s2d, 4 taps) and conv2-4; weight the algorithmic work by the launch mix
+        per_update = cnt / r['prof_steps']
+        n_stacks = per_update / 4.0
+        fl = by = 0.0
+        for l in (1, 2, 3):
+            f_, b_ = conv_layer_work(args.batch, l)
+            fl += f_ * n_stacks
+            by += b_ * n_stacks
+        # conv1: u8-exact bf16 s2d input [B][38*68][48] read, output written
+        by1 = args.batch * (38 * 68 * 48 * 2 + 37 * 67 * 32 * 2) + 4 * 32 * 48 * 2
+        fl1 = 2.0 * args.batch * 37 * 67 * 32 * 81
+        by += by1 * n_stacks
+        fl += fl1 * n_stacks
+        sec = tot / r['prof_steps'] / 1e3
+        ach = by / sec / 1e9
+        roof = {'kernel': 'k_conv_shift (conv fwd, all 4 layers)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
+                'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'peak_source': how,
+                'tflops': fl / sec / 1e12, 'launches_per_update': per_update,
+                'ms_per_update': tot / r['prof_steps']}
+    breakdown = {k: round(v[1] / r['prof_steps'], 4) for k, v in sorted(r['prof'].items(), key=lambda kv: -kv[1][1])}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sb = 128
+        sec = cpu_reference_updates(sb, args.cpu_baseline_steps, 1, cores)
+        cpu = {'value': sb / sec, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
+               'sample': 'oracle port of the reference update (torch fp32 CPU), batch %d x %d updates after 1 warm-up'
+                         % (sb, args.cpu_baseline_steps), 'updates_per_s_at_batch_%d' % args.batch: sb / sec / args.batch}
+    line = {'metric': 'sac_curl_update_obs_per_sec', 'value': value, 'unit': 'obs/s', 'updates_per_s': ups,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': config, 'clocks': r['clocks'],
+            'e2e': {'value': Bg * args.steps / r['e2e_s'], 'unit': 'obs/s', 'updates_per_s': args.steps / r['e2e_s'],
+                    'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': r['d2h'],
+                    'what': 'ReplayBuffer.add(host frame) + CurlSacAgent.update(...) + logged scalars read back, per step'},
+            'gpu_launches': r['launches'], 'roofline': roof, 'cpu_baseline': cpu,
+            'kernel_ms_per_update': breakdown, 'losses': r['last']}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -80,6 +80,10 @@ SIGNATURES = {
     'curla_agent_refresh_shadows': (_i, [c_vp, c_vp]),
     'curla_agent_update': (_i, [c_vp, C.POINTER(UpdateArgs), c_vp]),
     'curla_agent_last_launches': (_i, [c_vp]),
+    'curla_agent_set_opt_steps': (_i, [c_vp, _i, _i, _i, _i]),
+    'curla_agent_get_opt_steps': (_i, [c_vp, C.POINTER(_i)]),
+    'curla_profile_enable': (_i, [_i]),
+    'curla_profile_read': (_i, [C.c_char_p, _i]),
     'curla_agent_encode': (_i, [c_vp, _i, c_vp, _i, _i, c_vp, c_vp]),
     'curla_agent_actor_head': (_i, [c_vp, c_vp, _i, c_vp, C.c_ulonglong, C.c_ulonglong, _i, _i, c_vp, c_vp,
                                     c_vp, c_vp, c_vp]),

@@ -12,6 +12,7 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------- errors
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> 0 / -1 (+ message)
+void set_launch_tag(const char* tag);  // optional profiler label for the next launches (nullptr = default)
 
 #define CURLA_CHECK(cond, ...)                         \
     do {                                               \

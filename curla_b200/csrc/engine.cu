@@ -17,8 +17,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace curla {
@@ -32,13 +34,45 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 static thread_local long long g_launches = 0;
+
+// Optional CUDA-event profiler: one event after every launch on the engine's stream; the
+// interval between consecutive events is that launch's device time (single stream, so
+// launches are serialised).  Used by bench.py for the live per-kernel roofline numbers.
+struct Profiler {
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void mark(const char* what) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, stream);
+        marks.push_back({what, e});
+    }
+};
+static Profiler g_prof;
+void profile_mark(const char* what) { if (g_prof.on) g_prof.mark(what); }
+
+static thread_local const char* g_tag = nullptr;
+void set_launch_tag(const char* tag) { g_tag = tag; }
+
 int check_launch(const char* what) {
     ++g_launches;
+    if (g_tag) what = g_tag;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_last_error("%s: %s", what, cudaGetErrorString(e));
         return -1;
     }
+    if (g_prof.on) g_prof.mark(what);
     return 0;
 }
 int sm_count() {
@@ -443,8 +477,10 @@ struct Run {
     // fc (split-K) + bias + LayerNorm
     void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0) {
         if (!ok()) return;
+        set_launch_tag("gemm_fc_fwd");
         chk(curla_gemm_bf16(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
                             3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f, st));
+        set_launch_tag(nullptr);
         if (!ok()) return;
         chk(curla_ln_fwd(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
                          a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, st));
@@ -489,12 +525,16 @@ struct Run {
         chk(curla_ln_bwd(dz_a, dz_b, t.fc_out, P(e.ln_w), B, feat, a->dfc_f32, a->dfc_bf16, a->ln_scratch,
                          g(e.ln_w), g(e.ln_b), g(e.fc_b), st));
         // dWfc[feat][Kfc] = dfc^T . act4
+        set_launch_tag("gemm_fc_wgrad");
         if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
                                       a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+        set_launch_tag(nullptr);
         if (!conv) return;
         // d(act4) = relu'(act4) * dfc . Wfc
+        set_launch_tag("gemm_fc_dgrad");
         if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
                                       a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f, st));
+        set_launch_tag(nullptr);
         for (int i = 3; i >= 1 && ok(); --i) {
             chk(curla_conv_wgrad(acts[i - 1], a->act_sstride, a->dact[i], a->act_sstride, a->wgrad_ws, g(e.conv_w[i]),
                                  g(e.conv_b[i]), 1.f, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 32, 0, st));
@@ -541,6 +581,7 @@ int all_reduce(curla_agent* a, void* buf, size_t n, int dt, cudaStream_t st) {
     CURLA_CHECK(a->comm, "update: world>1 but no communicator (curla_agent_init_comm)");
     const int r = g_nccl.all_reduce(buf, buf, n, dt, NCCL_SUM, a->comm, st);
     CURLA_CHECK(r == 0, "ncclAllReduce: %s", g_nccl.err_str ? g_nccl.err_str(r) : "error");
+    profile_mark("nccl_all_reduce");
     return 0;
 }
 
@@ -572,6 +613,43 @@ extern "C" int curla_agent_refresh_shadows(curla_agent* a, cudaStream_t stream) 
 
 extern "C" int curla_agent_last_launches(const curla_agent* a) { return (int)a->last_launches; }
 
+extern "C" int curla_agent_set_opt_steps(curla_agent* a, int t_critic, int t_actor, int t_alpha, int t_cpc) {
+    a->t_critic = t_critic; a->t_actor = t_actor; a->t_alpha = t_alpha; a->t_cpc = t_cpc;
+    return 0;
+}
+extern "C" int curla_agent_get_opt_steps(const curla_agent* a, int* out4) {
+    out4[0] = a->t_critic; out4[1] = a->t_actor; out4[2] = a->t_alpha; out4[3] = a->t_cpc;
+    return 0;
+}
+
+extern "C" int curla_profile_enable(int on) {
+    g_prof.on = on != 0;
+    return 0;
+}
+// Synchronises the recorded events and writes "name count total_ms\n" lines (per launch
+// site name) into buf; clears the recording.  Returns bytes written or -1.
+extern "C" int curla_profile_read(char* buf, int cap) {
+    std::map<std::string, std::pair<long long, double>> acc;
+    for (size_t i = 1; i < g_prof.marks.size(); ++i) {
+        if (!strcmp(g_prof.marks[i].first, "__begin__")) continue;
+        cudaError_t e = cudaEventSynchronize(g_prof.marks[i].second);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_prof.marks[i - 1].second, g_prof.marks[i].second);
+        CURLA_CHECK(e == cudaSuccess, "profile_read: %s", cudaGetErrorString(e));
+        auto& slot = acc[g_prof.marks[i].first];
+        slot.first += 1; slot.second += ms;
+    }
+    g_prof.marks.clear();
+    g_prof.used = 0;
+    int n = 0;
+    for (auto& kv : acc) {
+        const int w = snprintf(buf + n, cap - n, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (w < 0 || n + w >= cap) break;
+        n += w;
+    }
+    return n;
+}
+
 // ================================================================== the update
 extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
     CURLA_CHECK(a->bound, "agent not bound");
@@ -579,6 +657,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     const int B = c.batch, A = c.action_dim, feat = c.feature_dim;
     const float gs = 1.0f / (float)c.global_batch;
     const long long launches0 = g_launches;
+    if (g_prof.on) { g_prof.stream = st; g_prof.mark("__begin__"); }
     Run r{a, st};
     const bool do_sac = !u->only_cpc;
     const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0);
@@ -679,6 +758,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             CURLA_CHECK(a->comm, "update: world>1 but no communicator");
             const int rc = g_nccl.all_gather(a->t_p7.z, a->z_pos_all, (size_t)B * 64, NCCL_F32, a->comm, st);
             CURLA_CHECK(rc == 0, "ncclAllGather failed (%d)", rc);
+            profile_mark("nccl_all_gather");
             zpos = a->z_pos_all;
         }
         float* gK = a->G + a->g_cpc;

@@ -184,6 +184,14 @@ typedef struct curla_update_args {
 int curla_agent_update(curla_agent* a, const curla_update_args* args, curla_stream_t stream);
 /* number of kernel launches issued by the last curla_agent_update */
 int curla_agent_last_launches(const curla_agent* a);
+/* per-optimizer Adam step counters {critic, actor, log_alpha, encoder+cpc} (the reference
+ * keeps them in torch.optim.Adam.state[...]['step']); settable so a run can be resumed or
+ * teacher-forced from another implementation's optimizer state */
+int curla_agent_set_opt_steps(curla_agent* a, int t_critic, int t_actor, int t_alpha, int t_cpc);
+int curla_agent_get_opt_steps(const curla_agent* a, int* out4);
+/* CUDA-event profiler: per-launch device times on the engine stream (measurement only) */
+int curla_profile_enable(int on);
+int curla_profile_read(char* buf, int cap);
 
 /* inference entry points (sample_action / select_action / eval / latent extraction:
  * curl_sac.py:330-347, plot_tsne/latent_data.py:63-104).  obs_s2d rows as produced by

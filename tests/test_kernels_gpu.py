@@ -37,16 +37,16 @@ def test_gather_crop_bit_exact(B, crop):
     h1 = rs.randint(0, Hf - oh + 1, size=B)
     w1 = rs.randint(0, Wf - ow + 1, size=B)
     ref = O.gather_crop(frames, idxs, h1, w1, (oh, ow))
-    fr = dv(frames)
+    fr, di, dh, dw = dv(frames), dv(idxs), dv(h1), dv(w1)     # keep the device copies alive
     out = torch.empty((B, Cc, oh, ow), dtype=torch.float32, device=DEV)
-    _lib.call('curla_gather_crop_f32', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(dv(idxs)), _lib.ptr(dv(h1)),
-              _lib.ptr(dv(w1)), B, oh, ow, _lib.ptr(out), stream())
+    _lib.call('curla_gather_crop_f32', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(di), _lib.ptr(dh),
+              _lib.ptr(dw), B, oh, ow, _lib.ptr(out), stream())
     assert torch.equal(out.cpu(), torch.from_numpy(ref).float())
     # space-to-depth bf16 variant: exact as well (uint8 is exact in bf16)
     g = Geom(oh, ow, B)
     full, view = g.alloc(g.CP1)
-    _lib.call('curla_gather_crop_s2d', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(dv(idxs)), _lib.ptr(dv(h1)),
-              _lib.ptr(dv(w1)), B, oh, ow, g.CP1, g.S * g.CP1, _lib.ptr(view), stream())
+    _lib.call('curla_gather_crop_s2d', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(di), _lib.ptr(dh),
+              _lib.ptr(dw), B, oh, ow, g.CP1, g.S * g.CP1, _lib.ptr(view), stream())
     want = g.s2d_ref(torch.from_numpy(ref).to(DEV))
     assert torch.equal(view.view(B, g.Hs, g.pitch, g.CP1).float(), want)
     assert float(full[:g.PAD].abs().sum()) == 0 and float(full[g.PAD + B * g.S:].abs().sum()) == 0
@@ -61,7 +61,8 @@ def test_gather_rows():
     src = rs.standard_normal((17, 2)).astype(np.float32)
     idxs = rs.randint(0, 17, size=9)
     out = torch.empty((9, 2), dtype=torch.float32, device=DEV)
-    _lib.call('curla_gather_rows_f32', _lib.ptr(dv(src)), _lib.ptr(dv(idxs)), 9, 2, _lib.ptr(out), stream())
+    ds, di = dv(src), dv(idxs)
+    _lib.call('curla_gather_rows_f32', _lib.ptr(ds), _lib.ptr(di), 9, 2, _lib.ptr(out), stream())
     assert np.array_equal(out.cpu().numpy(), src[idxs])
 
 
@@ -86,7 +87,9 @@ def _run_conv_stack(g, x, ws, bs):
     for l in range(4):
         wsh = pack_conv_w(ws[l], l == 0)
         full, out = g.alloc(32)
-        _lib.call('curla_conv_fwd', _lib.ptr(inp), stride, _lib.ptr(wsh), _lib.ptr(bs[l].to(DEV)),
+        bd = bs[l].to(DEV)
+        keep.append(bd)
+        _lib.call('curla_conv_fwd', _lib.ptr(inp), stride, _lib.ptr(wsh), _lib.ptr(bd),
                   1.0 / 255.0 if l == 0 else 1.0, _lib.ptr(out), g.S * 32, g.B, g.pitch, g.S, g.Ho[l], g.Wo[l],
                   1 if l == 0 else 0, stream())
         acts.append(out)
@@ -152,7 +155,9 @@ def test_conv_backward(H, W, B):
         assert rel_l2(db, grads[-1]) < 5e-3, ('db', l)
         if l > 0:
             full, dx = g.alloc(32)
-            _lib.call('curla_conv_dgrad', _lib.ptr(dcur), g.S * 32, _lib.ptr(pack_conv_w(ws[l], False)),
+            wsh = pack_conv_w(ws[l], False)
+            keep.append(wsh)
+            _lib.call('curla_conv_dgrad', _lib.ptr(dcur), g.S * 32, _lib.ptr(wsh),
                       _lib.ptr(acts[l - 1]), _lib.ptr(dx), g.S * 32, B, g.pitch, g.S, g.Ho[l - 1], g.Wo[l - 1],
                       stream())
             mask = (g.from_pitch(acts[l - 1], g.Ho[l - 1], g.Wo[l - 1]) > 0)
@@ -265,7 +270,8 @@ def test_policy_head_fwd_bwd():
     dx1 = torch.zeros((B, 64), device=DEV); dx1[:, 50:52] = gpi * 0.25
     dx2 = torch.zeros((B, 64), device=DEV); dx2[:, 50:52] = gpi * 0.75
     dt = torch.zeros((B, 2 * A), device=DEV)
-    _lib.call('curla_policy_bwd', _lib.ptr(dx1), _lib.ptr(dx2), 50, _lib.ptr(torch.tensor([glp], device=DEV)),
+    glp_d = torch.tensor([glp], device=DEV)
+    _lib.call('curla_policy_bwd', _lib.ptr(dx1), _lib.ptr(dx2), 50, _lib.ptr(glp_d),
               _lib.ptr(t.detach()), _lib.ptr(noise), _lib.ptr(o[1]), _lib.ptr(o[3]), B, A, -10.0, 2.0, _lib.ptr(dt),
               stream())
     assert rel_l2(dt, t.grad) < 1e-3, rel_l2(dt, t.grad)
@@ -376,8 +382,10 @@ def test_adam_matches_oracle_adam():
     for t in range(1, 4):
         gg = torch.tensor([0.3 * t - 0.5], dtype=torch.float64)
         la.grad = gg.clone(); o2.step()
-        _lib.call('curla_adam_f64_scalar', _lib.ptr(pa), _lib.ptr(gg.to(DEV)), _lib.ptr(sa), 1e-4, 0.5, 0.999, 1e-8, t,
+        ggd = gg.to(DEV)
+        _lib.call('curla_adam_f64_scalar', _lib.ptr(pa), _lib.ptr(ggd), _lib.ptr(sa), 1e-4, 0.5, 0.999, 1e-8, t,
                   None, stream())
+        torch.cuda.synchronize()
     assert abs(float(pa) - float(la)) < 1e-12
 
 
@@ -388,8 +396,8 @@ def test_ema_bit_exact():
     want = t.clone()
     want[:2000] = 0.05 * p[:2000] + (1 - 0.05) * t[:2000]
     want[2000:] = 0.01 * p[2000:] + (1 - 0.01) * t[2000:]
-    td = t.to(DEV)
-    _lib.call('curla_ema_f32', _lib.ptr(td), _lib.ptr(p.to(DEV)), n, 2000, 0.05, 0.01, stream())
+    td, pd_ = t.to(DEV), p.to(DEV)
+    _lib.call('curla_ema_f32', _lib.ptr(td), _lib.ptr(pd_), n, 2000, 0.05, 0.01, stream())
     assert torch.equal(td.cpu(), want)
 
 
