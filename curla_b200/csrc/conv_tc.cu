@@ -1,0 +1,352 @@
+// K4/K5 on the 5th-generation tensor cores: conv forward and dgrad as shifted GEMMs issued
+// with tcgen05.mma, accumulators in TMEM.
+//
+// Replaces cuDNN conv fwd / dgrad (+ ReLU, + obs/255) launched by
+//   encoder.py:77-90     CNNEncoder.forward_conv
+//   curl_sac.py:367,417  loss.backward() through the conv layers
+//
+// Same data layout as conv.cu: NHWC bf16 activations with a fixed row
+// pitch, so a 3x3 valid conv over the flattened position index P is
+//     out[P][0:32] = sum_t in[P + off_t][0:CP] . W_t          (off_t = dy*pitch + dx)
+// i.e. nine GEMMs whose A operand is the SAME matrix shifted by off_t rows.
+//
+// Shared-memory operand layout -- the point of this file.  tcgen05.mma reads A and B through
+// 64-bit matrix descriptors.  In the K-major / no-swizzle canonical layout a core matrix is
+// 8 rows x 16 bytes stored contiguously (rows 16 B apart), 8-row groups are SBO bytes apart
+// and the two 16-byte K chunks of one K=16 step are LBO bytes apart.  The slab is stored as
+// CHANNEL-CHUNK PLANES  slab[chunk c][row r][8 channels]  (16 B per row per plane), so that
+// SBO = 128 makes ALL rows of a plane 16 B apart and LBO = plane size.  A tap shift of off_t
+// rows is then just  start_address += 16 * off_t : nine taps = nine descriptors into one
+// slab, no im2col, no data movement, any shift (only 16-byte alignment is required when no
+// swizzle is used).  Weights use the same layout [tap][chunk][32 n][8 k].
+//
+// One CTA = NSUB*128 threads, persistent over tiles of NSUB*128 positions: cp.async fills the
+// next slab (double buffered) while one elected thread issues NSUB*NTAPS*(CP/16) MMAs
+// (M=128, N=32, K=16, bf16 -> fp32) into NSUB TMEM accumulators of 32 columns; a
+// tcgen05.commit arrives on an mbarrier; every warp then pulls its 32 TMEM lanes with
+// tcgen05.ld (one output position per thread, 32 channels) and runs the epilogue
+// (scale+bias+ReLU, or the ReLU mask of dgrad) with 64-byte row stores.  3 CTAs per SM
+// overlap load / MMA / epilogue across CTAs.
+#include "common.cuh"
+
+namespace curla {
+
+struct TcGeom {
+    int pitch, S, Hv, Wv;
+    int tiles_per_sample, total_tiles;
+    int slab_rows;       // rows actually loaded (TM + span)
+    int plane_rows;      // slab_rows rounded up to 8 (plane stride = plane_rows * 16 B)
+    int min_off;         // most negative tap shift
+};
+struct TcTaps { int off[9]; };
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+// smem matrix descriptor, no swizzle (layout_type 0), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=32, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- the kernel
+//  DGRAD=false: B = W_t[n][k]            -> out = relu(acc*scale + bias)
+//  DGRAD=true : B = W_t^T (n=ci, k=co)   -> out = (X > 0) ? acc : 0
+template <int CP, int NTAPS, bool DGRAD, int NSUB>
+__global__ void __launch_bounds__(NSUB * 128)
+k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ wts,   // [NTAPS][32][CP]
+          const float* __restrict__ bias, float scale, const bf16* __restrict__ relu_src,
+          bf16* __restrict__ out, long long out_sstride, TcGeom g, TcTaps taps) {
+    constexpr int CH = CP / 8, KS = CP / 16, NT = NSUB * 128, TM = NSUB * 128;
+    constexpr uint32_t W_BYTES = NTAPS * CH * 512;
+    constexpr uint32_t TMEM_COLS = NSUB * 32 < 32 ? 32 : NSUB * 32;
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_bar = s_base, s_tptr = s_base + 8, s_bias = s_base + 16;
+    const uint32_t s_w = s_base + 256;
+    const uint32_t PS = (uint32_t)g.plane_rows * 16u;
+    const uint32_t slab_bytes = CH * PS;
+    const uint32_t s_slab0 = s_w + W_BYTES;
+
+    // ---- one-time setup: barrier, TMEM, weights, bias
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (!DGRAD) {
+        for (int i = tid; i < NTAPS * 32 * CH; i += NT) {
+            const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
+            cp_async16(s_w + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
+        }
+        if (tid < 32) reinterpret_cast<float*>(smem + 16)[tid] = bias[tid];
+    } else {
+        // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
+        for (int i = tid; i < NTAPS * 32 * CP; i += NT) {
+            const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
+            reinterpret_cast<bf16*>(smem + 256)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
+        }
+    }
+
+    auto prefetch = [&](int t, int buf) {
+        const int b = t / g.tiles_per_sample;
+        const int p0 = (t - b * g.tiles_per_sample) * TM;
+        const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * CP;
+        const uint32_t dst = s_slab0 + buf * slab_bytes;
+        const int total = g.slab_rows * CH;
+        for (int i = tid; i < total; i += NT) {
+            const int row = i / CH, c = i - row * CH;
+            cp_async16(dst + c * PS + row * 16, src + (long long)row * CP + c * 8, 16);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < g.total_tiles) prefetch(tile, 0);
+    cp_async_commit();
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 8);
+
+    const int sub = warp >> 2, quarter = warp & 3;
+    const int row_in_tile = sub * 128 + quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 32);
+
+    uint32_t phase = 0;
+    int buf = 0;
+    for (; tile < g.total_tiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < g.total_tiles) prefetch(next, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t s_slab = s_slab0 + buf * slab_bytes;
+#pragma unroll
+                for (int s = 0; s < NSUB; ++s) {
+#pragma unroll
+                    for (int t = 0; t < NTAPS; ++t) {
+                        const uint32_t a_row = (uint32_t)(s * 128 + taps.off[t] - g.min_off);
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t ad = make_desc(s_slab + (uint32_t)(2 * ks) * PS + a_row * 16u, PS, 128);
+                            const uint64_t bd = make_desc(s_w + (uint32_t)((t * CH + 2 * ks) * 512), 512, 128);
+                            umma_bf16(tmem_base + (uint32_t)(s * 32), ad, bd, (t | ks) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(s_bar);
+            }
+            __syncwarp();
+        }
+
+        // ---- epilogue: one output position per thread
+        const int b = tile / g.tiles_per_sample;
+        const int p = (tile - b * g.tiles_per_sample) * TM + row_in_tile;
+        const int y = p / g.pitch, x = p - y * g.pitch;
+        const bool valid = (y < g.Hv) && (x < g.Wv);
+        const long long o = (long long)b * out_sstride + (long long)p * 32;
+        uint4 xm[4];
+        if (DGRAD) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xm[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && p < g.S) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) xm[c] = *reinterpret_cast<const uint4*>(relu_src + o + c * 8);
+            }
+        }
+        mbar_wait(s_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld32(taddr, acc);
+        if (p < g.S) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v0 = __uint_as_float(acc[c * 8 + j * 2]), v1 = __uint_as_float(acc[c * 8 + j * 2 + 1]);
+                    if (!DGRAD) {
+                        const float2 bb = *reinterpret_cast<const float2*>(smem + 16 + (c * 8 + j * 2) * 4);
+                        v0 = valid ? fmaxf(fmaf(v0, scale, bb.x), 0.f) : 0.f;
+                        v1 = valid ? fmaxf(fmaf(v1, scale, bb.y), 0.f) : 0.f;
+                    } else {
+                        const uint32_t m = j == 0 ? xm[c].x : (j == 1 ? xm[c].y : (j == 2 ? xm[c].z : xm[c].w));
+                        const float2 xv = unpack_bf16x2(m);
+                        v0 = xv.x > 0.f ? v0 : 0.f;
+                        v1 = xv.y > 0.f ? v1 : 0.f;
+                    }
+                    w[j] = pack_bf16x2(v0, v1);
+                }
+                *reinterpret_cast<uint4*>(out + o + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // slab[buf] and the TMEM accumulators are free again
+    }
+    cp_async_wait<0>();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+constexpr int kTcSub = 2;   // 256 positions per tile
+
+static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, int min_off) {
+    TcGeom g;
+    g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv;
+    g.tiles_per_sample = cdiv((long long)Hv * pitch, kTcSub * 128);
+    g.total_tiles = B * g.tiles_per_sample;
+    g.slab_rows = kTcSub * 128 + span;
+    g.plane_rows = (g.slab_rows + 7) / 8 * 8;
+    g.min_off = min_off;
+    return g;
+}
+
+template <typename K>
+static int tc_set_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
+template <int CP, int NTAPS, bool DGRAD>
+static int launch_tc(const void* in, long long in_sstride, const void* wts, const float* bias, float scale,
+                     const void* relu_src, void* out, long long out_sstride, const TcGeom& g, const TcTaps& taps,
+                     cudaStream_t stream) {
+    constexpr int CH = CP / 8;
+    const size_t smem = 256 + (size_t)NTAPS * CH * 512 + 2 * (size_t)CH * g.plane_rows * 16;
+    auto kern = k_conv_tc<CP, NTAPS, DGRAD, kTcSub>;
+    if (smem > 227 * 1024) { set_last_error("conv_tc: pitch %d needs %zu B of shared memory", g.pitch, smem); return -1; }
+    if (tc_set_smem(kern, smem)) return -1;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    const int cap = sm_count() * per_sm;
+    const int grid = g.total_tiles < cap ? g.total_tiles : cap;
+    kern<<<grid, kTcSub * 128, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
+                                               (const bf16*)relu_src, (bf16*)out, out_sstride, g, taps);
+    return 0;
+}
+
+}  // namespace curla
+
+using namespace curla;
+
+// Rows of zero padding the caller keeps in front of sample 0 and behind sample B-1 of every
+// activation buffer handed to the conv kernels (slabs read past the tile on both sides).
+extern "C" int curla_conv_pad_rows(int pitch) { return 128 * (kTcSub + 1) + 2 * pitch + 2; }
+
+// layer 1: in = s2d bf16 [B][S][48]; layers 2..4: in = bf16 [B][S][32].  out bf16 [B][S][32].
+// Hv/Wv = valid output dims of this layer.
+extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* wts,
+                              const float* bias, float scale, void* out, long long out_sstride,
+                              int B, int pitch, int S, int Hv, int Wv, int first_layer,
+                              cudaStream_t stream) {
+    TcTaps taps;
+    if (first_layer) {
+        for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
+        for (int t = 4; t < 9; ++t) taps.off[t] = 0;
+        const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, pitch + 1, 0);
+        if (launch_tc<48, 4, false>(in, in_sstride, wts, bias, scale, nullptr, out, out_sstride, g, taps, stream)) return -1;
+    } else {
+        for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
+        const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
+        if (launch_tc<32, 9, false>(in, in_sstride, wts, bias, scale, nullptr, out, out_sstride, g, taps, stream)) return -1;
+    }
+    return check_launch("conv_fwd");
+}
+
+// dX[P] = relu'(X[P]) * sum_t dY[P - off_t] . Wt^T ; Hv/Wv = valid dims of X (this layer's INPUT).
+extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
+                                const void* x, void* dx, long long dx_sstride, int B, int pitch,
+                                int S, int Hv, int Wv, cudaStream_t stream) {
+    TcTaps taps;
+    for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
+    const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
+    if (launch_tc<32, 9, true>(dy, dy_sstride, wts, nullptr, 1.f, x, dx, dx_sstride, g, taps, stream)) return -1;
+    return check_launch("conv_dgrad");
+}
