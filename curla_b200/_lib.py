@@ -30,7 +30,7 @@ class UpdateArgs(C.Structure):
         'h1_next', 'w1_next', 'h1_pos', 'w1_pos', 'obs_f32', 'next_f32', 'pos_f32',
         'noise_next', 'noise_cur')] + \
         [('seed', C.c_ulonglong), ('offset', C.c_ulonglong), ('step', C.c_int),
-         ('only_cpc', C.c_int), ('pos_is_obs', C.c_int)]
+         ('only_cpc', C.c_int), ('pos_is_obs', C.c_int), ('phases', C.c_int)]
 
 
 # name -> (restype, argtypes); mirrors include/curla_b200.h one to one
@@ -42,6 +42,7 @@ SIGNATURES = {
     'curla_gather_crop_s2d': (_i, [c_vp, _i, _i, _i, c_vp, c_vp, c_vp, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_f32_to_s2d': (_i, [c_vp, _i, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_gather_rows_f32': (_i, [c_vp, c_vp, _i, _i, c_vp, c_vp]),
+    'curla_conv_pad_rows': (_i, [_i]),
     'curla_conv_fwd': (_i, [c_vp, c_ll, c_vp, c_vp, _f, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_dgrad': (_i, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_wgrad_workspace_floats': (c_ll, [_i]),

@@ -297,14 +297,22 @@ k_conv_wgrad(const bf16* __restrict__ in, long long in_sstride,
 // Deterministic second stage: sum CTA partials, write OIHW fp32 grads (+ bias grad).
 //  s2d=0: dW[co][ci][t]      = scale * sum ws[cta][t][ci][co]           (Cin = 32)
 //  s2d=1: dW[co][c][ky][kx]  = scale * sum ws[cta][by*2+bx][c*4+sy*2+sx][co]
-__global__ void k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
-                                    int CP, int Cin, int s2d, float scale,
-                                    float* __restrict__ dW, float* __restrict__ db) {
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
+                    int CP, int Cin, int s2d, float scale,
+                    float* __restrict__ dW, float* __restrict__ db) {
+    // block = 32 consecutive elements x 8 partial-slices; fixed summation tree => deterministic
+    __shared__ float red[8][33];
     const int per = ntaps * CP * 32 + 32;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per) return;
+    const int i = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int c = 0; c < nparts; ++c) s += partial[(long long)c * per + i];
+    if (i < per)
+        for (int c = threadIdx.y; c < nparts; c += 8) s += partial[(long long)c * per + i];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || i >= per) return;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) s += red[r][threadIdx.x];
     if (i >= ntaps * CP * 32) { db[i - ntaps * CP * 32] = s; return; }
     const int co = i & 31, ci = (i >> 5) % CP, t = (i >> 5) / CP;
     if (!s2d) {
@@ -340,10 +348,10 @@ using namespace curla;
 
 // layer 1: in = s2d bf16 [B][S][48]; layers 2..4: in = bf16 [B][S][32].  out bf16 [B][S][32].
 // Hv/Wv = valid output dims of this layer.
-extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* wts,
-                              const float* bias, float scale, void* out, long long out_sstride,
-                              int B, int pitch, int S, int Hv, int Wv, int first_layer,
-                              cudaStream_t stream) {
+int curla::legacy_conv_fwd(const void* in, long long in_sstride, const void* wts,
+                           const float* bias, float scale, void* out, long long out_sstride,
+                           int B, int pitch, int S, int Hv, int Wv, int first_layer,
+                           cudaStream_t stream) {
     TapOffsets taps;
     int grid_cap = sm_count() * 4;
     if (first_layer) {
@@ -369,9 +377,9 @@ extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* 
 }
 
 // dX[P] = relu'(X[P]) * sum_t dY[P - off_t] . Wt^T ; Hv/Wv = valid dims of X (this layer's INPUT).
-extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
-                                const void* x, void* dx, long long dx_sstride, int B, int pitch,
-                                int S, int Hv, int Wv, cudaStream_t stream) {
+int curla::legacy_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
+                             const void* x, void* dx, long long dx_sstride, int B, int pitch,
+                             int S, int Hv, int Wv, cudaStream_t stream) {
     TapOffsets taps;
     for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
     ConvGeom g = make_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
@@ -409,7 +417,7 @@ extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void
                                           workspace, g, taps);
         if (check_launch("conv_wgrad")) return -1;
         const int per = 4 * 48 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 256), 256, 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
+        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
     } else {
         for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
         ConvGeom g = make_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
@@ -421,7 +429,7 @@ extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void
                                           workspace, g, taps);
         if (check_launch("conv_wgrad")) return -1;
         const int per = 9 * 32 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 256), 256, 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
+        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
     }
     return check_launch("conv_wgrad_reduce");
 }

@@ -29,6 +29,8 @@
 // overlap load / MMA / epilogue across CTAs.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace curla {
 
 struct TcGeom {
@@ -133,7 +135,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_bar = s_base, s_tptr = s_base + 8, s_bias = s_base + 16;
+    const uint32_t s_bar = s_base, s_tptr = s_base + 8;   // bias lives at smem + 16
     const uint32_t s_w = s_base + 256;
     const uint32_t PS = (uint32_t)g.plane_rows * 16u;
     const uint32_t slab_bytes = CH * PS;
@@ -145,6 +147,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         fence_mbar_init();
     }
     if (warp == 0) {
+        __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr),
                      "r"(TMEM_COLS)
                      : "memory");
@@ -326,6 +329,8 @@ extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* 
                               const float* bias, float scale, void* out, long long out_sstride,
                               int B, int pitch, int S, int Hv, int Wv, int first_layer,
                               cudaStream_t stream) {
+    static const bool legacy = getenv("CURLA_CONV_LEGACY") != nullptr;
+    if (legacy) return legacy_conv_fwd(in, in_sstride, wts, bias, scale, out, out_sstride, B, pitch, S, Hv, Wv, first_layer, stream);
     TcTaps taps;
     if (first_layer) {
         for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
@@ -344,6 +349,8 @@ extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* 
 extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
                                 const void* x, void* dx, long long dx_sstride, int B, int pitch,
                                 int S, int Hv, int Wv, cudaStream_t stream) {
+    static const bool legacy = getenv("CURLA_CONV_LEGACY") != nullptr;
+    if (legacy) return legacy_conv_dgrad(dy, dy_sstride, wts, x, dx, dx_sstride, B, pitch, S, Hv, Wv, stream);
     TcTaps taps;
     for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
     const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));

@@ -252,7 +252,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     for (int i = 1; i < 4; ++i) { a->Ho[i] = a->Ho[i - 1] - 2; a->Wo[i] = a->Wo[i - 1] - 2; }
     a->Kfc = a->Ho[3] * a->pitch * 32;
     a->CP1 = 48;
-    a->PAD = 128 + 2 * a->pitch + 2;
+    a->PAD = curla_conv_pad_rows(a->pitch);
     const int B = c.batch, Bg = c.global_batch, hid = c.hidden_dim, feat = c.feature_dim, A = c.action_dim;
     Builder b; b.a = a;
 
@@ -659,10 +659,12 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     const long long launches0 = g_launches;
     if (g_prof.on) { g_prof.stream = st; g_prof.mark("__begin__"); }
     Run r{a, st};
+    const int ph = u->phases ? u->phases : CURLA_PHASE_ALL;
     const bool do_sac = !u->only_cpc;
-    const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0);
-    const bool do_ema = do_sac && (u->step % c.critic_target_update_freq == 0);
-    const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
+    const bool do_critic = do_sac && (ph & CURLA_PHASE_CRITIC);
+    const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0) && (ph & CURLA_PHASE_ACTOR);
+    const bool do_ema = do_sac && (u->step % c.critic_target_update_freq == 0) && (ph & CURLA_PHASE_EMA);
+    const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0) && (ph & CURLA_PHASE_CPC);
 
     // ---- sample: gather (+crop) straight into the conv stack's input layout
     auto stage = [&](const float* f32, const uint8_t* frames, const int64_t* h1, const int64_t* w1, bf16* dst) {
@@ -670,10 +672,12 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         if (f32) r.chk(curla_f32_to_s2d(f32, c.C, c.H, c.W, B, a->CP1, a->s2d_sstride, dst, st));
         else r.chk(curla_gather_crop_s2d(frames, c.C, c.Hf, c.Wf, u->idxs, h1, w1, B, c.H, c.W, a->CP1, a->s2d_sstride, dst, st));
     };
-    stage(u->obs_f32, u->obses, u->h1_obs, u->w1_obs, a->s2d_obs);
-    const bf16* s2d_pos = a->s2d_obs;
-    if (do_cpc && !u->pos_is_obs) { stage(u->pos_f32, u->obses, u->h1_pos, u->w1_pos, a->s2d_pos); s2d_pos = a->s2d_pos; }
-    if (do_sac) {
+    const bool do_sample = (ph & CURLA_PHASE_SAMPLE) != 0;
+    const bool want_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
+    if (do_sample) stage(u->obs_f32, u->obses, u->h1_obs, u->w1_obs, a->s2d_obs);
+    const bf16* s2d_pos = u->pos_is_obs ? a->s2d_obs : a->s2d_pos;
+    if (do_sample && want_cpc && !u->pos_is_obs) stage(u->pos_f32, u->obses, u->h1_pos, u->w1_pos, a->s2d_pos);
+    if (do_sample && do_sac) {
         stage(u->next_f32, u->next_obses, u->h1_next, u->w1_next, a->s2d_next);
         if (r.ok()) r.chk(curla_gather_rows_f32(u->actions, u->idxs, B, A, a->act_b, st));
         if (r.ok()) r.chk(curla_gather_rows_f32(u->rewards, u->idxs, B, 1, a->rew_b, st));
@@ -681,7 +685,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     }
 
     bool have_p5 = false;
-    if (do_sac) {
+    if (do_critic) {
         // ---------------- update_critic (curl_sac.py:349-371)
         // F1: actor(next_obs) -> a', log_pi'
         r.conv_stack(a->s2d_next, a->enc_critic, a->s_critic, a->actB);
@@ -708,7 +712,8 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, a->n_critic, a->n_critic,
                                          c.critic_lr, c.critic_beta, 0.999, 1e-8, ++a->t_critic, nullptr, st));
         r.pack(a->pack_critic);
-
+    }
+    if (do_sac) {
         if (do_actor) {
             // ---------------- update_actor_and_alpha (curl_sac.py:373-404)
             // F4: conv_theta'(obs) shared by actor(obs), critic(obs, pi) and the CURL anchor

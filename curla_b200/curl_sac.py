@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from . import augmentations
+from . import dp
 from . import encoder
 from . import utils
 from .engine import Engine
@@ -471,9 +472,7 @@ class CurlSacAgent(_Host):
         self.target_entropy = -np.prod(action_shape)        # curl_sac.py:296
 
         # data parallel: one process per GPU; the engine all-reduces grads / all-gathers keys
-        self.world, self.rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        self.rank, self.world = dp.world_info()
 
         self._cfg = dict(
             C=obs_shape[0], H=obs_shape[1], W=obs_shape[2], feature_dim=encoder_feature_dim,
@@ -540,15 +539,8 @@ class CurlSacAgent(_Host):
             self._init_comm()
 
     def _init_comm(self):
-        import torch.distributed as dist
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if self.rank == 0:
-            buf = (C.c_char * 128)()
-            _lib.call('curla_nccl_unique_id', C.cast(buf, C.c_void_p))
-            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.to(self.device) if dist.get_backend() == 'nccl' else uid
-        dist.broadcast(uid, 0)
-        raw = bytes(uid.cpu().numpy().tobytes())
+        uid = dp.nccl_unique_id(self.engine.lib) if self.rank == 0 else b''
+        raw = dp.broadcast_bytes(uid, 128, self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.engine.lib.curla_agent_init_comm(self.engine.h, C.c_char_p(raw)), 'init_comm')
 
@@ -588,11 +580,18 @@ class CurlSacAgent(_Host):
             mu, pi, _, _ = self.actor(obs, compute_log_pi=False)
             return pi.cpu().data.numpy().flatten()
 
-    def update(self, replay_buffer, L, step, only_cpc=False):
-        """One whole SAC+CURL update (curl_sac.py:426-451) as a single engine call."""
+    def update(self, replay_buffer, L, step, only_cpc=False, _phases=0):
+        """One whole SAC+CURL update (curl_sac.py:426-451) as a single engine call.
+
+        `_phases` (tests only) is a CURLA_PHASE_* mask: the parity tests run sample / critic /
+        actor / EMA / CPC as separate calls on one staged minibatch (include/curla_b200.h)."""
+        if _phases and not (_phases & 1):
+            a = self._last_args                  # same minibatch, noise and step as the SAMPLE call
+            a.phases = int(_phases)
+            self.engine.update(a)
+            return
         Bg = replay_buffer.batch_size
-        assert Bg % self.world == 0, 'global batch must divide evenly over the ranks'
-        B = Bg // self.world
+        B = dp.local_batch(Bg, self.world)
         a = _lib.UpdateArgs()
         keep = []
         fused = isinstance(replay_buffer, utils.ReplayBuffer) and \
@@ -601,7 +600,7 @@ class CurlSacAgent(_Host):
             # sample_cpc's RNG draws (utils.py:147,156-158), gather fused into the update
             self._ensure_engine(B, replay_buffer.obs_shape[1:])
             d, dev = replay_buffer.draw_indices()
-            sl = slice(self.rank * B, (self.rank + 1) * B)
+            sl = dp.shard_slice(self.rank, self.world, Bg)
             a.obses, a.next_obses = replay_buffer.obses.data_ptr(), replay_buffer.next_obses.data_ptr()
             a.actions, a.rewards = replay_buffer.actions.data_ptr(), replay_buffer.rewards.data_ptr()
             a.not_dones = replay_buffer.not_dones.data_ptr()
@@ -618,7 +617,7 @@ class CurlSacAgent(_Host):
             # any other buffer / augmentation: its own sample_cpc() output (float tensors)
             obs, action, reward, next_obs, not_done, kw = replay_buffer.sample_cpc()
             self._ensure_engine(B, self.image_shape)
-            sl = slice(self.rank * B, (self.rank + 1) * B)
+            sl = dp.shard_slice(self.rank, self.world, Bg)
             f = lambda t: t[sl].to(self.device, torch.float32).contiguous()
             obs_l, next_l, pos_l = f(obs), f(next_obs), f(kw['obs_pos'])
             act_l, rew_l, nd_l = f(action), f(reward), f(not_done)
@@ -638,6 +637,8 @@ class CurlSacAgent(_Host):
             a.noise_next, a.noise_cur = n1.data_ptr(), n2.data_ptr()
         a.seed, a.offset = self._noise_seed, self._update_count
         a.step, a.only_cpc = int(step), int(bool(only_cpc))
+        a.phases = int(_phases)
+        self._last_args, self._last_keep = a, keep
         self.engine.update(a)
         self._update_count += 1
 

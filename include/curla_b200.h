@@ -47,7 +47,11 @@ int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
 int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
                           curla_stream_t stream);
 
-/* ---- K4-K6: conv stack as shifted GEMMs  (encoder.py:77-90 + autograd) ------------------ */
+/* ---- K4-K6: conv stack as shifted GEMMs  (encoder.py:77-90 + autograd) ------------------
+ * fwd/dgrad: tcgen05.mma + TMEM (conv_tc.cu); wgrad: split-K over positions (conv.cu).
+ * Every activation buffer needs curla_conv_pad_rows(pitch) zero rows before sample 0 and
+ * after sample B-1.                                                                       */
+int curla_conv_pad_rows(int pitch);
 int curla_conv_fwd(const void* in, long long in_sstride, const void* wts, const float* bias,
                    float scale, void* out, long long out_sstride, int B, int pitch, int S,
                    int Hv, int Wv, int first_layer, curla_stream_t stream);
@@ -177,7 +181,13 @@ typedef struct curla_update_args {
     int step;                 /* global env step (frequencies use it: curl_sac.py:439-449) */
     int only_cpc;
     int pos_is_obs;           /* identity branch: pos is a value-equal clone of obs      */
+    int phases;               /* 0 = the whole update; else a mask of CURLA_PHASE_* so that a
+                                 caller (the parity tests) can run curl_sac.py:429 sample,
+                                 :349-371 critic, :373-404 actor+alpha, :442-445 EMA and
+                                 :406-423 CPC as separate calls on the same staged minibatch */
 } curla_update_args;
+enum { CURLA_PHASE_SAMPLE = 1, CURLA_PHASE_CRITIC = 2, CURLA_PHASE_ACTOR = 4, CURLA_PHASE_EMA = 8,
+       CURLA_PHASE_CPC = 16, CURLA_PHASE_ALL = 31 };
 
 /* One whole update.  metrics: device float[16]
  * {batch_reward, critic_loss, actor_loss, entropy, alpha_loss, alpha, curl_loss, target_entropy} */

@@ -35,7 +35,7 @@ class Geom:
         for _ in range(3):
             self.Ho.append(self.Ho[-1] - 2)
             self.Wo.append(self.Wo[-1] - 2)
-        self.PAD = 128 + 2 * self.pitch + 2
+        self.PAD = _lib.load().curla_conv_pad_rows(self.pitch)
         self.CP1 = 48
 
     def alloc(self, ch, dtype=torch.bfloat16):
