@@ -49,6 +49,8 @@ SIGNATURES = {
     'curla_conv_wgrad': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, _f, _i, _i, _i, _i, _i, _i, _i, c_vp]),
     'curla_gemm_bf16': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,
                              c_ll, _i, c_ll, _f, c_vp]),
+    'curla_gemm_bf16_seg': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,
+                                 c_ll, _i, c_ll, _f, _i, c_ll, _i, c_vp]),
     'curla_gemm_effective_splits': (_i, [_i, _i]),
     'curla_ln_fwd': (_i, [c_vp, _i, c_ll, c_vp, c_vp, c_vp, _i, _i, _i, c_vp, c_vp, c_vp]),
     'curla_ln_bwd': (_i, [c_vp, c_vp, c_vp, c_vp, _i, _i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

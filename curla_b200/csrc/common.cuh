@@ -88,13 +88,6 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// v1 mma.sync conv kernels (conv.cu), kept only for A/B timing against conv_tc.cu
-int legacy_conv_fwd(const void* in, long long in_sstride, const void* wts, const float* bias, float scale,
-                    void* out, long long out_sstride, int B, int pitch, int S, int Hv, int Wv, int first_layer,
-                    cudaStream_t stream);
-int legacy_conv_dgrad(const void* dy, long long dy_sstride, const void* wts, const void* x, void* dx,
-                      long long dx_sstride, int B, int pitch, int S, int Hv, int Wv, cudaStream_t stream);
-
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 }  // namespace curla

@@ -16,8 +16,8 @@
 // with 4 taps x 48 channels (36 real).  dgrad is the same kernel with negated shifts and
 // the transposed weight operand; wgrad reduces over positions with one warp per tap.
 //
-// Tensor path: mma.sync m16n8k16 bf16 -> fp32 (v1).  The tcgen05 variant reuses this
-// layout (64-byte rows, 64B swizzle) -- see conv_tc.cu when present.
+// This file holds wgrad (mma.sync m16n8k16 bf16 -> fp32, split over positions with a
+// deterministic second stage); forward and dgrad are the tcgen05 kernels of conv_tc.cu.
 #include "common.cuh"
 
 namespace curla {
@@ -51,139 +51,16 @@ struct ConvGeom {
 
 struct TapOffsets { int off[9]; };
 
+// global activations are channel planes [CP/8][S][8] per sample; the
+// shared-memory rows keep all CP channels of a position together for ldmatrix.
 template <int CP>
-__device__ __forceinline__ void load_rows_async(uint32_t smem_base, const bf16* gsrc, int nrows,
-                                                int tid, int nthreads) {
+__device__ __forceinline__ void load_rows_async(uint32_t smem_base, const bf16* gsrc, long long plane,
+                                                int nrows, int tid, int nthreads) {
     constexpr int CH = CP / 8;
-    const int total = nrows * CH;
-    for (int i = tid; i < total; i += nthreads) {
-        const int row = i / CH, c = i % CH;
-        cp_async16(smem_base + RowLayout<CP>::off(row, c), gsrc + (long long)row * CP + c * 8, 16);
-    }
-}
-
-// ------------------------------------------------------------------ fwd / dgrad
-// out[P][0:32] = epilogue( sum_t slab[P + off_t][0:CP] . Wt )
-//  DGRAD=false: Wt[n][k] (n = out channel rows, k contiguous)         -> relu(acc*scale + bias)
-//  DGRAD=true : Wt[k][n] (same memory, read transposed), mask by X>0  -> dX
-template <int CP, int NTAPS, bool DGRAD>
-__global__ void __launch_bounds__(128)
-k_conv_shift(const bf16* __restrict__ in, long long in_sstride,      // elements per sample
-             const bf16* __restrict__ wts,                            // [NTAPS][32][CP]
-             const float* __restrict__ bias, float scale,
-             const bf16* __restrict__ relu_src,                       // DGRAD: activation X (same geometry as out)
-             bf16* __restrict__ out, long long out_sstride,           // elements per sample
-             ConvGeom g, TapOffsets taps) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    using L = RowLayout<CP>;
-    constexpr int KS = CP / 16;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_w = smem_u32(smem);
-    const uint32_t w_bytes = NTAPS * 32 * L::kRowBytes;
-    const uint32_t slab_bytes = ((uint32_t)g.slab_rows * L::kRowBytes + 127u) & ~127u;
-    const uint32_t s_slab0 = s_w + ((w_bytes + 127u) & ~127u);
-
-    // weights -> smem once per CTA
-    load_rows_async<CP>(s_w, wts, NTAPS * 32, tid, 128);
-
-    int tile = blockIdx.x;
-    auto prefetch = [&](int t, int buf) {
-        const int b = t / g.tiles_per_sample;
-        const int p0 = (t - b * g.tiles_per_sample) * TM;
-        const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * CP;
-        load_rows_async<CP>(s_slab0 + buf * slab_bytes, src, g.slab_rows, tid, 128);
-    };
-    if (tile < g.total_tiles) prefetch(tile, 0);
-    cp_async_commit();
-
-    const int gq = lane >> 2, q = lane & 3;
-    // ldmatrix lane roles
-    const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7);   // A (non-trans): rows = positions
-    const int a_chk = lane >> 4;
-    int b_row, b_chk;
-    if (!DGRAD) { b_row = (lane >> 4) * 8 + (lane & 7); b_chk = (lane >> 3) & 1; }   // rows = n
-    else        { b_row = ((lane >> 3) & 1) * 8 + (lane & 7); b_chk = lane >> 4; }   // rows = k
-
-    int buf = 0;
-    for (; tile < g.total_tiles; tile += gridDim.x, buf ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < g.total_tiles) prefetch(next, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
-
-        const uint32_t s_slab = s_slab0 + buf * slab_bytes;
-        float acc[2][4][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-
-#pragma unroll
-        for (int t = 0; t < NTAPS; ++t) {
-            const int rbase = warp * 32 + taps.off[t] - g.min_off;   // slab-local row
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                uint32_t a[2][4], bfr[4][2];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-                    ldmatrix_x4(s_slab + L::off(rbase + mt * 16 + a_row, ks * 2 + a_chk),
-                                a[mt][0], a[mt][1], a[mt][2], a[mt][3]);
-#pragma unroll
-                for (int np = 0; np < 2; ++np) {
-                    if (!DGRAD) {
-                        // rows n = np*16 + b_row, chunk = k chunk
-                        ldmatrix_x4(s_w + L::off(t * 32 + np * 16 + b_row, ks * 2 + b_chk),
-                                    bfr[np * 2][0], bfr[np * 2][1], bfr[np * 2 + 1][0], bfr[np * 2 + 1][1]);
-                    } else {
-                        // rows k = ks*16 + b_row, chunk = n chunk (np*2 + b_chk)
-                        ldmatrix_x4_trans(s_w + L::off(t * 32 + ks * 16 + b_row, np * 2 + b_chk),
-                                          bfr[np * 2][0], bfr[np * 2][1], bfr[np * 2 + 1][0], bfr[np * 2 + 1][1]);
-                    }
-                }
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-                        mma_bf16(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3],
-                                 bfr[nt][0], bfr[nt][1]);
-            }
-        }
-
-        // ---- epilogue
-        const int b = tile / g.tiles_per_sample;
-        const int p0 = (tile - b * g.tiles_per_sample) * TM;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int p = p0 + warp * 32 + mt * 16 + h * 8 + gq;
-                if (p >= g.S) continue;
-                const int y = p / g.pitch, x = p - y * g.pitch;
-                const bool valid = (y < g.Hv) && (x < g.Wv);
-                const long long o = (long long)b * out_sstride + (long long)p * 32;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int n = nt * 8 + q * 2;
-                    float v0 = acc[mt][nt][h * 2], v1 = acc[mt][nt][h * 2 + 1];
-                    if (!DGRAD) {
-                        v0 = fmaxf(fmaf(v0, scale, bias[n]), 0.f);
-                        v1 = fmaxf(fmaf(v1, scale, bias[n + 1]), 0.f);
-                        if (!valid) { v0 = 0.f; v1 = 0.f; }
-                    } else {
-                        float2 xv = make_float2(0.f, 0.f);
-                        if (valid) xv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(relu_src + o + n));
-                        v0 = xv.x > 0.f ? v0 : 0.f;
-                        v1 = xv.y > 0.f ? v1 : 0.f;
-                    }
-                    *reinterpret_cast<uint32_t*>(out + o + n) = pack_bf16x2(v0, v1);
-                }
-            }
-        __syncthreads();   // slab[buf] is overwritten by the prefetch of the next iteration
-    }
-    cp_async_wait<0>();
+    for (int c = 0; c < CH; ++c)
+        for (int row = tid; row < nrows; row += nthreads)
+            cp_async16(smem_base + RowLayout<CP>::off(row, c), gsrc + c * plane + (long long)row * 8, 16);
 }
 
 // ------------------------------------------------------------------ wgrad
@@ -209,8 +86,9 @@ k_conv_wgrad(const bf16* __restrict__ in, long long in_sstride,
         const int b = t / g.tiles_per_sample;
         const int p0 = (t - b * g.tiles_per_sample) * TM;
         const uint32_t s = s_base + buf * stage_bytes;
-        load_rows_async<CP>(s, in + (long long)b * in_sstride + (long long)p0 * CP, g.slab_rows, tid, NTH);
-        load_rows_async<32>(s + slab_bytes, dy + (long long)b * dy_sstride + (long long)p0 * 32, TM, tid, NTH);
+        const long long plane = (long long)g.S * 8;
+        load_rows_async<CP>(s, in + (long long)b * in_sstride + (long long)p0 * 8, plane, g.slab_rows, tid, NTH);
+        load_rows_async<32>(s + slab_bytes, dy + (long long)b * dy_sstride + (long long)p0 * 8, plane, TM, tid, NTH);
     };
     int tile = blockIdx.x;
     if (tile < g.total_tiles) prefetch(tile, 0);
@@ -345,53 +223,6 @@ static ConvGeom make_geom(int B, int pitch, int S, int Hv, int Wv, int span, int
 }  // namespace curla
 
 using namespace curla;
-
-// layer 1: in = s2d bf16 [B][S][48]; layers 2..4: in = bf16 [B][S][32].  out bf16 [B][S][32].
-// Hv/Wv = valid output dims of this layer.
-int curla::legacy_conv_fwd(const void* in, long long in_sstride, const void* wts,
-                           const float* bias, float scale, void* out, long long out_sstride,
-                           int B, int pitch, int S, int Hv, int Wv, int first_layer,
-                           cudaStream_t stream) {
-    TapOffsets taps;
-    int grid_cap = sm_count() * 4;
-    if (first_layer) {
-        for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
-        ConvGeom g = make_geom(B, pitch, S, Hv, Wv, pitch + 1, 0);
-        size_t smem = ((4 * 32 * 112 + 127) & ~127) + 2 * (((size_t)g.slab_rows * 112 + 127) & ~127);
-        auto kern = k_conv_shift<48, 4, false>;
-        if (set_smem(kern, smem)) return -1;
-        int grid = g.total_tiles < grid_cap ? g.total_tiles : grid_cap;
-        kern<<<grid, 128, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
-                                          nullptr, (bf16*)out, out_sstride, g, taps);
-    } else {
-        for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
-        ConvGeom g = make_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
-        size_t smem = 9 * 32 * 64 + 2 * (((size_t)g.slab_rows * 64 + 127) & ~127);
-        auto kern = k_conv_shift<32, 9, false>;
-        if (set_smem(kern, smem)) return -1;
-        int grid = g.total_tiles < grid_cap ? g.total_tiles : grid_cap;
-        kern<<<grid, 128, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
-                                          nullptr, (bf16*)out, out_sstride, g, taps);
-    }
-    return check_launch("conv_fwd");
-}
-
-// dX[P] = relu'(X[P]) * sum_t dY[P - off_t] . Wt^T ; Hv/Wv = valid dims of X (this layer's INPUT).
-int curla::legacy_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
-                             const void* x, void* dx, long long dx_sstride, int B, int pitch,
-                             int S, int Hv, int Wv, cudaStream_t stream) {
-    TapOffsets taps;
-    for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
-    ConvGeom g = make_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
-    size_t smem = 9 * 32 * 64 + 2 * (((size_t)g.slab_rows * 64 + 127) & ~127);
-    auto kern = k_conv_shift<32, 9, true>;
-    if (set_smem(kern, smem)) return -1;
-    int grid_cap = sm_count() * 4;
-    int grid = g.total_tiles < grid_cap ? g.total_tiles : grid_cap;
-    kern<<<grid, 128, smem, stream>>>((const bf16*)dy, dy_sstride, (const bf16*)wts, nullptr, 1.f,
-                                      (const bf16*)x, (bf16*)dx, dx_sstride, g, taps);
-    return check_launch("conv_dgrad");
-}
 
 extern "C" long long curla_conv_wgrad_workspace_floats(int first_layer) {
     const long long per = first_layer ? (4 * 48 * 32 + 32) : (9 * 32 * 32 + 32);

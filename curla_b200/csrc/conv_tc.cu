@@ -20,13 +20,12 @@
 // slab, no im2col, no data movement, any shift (only 16-byte alignment is required when no
 // swizzle is used).  Weights use the same layout [tap][chunk][32 n][8 k].
 //
-// One CTA = NSUB*128 threads, persistent over tiles of NSUB*128 positions: cp.async fills the
-// next slab (double buffered) while one elected thread issues NSUB*NTAPS*(CP/16) MMAs
-// (M=128, N=32, K=16, bf16 -> fp32) into NSUB TMEM accumulators of 32 columns; a
-// tcgen05.commit arrives on an mbarrier; every warp then pulls its 32 TMEM lanes with
-// tcgen05.ld (one output position per thread, 32 channels) and runs the epilogue
-// (scale+bias+ReLU, or the ReLU mask of dgrad) with 64-byte row stores.  3 CTAs per SM
-// overlap load / MMA / epilogue across CTAs.
+// One persistent CTA per SM over tiles of 256 positions, warp-specialised (producer warps fill
+// a ring of slabs with cp.async; one elected thread issues 2*NTAPS*(CP/16) MMAs of
+// M=128, N=32, K=16, bf16 -> fp32 per tile into double-buffered TMEM accumulators;
+// tcgen05.commit arrives on mbarriers; eight epilogue warps pull their 32 TMEM lanes with
+// tcgen05.ld -- one output position per thread, 32 channels -- and apply scale+bias+ReLU or
+// the ReLU mask of dgrad with 64-byte row stores).  See the kernel for the pipeline.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -39,6 +38,8 @@ struct TcGeom {
     int slab_rows;       // rows actually loaded (TM + span)
     int plane_rows;      // slab_rows rounded up to 8 (plane stride = plane_rows * 16 B)
     int min_off;         // most negative tap shift
+    int stages;          // slab ring depth (host: as many as fit in shared memory, <= 8)
+    int debug;           // CURLA_TC_DEBUG bitmask (timing experiments only): 1 no loads, 2 no MMA, 4 no stores
 };
 struct TcTaps { int off[9]; };
 
@@ -94,12 +95,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=32, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+template <int ACCUMULATE>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "n"(ACCUMULATE)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -121,29 +123,68 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------- the kernel
+// Warp-specialised, persistent, one CTA per SM:
+//   warps 0..7   epilogue   (TMEM -> registers -> bias/ReLU or ReLU-mask -> plane stores: a
+//                            warp writes 32 consecutive positions x 16 B = 512 contiguous bytes)
+//   warp  8      MMA issuer (one elected lane; 2 x NTAPS x CP/16 tcgen05.mma per tile)
+//   warp  9      producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
+//                            per tile, one per channel plane -- the global layout IS the
+//                            shared-memory operand layout -- completing on the stage's mbarrier)
+// Pipelines: full/empty per slab stage (producer <-> MMA), tfull/tempty per TMEM accumulator
+// stage (MMA <-> epilogue; 4 stages x 2 sub-tiles x 32 columns = 256 TMEM columns), so loads
+// of tile i+k, the MMAs of tile i+1 and the epilogue of tile i all run concurrently.
 //  DGRAD=false: B = W_t[n][k]            -> out = relu(acc*scale + bias)
 //  DGRAD=true : B = W_t^T (n=ci, k=co)   -> out = (X > 0) ? acc : 0
-template <int CP, int NTAPS, bool DGRAD, int NSUB>
-__global__ void __launch_bounds__(NSUB * 128)
+constexpr int kTcSub = 2;                 // 256 positions per tile
+constexpr int kEpiWarps = 4 * kTcSub;     // 8
+constexpr int kTcThreads = (kEpiWarps + 2) * 32;   // 320
+constexpr int kMaxStages = 8;
+constexpr int kAccStages = 4;
+constexpr int kSmemHdr = 512;             // barriers + tmem ptr + bias
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int CP, int NTAPS, bool DGRAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
 k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ wts,   // [NTAPS][32][CP]
           const float* __restrict__ bias, float scale, const bf16* __restrict__ relu_src,
           bf16* __restrict__ out, long long out_sstride, TcGeom g, TcTaps taps) {
-    constexpr int CH = CP / 8, KS = CP / 16, NT = NSUB * 128, TM = NSUB * 128;
+    constexpr int CH = CP / 8, KS = CP / 16, TM = kTcSub * 128;
     constexpr uint32_t W_BYTES = NTAPS * CH * 512;
-    constexpr uint32_t TMEM_COLS = NSUB * 32 < 32 ? 32 : NSUB * 32;
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+    constexpr uint32_t TMEM_COLS = kAccStages * kTcSub * 32;   // 256
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_bar = s_base, s_tptr = s_base + 8;   // bias lives at smem + 16
-    const uint32_t s_w = s_base + 256;
+    // header: full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem ptr @192, bias @256
+    const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 160;
+    const uint32_t s_tptr = s_base + 192;
+    const uint32_t s_w = s_base + kSmemHdr;
     const uint32_t PS = (uint32_t)g.plane_rows * 16u;
     const uint32_t slab_bytes = CH * PS;
     const uint32_t s_slab0 = s_w + W_BYTES;
+    const int stages = g.stages;
+    const long long plane = (long long)g.S * 8;      // elements between channel planes (in and out)
 
-    // ---- one-time setup: barrier, TMEM, weights, bias
+    // ---- one-time setup: barriers, TMEM, weights, bias
     if (tid == 0) {
-        mbar_init(s_bar, 1);
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(s_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(s_tfull + 8 * i, 1);
+            mbar_init(s_tempty + 8 * i, kEpiWarps);
+        }
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -154,129 +195,167 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (!DGRAD) {
-        for (int i = tid; i < NTAPS * 32 * CH; i += NT) {
+        for (int i = tid; i < NTAPS * 32 * CH; i += kTcThreads) {
             const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
             cp_async16(s_w + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
         }
-        if (tid < 32) reinterpret_cast<float*>(smem + 16)[tid] = bias[tid];
+        if (tid < 32) reinterpret_cast<float*>(smem + 256)[tid] = bias[tid];
     } else {
         // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
-        for (int i = tid; i < NTAPS * 32 * CP; i += NT) {
+        for (int i = tid; i < NTAPS * 32 * CP; i += kTcThreads) {
             const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
-            reinterpret_cast<bf16*>(smem + 256)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
+            reinterpret_cast<bf16*>(smem + kSmemHdr)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
         }
     }
-
-    auto prefetch = [&](int t, int buf) {
-        const int b = t / g.tiles_per_sample;
-        const int p0 = (t - b * g.tiles_per_sample) * TM;
-        const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * CP;
-        const uint32_t dst = s_slab0 + buf * slab_bytes;
-        const int total = g.slab_rows * CH;
-        for (int i = tid; i < total; i += NT) {
-            const int row = i / CH, c = i - row * CH;
-            cp_async16(dst + c * PS + row * 16, src + (long long)row * CP + c * 8, 16);
-        }
-    };
-    int tile = blockIdx.x;
-    if (tile < g.total_tiles) prefetch(tile, 0);
     cp_async_commit();
-
+    cp_async_wait<0>();
+    fence_proxy_async();          // generic-proxy writes of the weights -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 8);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 192);
 
-    const int sub = warp >> 2, quarter = warp & 3;
-    const int row_in_tile = sub * 128 + quarter * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 32);
-
-    uint32_t phase = 0;
-    int buf = 0;
-    for (; tile < g.total_tiles; tile += gridDim.x, buf ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < g.total_tiles) prefetch(next, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-
-        if (warp == 0) {
+    if (warp < kEpiWarps) {
+        // ================= epilogue: one output position per thread per tile
+        const int sub = warp >> 2, quarter = warp & 3;
+        const int row_in_tile = sub * 128 + quarter * 32 + lane;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 32);
+        uint32_t acc = 0, acc_phase = 0;
+        // bias in registers: shared memory is saturated by the tensor core's operand reads
+        float bz[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bz[i] = DGRAD ? 0.f : reinterpret_cast<const float*>(smem + 256)[i];
+        // dgrad: the ReLU mask (X at the same position) is fetched one tile ahead so that its
+        // DRAM latency never sits between an accumulator becoming ready and being drained
+        uint4 xn[4];
+        auto load_mask = [&](int tile_, uint4 (&dst)[4]) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (tile_ < g.total_tiles) {
+                const int b_ = tile_ / g.tiles_per_sample;
+                const int p_ = (tile_ - b_ * g.tiles_per_sample) * TM + row_in_tile;
+                const int y_ = p_ / g.pitch, x_ = p_ - y_ * g.pitch;
+                if (y_ < g.Hv && x_ < g.Wv && p_ < g.S) {
+                    const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(relu_src + o_ + c * plane);
+                }
+            }
+        };
+        if (DGRAD) load_mask(blockIdx.x, xn);
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            const int b = tile / g.tiles_per_sample;
+            const int p = (tile - b * g.tiles_per_sample) * TM + row_in_tile;
+            const int y = p / g.pitch, x = p - y * g.pitch;
+            const bool valid = (y < g.Hv) && (x < g.Wv);
+            const long long o = (long long)b * out_sstride + (long long)p * 8;   // + c*plane
+            uint4 xm[4];
+            if (DGRAD) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) xm[c] = xn[c];
+                load_mask(tile + gridDim.x, xn);
+            }
+            mbar_wait(s_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(taddr0 + acc * (kTcSub * 32), r);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tempty + 8 * acc);   // this warp's 32 lanes are drained
+            if (p < g.S && !(g.debug & 4)) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v0 = __uint_as_float(r[c * 8 + j * 2]), v1 = __uint_as_float(r[c * 8 + j * 2 + 1]);
+                        if (!DGRAD) {
+                            v0 = valid ? fmaxf(fmaf(v0, scale, bz[c * 8 + j * 2]), 0.f) : 0.f;
+                            v1 = valid ? fmaxf(fmaf(v1, scale, bz[c * 8 + j * 2 + 1]), 0.f) : 0.f;
+                        } else {
+                            const uint32_t m = j == 0 ? xm[c].x : (j == 1 ? xm[c].y : (j == 2 ? xm[c].z : xm[c].w));
+                            const float2 xv = unpack_bf16x2(m);
+                            v0 = xv.x > 0.f ? v0 : 0.f;
+                            v1 = xv.y > 0.f ? v1 : 0.f;
+                        }
+                        w[j] = pack_bf16x2(v0, v1);
+                    }
+                    *reinterpret_cast<uint4*>(out + o + c * plane) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == kEpiWarps) {
+        // ================= MMA issuer
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        // descriptors differ only in the 14-bit start-address field: precompute the field
+        // offsets (16-byte units) once, add the stage base per tile
+        const uint64_t a_hi = make_desc(0, PS, 128), b_hi = make_desc(0, 512, 128);
+        uint32_t a_off[NTAPS * KS];
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                a_off[t * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)(taps.off[t] - g.min_off) * 16u) >> 4;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            mbar_wait(s_full + 8 * stage, phase);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t s_slab = s_slab0 + buf * slab_bytes;
+                const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
+                if (!(g.debug & 2))
 #pragma unroll
-                for (int s = 0; s < NSUB; ++s) {
+                for (int s = 0; s < kTcSub; ++s) {
+                    const uint32_t d = tmem_base + acc * (kTcSub * 32) + (uint32_t)(s * 32);
 #pragma unroll
                     for (int t = 0; t < NTAPS; ++t) {
-                        const uint32_t a_row = (uint32_t)(s * 128 + taps.off[t] - g.min_off);
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
-                            const uint64_t ad = make_desc(s_slab + (uint32_t)(2 * ks) * PS + a_row * 16u, PS, 128);
-                            const uint64_t bd = make_desc(s_w + (uint32_t)((t * CH + 2 * ks) * 512), 512, 128);
-                            umma_bf16(tmem_base + (uint32_t)(s * 32), ad, bd, (t | ks) ? 1u : 0u);
+                            const uint64_t ad = a_hi | (uint64_t)((slab16 + (uint32_t)(s * 128) + a_off[t * KS + ks]) & 0x3FFFu);
+                            const uint64_t bd = b_hi | (uint64_t)(((s_w >> 4) + (uint32_t)((t * CH + 2 * ks) * 32)) & 0x3FFFu);
+                            if (t | ks) umma_bf16<1>(d, ad, bd); else umma_bf16<0>(d, ad, bd);
                         }
                     }
                 }
-                umma_commit(s_bar);
+                umma_commit(s_empty + 8 * stage);     // slab free once these MMAs have read it
+                umma_commit(s_tfull + 8 * acc);       // accumulators complete
             }
             __syncwarp();
+            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
-
-        // ---- epilogue: one output position per thread
-        const int b = tile / g.tiles_per_sample;
-        const int p = (tile - b * g.tiles_per_sample) * TM + row_in_tile;
-        const int y = p / g.pitch, x = p - y * g.pitch;
-        const bool valid = (y < g.Hv) && (x < g.Wv);
-        const long long o = (long long)b * out_sstride + (long long)p * 32;
-        uint4 xm[4];
-        if (DGRAD) {
+    } else {
+        // ================= producer: slab[c][0:rows][16 B] <- plane c rows [p0+min_off, +rows)
+        uint32_t stage = 0, phase = 0;
+        const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            const int b = tile / g.tiles_per_sample;
+            const int p0 = (tile - b * g.tiles_per_sample) * TM;
+            const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * 8;
+            const uint32_t dst = s_slab0 + stage * slab_bytes;
+            mbar_wait(s_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
+                const uint32_t bar = s_full + 8 * stage;
+                if (g.debug & 1) {
+                    mbar_arrive(bar);
+                } else {
+                    mbar_expect_tx(bar, bytes * CH);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) xm[c] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && p < g.S) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) xm[c] = *reinterpret_cast<const uint4*>(relu_src + o + c * 8);
-            }
-        }
-        mbar_wait(s_bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        uint32_t acc[32];
-        tmem_ld32(taddr, acc);
-        if (p < g.S) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v0 = __uint_as_float(acc[c * 8 + j * 2]), v1 = __uint_as_float(acc[c * 8 + j * 2 + 1]);
-                    if (!DGRAD) {
-                        const float2 bb = *reinterpret_cast<const float2*>(smem + 16 + (c * 8 + j * 2) * 4);
-                        v0 = valid ? fmaxf(fmaf(v0, scale, bb.x), 0.f) : 0.f;
-                        v1 = valid ? fmaxf(fmaf(v1, scale, bb.y), 0.f) : 0.f;
-                    } else {
-                        const uint32_t m = j == 0 ? xm[c].x : (j == 1 ? xm[c].y : (j == 2 ? xm[c].z : xm[c].w));
-                        const float2 xv = unpack_bf16x2(m);
-                        v0 = xv.x > 0.f ? v0 : 0.f;
-                        v1 = xv.y > 0.f ? v1 : 0.f;
-                    }
-                    w[j] = pack_bf16x2(v0, v1);
+                    for (int c = 0; c < CH; ++c) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
                 }
-                *reinterpret_cast<uint4*>(out + o + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            __syncwarp();
+            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        tc_fence_before();
-        __syncthreads();   // slab[buf] and the TMEM accumulators are free again
     }
-    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                      : "memory");
     }
 }
-
-constexpr int kTcSub = 2;   // 256 positions per tile
 
 static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, int min_off) {
     TcGeom g;
@@ -286,6 +365,8 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     g.slab_rows = kTcSub * 128 + span;
     g.plane_rows = (g.slab_rows + 7) / 8 * 8;
     g.min_off = min_off;
+    g.stages = 2;
+    g.debug = 0;
     return g;
 }
 
@@ -298,20 +379,25 @@ static int tc_set_smem(K kern, size_t bytes) {
 
 template <int CP, int NTAPS, bool DGRAD>
 static int launch_tc(const void* in, long long in_sstride, const void* wts, const float* bias, float scale,
-                     const void* relu_src, void* out, long long out_sstride, const TcGeom& g, const TcTaps& taps,
+                     const void* relu_src, void* out, long long out_sstride, TcGeom g, const TcTaps& taps,
                      cudaStream_t stream) {
     constexpr int CH = CP / 8;
-    const size_t smem = 256 + (size_t)NTAPS * CH * 512 + 2 * (size_t)CH * g.plane_rows * 16;
-    auto kern = k_conv_tc<CP, NTAPS, DGRAD, kTcSub>;
-    if (smem > 227 * 1024) { set_last_error("conv_tc: pitch %d needs %zu B of shared memory", g.pitch, smem); return -1; }
+    const size_t fixed = kSmemHdr + (size_t)NTAPS * CH * 512;
+    const size_t slab = (size_t)CH * g.plane_rows * 16;
+    const size_t budget = 200 * 1024;
+    int stages = (int)((budget - fixed) / slab);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) { set_last_error("conv_tc: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
+    g.stages = stages;
+    { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
+    { const char* e = getenv("CURLA_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) g.stages = atoi(e); }
+    const size_t smem = fixed + stages * slab;
+    auto kern = k_conv_tc<CP, NTAPS, DGRAD>;
     if (tc_set_smem(kern, smem)) return -1;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 3) per_sm = 3;
-    if (per_sm < 1) per_sm = 1;
-    const int cap = sm_count() * per_sm;
+    const int cap = sm_count();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
-    kern<<<grid, kTcSub * 128, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
-                                               (const bf16*)relu_src, (bf16*)out, out_sstride, g, taps);
+    kern<<<grid, kTcThreads, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
+                                             (const bf16*)relu_src, (bf16*)out, out_sstride, g, taps);
     return 0;
 }
 
@@ -329,8 +415,6 @@ extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* 
                               const float* bias, float scale, void* out, long long out_sstride,
                               int B, int pitch, int S, int Hv, int Wv, int first_layer,
                               cudaStream_t stream) {
-    static const bool legacy = getenv("CURLA_CONV_LEGACY") != nullptr;
-    if (legacy) return legacy_conv_fwd(in, in_sstride, wts, bias, scale, out, out_sstride, B, pitch, S, Hv, Wv, first_layer, stream);
     TcTaps taps;
     if (first_layer) {
         for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
@@ -349,8 +433,6 @@ extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* 
 extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts,
                                 const void* x, void* dx, long long dx_sstride, int B, int pitch,
                                 int S, int Hv, int Wv, cudaStream_t stream) {
-    static const bool legacy = getenv("CURLA_CONV_LEGACY") != nullptr;
-    if (legacy) return legacy_conv_dgrad(dy, dy_sstride, wts, x, dx, dx_sstride, B, pitch, S, Hv, Wv, stream);
     TcTaps taps;
     for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
     const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));

@@ -193,8 +193,8 @@ void layout_encoder(Builder& b, const std::string& pre, EncP& e, const curla_age
         e.conv_w[i] = b.p(pre + "convs." + std::to_string(i) + ".weight", {c.num_filters, cin, 3, 3});
         e.conv_b[i] = b.p(pre + "convs." + std::to_string(i) + ".bias", {c.num_filters});
     }
-    // canonical fc layout is the kernel layout: [feat][Ho4][pitch][F] (zero in pad columns)
-    e.fc_w = b.p(pre + "fc.weight_canon", {c.feature_dim, a->Ho[3], a->pitch, c.num_filters});
+    // canonical fc layout is the kernel layout: [feat][F/8 planes][Ho4*pitch][8] (zero in pad columns)
+    e.fc_w = b.p(pre + "fc.weight_canon", {c.feature_dim, c.num_filters / 8, a->Ho[3] * a->pitch, 8});
     e.fc_b = b.p(pre + "fc.bias", {c.feature_dim});
     e.ln_w = b.p(pre + "ln.weight", {c.feature_dim});
     e.ln_b = b.p(pre + "ln.bias", {c.feature_dim});
@@ -269,7 +269,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     {   // actor-own: fc, ln (convs tied to the critic's: curl_sac.py:290)
         EncP& e = a->enc_actor;
         for (int i = 0; i < 4; ++i) { e.conv_w[i] = a->enc_critic.conv_w[i]; e.conv_b[i] = a->enc_critic.conv_b[i]; }
-        e.fc_w = b.p("actor.encoder.fc.weight_canon", {feat, a->Ho[3], a->pitch, 32});
+        e.fc_w = b.p("actor.encoder.fc.weight_canon", {feat, 4, a->Ho[3] * a->pitch, 8});
         e.fc_b = b.p("actor.encoder.fc.bias", {feat});
         e.ln_w = b.p("actor.encoder.ln.weight", {feat});
         e.ln_b = b.p("actor.encoder.ln.bias", {feat});
@@ -478,8 +478,9 @@ struct Run {
     void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0) {
         if (!ok()) return;
         set_launch_tag("gemm_fc_fwd");
-        chk(curla_gemm_bf16(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
-                            3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f, st));
+        chk(curla_gemm_bf16_seg(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
+                                3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f,
+                                a->Kfc / 4, (long long)a->S * 8, 1, st));
         set_launch_tag(nullptr);
         if (!ok()) return;
         chk(curla_ln_fwd(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
@@ -526,14 +527,16 @@ struct Run {
                          g(e.ln_w), g(e.ln_b), g(e.fc_b), st));
         // dWfc[feat][Kfc] = dfc^T . act4
         set_launch_tag("gemm_fc_wgrad");
-        if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
-                                      a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+        if (ok()) chk(curla_gemm_bf16_seg(a->dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
+                                          a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f,
+                                          a->Kfc / 4, (long long)a->S * 8, 2, st));
         set_launch_tag(nullptr);
         if (!conv) return;
         // d(act4) = relu'(act4) * dfc . Wfc
         set_launch_tag("gemm_fc_dgrad");
-        if (ok()) chk(curla_gemm_bf16(a->dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
-                                      a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f, st));
+        if (ok()) chk(curla_gemm_bf16_seg(a->dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
+                                          a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f,
+                                          a->Kfc / 4, (long long)a->S * 8, 4, st));
         set_launch_tag(nullptr);
         for (int i = 3; i >= 1 && ok(); --i) {
             chk(curla_conv_wgrad(acts[i - 1], a->act_sstride, a->dact[i], a->act_sstride, a->wgrad_ws, g(e.conv_w[i]),

@@ -10,7 +10,8 @@
 //   * NCHW float32  -- what sample_cpc() hands to user code (public API parity)
 //   * "s2d" bf16    -- what the conv stack consumes: space-to-depth by 2 so that the
 //                      stride-2 3x3 conv1 becomes a stride-1 2x2 "shifted GEMM" with the
-//                      same flattened-position indexing as conv2..4.
+//                      same flattened-position indexing as conv2..4, stored as channel
+//                      planes [CP/8][S][8] per sample.
 //                      uint8 values are exact in bf16.
 #include "common.cuh"
 
@@ -41,52 +42,68 @@ k_gather_crop_f32(const uint8_t* __restrict__ frames, int C, int Hf, int Wf,
     }
 }
 
-// ------------------------------------------------------------------ s2d bf16
-// One CTA per (sample b, s2d block-row yb).  Stage the 2*C source rows in shared memory
-// with coalesced loads, then emit Ws positions x CP channels with 16-byte stores.
-//   out[b][yb*Ws + xb][c*4 + sy*2 + sx] = frame[idx[b]][c][oy + 2yb+sy][ox + 2xb+sx]
-// zero where 2yb+sy >= H, 2xb+sx >= W or channel >= 4C.
+// ------------------------------------------------------------------ s2d bf16 (channel planes)
+// One CTA per (sample b, s2d block-row yb).  The 2*C source rows are staged in shared memory
+// with 16-byte loads of WHOLE stored rows (a crop window at an arbitrary byte offset touches
+// every 32-byte sector of the row anyway), then every thread emits one 16-byte group of 8
+// s2d channels; consecutive threads write consecutive positions of one channel plane, so the
+// stores of a warp are 512 contiguous bytes.
+//   out[b][j][yb*Ws + xb][e]  with s2d channel ch = j*8 + e = c*4 + sy*2 + sx
+//                             = frame[idx[b]][c][oy + 2yb+sy][ox + 2xb+sx]
+// zero where 2yb+sy >= H, 2xb+sx >= W or ch >= 4C.  Plane stride = S positions (S*8 elements).
 template <typename SrcT>
 __global__ void __launch_bounds__(128)
 k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
              const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
              const int64_t* __restrict__ w1, int H, int W, int Hs, int Ws, int CP,
              long long out_sample_stride, bf16* __restrict__ out) {
-    extern __shared__ float s_rows[];   // [2*C][2*Ws] values (float holds u8 and f32 alike)
+    extern __shared__ __align__(16) uint8_t s_raw[];
     const int b = blockIdx.y, yb = blockIdx.x;
     const long long fi = idxs ? idxs[b] : b;
     const int oy = h1 ? (int)h1[b] : 0;
     const int ox = w1 ? (int)w1[b] : 0;
-    const int W2 = 2 * Ws;
-    for (int i = threadIdx.x; i < 2 * C * W2; i += blockDim.x) {
-        const int x = i % W2;
-        const int r = i / W2;          // r = c*2 + sy
-        const int c = r >> 1, sy = r & 1;
-        const int y = 2 * yb + sy;
-        float v = 0.f;
-        if (y < H && x < W)
-            v = (float)frames[((fi * C + c) * Hf + (oy + y)) * (long long)Wf + ox + x];
-        s_rows[i] = v;
+    const int nrows = 2 * C;                       // r = c*2 + sy
+    constexpr int V = 16 / (int)sizeof(SrcT);      // source elements per 16-byte vector
+    const int rowv = (Wf + V - 1) / V;             // vectors per staged row
+    const int rpitch = rowv * V + V;               // elements; +V keeps rows apart in the banks
+    SrcT* s_rows = reinterpret_cast<SrcT*>(s_raw);
+    const bool vec_ok = (Wf % V == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
+    if (vec_ok) {
+        for (int i = threadIdx.x; i < nrows * rowv; i += blockDim.x) {
+            const int r = i / rowv, v = i - r * rowv;
+            const int c = r >> 1, y = 2 * yb + (r & 1);
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (y < H)
+                val = *reinterpret_cast<const uint4*>(frames + ((fi * C + c) * Hf + (oy + y)) * (long long)Wf + v * V);
+            *reinterpret_cast<uint4*>(s_rows + r * rpitch + v * V) = val;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nrows * Wf; i += blockDim.x) {
+            const int r = i / Wf, x = i - r * Wf;
+            const int c = r >> 1, y = 2 * yb + (r & 1);
+            s_rows[r * rpitch + x] = (y < H) ? frames[((fi * C + c) * Hf + (oy + y)) * (long long)Wf + x] : (SrcT)0;
+        }
     }
     __syncthreads();
     const int chunks = CP / 8;
-    bf16* orow = out + b * out_sample_stride + (long long)yb * Ws * CP;
+    const long long S = (long long)Hs * Ws;
+    bf16* obase = out + b * out_sample_stride + (long long)yb * Ws * 8;
     for (int i = threadIdx.x; i < Ws * chunks; i += blockDim.x) {
-        const int j = i % chunks, xb = i / chunks;
+        const int j = i / Ws, xb = i - j * Ws;
         uint32_t w[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {          // two channels-of-s2d per 32-bit word
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int ch = j * 8 + h * 2 + e;       // = c*4 + sy*2 + sx
-                const int c = ch >> 2, sy = (ch >> 1) & 1, sx = ch & 1;
-                v[e] = (c < C) ? s_rows[(c * 2 + sy) * W2 + 2 * xb + sx] : 0.f;
+        for (int h = 0; h < 4; ++h) {          // two s2d channels per 32-bit word: sx = 0, 1
+            const int ch = j * 8 + h * 2;       // = c*4 + sy*2 (+ sx)
+            const int c = ch >> 2, sy = (ch >> 1) & 1;
+            float v0 = 0.f, v1 = 0.f;
+            if (c < C) {
+                const SrcT* rp = s_rows + (c * 2 + sy) * rpitch + ox + 2 * xb;
+                if (2 * xb < W) v0 = (float)rp[0];
+                if (2 * xb + 1 < W) v1 = (float)rp[1];
             }
-            w[h] = pack_bf16x2(v[0], v[1]);
+            w[h] = pack_bf16x2(v0, v1);
         }
-        *reinterpret_cast<uint4*>(orow + (long long)xb * CP + j * 8) =
-            make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(obase + (long long)j * S * 8 + (long long)xb * 8) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -126,7 +143,8 @@ static int launch_s2d(const SrcT* frames, int C, int Hf, int Wf, const int64_t* 
     const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
     CURLA_CHECK(out_sample_stride >= (long long)Hs * Ws * CP, "gather_s2d: sample stride too small");
     dim3 grid(Hs, B);
-    size_t smem = (size_t)2 * C * 2 * Ws * sizeof(float);
+    const int V = 16 / (int)sizeof(SrcT);
+    size_t smem = (size_t)2 * C * ((Wf + V - 1) / V * V + V) * sizeof(SrcT);
     k_gather_s2d<SrcT><<<grid, 128, smem, stream>>>(frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
                                                     CP, out_sample_stride, out);
     return check_launch("gather_s2d");

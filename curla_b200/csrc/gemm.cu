@@ -10,6 +10,7 @@
 // must be multiples of 8 elements (16-byte cp.async chunks, zero padded buffers).
 // 64x64x32 CTA tile, 4 warps, 3-stage cp.async pipeline, mma.sync m16n8k16 bf16->fp32.
 #include "common.cuh"
+#include "../../include/curla_b200.h"
 
 namespace curla {
 
@@ -28,7 +29,20 @@ struct GemmArgs {
     int k_per_split;          // multiple of BK; blockIdx.z selects the K range
     long long split_stride;   // elements between split outputs (fp32 partials)
     float alpha;
+    // Segmented contiguous index (the channel-plane activation layout of the conv stack,
+    // DESIGN.md section 3): index i of the chosen operand lives at (i / seg_len) * seg_stride +
+    // i % seg_len.  seg_mask: 1 = A's contiguous index, 2 = B's, 4 = C's and the mask's column.
+    int seg_len; long long seg_stride; int seg_mask; float seg_inv;
 };
+
+// i / seg_len through a float reciprocal: exact here because i is a multiple of 2 (columns)
+// or 8 (chunks) below 2^22 with only a handful of segments, so (i + 0.5) / seg_len is never
+// within float rounding of an integer.
+__device__ __forceinline__ long long seg_off(int i, int seg_len, long long seg_stride, float inv_len, bool on) {
+    if (!on) return i;
+    const int s = __float2int_rd(((float)i + 0.5f) * inv_len);
+    return (long long)s * seg_stride + (i - s * seg_len);
+}
 
 __device__ __forceinline__ uint32_t off64(int row, int chunk) {      // 64-byte rows
     return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
@@ -37,7 +51,7 @@ __device__ __forceinline__ uint32_t off128(int row, int chunk) {     // 128-byte
     return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, bool SEG>
 __global__ void __launch_bounds__(128)
 k_gemm(GemmArgs p) {
     __shared__ __align__(128) uint8_t smem[STAGES * (BM * BK * 2 + BN * BK * 2)];
@@ -60,23 +74,23 @@ k_gemm(GemmArgs p) {
                 const int r = c >> 2, ch = c & 3;
                 const int m = m0 + r, k = k0 + ch * 8;
                 const bool ok = (m < p.M) && (k < kend);
-                cp_async16(sA + off64(r, ch), ok ? (const void*)(p.A + (long long)m * p.lda + k) : (const void*)p.A, ok ? 16 : 0);
+                cp_async16(sA + off64(r, ch), ok ? (const void*)(p.A + (long long)m * p.lda + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
             } else {
                 const int r = c >> 3, ch = c & 7;
                 const int k = k0 + r, m = m0 + ch * 8;
                 const bool ok = (k < kend) && (m < p.M);
-                cp_async16(sA + off128(r, ch), ok ? (const void*)(p.A + (long long)k * p.lda + m) : (const void*)p.A, ok ? 16 : 0);
+                cp_async16(sA + off128(r, ch), ok ? (const void*)(p.A + (long long)k * p.lda + seg_off(m, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
             }
             if (B_KMAJOR) {
                 const int r = c >> 2, ch = c & 3;
                 const int n = n0 + r, k = k0 + ch * 8;
                 const bool ok = (n < p.N) && (k < kend);
-                cp_async16(sB + off64(r, ch), ok ? (const void*)(p.B + (long long)n * p.ldb + k) : (const void*)p.B, ok ? 16 : 0);
+                cp_async16(sB + off64(r, ch), ok ? (const void*)(p.B + (long long)n * p.ldb + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
             } else {
                 const int r = c >> 3, ch = c & 7;
                 const int k = k0 + r, n = n0 + ch * 8;
                 const bool ok = (k < kend) && (n < p.N);
-                cp_async16(sB + off128(r, ch), ok ? (const void*)(p.B + (long long)k * p.ldb + n) : (const void*)p.B, ok ? 16 : 0);
+                cp_async16(sB + off128(r, ch), ok ? (const void*)(p.B + (long long)k * p.ldb + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
             }
         }
     };
@@ -151,12 +165,13 @@ k_gemm(GemmArgs p) {
                 float v0 = acc[mt][nt][h * 2] * p.alpha, v1 = acc[mt][nt][h * 2 + 1] * p.alpha;
                 if (p.bias) { v0 += p.bias[n]; v1 += (n + 1 < p.n_store) ? p.bias[n + 1] : 0.f; }
                 if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
                 if (p.mask) {
-                    const float2 mk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.mask + (long long)m * p.ldmask + n));
+                    const float2 mk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.mask + (long long)m * p.ldmask + nc));
                     v0 = mk.x > 0.f ? v0 : 0.f;
                     v1 = mk.y > 0.f ? v1 : 0.f;
                 }
-                const long long o = (long long)m * p.ldc + n;
+                const long long o = (long long)m * p.ldc + nc;
                 if (p.out_bf16) {
                     *reinterpret_cast<uint32_t*>(Cb + o) = pack_bf16x2(v0, v1);
                 } else if (n + 1 < p.n_store) {
@@ -179,7 +194,19 @@ extern "C" int curla_gemm_bf16(const void* A, long long lda, const void* B, long
                                int out_bf16, const float* bias, int relu, const void* mask,
                                long long ldmask, int splits, long long split_stride, float alpha,
                                cudaStream_t stream) {
+    return curla_gemm_bf16_seg(A, lda, B, ldb, C, ldc, M, N, K, layout, n_store, out_bf16, bias, relu, mask,
+                               ldmask, splits, split_stride, alpha, 0, 0, 0, stream);
+}
+
+// Same GEMM with one operand's contiguous index split into equal segments (see GemmArgs).
+extern "C" int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long ldb, void* C,
+                                   long long ldc, int M, int N, int K, int layout, int n_store,
+                                   int out_bf16, const float* bias, int relu, const void* mask,
+                                   long long ldmask, int splits, long long split_stride, float alpha,
+                                   int seg_len, long long seg_stride, int seg_mask, cudaStream_t stream) {
     CURLA_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+    CURLA_CHECK(seg_mask == 0 || (seg_len > 0 && seg_len % 8 == 0 && seg_stride % 8 == 0),
+                "gemm: segment length/stride must be positive multiples of 8");
     CURLA_CHECK(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8");
     CURLA_CHECK((ldc % 2) == 0, "gemm: ldc must be even");
     CURLA_CHECK(splits >= 1 && (splits == 1 || !out_bf16), "gemm: split-K needs fp32 output");
@@ -191,12 +218,18 @@ extern "C" int curla_gemm_bf16(const void* A, long long lda, const void* B, long
     p.k_per_split = cdiv(kt, splits) * BK;
     const int zs = cdiv(K, p.k_per_split);
     p.split_stride = split_stride; p.alpha = alpha;
+    p.seg_len = seg_len; p.seg_stride = seg_stride; p.seg_mask = seg_mask;
     dim3 grid(cdiv(N, BN), cdiv(M, BM), zs);
-    switch (layout & 3) {
-        case 3: k_gemm<true, true><<<grid, 128, 0, stream>>>(p); break;
-        case 1: k_gemm<true, false><<<grid, 128, 0, stream>>>(p); break;
-        case 2: k_gemm<false, true><<<grid, 128, 0, stream>>>(p); break;
-        default: k_gemm<false, false><<<grid, 128, 0, stream>>>(p); break;
+    p.seg_inv = seg_mask ? 1.0f / (float)seg_len : 0.f;
+    switch ((layout & 3) | (seg_mask ? 4 : 0)) {
+        case 3: k_gemm<true, true, false><<<grid, 128, 0, stream>>>(p); break;
+        case 1: k_gemm<true, false, false><<<grid, 128, 0, stream>>>(p); break;
+        case 2: k_gemm<false, true, false><<<grid, 128, 0, stream>>>(p); break;
+        case 0: k_gemm<false, false, false><<<grid, 128, 0, stream>>>(p); break;
+        case 7: k_gemm<true, true, true><<<grid, 128, 0, stream>>>(p); break;
+        case 5: k_gemm<true, false, true><<<grid, 128, 0, stream>>>(p); break;
+        case 6: k_gemm<false, true, true><<<grid, 128, 0, stream>>>(p); break;
+        default: k_gemm<false, false, true><<<grid, 128, 0, stream>>>(p); break;
     }
     return check_launch("gemm_bf16");
 }

@@ -79,20 +79,23 @@ class Engine:
 
     # -- canonical <-> PyTorch layout of the encoder fc weight ---------------------
     def fc_geometry(self):
-        feat, ho, pitch, f = self.t['critic.encoder.fc.weight_canon'].shape
-        wo = self._wo4()
-        return feat, ho, wo, pitch, f
+        """(feat, Ho, Wo, pitch, planes): canon is [feat][planes][Ho*pitch][8] -- the K order in
+        which the conv stack's channel-plane activations are read by the fc GEMM."""
+        feat, planes, hp, _ = self.t['critic.encoder.fc.weight_canon'].shape
+        pitch = (self.cfg.W + 1) // 2
+        return feat, hp // pitch, self._wo4(), pitch, planes
 
     def _wo4(self):
         return (self.cfg.W - 3) // 2 + 1 - 6
 
     def fc_to_torch(self, canon):
-        """[feat][Ho][pitch][F] -> PyTorch nn.Linear weight [feat][F*Ho*Wo] (NCHW flatten,
-        encoder.py:89)."""
-        feat, ho, wo, pitch, f = self.fc_geometry()
-        return canon[:, :, :wo, :].permute(0, 3, 1, 2).reshape(feat, f * ho * wo).contiguous()
+        """canon -> PyTorch nn.Linear weight [feat][F*Ho*Wo] (NCHW flatten, encoder.py:89)."""
+        feat, ho, wo, pitch, planes = self.fc_geometry()
+        v = canon.view(feat, planes, ho, pitch, 8)[:, :, :, :wo, :]          # f, j, y, x, e
+        return v.permute(0, 1, 4, 2, 3).reshape(feat, planes * 8 * ho * wo).contiguous()
 
     def fc_from_torch(self, weight, canon_out):
-        feat, ho, wo, pitch, f = self.fc_geometry()
+        feat, ho, wo, pitch, planes = self.fc_geometry()
         canon_out.zero_()
-        canon_out[:, :, :wo, :] = weight.reshape(feat, f, ho, wo).permute(0, 2, 3, 1).to(canon_out.dtype)
+        w = weight.reshape(feat, planes, 8, ho, wo).permute(0, 1, 3, 4, 2)   # f, j, y, x, e
+        canon_out.view(feat, planes, ho, pitch, 8)[:, :, :, :wo, :] = w.to(canon_out.dtype)

@@ -68,6 +68,13 @@ int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, 
                     long long ldc, int M, int N, int K, int layout, int n_store, int out_bf16,
                     const float* bias, int relu, const void* mask, long long ldmask, int splits,
                     long long split_stride, float alpha, curla_stream_t stream);
+/* same, with the contiguous index of A (seg_mask&1), B (&2) or C+mask columns (&4) split into
+ * segments of seg_len elements seg_stride apart (channel-plane activations) */
+int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long ldb, void* C,
+                        long long ldc, int M, int N, int K, int layout, int n_store, int out_bf16,
+                        const float* bias, int relu, const void* mask, long long ldmask, int splits,
+                        long long split_stride, float alpha, int seg_len, long long seg_stride,
+                        int seg_mask, curla_stream_t stream);
 int curla_gemm_effective_splits(int K, int splits);
 
 /* ---- K8 LayerNorm, K10 policy head, K11 losses, MLP heads  (encoder.py:98-110;

@@ -1,0 +1,51 @@
+"""Timing experiment (not a test): one conv layer in isolation at the bench geometry.
+usage: python tests/bench_conv.py [layer(0..3)] [dgrad]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from curla_b200 import _lib
+from helpers import Geom, pack_conv_w, stream
+
+layer = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+dgrad = len(sys.argv) > 2
+B = 512
+g = Geom(76, 135, B)
+torch.manual_seed(0)
+cin = g.CP1 if layer == 0 else 32
+fin, vin = g.alloc(cin)
+vin.copy_((torch.rand(vin.shape, device='cuda') * 2).to(torch.bfloat16))
+fout, vout = g.alloc(32)
+w = torch.randn(32, 9 if layer == 0 else 32, 3, 3) * 0.05
+wsh = pack_conv_w(w, layer == 0)
+bias = torch.zeros(32, device='cuda')
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+
+def run():
+    if dgrad:
+        _lib.call('curla_conv_dgrad', _lib.ptr(vin), g.S * 32, _lib.ptr(wsh), _lib.ptr(vout), _lib.ptr(vout), g.S * 32,
+                  B, g.pitch, g.S, g.Ho[layer - 1], g.Wo[layer - 1], stream())
+    else:
+        _lib.call('curla_conv_fwd', _lib.ptr(vin), g.S * cin, _lib.ptr(wsh), _lib.ptr(bias), 1.0, _lib.ptr(vout),
+                  g.S * 32, B, g.pitch, g.S, g.Ho[layer], g.Wo[layer], 1 if layer == 0 else 0, stream())
+
+
+for _ in range(3):
+    run()
+ts = []
+for _ in range(10):
+    flush.fill_(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+ts.sort()
+print('layer %d %s debug=%s stages=%s: median %.1f us  min %.1f us' % (
+    layer, 'dgrad' if dgrad else 'fwd', os.environ.get('CURLA_TC_DEBUG', '0'), os.environ.get('CURLA_TC_STAGES', 'max'),
+    ts[len(ts) // 2], ts[0]))

@@ -43,18 +43,22 @@ class Geom:
         full = torch.zeros((2 * self.PAD + self.B * self.S, ch), dtype=dtype, device=DEV)
         return full, full[self.PAD:self.PAD + self.B * self.S]
 
+    def nhwc(self, view):
+        """kernel layout (channel planes [ch/8][S][8] per sample) -> [B][Hs][pitch][ch] view."""
+        ch = view.shape[1]
+        v = view.reshape(self.B, ch // 8, self.Hs, self.pitch, 8)
+        return v.permute(0, 2, 3, 1, 4).reshape(self.B, self.Hs, self.pitch, ch)
+
     def to_pitch(self, x_nchw, layer):
-        """NCHW fp32 (B, 32, Ho, Wo) -> logical pitch layout [B*S][32] bf16 (zeros elsewhere)."""
+        """NCHW fp32 (B, 32, Ho, Wo) -> kernel layout bf16 (zeros elsewhere)."""
         B, ch, h, w = x_nchw.shape
         full, view = self.alloc(ch)
-        v = view.view(B, self.Hs, self.pitch, ch)
-        v[:, :h, :w, :] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+        v = view.view(B, ch // 8, self.Hs, self.pitch, 8)
+        v[:, :, :h, :w, :] = x_nchw.reshape(B, ch // 8, 8, h, w).permute(0, 1, 3, 4, 2).to(torch.bfloat16)
         return full, view
 
     def from_pitch(self, view, h, w):
-        B = self.B
-        v = view.view(B, self.Hs, self.pitch, view.shape[1])
-        return v[:, :h, :w, :].permute(0, 3, 1, 2).float()
+        return self.nhwc(view)[:, :h, :w, :].permute(0, 3, 1, 2).float()
 
     def s2d_ref(self, x_nchw):
         """reference space-to-depth: (B, C, H, W) -> [B][Hs][Ws][CP1] float."""

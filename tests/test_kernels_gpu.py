@@ -48,7 +48,7 @@ def test_gather_crop_bit_exact(B, crop):
     _lib.call('curla_gather_crop_s2d', _lib.ptr(fr), Cc, Hf, Wf, _lib.ptr(di), _lib.ptr(dh),
               _lib.ptr(dw), B, oh, ow, g.CP1, g.S * g.CP1, _lib.ptr(view), stream())
     want = g.s2d_ref(torch.from_numpy(ref).to(DEV))
-    assert torch.equal(view.view(B, g.Hs, g.pitch, g.CP1).float(), want)
+    assert torch.equal(g.nhwc(view).float(), want)
     assert float(full[:g.PAD].abs().sum()) == 0 and float(full[g.PAD + B * g.S:].abs().sum()) == 0
     # float-input variant
     full2, view2 = g.alloc(g.CP1)
@@ -119,7 +119,7 @@ def test_conv_forward(H, W, B):
         assert e < 6e-3, (l, e)          # bf16 storage rounding of the output + accumulation order
         assert rel_l2(ours, cur_exact) < 3e-2, l
         # invalid positions are exact zeros
-        v = acts[l].view(B, g.Hs, g.pitch, 32).float()
+        v = g.nhwc(acts[l]).float()
         assert float(v[:, g.Ho[l]:].abs().sum()) == 0 and float(v[:, :, g.Wo[l]:].abs().sum()) == 0
         cur = bf16r(ours)                 # feed OUR stored activations to the next reference layer
 
@@ -164,7 +164,7 @@ def test_conv_backward(H, W, B):
             dx_ref = grads[0] * mask
             ours = g.from_pitch(dx, g.Ho[l - 1], g.Wo[l - 1])
             assert rel_l2(ours, dx_ref) < 6e-3, ('dx', l, rel_l2(ours, dx_ref))
-            v = dx.view(B, g.Hs, g.pitch, 32).float()
+            v = g.nhwc(dx).float()
             assert float(v[:, g.Ho[l - 1]:].abs().sum()) == 0 and float(v[:, :, g.Wo[l - 1]:].abs().sum()) == 0
             keep.append(full)
             dcur = dx
@@ -216,6 +216,47 @@ def test_gemm_epilogues_and_splitk():
     want = torch.relu(ref * 0.5 + bias) * mask.float()
     assert rel_l2(out[:, :50].float(), want[:, :50]) < 6e-3
     assert float(out[:, 50:].abs().sum()) == 0
+
+
+def test_gemm_segmented_operands():
+    """the channel-plane activation layout: the contiguous index of A (fc fwd), B (fc wgrad) or
+    C + mask (fc dgrad) is 4 segments of seg_len elements, seg_stride apart."""
+    torch.manual_seed(11)
+    Bn, feat, seg_len, seg_stride, nseg = 9, 48, 40, 56, 4
+    K = seg_len * nseg
+    act = torch.randn(Bn, K, device=DEV).to(torch.bfloat16)                 # logical [B][K]
+    W = torch.randn(64, K, device=DEV).to(torch.bfloat16)
+    W[feat:] = 0
+
+    def scatter(x):   # logical [rows][K] -> segmented storage [rows][nseg*seg_stride] (junk in the gaps)
+        st = torch.full((x.shape[0], nseg * seg_stride), 3.0, device=DEV, dtype=x.dtype)
+        for s_ in range(nseg):
+            st[:, s_ * seg_stride:s_ * seg_stride + seg_len] = x[:, s_ * seg_len:(s_ + 1) * seg_len]
+        return st
+
+    act_s = scatter(act)
+    lds = act_s.shape[1]
+    # fwd: z[B][64] = act . W^T, A segmented (mask 1)
+    z = torch.zeros(Bn, 64, device=DEV)
+    _lib.call('curla_gemm_bf16_seg', _lib.ptr(act_s), lds, _lib.ptr(W), K, _lib.ptr(z), 64, Bn, 64, K, 3, 64, 0, None, 0,
+              None, 0, 1, 0, 1.0, seg_len, seg_stride, 1, stream())
+    assert rel_l2(z, act.float() @ W.float().t()) < 2e-3
+    # wgrad: dW[64][K] = dz^T . act, B segmented (mask 2); dz stored [B][64] = A MN-major
+    dz = torch.randn(Bn, 64, device=DEV).to(torch.bfloat16)
+    dW = torch.zeros(64, K, device=DEV)
+    _lib.call('curla_gemm_bf16_seg', _lib.ptr(dz), 64, _lib.ptr(act_s), lds, _lib.ptr(dW), K, 64, K, Bn, 0, K, 0, None, 0,
+              None, 0, 1, 0, 1.0, seg_len, seg_stride, 2, stream())
+    assert rel_l2(dW, dz.float().t() @ act.float()) < 2e-3
+    # dgrad: dact[B][K] = (act > 0) * dz . W, C and mask segmented (mask 4), bf16 out
+    dact_s = torch.full((Bn, lds), 5.0, device=DEV, dtype=torch.bfloat16)
+    _lib.call('curla_gemm_bf16_seg', _lib.ptr(dz), 64, _lib.ptr(W), K, _lib.ptr(dact_s), lds, Bn, K, 64, 1, K, 1, None, 0,
+              _lib.ptr(act_s), lds, 1, 0, 1.0, seg_len, seg_stride, 4, stream())
+    want = scatter(((dz.float() @ W.float()) * (act.float() > 0)).to(torch.bfloat16))
+    gaps = torch.ones(lds, dtype=torch.bool, device=DEV)
+    for s_ in range(nseg):
+        gaps[s_ * seg_stride:s_ * seg_stride + seg_len] = False
+    assert rel_l2(dact_s[:, ~gaps].float(), want[:, ~gaps].float()) < 6e-3
+    assert bool((dact_s[:, gaps] == 5.0).all())          # gaps between segments untouched
 
 
 # ------------------------------------------------------------------ LayerNorm / heads / policy / losses

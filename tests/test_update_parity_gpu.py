@@ -160,7 +160,9 @@ def snapshot(o):
 
 def unpack_s2d(eng, key, B, Cc, H, W):
     Hs, Ws = (H + 1) // 2, (W + 1) // 2
-    v = eng.t[key].view(B, Hs, Ws, -1)[..., :Cc * 4].float().view(B, Hs, Ws, Cc, 2, 2)
+    ch = eng.t[key].shape[1]                    # kernel layout: channel planes [ch/8][S][8] per sample
+    v = eng.t[key].view(B, ch // 8, Hs, Ws, 8).permute(0, 2, 3, 1, 4).reshape(B, Hs, Ws, ch)
+    v = v[..., :Cc * 4].float().view(B, Hs, Ws, Cc, 2, 2)
     return v.permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, 2 * Hs, 2 * Ws)[:, :, :H, :W].to(torch.uint8).cpu().numpy()
 
 
