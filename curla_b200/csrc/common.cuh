@@ -86,6 +86,27 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Philox4x32-10 counter-based generator + Box-Muller (policy noise, augmentation noise)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
+    const float u2 = (float)b * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.f * logf(u1));
+    float s, c;
+    sincospif(2.f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ float u01(uint32_t a) { return (float)a * 2.3283064365386963e-10f; }   // [0,1)
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device

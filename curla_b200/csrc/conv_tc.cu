@@ -124,10 +124,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // ---------------------------------------------------------------- the kernel
 // Warp-specialised, persistent, one CTA per SM:
-//   warps 0..7   epilogue   (TMEM -> registers -> bias/ReLU or ReLU-mask -> plane stores: a
+//   warps 0..15  epilogue   (two groups of 8 alternating tiles; TMEM -> registers -> bias/ReLU or ReLU-mask -> plane stores: a
 //                            warp writes 32 consecutive positions x 16 B = 512 contiguous bytes)
-//   warp  8      MMA issuer (one elected lane; 2 x NTAPS x CP/16 tcgen05.mma per tile)
-//   warp  9      producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
+//   warp  16     MMA issuer (one elected lane; 2 x NTAPS x CP/16 tcgen05.mma per tile)
+//   warp  17     producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
 //                            per tile, one per channel plane -- the global layout IS the
 //                            shared-memory operand layout -- completing on the stage's mbarrier)
 // Pipelines: full/empty per slab stage (producer <-> MMA), tfull/tempty per TMEM accumulator
@@ -136,8 +136,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 //  DGRAD=false: B = W_t[n][k]            -> out = relu(acc*scale + bias)
 //  DGRAD=true : B = W_t^T (n=ci, k=co)   -> out = (X > 0) ? acc : 0
 constexpr int kTcSub = 2;                 // 256 positions per tile
-constexpr int kEpiWarps = 4 * kTcSub;     // 8
-constexpr int kTcThreads = (kEpiWarps + 2) * 32;   // 320
+constexpr int kEpiWarps = 4 * kTcSub;     // 8 warps drain one tile (2 sub-tiles x 4 lane quarters)
+constexpr int kEpiGroups = 2;             // two such groups alternate tiles: a warp's per-tile latency
+                                          // (wait, TMEM load, math, stores) is hidden behind the other group
+constexpr int kEpiAll = kEpiWarps * kEpiGroups;      // 16
+constexpr int kTcThreads = (kEpiAll + 2) * 32;       // 576
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 4;
 constexpr int kSmemHdr = 512;             // barriers + tmem ptr + bias
@@ -215,9 +218,10 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 192);
 
-    if (warp < kEpiWarps) {
+    if (warp < kEpiAll) {
         // ================= epilogue: one output position per thread per tile
-        const int sub = warp >> 2, quarter = warp & 3;
+        const int egroup = warp / kEpiWarps, ew = warp % kEpiWarps;
+        const int sub = ew >> 2, quarter = ew & 3;
         const int row_in_tile = sub * 128 + quarter * 32 + lane;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 32);
         uint32_t acc = 0, acc_phase = 0;
@@ -242,8 +246,11 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                 }
             }
         };
-        if (DGRAD) load_mask(blockIdx.x, xn);
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int tstep = gridDim.x * kEpiGroups;
+        const int tile0 = blockIdx.x + egroup * gridDim.x;
+        acc = egroup;                              // local tile j uses accumulator stage j % 4
+        if (DGRAD) load_mask(tile0, xn);
+        for (int tile = tile0; tile < g.total_tiles; tile += tstep) {
             const int b = tile / g.tiles_per_sample;
             const int p = (tile - b * g.tiles_per_sample) * TM + row_in_tile;
             const int y = p / g.pitch, x = p - y * g.pitch;
@@ -253,7 +260,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
             if (DGRAD) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) xm[c] = xn[c];
-                load_mask(tile + gridDim.x, xn);
+                load_mask(tile + tstep, xn);
             }
             mbar_wait(s_tfull + 8 * acc, acc_phase);
             tc_fence_after();
@@ -283,9 +290,10 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                     *reinterpret_cast<uint4*>(out + o + c * plane) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            acc += kEpiGroups;
+            if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
         }
-    } else if (warp == kEpiWarps) {
+    } else if (warp == kEpiAll) {
         // ================= MMA issuer
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         // descriptors differ only in the 14-bit start-address field: precompute the field

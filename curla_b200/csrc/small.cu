@@ -198,25 +198,6 @@ k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ d
 // ------------------------------------------------------------------ policy head
 // Philox4x32-10 for the built-in noise source (torch.randn_like replacement,
 // curl_sac.py:97); tests inject the noise instead.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-    }
-    return ctr;
-}
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
-    const float u2 = (float)b * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.f * logf(u1));
-    float s, c;
-    sincospif(2.f * u2, &s, &c);
-    return make_float2(r * c, r * s);
-}
-
 // t[b][0:A]=mu_raw, t[b][A:2A]=log_std_raw.  A <= 4.
 // Outputs: mu=tanh(mu_raw), pi=tanh(mu_raw + n*exp(ls)), log_pi, ls (rescaled log_std),
 // noise_out (the noise actually used; kept for the backward).

@@ -47,6 +47,21 @@ int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
 int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
                           curla_stream_t stream);
 
+/* ---- K2/K3: device-side augmentations of the non-crop sample_cpc branch (utils.py:168-182)
+ * x: float [n_images][3][H][W] in [0,255], modified in place; one image = one RGB frame of a
+ * frame stack.  color_jiggle (augmentations.py:106-136): params NULL => per-image contrast
+ * U[1-c,1+c], saturation U[1-s,1+s], hue U[-h,h], apply ~ Bernoulli(p) from Philox(seed,offset);
+ * else params = float [4][n_images] {contrast, saturation, hue, apply}.  order: op codes
+ * (1 contrast, 2 saturation, 3 hue, 0 brightness = no-op) 4 bits each, first op lowest.
+ * noisy_cover (augmentations.py:172-205): cover3 = HOST float[3]; noise_in NULL => std*N(0,1). */
+int curla_color_jiggle(float* x, int n_images, int H, int W, const float* params,
+                       unsigned long long seed, unsigned long long offset, float contrast,
+                       float saturation, float hue, float p, int order, float* params_out,
+                       curla_stream_t stream);
+int curla_noisy_cover(float* x, int n_images, int H, int W, int top, int bottom,
+                      const float* cover3, float stdv, const float* noise_in,
+                      unsigned long long seed, unsigned long long offset, curla_stream_t stream);
+
 /* ---- K4-K6: conv stack as shifted GEMMs  (encoder.py:77-90 + autograd) ------------------
  * fwd/dgrad: tcgen05.mma + TMEM (conv_tc.cu); wgrad: split-K over positions (conv.cu).
  * Every activation buffer needs curla_conv_pad_rows(pitch) zero rows before sample 0 and

@@ -50,7 +50,7 @@ def test_engine_layout_host_side(lib):
                                            C.byref(dt)) == 0
         info[name.value.decode()] = (arena.value, off.value, [dims[k] for k in range(ndim.value)], dt.value)
     # fc_in 60,512 = 32*31*61 lives in a [50][31][68][32] canonical tensor
-    assert info['critic.encoder.fc.weight_canon'][2] == [50, 31, 68, 32]
+    assert info['critic.encoder.fc.weight_canon'][2] == [50, 4, 31 * 68, 8]     # [feat][planes][Ho*pitch][8]
     assert info['critic.Q1.trunk.0.weight'][2] == [1024, 52]
     assert info['actor.trunk.4.weight'][2] == [4, 1024]
     # critic and target segments have identical structure (EMA runs flat over them)

@@ -449,3 +449,85 @@ def test_pack_rows():
     _lib.call('curla_pack_shadows', _lib.ptr(src), _lib.ptr(dst), seg.ctypes.data_as(C.c_void_p), 1, stream())
     want = torch.zeros((64, 64), device=DEV); want[:50, :52] = src[3:].view(50, 52)
     assert torch.equal(dst, want.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------ augmentations (K2/K3)
+def test_noisy_cover_exact_with_injected_noise():
+    """augmentations.py:172-205: cover rows exact, + injected noise, clamp -- equals the oracle."""
+    from curla_b200 import augmentations
+    from oracle import curla_oracle as O
+    torch.manual_seed(0)
+    aug = augmentations.make_augmentor('noisy_cover', (90, 160))
+    assert (aug.top, aug.bottom) == O.noisy_cover_rows(90) == (28, 18)
+    x = torch.randint(0, 256, (5, 9, 90, 160)).float()
+    noise = torch.randn(5, 9, 90, 160) * 10.0
+    np.random.seed(4)
+    cover = [np.random.randint(0, 255) for _ in range(3)]
+    want = O.noisy_cover(x, cover, noise, aug.top, aug.bottom)
+    np.random.seed(4)                       # the augmentor draws the same three values itself
+    from curla_b200 import augment
+    got = augment.noisy_cover(x.to(DEV), aug, noise=noise.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    assert np.random.randint(0, 255) == np.random.RandomState(4).randint(0, 255, size=4)[3]   # 3 draws consumed
+
+
+def test_noisy_cover_builtin_noise_is_gaussian():
+    from curla_b200 import augmentations
+    aug = augmentations.make_augmentor('noisy_cover', (90, 160))
+    x = torch.full((8, 9, 90, 160), 128.0, device=DEV)
+    y = aug.training_augmentation(x.clone())
+    mid = y.view(-1, 3, 90, 160)[:, :, aug.top:90 - aug.bottom, :] - 128.0        # uncovered rows
+    assert abs(float(mid.mean())) < 0.05 and abs(float(mid.std()) - 10.0) < 0.05
+    k = float(((mid / 10.0) ** 4).mean())
+    assert abs(k - 3.0) < 0.1                                                      # Gaussian kurtosis
+    cov = y.view(-1, 3, 90, 160)[:, :, :aug.top, :]
+    per_ch = cov.mean(dim=(0, 2, 3))
+    assert float(cov.std(dim=(0, 2, 3)).max()) < 10.5                               # constant + noise
+    assert all(0 <= float(v) <= 255 for v in per_ch)
+    y2 = aug.training_augmentation(x.clone())
+    assert not torch.equal(y, y2)                                                   # fresh noise per call
+
+
+def test_color_jiggle_matches_oracle_with_injected_params():
+    """augmentations.py:106-136 with kornia's per-image parameters injected."""
+    from curla_b200 import augment, augmentations
+    from oracle import curla_oracle as O
+    torch.manual_seed(1)
+    aug = augmentations.make_augmentor('color_jiggle', (90, 160))
+    B, fs = 4, 3
+    x = torch.randint(0, 256, (B, 3 * fs, 90, 160)).float()
+    n = B * fs
+    contrast = 1.0 + 0.2 * (2 * torch.rand(n) - 1)
+    saturation = 1.0 + 0.5 * (2 * torch.rand(n) - 1)
+    hue = 0.5 * (2 * torch.rand(n) - 1)
+    apply = (torch.rand(n) < 0.85).float()
+    for order in ([0, 1, 2, 3], [3, 2, 1, 0], [2, 0, 3, 1]):
+        want = O.color_jiggle(x, contrast, saturation, hue, apply, order)
+        params = torch.stack([contrast, saturation, hue, apply]).to(DEV)
+        got = augment.color_jiggle(x.clone().to(DEV), aug, params=params, order=order).cpu()
+        # fp32 on both sides, different op order inside the HSV maths: 2e-3 of the 0..255 range
+        assert float((got - want).abs().max()) < 0.5, (order, float((got - want).abs().max()))
+        assert float((got - want).abs().mean()) < 2e-3
+        untouched = apply.view(B, fs) == 0
+        for b in range(B):
+            for f in range(fs):
+                if untouched[b, f]:
+                    assert torch.equal(got[b, 3 * f:3 * f + 3], x[b, 3 * f:3 * f + 3])
+
+
+def test_color_jiggle_builtin_parameter_distribution():
+    from curla_b200 import augment, augmentations
+    aug = augmentations.make_augmentor('color_jiggle', (90, 160))
+    n = 3 * 1024
+    x = torch.randint(0, 256, (n // 3, 9, 90, 160), device=DEV).float()[:, :, :8, :16].contiguous()
+    aug8 = augmentations.ColorJiggle((8, 16))
+    pout = torch.zeros(4, n, device=DEV)
+    y = augment.color_jiggle(x.clone(), aug8, params_out=pout)
+    c, s_, h, a = pout.cpu()
+    assert 0.8 <= float(c.min()) and float(c.max()) <= 1.2 and abs(float(c.mean()) - 1.0) < 0.01
+    assert 0.5 <= float(s_.min()) and float(s_.max()) <= 1.5 and abs(float(s_.mean()) - 1.0) < 0.03
+    assert -0.5 <= float(h.min()) and float(h.max()) <= 0.5 and abs(float(h.mean())) < 0.03
+    assert abs(float(a.mean()) - 0.85) < 0.03
+    assert float(y.min()) >= 0.0 and float(y.max()) <= 255.0 + 1e-3
+    same = (y.view(n, -1) == x.view(n, -1)).all(dim=1).cpu()
+    assert bool((same == (a == 0)).all())           # exactly the non-selected frames are untouched
