@@ -311,30 +311,51 @@ def main():
     ups = 1e3 / r['ms_per_step']
     value = Bg * ups
     hbm, tf, how = peaks()
-    # dominant kernel: the 32->32 3x3 conv forward (15 launches per update); per-launch
-    # duration from the live CUDA-event profile
+    # per-kernel rooflines from the live CUDA-event profile (algorithmic bytes: DESIGN.md section 4);
+    # the headline `roofline` entry is the kernel with the largest share of the update
+    ho, wo = [37, 35, 33, 31], [67, 65, 63, 61]
+    Bb = args.batch
+    act = lambda l: Bb * ho[l] * wo[l] * 64                      # valid bf16 positions x 32 channels
+    s2d_bytes = Bb * 38 * 68 * 48 * 2
+    conv_flops = lambda l: 2.0 * Bb * ho[l] * wo[l] * 32 * (81 if l == 0 else 288)
+    stacks = {'conv_fwd': 5, 'conv_dgrad': 2, 'conv_wgrad': 2}       # conv-stack passes per update pair avg
+    table = {
+        'conv_fwd': dict(kernel='k_conv_tc<fwd> (tcgen05 conv forward, 4 layers)', launches=4,
+                         bytes=s2d_bytes + act(0) + sum(act(l - 1) + act(l) for l in (1, 2, 3)),
+                         flops=sum(conv_flops(l) for l in range(4))),
+        'conv_dgrad': dict(kernel='k_conv_tc<dgrad> (tcgen05 conv dgrad, layers 4..2)', launches=3,
+                           bytes=sum(act(l) + 2 * act(l - 1) for l in (1, 2, 3)),
+                           flops=sum(conv_flops(l) for l in (1, 2, 3))),
+        'conv_wgrad': dict(kernel='k_conv_wgrad (conv wgrad, 4 layers)', launches=4,
+                           bytes=s2d_bytes + act(0) + sum(act(l - 1) + act(l) for l in (1, 2, 3)),
+                           flops=sum(conv_flops(l) for l in range(4))),
+        'gather_s2d': dict(kernel='k_gather_s2d (replay gather + crop + u8->bf16 s2d)', launches=1,
+                           bytes=Bb * 9 * 76 * 135 + s2d_bytes, flops=0.0),
+        'adam_f32': dict(kernel='k_adam (fused multi-tensor Adam)', launches=None, bytes=None, flops=0.0),
+    }
+    traffic_db = {}
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')       # per-launch dram bytes from ncu --set full
+    if os.path.exists(tp):
+        traffic_db = json.load(open(tp))
+    roofs = {}
+    for name, t_ in table.items():
+        if name not in r['prof'] or not t_['bytes']:
+            continue
+        cnt, tot = r['prof'][name]
+        passes = cnt / float(t_['launches'])                      # conv-stack passes in the profiled steps
+        sec = tot / 1e3
+        ach = t_['bytes'] * passes / sec / 1e9
+        roofs[name] = {'kernel': t_['kernel'], 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+                       'frac': ach / hbm, 'traffic': traffic_db.get(name), 'peak_source': how,
+                       'algorithmic_bytes_per_launch': t_['bytes'] / t_['launches'],
+                       'avg_launch_us': tot * 1e3 / cnt, 'tflops': t_['flops'] * passes / sec / 1e12,
+                       'launches_per_update': cnt / r['prof_steps'], 'ms_per_update': tot / r['prof_steps']}
     roof = None
-    if 'conv_fwd' in r['prof']:
-        cnt, tot = r['prof']['conv_fwd']
-        # conv_fwd covers conv1 (s2d, 4 taps) and conv2-4; weight the algorithmic work by the launch mix
-        per_update = cnt / r['prof_steps']
-        n_stacks = per_update / 4.0
-        fl = by = 0.0
-        for l in (1, 2, 3):
-            f_, b_ = conv_layer_work(args.batch, l)
-            fl += f_ * n_stacks
-            by += b_ * n_stacks
-        # conv1: u8-exact bf16 s2d input [B][38*68][48] read, output written
-        by1 = args.batch * (38 * 68 * 48 * 2 + 37 * 67 * 32 * 2) + 4 * 32 * 48 * 2
-        fl1 = 2.0 * args.batch * 37 * 67 * 32 * 81
-        by += by1 * n_stacks
-        fl += fl1 * n_stacks
-        sec = tot / r['prof_steps'] / 1e3
-        ach = by / sec / 1e9
-        roof = {'kernel': 'k_conv_shift (conv fwd, all 4 layers)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
-                'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'peak_source': how,
-                'tflops': fl / sec / 1e12, 'launches_per_update': per_update,
-                'ms_per_update': tot / r['prof_steps']}
+    if roofs:
+        top = max(roofs, key=lambda k: roofs[k]['ms_per_update'])
+        roof = dict(roofs[top])
+        roof['other_kernels'] = {k: {kk: v[kk] for kk in ('achieved', 'frac', 'avg_launch_us', 'ms_per_update', 'tflops')}
+                                 for k, v in roofs.items() if k != top}
     breakdown = {k: round(v[1] / r['prof_steps'], 4) for k, v in sorted(r['prof'].items(), key=lambda kv: -kv[1][1])}
 
     cpu = None

@@ -176,7 +176,7 @@ k_conv_wgrad(const bf16* __restrict__ in, long long in_sstride,
 //  s2d=0: dW[co][ci][t]      = scale * sum ws[cta][t][ci][co]           (Cin = 32)
 //  s2d=1: dW[co][c][ky][kx]  = scale * sum ws[cta][by*2+bx][c*4+sy*2+sx][co]
 __global__ void __launch_bounds__(256)
-k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
+k_conv_wgrad_reduce_legacy(const float* __restrict__ partial, int nparts, int ntaps,
                     int CP, int Cin, int s2d, float scale,
                     float* __restrict__ dW, float* __restrict__ db) {
     // block = 32 consecutive elements x 8 partial-slices; fixed summation tree => deterministic
@@ -224,16 +224,12 @@ static ConvGeom make_geom(int B, int pitch, int S, int Hv, int Wv, int span, int
 
 using namespace curla;
 
-extern "C" long long curla_conv_wgrad_workspace_floats(int first_layer) {
-    const long long per = first_layer ? (4 * 48 * 32 + 32) : (9 * 32 * 32 + 32);
-    return per * (long long)(sm_count() * 2);
-}
 
 // dW (OIHW fp32, Cin real channels), db[32].  Hv/Wv = valid dims of dY (this layer's OUTPUT).
-extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void* dy,
-                                long long dy_sstride, float* workspace, float* dW, float* db,
-                                float scale, int B, int pitch, int S, int Hv, int Wv, int Cin,
-                                int first_layer, cudaStream_t stream) {
+int curla::legacy_conv_wgrad(const void* in, long long in_sstride, const void* dy,
+                             long long dy_sstride, float* workspace, float* dW, float* db,
+                             float scale, int B, int pitch, int S, int Hv, int Wv, int Cin,
+                             int first_layer, cudaStream_t stream) {
     TapOffsets taps;
     const int grid_cap = sm_count() * 2;
     int grid;
@@ -248,7 +244,7 @@ extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void
                                           workspace, g, taps);
         if (check_launch("conv_wgrad")) return -1;
         const int per = 4 * 48 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
+        k_conv_wgrad_reduce_legacy<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
     } else {
         for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
         ConvGeom g = make_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
@@ -260,7 +256,7 @@ extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void
                                           workspace, g, taps);
         if (check_launch("conv_wgrad")) return -1;
         const int per = 9 * 32 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
+        k_conv_wgrad_reduce_legacy<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
     }
     return check_launch("conv_wgrad_reduce");
 }

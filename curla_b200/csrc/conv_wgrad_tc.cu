@@ -1,0 +1,298 @@
+// K6 on the 5th-generation tensor cores: conv weight gradient.
+//
+// Replaces cuDNN wgrad launched by loss.backward() (curl_sac.py:367,417) through
+// encoder.py:81-87:   dW[ky][kx][ci][co] = sum_P in[P + ky*pitch + kx][ci] * dy[P][co],
+//                     db[co] = sum_P dy[P][co]            (P over all positions of the batch)
+//
+// GEMM shape.  The reduction runs over positions, so positions are the K dimension and both
+// operands are "MN-major" (8 channels contiguous, K rows 16 B apart): exactly the channel-plane
+// layout the activations already have.  tcgen05.mma needs M >= 64 while a
+// tap only has 32 input channels, and the M chunks (8 channels each) of one descriptor must be
+// a CONSTANT byte stride apart.  Trick: shared memory holds the input one IMAGE ROW per slot,
+//     slot r = [plane 0 | plane 1 | ... | plane CH-1 | ones-plane]   each `pitch` rows x 16 B,
+// slots of consecutive image rows back to back.  With chunk stride = one plane, chunk index
+// i = g*(CH+1) + c  addresses plane c of image row y+g: ONE M=128 descriptor covers all the
+// vertical taps g of all input-channel chunks c (plus a ones-plane per row whose D rows are
+// the bias gradient for free), with no data replication.  The horizontal taps are start-address
+// shifts of +16 B per column, one MMA each into its own TMEM accumulator.
+//   D_kx[(g, c, e)][co] += sum_{16 positions} A[(g,c,e)][k] * dy[k][co]
+// K windows are 16 positions inside one image row; dy planes are staged with zero rows behind
+// `pitch` so that the last window of a row reads zeros instead of the next plane.
+//
+// One persistent CTA per SM: producer warp (cp.async.bulk, one copy per plane per image row),
+// MMA warp (R rows x ceil(Wv/16) windows x NDX MMAs per stage), accumulators stay in TMEM for
+// the CTA's whole share of the batch; 4 epilogue warps write one fp32 partial per CTA and a
+// deterministic second-stage kernel sums the partials into OIHW (run-to-run reproducible).
+#include "common.cuh"
+#include "tc.cuh"
+
+#include <stdlib.h>
+
+namespace curla {
+
+struct WgGeom {
+    int pitch, S, Hv, Wv, B;
+    int R;                 // dy image rows per stage
+    int runs_per_sample, total_runs;
+    int kwin;              // 16-position K windows per image row = ceil(Wv / 16)
+    int dyr;               // rows of a staged dy plane (>= pitch, >= kwin*16), zero behind pitch
+};
+
+constexpr int kWgThreads = 6 * 32;      // 4 epilogue warps + MMA + producer
+// D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N=32, M=128
+constexpr uint32_t kIdescMN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) |
+                              ((128u >> 4) << 24);
+
+// CP: input channels (32, or 48 for the space-to-depth conv1 input); GR x NDX taps (3x3 or 2x2)
+template <int CP, int GR, int NDX>
+__global__ void __launch_bounds__(kWgThreads, 1)
+k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ dy,
+                long long dy_sstride, float* __restrict__ partial, WgGeom g) {
+    constexpr int CH = CP / 8, CPL = CH + 1;          // planes per slot incl. the ones-plane
+    static_assert(GR * CPL <= 16, "M = 128 holds 16 chunks");
+    constexpr uint32_t TMEM_COLS = 128;
+    constexpr int NTAPS = GR * NDX;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    // header: full[2] @0, empty[2] @16, done @32, tmem ptr @40
+    const uint32_t s_full = s_base, s_empty = s_base + 16, s_done = s_base + 32, s_tptr = s_base + 40;
+    const uint32_t PS = (uint32_t)g.pitch * 16u;                       // one plane of one image row
+    const uint32_t slot_bytes = CPL * PS;
+    const int slots = g.R + GR - 1;
+    const uint32_t a_bytes = (uint32_t)slots * slot_bytes;
+    const uint32_t DYB = (uint32_t)g.dyr * 16u;                         // one staged dy plane
+    const uint32_t dy_bytes = (uint32_t)g.R * 4u * DYB;
+    const uint32_t stage_bytes = (a_bytes + dy_bytes + 127u) & ~127u;
+    const uint32_t s_stage0 = s_base + 128;
+    const long long plane = (long long)g.S * 8;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
+        mbar_init(s_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // every byte the tensor core may touch must be finite (junk rows are multiplied by exact
+    // zeros of dy, and 0 * NaN would poison a useful accumulator row): clear both stages once
+    for (uint32_t i = tid; i < (2 * stage_bytes) / 16; i += kWgThreads)
+        reinterpret_cast<uint4*>(smem + 128)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // constant parts of both stages: ones-planes (bf16 1.0); the tail of every dy plane stays zero
+    for (int st = 0; st < 2; ++st) {
+        uint8_t* sb = smem + 128 + (size_t)st * stage_bytes;
+        const int ones16 = slots * g.pitch;                              // 16-byte rows of ones
+        for (int i = tid; i < ones16; i += kWgThreads) {
+            const int r = i / g.pitch, row = i - r * g.pitch;
+            *reinterpret_cast<uint4*>(sb + (size_t)r * slot_bytes + (size_t)CH * PS + (size_t)row * 16) =
+                make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 40);
+    const int my_runs = g.total_runs > (int)blockIdx.x ? (g.total_runs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 5) {
+        // ================= producer
+        uint32_t stage = 0, phase = 0;
+        for (int run = blockIdx.x; run < g.total_runs; run += gridDim.x) {
+            const int b = run / g.runs_per_sample;
+            const int y0 = (run - b * g.runs_per_sample) * g.R;
+            const int rv = (g.Hv - y0) < g.R ? (g.Hv - y0) : g.R;          // valid dy rows of this run
+            const uint32_t sa = s_stage0 + stage * stage_bytes, sd = sa + a_bytes;
+            mbar_wait(s_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
+                const uint32_t bar = s_full + 8 * stage;
+                const int arows = rv + GR - 1;
+                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4) * PS);
+                const bf16* src_a = in + (long long)b * in_sstride + (long long)y0 * g.pitch * 8;
+                for (int r = 0; r < arows; ++r)
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        bulk_g2s(sa + (uint32_t)r * slot_bytes + (uint32_t)c * PS,
+                                 src_a + c * plane + (long long)r * g.pitch * 8, PS, bar);
+                const bf16* src_d = dy + (long long)b * dy_sstride + (long long)y0 * g.pitch * 8;
+                for (int r = 0; r < rv; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        bulk_g2s(sd + (uint32_t)(r * 4 + c) * DYB, src_d + c * plane + (long long)r * g.pitch * 8, PS, bar);
+            }
+            __syncwarp();
+            stage ^= 1;
+            if (stage == 0) phase ^= 1;
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer
+        uint32_t stage = 0, phase = 0, accum = 0;
+        const uint64_t a_hi = make_desc(0, 128, PS), b_hi = make_desc(0, 128, DYB);   // (lbo = K groups, sbo = chunks)
+        for (int run = blockIdx.x; run < g.total_runs; run += gridDim.x) {
+            const int b = run / g.runs_per_sample;
+            const int y0 = (run - b * g.runs_per_sample) * g.R;
+            const int rv = (g.Hv - y0) < g.R ? (g.Hv - y0) : g.R;
+            mbar_wait(s_full + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa16 = (s_stage0 + stage * stage_bytes) >> 4, sd16 = sa16 + (a_bytes >> 4);
+                for (int r = 0; r < rv; ++r) {
+                    for (int kw = 0; kw < g.kwin; ++kw) {
+                        const uint32_t a0 = sa16 + (uint32_t)r * (slot_bytes >> 4) + (uint32_t)kw * 16u;
+                        const uint64_t bd = b_hi | (uint64_t)((sd16 + (uint32_t)(r * 4) * (DYB >> 4) + (uint32_t)kw * 16u) & 0x3FFFu);
+#pragma unroll
+                        for (int dx = 0; dx < NDX; ++dx) {
+                            const uint64_t ad = a_hi | (uint64_t)((a0 + (uint32_t)dx) & 0x3FFFu);
+                            umma_bf16_rt(tmem_base + (uint32_t)(dx * 32), ad, bd, kIdescMN, accum);
+                        }
+                        accum = 1;
+                    }
+                }
+                umma_commit(s_empty + 8 * stage);
+            }
+            accum = 1;
+            __syncwarp();
+            stage ^= 1;
+            if (stage == 0) phase ^= 1;
+        }
+        if (elect_one()) umma_commit(s_done);
+        __syncwarp();
+    } else {
+        // ================= epilogue (once): TMEM -> this CTA's fp32 partial [tap][ci][co] + bias[co]
+        float* ws = partial + (long long)blockIdx.x * (NTAPS * CP * 32 + 32);
+        const int m = warp * 32 + lane;                     // D row = chunk*8 + e
+        const int chunk = m >> 3, e = m & 7;
+        const int gg = chunk / CPL, c = chunk - gg * CPL;
+        uint32_t r[32];
+        if (my_runs > 0) {
+            mbar_wait(s_done, 0);
+            tc_fence_after();
+        }
+#pragma unroll
+        for (int dx = 0; dx < NDX; ++dx) {
+            if (my_runs > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dx * 32), r);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = 0u;
+            }
+            if (gg < GR && c < CH) {
+                float* dst = ws + ((long long)(gg * NDX + dx) * CP + c * 8 + e) * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(dst + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            } else if (gg == 0 && c == CH && e == 0 && dx == 0) {
+                float* dst = ws + (long long)NTAPS * CP * 32;          // ones-plane row: sum_P dy[P][co]
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(dst + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// Deterministic second stage: sum CTA partials, write OIHW fp32 grads (+ bias grad).
+//  s2d=0: dW[co][ci][t]      = scale * sum ws[cta][t][ci][co]           (Cin = 32)
+//  s2d=1: dW[co][c][ky][kx]  = scale * sum ws[cta][by*2+bx][c*4+sy*2+sx][co]
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
+                    int CP, int Cin, int s2d, float scale,
+                    float* __restrict__ dW, float* __restrict__ db) {
+    // block = 32 consecutive elements x 8 partial-slices; fixed summation tree => deterministic
+    __shared__ float red[8][33];
+    const int per = ntaps * CP * 32 + 32;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (i < per)
+        for (int c = threadIdx.y; c < nparts; c += 8) s += partial[(long long)c * per + i];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || i >= per) return;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) s += red[r][threadIdx.x];
+    if (i >= ntaps * CP * 32) { db[i - ntaps * CP * 32] = s; return; }
+    const int co = i & 31, ci = (i >> 5) % CP, t = (i >> 5) / CP;
+    if (!s2d) {
+        if (ci < Cin) dW[((long long)co * Cin + ci) * 9 + t] = s * scale;
+    } else {
+        const int c = ci >> 2, ky = 2 * (t >> 1) + ((ci >> 1) & 1), kx = 2 * (t & 1) + (ci & 1);
+        if (c < Cin && ky < 3 && kx < 3) dW[((long long)co * Cin + c) * 9 + ky * 3 + kx] = s * scale;
+    }
+}
+
+template <int CP, int GR, int NDX>
+static int launch_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
+                        float* workspace, int B, int pitch, int S, int Hv, int Wv, int* grid_out,
+                        cudaStream_t stream) {
+    constexpr int CPL = CP / 8 + 1;
+    WgGeom g;
+    g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv; g.B = B;
+    g.kwin = cdiv(Wv, 16);
+    g.dyr = g.kwin * 16 > pitch ? g.kwin * 16 : pitch;
+    const size_t PS = (size_t)pitch * 16, DYB = (size_t)g.dyr * 16;
+    const size_t budget = 225 * 1024 - 256;
+    int R = 0;
+    for (int r = 1; r <= 16; ++r) {
+        const size_t stage = (((size_t)(r + GR - 1) * CPL * PS + (size_t)r * 4 * DYB) + 127) & ~(size_t)127;
+        // the junk chunks of the last row (up to chunk 15) must stay inside the stage: reads reach
+        // slot r-1 + ceil(16 / CPL) planes, covered by the dy region behind the A slots
+        if (2 * stage <= budget) R = r;
+    }
+    if (R < 1) { set_last_error("conv_wgrad: pitch %d does not fit shared memory", pitch); return -1; }
+    if (R > Hv) R = Hv;
+    g.R = R;
+    g.runs_per_sample = cdiv(Hv, R);
+    g.total_runs = B * g.runs_per_sample;
+    const size_t stage = (((size_t)(R + GR - 1) * CPL * PS + (size_t)R * 4 * DYB) + 127) & ~(size_t)127;
+    const size_t smem = 128 + 2 * stage;
+    auto kern = k_conv_wgrad_tc<CP, GR, NDX>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }
+    const int cap = sm_count();
+    const int grid = g.total_runs < cap ? g.total_runs : cap;
+    kern<<<grid, kWgThreads, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride, workspace, g);
+    *grid_out = grid;
+    return 0;
+}
+
+}  // namespace curla
+
+using namespace curla;
+
+extern "C" long long curla_conv_wgrad_workspace_floats(int first_layer) {
+    const long long per = first_layer ? (4 * 48 * 32 + 32) : (9 * 32 * 32 + 32);
+    return per * (long long)(sm_count() * 2);
+}
+
+// dW (OIHW fp32, Cin real channels), db[32].  Hv/Wv = valid dims of dY (this layer's OUTPUT).
+extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void* dy,
+                                long long dy_sstride, float* workspace, float* dW, float* db,
+                                float scale, int B, int pitch, int S, int Hv, int Wv, int Cin,
+                                int first_layer, cudaStream_t stream) {
+    int grid = 0;
+    if (first_layer) {
+        if (launch_wgrad<48, 2, 2>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, &grid, stream)) return -1;
+        if (check_launch("conv_wgrad")) return -1;
+        const int per = 4 * 48 * 32 + 32;
+        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
+    } else {
+        if (launch_wgrad<32, 3, 3>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, &grid, stream)) return -1;
+        if (check_launch("conv_wgrad")) return -1;
+        const int per = 9 * 32 * 32 + 32;
+        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
+    }
+    return check_launch("conv_wgrad_reduce");
+}

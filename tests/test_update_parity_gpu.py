@@ -414,3 +414,44 @@ def test_fused_update_equals_phased(name):
         p1, p2 = a1.engine.arenas[0].view(torch.float32), a2.engine.arenas[0].view(torch.float32)
         assert torch.equal(p1, p2), (name, u, float((p1 - p2).abs().max()))
         assert float(a1.log_alpha) == float(a2.log_alpha)
+
+
+@pytest.mark.parametrize('aug_name', ['color_jiggle', 'noisy_cover'])
+def test_update_with_device_augmentations(aug_name):
+    """The non-crop branch of sample_cpc (utils.py:168-182) with the two kornia-based
+    augmentations: the update consumes the numpy stream exactly like the reference (idxs, then
+    for noisy_cover three randint(0,255) per call x 3 calls, augmentations.py:192-194), the
+    anchor IS the critic's obs tensor, and the update runs on the augmented float batches."""
+    from curla_b200 import augmentations, curl_sac, utils
+    B, cap, hw = 8, 32, (90, 160)
+    aug = augmentations.make_augmentor(aug_name, hw)
+    rb = utils.ReplayBuffer((S.FRAME_C, *hw), (S.ACTION_DIM,), cap, B, DEV, aug)
+    arrays = S.make_replay_arrays(cap, hw)
+    for dst, src in zip((rb.obses, rb.next_obses, rb.actions, rb.rewards, rb.not_dones), arrays):
+        dst.copy_(torch.from_numpy(src))
+    rb.idx, rb.full = 0, True
+    torch.manual_seed(0)
+    agent = curl_sac.CurlSacAgent((S.FRAME_C, *hw), (S.ACTION_DIM,), DEV, aug, hidden_dim=64, log_interval=1, **S.HP)
+    # sample_cpc contract
+    np.random.seed(5)
+    obs, act, rew, nxt, nd, kw = rb.sample_cpc()
+    ref_state = np.random.RandomState(5)
+    idxs = ref_state.randint(0, cap, size=B)
+    if aug_name == 'noisy_cover':
+        [ref_state.randint(0, 255) for _ in range(9)]
+    assert np.random.randint(0, 1 << 30) == ref_state.randint(0, 1 << 30), 'numpy stream consumption differs'
+    assert kw['obs_anchor'] is obs and kw['obs_pos'] is not obs
+    assert obs.shape == (B, S.FRAME_C, *hw) and obs.dtype == torch.float32 and obs.is_cuda
+    assert float(obs.min()) >= 0.0 and float(obs.max()) <= 255.0 + 1e-3
+    assert torch.equal(act.cpu(), torch.from_numpy(arrays[2][idxs]))
+    raw = torch.from_numpy(arrays[0][idxs]).float()
+    assert not torch.equal(obs.cpu(), raw)                      # it really is augmented
+    if aug_name == 'noisy_cover':
+        mid = (obs.cpu() - raw)[:, :, aug.top:hw[0] - aug.bottom, :]
+        inner = (raw[:, :, aug.top:hw[0] - aug.bottom, :] > 40) & (raw[:, :, aug.top:hw[0] - aug.bottom, :] < 215)
+        assert abs(float(mid[inner].std()) - 10.0) < 0.3        # N(0, 10^2) where the clamp is inactive
+    L = NullLogger()
+    for step in range(2):
+        agent.update(rb, L, step)
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for v in L.rows.values()) and ('train/curl_loss' in {k for _, k in L.rows})
