@@ -164,35 +164,68 @@ k_head_bwd(const float* __restrict__ dOut, const float* __restrict__ W,
 }
 
 // dW[o][j] = sum_b dOut[b][o]*H[b][j];  db[o] = sum_b dOut[b][o]
-__global__ void __launch_bounds__(256)
+// block = 64 columns (32 bf16x2 lanes) x 16 row groups, fixed-order shared-memory tree
+// (deterministic); grid = hid / 64.
+__global__ void __launch_bounds__(512)
 k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, int hid, int No,
              float* __restrict__ dW, float* __restrict__ db) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red[16][4][64];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = (blockIdx.x * 32 + tx) * 2;
+    float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     if (j < hid) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int b = 0; b < B; ++b) {
-            const float h = __bfloat162float(H[(long long)b * hid + j]);
+        for (int b = ty; b < B; b += 16) {
+            const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(H + (long long)b * hid + j));
 #pragma unroll
             for (int o = 0; o < 4; ++o)
-                if (o < No) acc[o] += dOut[b * No + o] * h;
+                if (o < No) {
+                    const float d = dOut[b * No + o];
+                    acc[o][0] += d * h.x; acc[o][1] += d * h.y;
+                }
         }
-        for (int o = 0; o < No; ++o) dW[o * hid + j] = acc[o];
     }
-    if (blockIdx.x == 0 && threadIdx.x < No) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += dOut[b * No + threadIdx.x];
-        db[threadIdx.x] = s;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { red[ty][o][tx * 2] = acc[o][0]; red[ty][o][tx * 2 + 1] = acc[o][1]; }
+    __syncthreads();
+    const int t = ty * 32 + tx;                      // 0..511: (o, column) pairs of this block
+    if (t < 4 * 64) {
+        const int o = t >> 6, c = t & 63;
+        if (o < No && blockIdx.x * 64 + c < hid) {
+            float sum = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) sum += red[r][o][c];
+            dW[o * hid + blockIdx.x * 64 + c] = sum;
+        }
+    }
+    if (blockIdx.x == 0 && ty == 0 && tx < No) {
+        float sum = 0.f;
+        for (int b = 0; b < B; ++b) sum += dOut[b * No + tx];
+        db[tx] = sum;
     }
 }
 
-// db[j] = sum_b dH[b][j]  (bias grads of the hidden layers)
-__global__ void __launch_bounds__(256)
+// db[j] = sum_b dH[b][j]  (bias grads of the hidden layers); same block shape as above
+__global__ void __launch_bounds__(512)
 k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ db) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= hid) return;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += __bfloat162float(dH[(long long)b * hid + j]);
-    db[j] = s;
+    __shared__ float red[16][64];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = (blockIdx.x * 32 + tx) * 2;
+    float s0 = 0.f, s1 = 0.f;
+    if (j < hid) {
+        for (int b = ty; b < B; b += 16) {
+            const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dH + (long long)b * hid + j));
+            s0 += h.x; s1 += h.y;
+        }
+    }
+    red[ty][tx * 2] = s0; red[ty][tx * 2 + 1] = s1;
+    __syncthreads();
+    const int t = ty * 32 + tx;
+    if (t < 64 && blockIdx.x * 64 + t < hid) {
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sum += red[r][t];
+        db[blockIdx.x * 64 + t] = sum;
+    }
 }
 
 // ------------------------------------------------------------------ policy head
@@ -392,12 +425,12 @@ extern "C" int curla_head_bwd(const float* dOut, const float* W, const void* H, 
 
 extern "C" int curla_head_wgrad(const float* dOut, const void* H, int B, int hid, int No,
                                 float* dW, float* db, cudaStream_t stream) {
-    k_head_wgrad<<<cdiv(hid, 256), 256, 0, stream>>>(dOut, (const bf16*)H, B, hid, No, dW, db);
+    k_head_wgrad<<<cdiv(hid, 64), dim3(32, 16), 0, stream>>>(dOut, (const bf16*)H, B, hid, No, dW, db);
     return check_launch("head_wgrad");
 }
 
 extern "C" int curla_colsum_bf16(const void* dH, int B, int hid, float* db, cudaStream_t stream) {
-    k_colsum_bf16<<<cdiv(hid, 256), 256, 0, stream>>>((const bf16*)dH, B, hid, db);
+    k_colsum_bf16<<<cdiv(hid, 64), dim3(32, 16), 0, stream>>>((const bf16*)dH, B, hid, db);
     return check_launch("colsum_bf16");
 }
 
