@@ -54,6 +54,13 @@ SIGNATURES = {
     'curla_gemm_bf16_seg': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,
                                  c_ll, _i, c_ll, _f, _i, c_ll, _i, c_vp]),
     'curla_gemm_effective_splits': (_i, [_i, _i]),
+    'curla_gemm_bf16_batched': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,
+                                     c_ll, _f, _i, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp]),
+    'curla_ln_fwd_x': (_i, [c_vp, _i, c_ll, c_vp, c_vp, c_vp, _i, _i, _i, c_vp, c_vp, c_vp, _i, c_vp, c_vp]),
+    'curla_head_fwd_batched': (_i, [c_vp, _i, c_vp, c_vp, _i, _i, _i, c_vp, _i, c_ll, c_ll, c_ll, c_vp]),
+    'curla_head_bwd_batched': (_i, [c_vp, c_vp, c_vp, _i, _i, _i, c_vp, _i, c_ll, c_ll, c_ll, c_ll, c_vp]),
+    'curla_head_wgrad_batched': (_i, [c_vp, c_vp, _i, _i, _i, c_vp, c_vp, _i, c_ll, c_ll, c_ll, c_vp]),
+    'curla_colsum_bf16_batched': (_i, [c_vp, _i, _i, c_vp, _i, c_ll, c_ll, c_vp]),
     'curla_ln_fwd': (_i, [c_vp, _i, c_ll, c_vp, c_vp, c_vp, _i, _i, _i, c_vp, c_vp, c_vp]),
     'curla_ln_bwd': (_i, [c_vp, c_vp, c_vp, c_vp, _i, _i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'curla_pack_x': (_i, [c_vp, c_vp, _i, _i, _i, c_vp, c_vp]),

@@ -40,7 +40,9 @@ struct TcGeom {
     int plane_rows;      // slab_rows rounded up to 8 (plane stride = plane_rows * 16 B)
     int min_off;         // most negative tap shift
     int stages;          // slab ring depth (host: as many as fit in shared memory, <= 8)
-    int debug;           // CURLA_TC_DEBUG bitmask (timing experiments only): 1 no loads, 2 no MMA, 4 no stores
+    int plane_bytes;     // shared-memory stride between channel planes of a slab
+    int debug;           // CURLA_TC_DEBUG bitmask (timing experiments only): 1 no loads, 2 no MMA, 4 no stores,
+                         // 8 tap shifts rounded to 8 rows (WRONG results: aligned core matrices), 16 plane skew +64 B
 };
 struct TcTaps { int off[9]; };
 
@@ -82,7 +84,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
     const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 160;
     const uint32_t s_tptr = s_base + 192;
     const uint32_t s_w = s_base + kSmemHdr;
-    const uint32_t PS = (uint32_t)g.plane_rows * 16u;
+    const uint32_t PS = (uint32_t)g.plane_bytes;
     const uint32_t slab_bytes = CH * PS;
     const uint32_t s_slab0 = s_w + W_BYTES;
     const int stages = g.stages;
@@ -214,7 +216,8 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         for (int t = 0; t < NTAPS; ++t)
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
-                a_off[t * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)(taps.off[t] - g.min_off) * 16u) >> 4;
+                a_off[t * KS + ks] = ((uint32_t)(2 * ks) * PS +
+                                      (uint32_t)((g.debug & 8) ? ((taps.off[t] - g.min_off) & ~7) : (taps.off[t] - g.min_off)) * 16u) >> 4;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
             mbar_wait(s_full + 8 * stage, phase);
@@ -284,6 +287,7 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     g.plane_rows = (g.slab_rows + 7) / 8 * 8;
     g.min_off = min_off;
     g.stages = 2;
+    g.plane_bytes = g.plane_rows * 16;
     g.debug = 0;
     return g;
 }
@@ -301,13 +305,14 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
                      cudaStream_t stream) {
     constexpr int CH = CP / 8;
     const size_t fixed = kSmemHdr + (size_t)NTAPS * CH * 512;
-    const size_t slab = (size_t)CH * g.plane_rows * 16;
+    { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
+    g.plane_bytes = g.plane_rows * 16 + ((g.debug & 16) ? 64 : 0);
+    const size_t slab = (size_t)CH * g.plane_bytes;
     const size_t budget = 200 * 1024;
     int stages = (int)((budget - fixed) / slab);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { set_last_error("conv_tc: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
     g.stages = stages;
-    { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
     { const char* e = getenv("CURLA_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) g.stages = atoi(e); }
     const size_t smem = fixed + stages * slab;
     auto kern = k_conv_tc<CP, NTAPS, DGRAD>;

@@ -13,14 +13,20 @@
 // slots of consecutive image rows back to back.  With chunk stride = one plane, chunk index
 // i = g*(CH+1) + c  addresses plane c of image row y+g: ONE M=128 descriptor covers all the
 // vertical taps g of all input-channel chunks c (plus a ones-plane per row whose D rows are
-// the bias gradient for free), with no data replication.  The horizontal taps are start-address
-// shifts of +16 B per column, one MMA each into its own TMEM accumulator.
-//   D_kx[(g, c, e)][co] += sum_{16 positions} A[(g,c,e)][k] * dy[k][co]
-// K windows are 16 positions inside one image row; dy planes are staged with zero rows behind
-// `pitch` so that the last window of a row reads zeros instead of the next plane.
+// the bias gradient for free), with no data replication.
+//
+// The horizontal taps ride in the N dimension.  An SS-mode tcgen05.mma streams its whole A tile
+// (128 rows x 32 B) from shared memory whatever N is, and at N = 32 that read -- not the tensor
+// pipe -- sets the pace (measured: ~64 clk per M128 N32 K16 instruction, 4x the N/256 floor).
+// So dy is staged NDX times, copy dx shifted DOWN by dx rows (cp.async.bulk with a +16*dx byte
+// destination offset; the second and third copies are L2 hits), and ONE MMA per K window
+// computes all horizontal taps at once with N = 32*NDX:
+//   D[(g, c, e)][(dx, co)] += sum_{k'} A[(g,c,e)][k'] * dy[k' - dx][co]
+// K windows are 16 positions inside one image row; every staged dy plane has zero rows in front
+// of (k' < dx) and behind (k' >= pitch + dx) the copied row, so out-of-row taps multiply zeros.
 //
 // One persistent CTA per SM: producer warp (cp.async.bulk, one copy per plane per image row),
-// MMA warp (R rows x ceil(Wv/16) windows x NDX MMAs per stage), accumulators stay in TMEM for
+// MMA warp (R rows x kwin windows, one N = 32*NDX MMA each per stage), accumulators stay in TMEM for
 // the CTA's whole share of the batch; 4 epilogue warps write one fp32 partial per CTA and a
 // deterministic second-stage kernel sums the partials into OIHW (run-to-run reproducible).
 #include "common.cuh"
@@ -34,14 +40,15 @@ struct WgGeom {
     int pitch, S, Hv, Wv, B;
     int R;                 // dy image rows per stage
     int runs_per_sample, total_runs;
-    int kwin;              // 16-position K windows per image row = ceil(Wv / 16)
-    int dyr;               // rows of a staged dy plane (>= pitch, >= kwin*16), zero behind pitch
+    int kwin;              // 16-position K windows per image row = ceil((Wv + NDX - 1) / 16)
+    int dyr;               // rows of a staged dy plane (>= pitch + NDX - 1, >= kwin*16), zero outside the copy
 };
 
 constexpr int kWgThreads = 6 * 32;      // 4 epilogue warps + MMA + producer
-// D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N=32, M=128
-constexpr uint32_t kIdescMN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) |
-                              ((128u >> 4) << 24);
+// D=f32, A=B=bf16, A and B MN-major (bits 15, 16), M=128, N = n
+constexpr uint32_t idesc_mn(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 // CP: input channels (32, or 48 for the space-to-depth conv1 input); GR x NDX taps (3x3 or 2x2)
 template <int CP, int GR, int NDX>
@@ -62,7 +69,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     const int slots = g.R + GR - 1;
     const uint32_t a_bytes = (uint32_t)slots * slot_bytes;
     const uint32_t DYB = (uint32_t)g.dyr * 16u;                         // one staged dy plane
-    const uint32_t dy_bytes = (uint32_t)g.R * 4u * DYB;
+    const uint32_t dy_bytes = (uint32_t)g.R * 4u * NDX * DYB;
     const uint32_t stage_bytes = (a_bytes + dy_bytes + 127u) & ~127u;
     const uint32_t s_stage0 = s_base + 128;
     const long long plane = (long long)g.S * 8;
@@ -113,7 +120,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
             if (elect_one()) {
                 const uint32_t bar = s_full + 8 * stage;
                 const int arows = rv + GR - 1;
-                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4) * PS);
+                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * NDX) * PS);
                 const bf16* src_a = in + (long long)b * in_sstride + (long long)y0 * g.pitch * 8;
                 for (int r = 0; r < arows; ++r)
 #pragma unroll
@@ -123,8 +130,11 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
                 const bf16* src_d = dy + (long long)b * dy_sstride + (long long)y0 * g.pitch * 8;
                 for (int r = 0; r < rv; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        bulk_g2s(sd + (uint32_t)(r * 4 + c) * DYB, src_d + c * plane + (long long)r * g.pitch * 8, PS, bar);
+                    for (int dx = 0; dx < NDX; ++dx)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            bulk_g2s(sd + (uint32_t)((r * NDX + dx) * 4 + c) * DYB + (uint32_t)dx * 16u,
+                                     src_d + c * plane + (long long)r * g.pitch * 8, PS, bar);
             }
             __syncwarp();
             stage ^= 1;
@@ -144,13 +154,9 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
                 const uint32_t sa16 = (s_stage0 + stage * stage_bytes) >> 4, sd16 = sa16 + (a_bytes >> 4);
                 for (int r = 0; r < rv; ++r) {
                     for (int kw = 0; kw < g.kwin; ++kw) {
-                        const uint32_t a0 = sa16 + (uint32_t)r * (slot_bytes >> 4) + (uint32_t)kw * 16u;
-                        const uint64_t bd = b_hi | (uint64_t)((sd16 + (uint32_t)(r * 4) * (DYB >> 4) + (uint32_t)kw * 16u) & 0x3FFFu);
-#pragma unroll
-                        for (int dx = 0; dx < NDX; ++dx) {
-                            const uint64_t ad = a_hi | (uint64_t)((a0 + (uint32_t)dx) & 0x3FFFu);
-                            umma_bf16_rt(tmem_base + (uint32_t)(dx * 32), ad, bd, kIdescMN, accum);
-                        }
+                        const uint64_t ad = a_hi | (uint64_t)((sa16 + (uint32_t)r * (slot_bytes >> 4) + (uint32_t)kw * 16u) & 0x3FFFu);
+                        const uint64_t bd = b_hi | (uint64_t)((sd16 + (uint32_t)(r * 4 * NDX) * (DYB >> 4) + (uint32_t)kw * 16u) & 0x3FFFu);
+                        umma_bf16_rt(tmem_base, ad, bd, idesc_mn(32 * NDX), accum);
                         accum = 1;
                     }
                 }
@@ -240,13 +246,14 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     constexpr int CPL = CP / 8 + 1;
     WgGeom g;
     g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv; g.B = B;
-    g.kwin = cdiv(Wv, 16);
-    g.dyr = g.kwin * 16 > pitch ? g.kwin * 16 : pitch;
+    g.kwin = cdiv(Wv + NDX - 1, 16);
+    g.dyr = g.kwin * 16 > pitch + NDX - 1 ? g.kwin * 16 : pitch + NDX - 1;
+    g.dyr = (g.dyr + 7) / 8 * 8;
     const size_t PS = (size_t)pitch * 16, DYB = (size_t)g.dyr * 16;
     const size_t budget = 225 * 1024 - 256;
     int R = 0;
     for (int r = 1; r <= 16; ++r) {
-        const size_t stage = (((size_t)(r + GR - 1) * CPL * PS + (size_t)r * 4 * DYB) + 127) & ~(size_t)127;
+        const size_t stage = (((size_t)(r + GR - 1) * CPL * PS + (size_t)r * 4 * NDX * DYB) + 127) & ~(size_t)127;
         // the junk chunks of the last row (up to chunk 15) must stay inside the stage: reads reach
         // slot r-1 + ceil(16 / CPL) planes, covered by the dy region behind the A slots
         if (2 * stage <= budget) R = r;
@@ -256,7 +263,7 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     g.R = R;
     g.runs_per_sample = cdiv(Hv, R);
     g.total_runs = B * g.runs_per_sample;
-    const size_t stage = (((size_t)(R + GR - 1) * CPL * PS + (size_t)R * 4 * DYB) + 127) & ~(size_t)127;
+    const size_t stage = (((size_t)(R + GR - 1) * CPL * PS + (size_t)R * 4 * NDX * DYB) + 127) & ~(size_t)127;
     const size_t smem = 128 + 2 * stage;
     auto kern = k_conv_wgrad_tc<CP, GR, NDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -55,59 +55,140 @@ k_sgemm_strided(const float* __restrict__ A, long long sam, long long sak,
         }
 }
 
-// one CTA per local row: softmax stats, per-row loss, logits -> dlogits in place.
+// Fused rows kernel: one CTA owns R local rows i.  Their logits row block [R][Bg] lives in
+// shared memory from the contraction to the gradient -- nothing of size B x Bg ever touches
+// HBM:   logits = z_a . U^T  ->  softmax / per-row loss  ->  dl = (p - onehot) * grad_scale
+//        dz_a[i] = dl[i] . U ,  V[i] = dl[i] . z_pos            (both [R][64])
+// U and z_pos ([Bg][64] fp32, <= 1 MB each at Bg = 4096) are streamed from L2 by every CTA.
+// dW = z_a^T . V is finished by k_curl_dw (the reference's dW = (dl^T z_a)^T z_pos
+// re-associated so that no [Bg][feat] intermediate and no strided pass over dl is needed).
+template <int R>
 __global__ void __launch_bounds__(256)
-k_curl_softmax(float* __restrict__ logits, int B, int Bg, int label0, float grad_scale,
-               float* __restrict__ row_loss) {
-    __shared__ float s_red[8];
-    __shared__ float s_b;
-    const int i = blockIdx.x;
-    float* row = logits + (long long)i * Bg;
-    float mx = -INFINITY;
-    for (int j = threadIdx.x; j < Bg; j += blockDim.x) mx = fmaxf(mx, row[j]);
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m = s_red[0];
-        for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
-        s_b = m;
+k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const float* __restrict__ z_pos,
+            int B, int Bg, int label0, float grad_scale, float* __restrict__ row_loss,
+            float* __restrict__ dz_a, float* __restrict__ V, float* __restrict__ logits_copy) {
+    extern __shared__ __align__(16) float s_dyn[];
+    const int BgP = (Bg + 3) & ~3;                // row stride of the logits block (keeps s_za 16-byte aligned)
+    float* s_log = s_dyn;                         // [R][BgP]
+    float* s_za = s_dyn + (size_t)R * BgP;        // [R][64]
+    float* s_red = s_za + R * 64;                 // [4][2][R][64]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * R;
+    for (int t = tid; t < R * 64; t += 256) {
+        const int r = t >> 6, i = i0 + r;
+        s_za[t] = i < B ? z_a[(long long)i * 64 + (t & 63)] : 0.f;
     }
     __syncthreads();
-    mx = s_b;
-    float se = 0.f;
-    for (int j = threadIdx.x; j < Bg; j += blockDim.x) se += expf(row[j] - mx);
-    se = warp_sum(se);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = se;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) s += s_red[w];
-        s_b = s;
-        row_loss[i] = logf(s) - (row[label0 + i] - mx);
+    // ---- logits[r][j] = z_a[i0+r] . U[j]
+    for (int j = tid; j < Bg; j += 256) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        const float4* u4 = reinterpret_cast<const float4*>(U + (long long)j * 64);
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const float4 u = u4[k];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 a = *reinterpret_cast<const float4*>(s_za + r * 64 + k * 4);
+                acc[r] += a.x * u.x + a.y * u.y + a.z * u.z + a.w * u.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) s_log[(size_t)r * BgP + j] = acc[r];
     }
     __syncthreads();
-    const float inv = 1.f / s_b;
-    for (int j = threadIdx.x; j < Bg; j += blockDim.x) {
-        const float p = expf(row[j] - mx) * inv;
-        row[j] = (p - (j == label0 + i ? 1.f : 0.f)) * grad_scale;
+    if (logits_copy)
+        for (int t = tid; t < R * Bg; t += 256) {
+            const int r = t / Bg, j = t - r * Bg;
+            if (i0 + r < B) logits_copy[(long long)(i0 + r) * Bg + j] = s_log[(size_t)r * BgP + j];
+        }
+    // ---- softmax statistics: one warp per row (rows r = warp, warp + 8, ...)
+    for (int r = warp; r < R; r += 8) {
+        float* row = s_log + (size_t)r * BgP;
+        const int i = i0 + r;
+        float mx = -INFINITY;
+        for (int j = lane; j < Bg; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int j = lane; j < Bg; j += 32) se += expf(row[j] - mx);
+        se = warp_sum(se);
+        const float inv = 1.f / se;
+        const int lab = label0 + i;
+        if (lane == 0 && i < B) row_loss[i] = logf(se) - (row[lab] - mx);
+        __syncwarp();
+        const float gsc = i < B ? grad_scale : 0.f;
+        for (int j = lane; j < Bg; j += 32) row[j] = (expf(row[j] - mx) * inv - (j == lab ? 1.f : 0.f)) * gsc;
+    }
+    __syncthreads();
+    // ---- dz_a[r][a] = sum_j dl[r][j] U[j][a] ; V[r][a] = sum_j dl[r][j] z_pos[j][a]
+    const int a = tid & 63, q = tid >> 6;
+    float dz[R], vv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { dz[r] = 0.f; vv[r] = 0.f; }
+    for (int j = q; j < Bg; j += 4) {
+        const float u = U[(long long)j * 64 + a], zp = z_pos[(long long)j * 64 + a];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float d = s_log[(size_t)r * BgP + j];
+            dz[r] += d * u;
+            vv[r] += d * zp;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s_red[((q * 2 + 0) * R + r) * 64 + a] = dz[r];
+        s_red[((q * 2 + 1) * R + r) * 64 + a] = vv[r];
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * R * 64; t += 256) {
+        const int w = t / (R * 64), rem = t - w * (R * 64);      // rem = r*64 + a
+        const float s = s_red[((0 * 2 + w) * R) * 64 + rem] + s_red[((1 * 2 + w) * R) * 64 + rem] +
+                        s_red[((2 * 2 + w) * R) * 64 + rem] + s_red[((3 * 2 + w) * R) * 64 + rem];
+        const int i = i0 + (rem >> 6);
+        if (i < B) (w ? V : dz_a)[(long long)i * 64 + (rem & 63)] = s;
     }
 }
 
+// dW[a][b] = sum_i z_a[i][a] * V[i][b] (one CTA per a; 64 columns x 4 row groups, fixed-order
+// tree => deterministic); CTA 0 also writes the mean of the per-row losses.
 __global__ void __launch_bounds__(256)
-k_mean_to(const float* __restrict__ v, int n, float* __restrict__ out) {
-    __shared__ float s_red[8];
+k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const float* __restrict__ row_loss,
+          int B, int feat, float* __restrict__ dW, float* __restrict__ loss_out) {
+    __shared__ float s_red[4][64];
+    __shared__ float s_l[8];
+    const int a = blockIdx.x, b = threadIdx.x & 63, q = threadIdx.x >> 6;
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    for (int i = q; i < B; i += 4) s += z_a[(long long)i * 64 + a] * V[(long long)i * 64 + b];
+    s_red[q][b] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_red[w];
-        *out = t / n;
+    if (q == 0 && b < feat) dW[a * feat + b] = s_red[0][b] + s_red[1][b] + s_red[2][b] + s_red[3][b];
+    if (blockIdx.x == 0) {
+        float l = 0.f;
+        for (int i = threadIdx.x; i < B; i += 256) l += row_loss[i];
+        l = warp_sum(l);
+        if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = l;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += s_l[w];
+            *loss_out = t / B;
+        }
     }
+}
+
+template <int R>
+static int launch_curl_rows(const float* z_a, const float* U, const float* z_pos, int B, int Bg, int label0,
+                            float grad_scale, float* row_loss, float* dz_a, float* V, float* logits_copy,
+                            cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)R * ((Bg + 3) & ~3) + R * 64 + 8 * R * 64);
+    auto kern = k_curl_rows<R>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_error("curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return -1; }
+    }
+    kern<<<cdiv(B, R), 256, smem, st>>>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy);
+    return check_launch("curl_rows");
 }
 
 static int sgemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk,
@@ -122,35 +203,37 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 using namespace curla;
 
 extern "C" long long curla_curl_workspace_floats(int B, int Bg) {
-    // U [Bg][64] + T [Bg][64] + logits [B][Bg] + row_loss [B]
-    return 2LL * Bg * 64 + (long long)B * Bg + B;
+    // U [Bg][64] + V [B][64] + row_loss [B]
+    return (long long)Bg * 64 + (long long)B * 64 + B;
 }
 
 // z_a [B][64] (local rows), z_pos [Bg][64] (all ranks' keys), W [feat][feat].
-// Outputs: loss_out (mean over the LOCAL rows), dz_a [B][64] (padded cols untouched ->
-// caller passes a zeroed buffer once), dW [feat][feat] (local contribution).
+// Outputs: loss_out (mean over the LOCAL rows), dz_a [B][64], dW [feat][feat] (local
+// contribution), logits_copy [B][Bg] (optional: the raw logits before the row-max shift).
 extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const float* W, int B,
                                   int Bg, int feat, int label0, float grad_scale,
                                   float* workspace, float* loss_out, float* dz_a, float* dW,
                                   float* logits_copy, cudaStream_t stream) {
+    CURLA_CHECK(feat <= 64 && B >= 1 && Bg >= B && label0 >= 0 && label0 + B <= Bg, "curl: bad shape");
     float* U = workspace;
-    float* T = U + (long long)Bg * 64;
-    float* logits = T + (long long)Bg * 64;
-    float* row_loss = logits + (long long)B * Bg;
-    // U[j][a] = sum_b z_pos[j][b] * W[a][b]
+    float* V = U + (long long)Bg * 64;
+    float* row_loss = V + (long long)B * 64;
+    // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace)
     if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Bg, feat, feat, stream)) return -1;
-    // logits[i][j] = sum_a z_a[i][a] * U[j][a]
-    if (sgemm(z_a, 64, 1, U, 1, 64, logits, Bg, B, Bg, feat, stream)) return -1;
-    if (logits_copy)
-        cudaMemcpyAsync(logits_copy, logits, sizeof(float) * (size_t)B * Bg, cudaMemcpyDeviceToDevice, stream);
-    k_curl_softmax<<<B, 256, 0, stream>>>(logits, B, Bg, label0, grad_scale, row_loss);
-    if (check_launch("curl_softmax")) return -1;
-    k_mean_to<<<1, 256, 0, stream>>>(row_loss, B, loss_out);
-    if (check_launch("curl_loss")) return -1;
-    // dz_a[i][a] = sum_j dl[i][j] * U[j][a]
-    if (sgemm(logits, Bg, 1, U, 64, 1, dz_a, 64, B, feat, Bg, stream)) return -1;
-    // T[j][a] = sum_i dl[i][j] * z_a[i][a]
-    if (sgemm(logits, 1, Bg, z_a, 64, 1, T, 64, Bg, feat, B, stream)) return -1;
-    // dW[a][b] = sum_j T[j][a] * z_pos[j][b]
-    return sgemm(T, 1, 64, z_pos, 64, 1, dW, feat, feat, feat, Bg, stream);
+    // rows per CTA: as many as keep the [R][Bg] logits block in shared memory, while leaving
+    // at least ~one CTA per SM
+    const size_t cap = 200 * 1024 / sizeof(float);
+    int R = 8;
+    while (R > 1 && ((size_t)R * (Bg + 3) + 9 * R * 64 > cap || cdiv(B, R) < sm_count() / 2)) R >>= 1;
+    CURLA_CHECK((size_t)R * (Bg + 3) + 9 * R * 64 <= cap, "curl: global batch %d does not fit shared memory", Bg);
+    int rc;
+    switch (R) {
+        case 8: rc = launch_curl_rows<8>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        case 4: rc = launch_curl_rows<4>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        case 2: rc = launch_curl_rows<2>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        default: rc = launch_curl_rows<1>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+    }
+    if (rc) return -1;
+    k_curl_dw<<<feat, 256, 0, stream>>>(z_a, V, row_loss, B, feat, dW, loss_out);
+    return check_launch("curl_dw");
 }

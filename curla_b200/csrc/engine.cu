@@ -338,9 +338,9 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
         a->actB[i] = b.w<bf16>("actB." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
         a->dact[i] = b.w<bf16>("dact." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
     }
-    {   // split-K for the fc forward: ~2 waves of 64x64 tiles
+    {   // split-K for the fc forward: ~4 CTAs of 64x64 tiles per SM (bytes in flight, not FLOPs, bound it)
         const int mt = cdiv(B, 64);
-        int sp = cdiv(2 * sm_count(), mt);
+        int sp = cdiv(4 * sm_count(), mt);
         const int ktiles = cdiv(a->Kfc, 32);
         if (sp > ktiles / 4) sp = ktiles / 4 > 0 ? ktiles / 4 : 1;
         a->fc_splits = curla_gemm_effective_splits(a->Kfc, sp);
@@ -384,7 +384,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->target_q = b.w<float>("target_q", DT_F32, {B});
     a->dq[0] = b.w<float>("dq1", DT_F32, {B}); a->dq[1] = b.w<float>("dq2", DT_F32, {B});
     a->dt4 = b.w<float>("d_trunk_out", DT_F32, {B, 2 * A});
-    a->dH2 = b.w<bf16>("dH2", DT_BF16, {B, hid}); a->dH1 = b.w<bf16>("dH1", DT_BF16, {B, hid});
+    a->dH2 = b.w<bf16>("dH2", DT_BF16, {2, B, hid}); a->dH1 = b.w<bf16>("dH1", DT_BF16, {2, B, hid});   // Q1 || Q2
     a->dX[0] = b.w<float>("dX1", DT_F32, {B, 64}); a->dX[1] = b.w<float>("dX2", DT_F32, {B, 64});
     a->dXa = b.w<float>("dXa", DT_F32, {B, 64});
     a->dz_curl = b.w<float>("dz_curl", DT_F32, {B, 64});
@@ -400,6 +400,17 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->g_log_alpha = b.w<double>("grad.log_alpha", DT_F64, {1});
     a->alpha_state = b.w<double>("adam.log_alpha", DT_F64, {2});
     a->arena_bytes[CURLA_ARENA_WORK] = (b.cur[4] + 255) / 256 * 256;
+    {   // the batched Q1 || Q2 launches rely on one constant stride per arena between the two heads
+        bool okp = true;
+        for (const MlpP* q : {a->q_critic, a->q_target}) {
+            const long long d = q[1].w0 - q[0].w0;
+            okp = okp && q[1].b0 - q[0].b0 == d && q[1].w1 - q[0].w1 == d && q[1].b1 - q[0].b1 == d &&
+                  q[1].w2 - q[0].w2 == d && q[1].b2 - q[0].b2 == d && d % 4 == 0;
+        }
+        for (const MlpS* q : {a->sq_critic, a->sq_target}) okp = okp && q[1].w1 - q[0].w1 == q[1].w0 - q[0].w0;
+        for (const MlpBuf* m : {a->m_p2q, a->m_p3q, a->m_p5q}) okp = okp && m[1].H2 - m[0].H2 == m[1].H1 - m[0].H1;
+        if (!okp) { set_last_error("agent: internal layout mismatch (Q1/Q2 strides)"); delete a; return nullptr; }
+    }
     a->bound = false;
     a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
     a->last_launches = 0;
@@ -475,7 +486,8 @@ struct Run {
                                a->act_sstride, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 0, st));
     }
     // fc (split-K) + bias + LayerNorm
-    void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0) {
+    void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
+              const float* act = nullptr, bf16* X_out = nullptr) {
         if (!ok()) return;
         set_launch_tag("gemm_fc_fwd");
         chk(curla_gemm_bf16_seg(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
@@ -483,39 +495,57 @@ struct Run {
                                 a->Kfc / 4, (long long)a->S * 8, 1, st));
         set_launch_tag(nullptr);
         if (!ok()) return;
-        chk(curla_ln_fwd(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
-                         a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, st));
+        chk(curla_ln_fwd_x(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
+                           a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, act, act ? a->cfg.action_dim : 0, X_out, st));
     }
-    void mlp_fwd(const float* z, const float* act, const MlpP& m, const MlpS& s, MlpBuf& buf, int B) {
+    // nb MLPs of one shape in one launch each (nb = 2: the critic's Q1 || Q2 on the shared input
+    // rows X; curl_sac.py:158-169).  m/s/buf point at nb consecutive descriptors; the strides
+    // between the two heads' parameters, shadows and buffers are constant by construction.
+    void mlp_fwd_n(const bf16* X, const MlpP* m, const MlpS* s, MlpBuf* buf, int nb, int B) {
         if (!ok()) return;
         const int hid = a->cfg.hidden_dim;
-        chk(curla_pack_x(z, act, B, a->cfg.feature_dim, a->cfg.action_dim, buf.X, st));
+        const long long sP = nb > 1 ? m[1].w0 - m[0].w0 : 0, sS = nb > 1 ? s[1].w0 - s[0].w0 : 0;
+        const long long sH = nb > 1 ? buf[1].H1 - buf[0].H1 : 0, sO = nb > 1 ? buf[1].out - buf[0].out : 0;
+        chk(curla_gemm_bf16_batched(X, 64, Sh(s[0].w0), 64, buf[0].H1, hid, B, hid, 64, 3, hid, 1, P(m[0].b0), 1,
+                                    nullptr, 0, 1.f, nb, 0, sS, sH, sP, 0, st));
         if (!ok()) return;
-        chk(curla_gemm_bf16(buf.X, 64, Sh(s.w0), 64, buf.H1, hid, B, hid, 64, 3, hid, 1, P(m.b0), 1, nullptr, 0, 1, 0, 1.f, st));
+        chk(curla_gemm_bf16_batched(buf[0].H1, hid, Sh(s[0].w1), hid, buf[0].H2, hid, B, hid, hid, 3, hid, 1, P(m[0].b1), 1,
+                                    nullptr, 0, 1.f, nb, sH, sS, sH, sP, 0, st));
         if (!ok()) return;
-        chk(curla_gemm_bf16(buf.H1, hid, Sh(s.w1), hid, buf.H2, hid, B, hid, hid, 3, hid, 1, P(m.b1), 1, nullptr, 0, 1, 0, 1.f, st));
-        if (!ok()) return;
-        chk(curla_head_fwd(buf.H2, hid, P(m.w2), P(m.b2), B, hid, m.out, buf.out, st));
+        chk(curla_head_fwd_batched(buf[0].H2, hid, P(m[0].w2), P(m[0].b2), B, hid, m[0].out, buf[0].out, nb, sH, sP, sO, st));
     }
-    // backward of one 3-layer MLP.  g = float offset of this MLP's w0 grad relative layout
-    // (same relative offsets as the params) or <0 for "input gradient only".
-    void mlp_bwd(const float* dOut, const MlpP& m, const MlpS& s, const MlpBuf& buf, float* gbase,
-                 long long pbase, float* dX) {
+    // single MLP from fp32 z (+ action): the inference entry points
+    void mlp_fwd(const float* z, const float* act, const MlpP& m, const MlpS& s, MlpBuf& buf, int B) {
         if (!ok()) return;
-        const int B = a->cfg.batch, hid = a->cfg.hidden_dim;
+        chk(curla_pack_x(z, act, B, a->cfg.feature_dim, a->cfg.action_dim, buf.X, st));
+        mlp_fwd_n(buf.X, &m, &s, &buf, 1, B);
+    }
+    // backward of nb 3-layer MLPs.  gbase = gradient buffer mirroring the parameter segment that
+    // starts at float offset pbase, or nullptr for "input gradient only".  dOut / dX: head 0's
+    // pointer + stride to head 1.
+    void mlp_bwd_n(const float* dOut, long long sDOut, const bf16* X, const MlpP* m, const MlpS* s, const MlpBuf* buf,
+                   int nb, float* gbase, long long pbase, float* dX, long long sDX) {
+        if (!ok()) return;
+        const int B = a->cfg.batch, hid = a->cfg.hidden_dim, No = m[0].out, in_real = m[0].in_real;
+        const long long sP = nb > 1 ? m[1].w0 - m[0].w0 : 0, sS = nb > 1 ? s[1].w0 - s[0].w0 : 0;
+        const long long sH = nb > 1 ? buf[1].H1 - buf[0].H1 : 0, sD = (long long)B * hid;
         auto g = [&](long long poff) { return gbase + (poff - pbase); };
-        chk(curla_head_bwd(dOut, P(m.w2), buf.H2, B, hid, m.out, a->dH2, st));
-        if (gbase && ok()) chk(curla_head_wgrad(dOut, buf.H2, B, hid, m.out, g(m.w2), g(m.b2), st));
+        chk(curla_head_bwd_batched(dOut, P(m[0].w2), buf[0].H2, B, hid, No, a->dH2, nb, sDOut, sP, sH, sD, st));
+        if (gbase && ok()) chk(curla_head_wgrad_batched(dOut, buf[0].H2, B, hid, No, g(m[0].w2), g(m[0].b2), nb, sDOut, sH, sP, st));
         if (gbase && ok()) {
-            chk(curla_gemm_bf16(a->dH2, hid, buf.H1, hid, g(m.w1), hid, hid, hid, B, 0, hid, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
-            if (ok()) chk(curla_colsum_bf16(a->dH2, B, hid, g(m.b1), st));
+            chk(curla_gemm_bf16_batched(a->dH2, hid, buf[0].H1, hid, g(m[0].w1), hid, hid, hid, B, 0, hid, 0, nullptr, 0,
+                                        nullptr, 0, 1.f, nb, sD, sH, sP, 0, 0, st));
+            if (ok()) chk(curla_colsum_bf16_batched(a->dH2, B, hid, g(m[0].b1), nb, sD, sP, st));
         }
-        if (ok()) chk(curla_gemm_bf16(a->dH2, hid, Sh(s.w1), hid, a->dH1, hid, B, hid, hid, 1, hid, 1, nullptr, 0, buf.H1, hid, 1, 0, 1.f, st));
+        if (ok()) chk(curla_gemm_bf16_batched(a->dH2, hid, Sh(s[0].w1), hid, a->dH1, hid, B, hid, hid, 1, hid, 1, nullptr, 0,
+                                              buf[0].H1, hid, 1.f, nb, sD, sS, sD, 0, sH, st));
         if (gbase && ok()) {
-            chk(curla_gemm_bf16(a->dH1, hid, buf.X, 64, g(m.w0), m.in_real, hid, 64, B, 0, m.in_real, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
-            if (ok()) chk(curla_colsum_bf16(a->dH1, B, hid, g(m.b0), st));
+            chk(curla_gemm_bf16_batched(a->dH1, hid, X, 64, g(m[0].w0), in_real, hid, 64, B, 0, in_real, 0, nullptr, 0,
+                                        nullptr, 0, 1.f, nb, sD, 0, sP, 0, 0, st));
+            if (ok()) chk(curla_colsum_bf16_batched(a->dH1, B, hid, g(m[0].b0), nb, sD, sP, st));
         }
-        if (dX && ok()) chk(curla_gemm_bf16(a->dH1, hid, Sh(s.w0), 64, dX, 64, B, 64, hid, 1, 64, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f, st));
+        if (dX && ok()) chk(curla_gemm_bf16_batched(a->dH1, hid, Sh(s[0].w0), 64, dX, 64, B, 64, hid, 1, 64, 0, nullptr, 0,
+                                                    nullptr, 0, 1.f, nb, sD, sS, sDX, 0, 0, st));
     }
     // LayerNorm + fc backward (+ conv stack backward when conv==true)
     void enc_bwd(const float* dz_a, const float* dz_b, const TailBuf& t, const EncP& e, long long fc_shadow,
@@ -692,23 +722,24 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         // ---------------- update_critic (curl_sac.py:349-371)
         // F1: actor(next_obs) -> a', log_pi'
         r.conv_stack(a->s2d_next, a->enc_critic, a->s_critic, a->actB);
-        r.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B);
-        r.mlp_fwd(a->t_p1.z, nullptr, a->trunk_actor, a->s_trunk, a->m_p1, B);
+        r.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X);
+        r.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
         if (r.ok()) r.chk(curla_policy_fwd(a->t_out1, u->noise_next, u->seed, u->offset * 2, B, A, (float)c.log_std_min,
                                            (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, st));
         // F2: critic_target(next_obs, a')
         r.conv_stack(a->s2d_next, a->enc_target, a->s_target, a->actB);
-        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p2, B);
-        for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p2.z, a->a_next, a->q_target[k], a->sq_target[k], a->m_p2q[k], B);
+        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X);
+        r.mlp_fwd_n(a->m_p2q[0].X, a->q_target, a->sq_target, a->m_p2q, 2, B);
         // F3: critic(obs, action)
         r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
-        r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p3, B);
-        for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p3.z, a->act_b, a->q_critic[k], a->sq_critic[k], a->m_p3q[k], B);
+        r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p3, B, 0, a->act_b, a->m_p3q[0].X);
+        r.mlp_fwd_n(a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, B);
         if (r.ok()) r.chk(curla_critic_loss(a->tq[0], a->tq[1], a->logpi_next, a->rew_b, a->nd_b, a->log_alpha, (float)c.discount,
                                             a->q3[0], a->q3[1], B, gs, a->target_q, a->dq[0], a->dq[1], a->metrics, st));
         // backward
         float* gC = a->G + a->g_critic;
-        for (int k = 0; k < 2; ++k) r.mlp_bwd(a->dq[k], a->q_critic[k], a->sq_critic[k], a->m_p3q[k], gC, a->off_critic, a->dX[k]);
+        r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, gC, a->off_critic,
+                    a->dX[0], a->dX[1] - a->dX[0]);
         r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
                   a->off_critic, !c.detach_encoder);
         if (r.ok()) r.chk(all_reduce(a, gC, (size_t)a->n_critic, NCCL_F32, st));
@@ -721,20 +752,21 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             // ---------------- update_actor_and_alpha (curl_sac.py:373-404)
             // F4: conv_theta'(obs) shared by actor(obs), critic(obs, pi) and the CURL anchor
             r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
-            r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B);
-            r.mlp_fwd(a->t_p4.z, nullptr, a->trunk_actor, a->s_trunk, a->m_p4, B);
+            r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B, 0, nullptr, a->m_p4.X);
+            r.mlp_fwd_n(a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, B);
             if (r.ok()) r.chk(curla_policy_fwd(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, B, A, (float)c.log_std_min,
                                                (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4, a->ls4, a->noise4, st));
-            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B);
+            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
             have_p5 = true;
-            for (int k = 0; k < 2; ++k) r.mlp_fwd(a->t_p5.z, a->pi4, a->q_critic[k], a->sq_critic[k], a->m_p5q[k], B);
+            r.mlp_fwd_n(a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, B);
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
                                                a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
-            for (int k = 0; k < 2; ++k) r.mlp_bwd(a->dq[k], a->q_critic[k], a->sq_critic[k], a->m_p5q[k], nullptr, 0, a->dX[k]);
+            r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, nullptr, 0,
+                        a->dX[0], a->dX[1] - a->dX[0]);
             if (r.ok()) r.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
                                                (float)c.log_std_min, (float)c.log_std_max, a->dt4, st));
             float* gA = a->G + a->g_actor;
-            r.mlp_bwd(a->dt4, a->trunk_actor, a->s_trunk, a->m_p4, gA, a->off_actor, a->dXa);
+            r.mlp_bwd_n(a->dt4, 0, a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, gA, a->off_actor, a->dXa, 0);
             r.enc_bwd(a->dXa, nullptr, a->t_p4, a->enc_actor, a->s_actor_fc, nullptr, a->actA, nullptr, gA, a->off_actor, false);
             if (r.ok()) r.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, st));
             if (r.ok()) r.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, st));

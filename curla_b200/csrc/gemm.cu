@@ -8,13 +8,13 @@
 //   B_KMAJOR : B stored [N][ldb] (k contiguous)     else stored [K][ldb] (n contiguous)
 // "Row" extents (the slow index of a stored matrix) may be ragged; contiguous extents
 // must be multiples of 8 elements (16-byte cp.async chunks, zero padded buffers).
-// 64x64x32 CTA tile, 4 warps, 3-stage cp.async pipeline, mma.sync m16n8k16 bf16->fp32.
+// 64x64x32 CTA tile, 4 warps, 4-stage cp.async pipeline, mma.sync m16n8k16 bf16->fp32.
 #include "common.cuh"
 #include "../../include/curla_b200.h"
 
 namespace curla {
 
-constexpr int BM = 64, BN = 64, BK = 32, STAGES = 3;
+constexpr int BM = 64, BN = 64, BK = 32, STAGES = 4;
 
 struct GemmArgs {
     const bf16* A; long long lda;
@@ -33,6 +33,9 @@ struct GemmArgs {
     // DESIGN.md section 3): index i of the chosen operand lives at (i / seg_len) * seg_stride +
     // i % seg_len.  seg_mask: 1 = A's contiguous index, 2 = B's, 4 = C's and the mask's column.
     int seg_len; long long seg_stride; int seg_mask; float seg_inv;
+    // Batched problems (Q1 || Q2 of the critic: same shapes, different weights): blockIdx.z is
+    // the batch index (split-K and batching are mutually exclusive); element strides.
+    int batch; long long bsA, bsB, bsC, bsBias, bsMask;
 };
 
 // i / seg_len through a float reciprocal: exact here because i is a multiple of 2 (columns)
@@ -58,7 +61,10 @@ k_gemm(GemmArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * p.k_per_split;
+    const int bz = p.batch > 1 ? blockIdx.z : 0, sz = p.batch > 1 ? 0 : blockIdx.z;
+    const bf16* __restrict__ Ap = p.A + bz * p.bsA;
+    const bf16* __restrict__ Bp = p.B + bz * p.bsB;
+    const int kbeg = sz * p.k_per_split;
     int kend = kbeg + p.k_per_split;
     if (kend > p.K) kend = p.K;
     const int nk = (kend - kbeg + BK - 1) / BK;
@@ -74,23 +80,23 @@ k_gemm(GemmArgs p) {
                 const int r = c >> 2, ch = c & 3;
                 const int m = m0 + r, k = k0 + ch * 8;
                 const bool ok = (m < p.M) && (k < kend);
-                cp_async16(sA + off64(r, ch), ok ? (const void*)(p.A + (long long)m * p.lda + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
+                cp_async16(sA + off64(r, ch), ok ? (const void*)(Ap + (long long)m * p.lda + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
             } else {
                 const int r = c >> 3, ch = c & 7;
                 const int k = k0 + r, m = m0 + ch * 8;
                 const bool ok = (k < kend) && (m < p.M);
-                cp_async16(sA + off128(r, ch), ok ? (const void*)(p.A + (long long)k * p.lda + seg_off(m, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
+                cp_async16(sA + off128(r, ch), ok ? (const void*)(Ap + (long long)k * p.lda + seg_off(m, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))) : (const void*)p.A, ok ? 16 : 0);
             }
             if (B_KMAJOR) {
                 const int r = c >> 2, ch = c & 3;
                 const int n = n0 + r, k = k0 + ch * 8;
                 const bool ok = (n < p.N) && (k < kend);
-                cp_async16(sB + off64(r, ch), ok ? (const void*)(p.B + (long long)n * p.ldb + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
+                cp_async16(sB + off64(r, ch), ok ? (const void*)(Bp + (long long)n * p.ldb + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
             } else {
                 const int r = c >> 3, ch = c & 7;
                 const int k = k0 + r, n = n0 + ch * 8;
                 const bool ok = (k < kend) && (n < p.N);
-                cp_async16(sB + off128(r, ch), ok ? (const void*)(p.B + (long long)k * p.ldb + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
+                cp_async16(sB + off128(r, ch), ok ? (const void*)(Bp + (long long)k * p.ldb + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))) : (const void*)p.B, ok ? 16 : 0);
             }
         }
     };
@@ -107,6 +113,27 @@ k_gemm(GemmArgs p) {
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) load_stage(s, s);
         cp_async_commit();
+    }
+
+    // The epilogue's ReLU-mask words are fetched now, behind the operand loads already in
+    // flight, so their DRAM latency is not serialised after the MMAs (fc dgrad: K = 64 only).
+    const bf16* __restrict__ maskp = p.mask ? p.mask + bz * p.bsMask : nullptr;
+    uint32_t mk[2][2][4];
+    if (maskp) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m0 + wm * 32 + mt * 16 + h * 8 + (lane >> 2);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int n = n0 + wn * 32 + nt * 8 + (lane & 3) * 2;
+                    mk[mt][h][nt] = 0u;
+                    if (m < p.M && n < p.n_store)
+                        mk[mt][h][nt] = __ldg(reinterpret_cast<const uint32_t*>(
+                            maskp + (long long)m * p.ldmask + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4))));
+                }
+            }
     }
 
     const int l7 = lane & 7, j1 = (lane >> 3) & 1, j2 = lane >> 4;
@@ -150,8 +177,9 @@ k_gemm(GemmArgs p) {
 
     // ---- epilogue
     const int gq = lane >> 2, q = lane & 3;
-    float* Cf = (float*)p.C + (long long)blockIdx.z * p.split_stride;
-    bf16* Cb = (bf16*)p.C;
+    float* Cf = (float*)p.C + (long long)sz * p.split_stride + bz * p.bsC;
+    bf16* Cb = (bf16*)p.C + bz * p.bsC;
+    const float* __restrict__ biasp = p.bias ? p.bias + bz * p.bsBias : nullptr;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -163,13 +191,13 @@ k_gemm(GemmArgs p) {
                 const int n = n0 + wn * 32 + nt * 8 + q * 2;
                 if (n >= p.n_store) continue;
                 float v0 = acc[mt][nt][h * 2] * p.alpha, v1 = acc[mt][nt][h * 2 + 1] * p.alpha;
-                if (p.bias) { v0 += p.bias[n]; v1 += (n + 1 < p.n_store) ? p.bias[n + 1] : 0.f; }
+                if (biasp) { v0 += biasp[n]; v1 += (n + 1 < p.n_store) ? biasp[n + 1] : 0.f; }
                 if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                 const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
-                if (p.mask) {
-                    const float2 mk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.mask + (long long)m * p.ldmask + nc));
-                    v0 = mk.x > 0.f ? v0 : 0.f;
-                    v1 = mk.y > 0.f ? v1 : 0.f;
+                if (maskp) {
+                    const float2 mv = unpack_bf16x2(mk[mt][h][nt]);
+                    v0 = mv.x > 0.f ? v0 : 0.f;
+                    v1 = mv.y > 0.f ? v1 : 0.f;
                 }
                 const long long o = (long long)m * p.ldc + nc;
                 if (p.out_bf16) {
@@ -198,6 +226,29 @@ extern "C" int curla_gemm_bf16(const void* A, long long lda, const void* B, long
                                ldmask, splits, split_stride, alpha, 0, 0, 0, stream);
 }
 
+static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream);
+
+// `batch` independent GEMMs of one shape in one launch (element strides between problems; a
+// stride of 0 shares that operand): the critic's Q1 || Q2 trunks (curl_sac.py:158-169).
+extern "C" int curla_gemm_bf16_batched(const void* A, long long lda, const void* B, long long ldb,
+                                       void* C, long long ldc, int M, int N, int K, int layout,
+                                       int n_store, int out_bf16, const float* bias, int relu,
+                                       const void* mask, long long ldmask, float alpha, int batch,
+                                       long long bsA, long long bsB, long long bsC, long long bsBias,
+                                       long long bsMask, cudaStream_t stream) {
+    CURLA_CHECK(M > 0 && N > 0 && K > 0 && batch >= 1, "gemm: empty problem");
+    CURLA_CHECK(lda % 8 == 0 && ldb % 8 == 0 && bsA % 8 == 0 && bsB % 8 == 0, "gemm: lda/ldb/batch strides must be multiples of 8");
+    CURLA_CHECK((ldc % 2) == 0 && (bsC % 2) == 0 && (bsMask % 2) == 0, "gemm: ldc / C batch stride must be even");
+    GemmArgs p;
+    p.A = (const bf16*)A; p.lda = lda; p.B = (const bf16*)B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.n_store = n_store > 0 ? n_store : N; p.out_bf16 = out_bf16;
+    p.bias = bias; p.relu = relu; p.mask = (const bf16*)mask; p.ldmask = ldmask;
+    p.split_stride = 0; p.alpha = alpha;
+    p.seg_len = 0; p.seg_stride = 0; p.seg_mask = 0;
+    p.batch = batch; p.bsA = bsA; p.bsB = bsB; p.bsC = bsC; p.bsBias = bsBias; p.bsMask = bsMask;
+    return gemm_launch(p, layout, 1, stream);
+}
+
 // Same GEMM with one operand's contiguous index split into equal segments (see GemmArgs).
 extern "C" int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long ldb, void* C,
                                    long long ldc, int M, int N, int K, int layout, int n_store,
@@ -214,14 +265,19 @@ extern "C" int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, 
     p.A = (const bf16*)A; p.lda = lda; p.B = (const bf16*)B; p.ldb = ldb; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.n_store = n_store > 0 ? n_store : N; p.out_bf16 = out_bf16;
     p.bias = bias; p.relu = relu; p.mask = (const bf16*)mask; p.ldmask = ldmask;
-    const int kt = cdiv(K, BK);
-    p.k_per_split = cdiv(kt, splits) * BK;
-    const int zs = cdiv(K, p.k_per_split);
     p.split_stride = split_stride; p.alpha = alpha;
     p.seg_len = seg_len; p.seg_stride = seg_stride; p.seg_mask = seg_mask;
-    dim3 grid(cdiv(N, BN), cdiv(M, BM), zs);
-    p.seg_inv = seg_mask ? 1.0f / (float)seg_len : 0.f;
-    switch ((layout & 3) | (seg_mask ? 4 : 0)) {
+    p.batch = 1; p.bsA = p.bsB = p.bsC = p.bsBias = p.bsMask = 0;
+    return gemm_launch(p, layout, splits, stream);
+}
+
+static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream) {
+    const int kt = cdiv(p.K, BK);
+    p.k_per_split = cdiv(kt, splits) * BK;
+    const int zs = cdiv(p.K, p.k_per_split);
+    dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.batch > 1 ? p.batch : zs);
+    p.seg_inv = p.seg_mask ? 1.0f / (float)p.seg_len : 0.f;
+    switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
         case 3: k_gemm<true, true, false><<<grid, 128, 0, stream>>>(p); break;
         case 1: k_gemm<true, false, false><<<grid, 128, 0, stream>>>(p); break;
         case 2: k_gemm<false, true, false><<<grid, 128, 0, stream>>>(p); break;

@@ -6,6 +6,7 @@
 //   curl_sac.py:79-110     Actor.forward tail (chunk, tanh-rescaled log_std, reparam sample)
 //   curl_sac.py:349-404    critic / actor / alpha losses (and their gradients)
 #include "common.cuh"
+#include "../../include/curla_b200.h"
 #include <math.h>
 
 namespace curla {
@@ -19,7 +20,8 @@ __global__ void __launch_bounds__(256)
 k_ln_fwd(const float* __restrict__ partial, int nsplit, long long split_stride,
          const float* __restrict__ bias, const float* __restrict__ gamma,
          const float* __restrict__ beta, int B, int feat, int apply_tanh,
-         float* __restrict__ x_out, float* __restrict__ z_out) {
+         float* __restrict__ x_out, float* __restrict__ z_out,
+         const float* __restrict__ act, int A, bf16* __restrict__ X_out) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -48,6 +50,10 @@ k_ln_fwd(const float* __restrict__ partial, int nsplit, long long split_stride,
         }
         x_out[(long long)row * FP + c] = x[e];
         z_out[(long long)row * FP + c] = z;
+        if (X_out) {   // the MLP input row [z | action | 0] (torch.cat([obs, action], dim=1), curl_sac.py:137)
+            if (act && c >= feat && c < feat + A) z = act[row * A + (c - feat)];
+            X_out[(long long)row * FP + c] = __float2bfloat16(z);
+        }
     }
 }
 
@@ -132,7 +138,9 @@ __global__ void k_pack_x(const float* __restrict__ z, const float* __restrict__ 
 // out[b][o] = sum_j H[b][j] * W[o][j] + bias[o],  No <= 4.  One warp per row.
 __global__ void __launch_bounds__(256)
 k_head_fwd(const bf16* __restrict__ H, int ldh, const float* __restrict__ W,
-           const float* __restrict__ bias, int B, int hid, int No, float* __restrict__ out) {
+           const float* __restrict__ bias, int B, int hid, int No, float* __restrict__ out,
+           long long bsH, long long bsW, long long bsOut) {
+    H += blockIdx.y * bsH; W += blockIdx.y * bsW; bias += blockIdx.y * bsW; out += blockIdx.y * bsOut;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -154,7 +162,9 @@ k_head_fwd(const bf16* __restrict__ H, int ldh, const float* __restrict__ W,
 // dH[b][j] = H[b][j] > 0 ? sum_o dOut[b][o] * W[o][j] : 0
 __global__ void __launch_bounds__(256)
 k_head_bwd(const float* __restrict__ dOut, const float* __restrict__ W,
-           const bf16* __restrict__ H, int B, int hid, int No, bf16* __restrict__ dH) {
+           const bf16* __restrict__ H, int B, int hid, int No, bf16* __restrict__ dH,
+           long long bsDOut, long long bsW, long long bsH, long long bsDH) {
+    dOut += blockIdx.y * bsDOut; W += blockIdx.y * bsW; H += blockIdx.y * bsH; dH += blockIdx.y * bsDH;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * hid) return;
     const int b = (int)(i / hid), j = (int)(i % hid);
@@ -168,7 +178,8 @@ k_head_bwd(const float* __restrict__ dOut, const float* __restrict__ W,
 // (deterministic); grid = hid / 64.
 __global__ void __launch_bounds__(512)
 k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, int hid, int No,
-             float* __restrict__ dW, float* __restrict__ db) {
+             float* __restrict__ dW, float* __restrict__ db, long long bsDOut, long long bsH, long long bsW) {
+    dOut += blockIdx.y * bsDOut; H += blockIdx.y * bsH; dW += blockIdx.y * bsW; db += blockIdx.y * bsW;
     __shared__ float red[16][4][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int j = (blockIdx.x * 32 + tx) * 2;
@@ -206,7 +217,9 @@ k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, 
 
 // db[j] = sum_b dH[b][j]  (bias grads of the hidden layers); same block shape as above
 __global__ void __launch_bounds__(512)
-k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ db) {
+k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ db, long long bsDH,
+              long long bsDb) {
+    dH += blockIdx.y * bsDH; db += blockIdx.y * bsDb;
     __shared__ float red[16][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int j = (blockIdx.x * 32 + tx) * 2;
@@ -384,9 +397,18 @@ extern "C" int curla_ln_fwd(const float* partial, int nsplit, long long split_st
                             const float* bias, const float* gamma, const float* beta, int B,
                             int feat, int apply_tanh, float* x_out, float* z_out,
                             cudaStream_t stream) {
-    CURLA_CHECK(feat <= FP, "ln_fwd: feature_dim > 64 unsupported");
+    return curla_ln_fwd_x(partial, nsplit, split_stride, bias, gamma, beta, B, feat, apply_tanh, x_out, z_out,
+                          nullptr, 0, nullptr, stream);
+}
+
+// Same, and also emits the bf16 input row of the MLP that consumes z: X[b] = [z | act[b] | 0].
+extern "C" int curla_ln_fwd_x(const float* partial, int nsplit, long long split_stride,
+                              const float* bias, const float* gamma, const float* beta, int B,
+                              int feat, int apply_tanh, float* x_out, float* z_out,
+                              const float* act, int A, void* X_out, cudaStream_t stream) {
+    CURLA_CHECK(feat <= FP && feat + A <= FP, "ln_fwd: feature_dim (+ action_dim) > 64 unsupported");
     k_ln_fwd<<<cdiv(B, 8), 256, 0, stream>>>(partial, nsplit, split_stride, bias, gamma, beta, B,
-                                             feat, apply_tanh, x_out, z_out);
+                                             feat, apply_tanh, x_out, z_out, act, A, (bf16*)X_out);
     return check_launch("ln_fwd");
 }
 
@@ -410,28 +432,52 @@ extern "C" int curla_pack_x(const float* z, const float* act, int B, int feat, i
     return check_launch("pack_x");
 }
 
-extern "C" int curla_head_fwd(const void* H, int ldh, const float* W, const float* bias, int B,
-                              int hid, int No, float* out, cudaStream_t stream) {
+// The *_batched forms run `nb` independent heads of one shape in one launch (Q1 || Q2);
+// strides in elements: bsP applies to every parameter / parameter-gradient pointer (W and
+// bias live at the same relative offsets in both heads).
+extern "C" int curla_head_fwd_batched(const void* H, int ldh, const float* W, const float* bias, int B,
+                                      int hid, int No, float* out, int nb, long long bsH, long long bsP,
+                                      long long bsOut, cudaStream_t stream) {
     CURLA_CHECK(No <= 4 && hid % 2 == 0, "head_fwd: No<=4, even hidden");
-    k_head_fwd<<<cdiv(B, 8), 256, 0, stream>>>((const bf16*)H, ldh, W, bias, B, hid, No, out);
+    k_head_fwd<<<dim3(cdiv(B, 8), nb), 256, 0, stream>>>((const bf16*)H, ldh, W, bias, B, hid, No, out, bsH, bsP, bsOut);
     return check_launch("head_fwd");
 }
+extern "C" int curla_head_fwd(const void* H, int ldh, const float* W, const float* bias, int B,
+                              int hid, int No, float* out, cudaStream_t stream) {
+    return curla_head_fwd_batched(H, ldh, W, bias, B, hid, No, out, 1, 0, 0, 0, stream);
+}
 
-extern "C" int curla_head_bwd(const float* dOut, const float* W, const void* H, int B, int hid,
-                              int No, void* dH, cudaStream_t stream) {
-    k_head_bwd<<<cdiv((long long)B * hid, 256), 256, 0, stream>>>(dOut, W, (const bf16*)H, B, hid, No, (bf16*)dH);
+extern "C" int curla_head_bwd_batched(const float* dOut, const float* W, const void* H, int B, int hid,
+                                      int No, void* dH, int nb, long long bsDOut, long long bsP,
+                                      long long bsH, long long bsDH, cudaStream_t stream) {
+    k_head_bwd<<<dim3(cdiv((long long)B * hid, 256), nb), 256, 0, stream>>>(dOut, W, (const bf16*)H, B, hid, No,
+                                                                         (bf16*)dH, bsDOut, bsP, bsH, bsDH);
     return check_launch("head_bwd");
 }
-
-extern "C" int curla_head_wgrad(const float* dOut, const void* H, int B, int hid, int No,
-                                float* dW, float* db, cudaStream_t stream) {
-    k_head_wgrad<<<cdiv(hid, 64), dim3(32, 16), 0, stream>>>(dOut, (const bf16*)H, B, hid, No, dW, db);
-    return check_launch("head_wgrad");
+extern "C" int curla_head_bwd(const float* dOut, const float* W, const void* H, int B, int hid,
+                              int No, void* dH, cudaStream_t stream) {
+    return curla_head_bwd_batched(dOut, W, H, B, hid, No, dH, 1, 0, 0, 0, 0, stream);
 }
 
-extern "C" int curla_colsum_bf16(const void* dH, int B, int hid, float* db, cudaStream_t stream) {
-    k_colsum_bf16<<<cdiv(hid, 64), dim3(32, 16), 0, stream>>>((const bf16*)dH, B, hid, db);
+extern "C" int curla_head_wgrad_batched(const float* dOut, const void* H, int B, int hid, int No,
+                                        float* dW, float* db, int nb, long long bsDOut, long long bsH,
+                                        long long bsP, cudaStream_t stream) {
+    k_head_wgrad<<<dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream>>>(dOut, (const bf16*)H, B, hid, No, dW, db,
+                                                                      bsDOut, bsH, bsP);
+    return check_launch("head_wgrad");
+}
+extern "C" int curla_head_wgrad(const float* dOut, const void* H, int B, int hid, int No,
+                                float* dW, float* db, cudaStream_t stream) {
+    return curla_head_wgrad_batched(dOut, H, B, hid, No, dW, db, 1, 0, 0, 0, stream);
+}
+
+extern "C" int curla_colsum_bf16_batched(const void* dH, int B, int hid, float* db, int nb, long long bsDH,
+                                         long long bsP, cudaStream_t stream) {
+    k_colsum_bf16<<<dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream>>>((const bf16*)dH, B, hid, db, bsDH, bsP);
     return check_launch("colsum_bf16");
+}
+extern "C" int curla_colsum_bf16(const void* dH, int B, int hid, float* db, cudaStream_t stream) {
+    return curla_colsum_bf16_batched(dH, B, hid, db, 1, 0, 0, stream);
 }
 
 extern "C" int curla_policy_fwd(const float* t, const float* noise_in, unsigned long long seed,

@@ -91,12 +91,26 @@ int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long l
                         long long split_stride, float alpha, int seg_len, long long seg_stride,
                         int seg_mask, curla_stream_t stream);
 int curla_gemm_effective_splits(int K, int splits);
+/* `batch` independent GEMMs of one shape in one launch (the critic's Q1 || Q2 trunks,
+ * curl_sac.py:158-169); bs* = element strides between problems, 0 shares the operand */
+int curla_gemm_bf16_batched(const void* A, long long lda, const void* B, long long ldb, void* C,
+                            long long ldc, int M, int N, int K, int layout, int n_store,
+                            int out_bf16, const float* bias, int relu, const void* mask,
+                            long long ldmask, float alpha, int batch, long long bsA, long long bsB,
+                            long long bsC, long long bsBias, long long bsMask,
+                            curla_stream_t stream);
 
 /* ---- K8 LayerNorm, K10 policy head, K11 losses, MLP heads  (encoder.py:98-110;
  *      curl_sac.py:20-35,79-110,349-404) ------------------------------------------------ */
 int curla_ln_fwd(const float* partial, int nsplit, long long split_stride, const float* bias,
                  const float* gamma, const float* beta, int B, int feat, int apply_tanh,
                  float* x_out, float* z_out, curla_stream_t stream);
+/* same + the bf16 input row of the MLP that consumes z: X[b] = [z | act[b] | 0]
+ * (torch.cat([obs, action], dim=1), curl_sac.py:137) */
+int curla_ln_fwd_x(const float* partial, int nsplit, long long split_stride, const float* bias,
+                   const float* gamma, const float* beta, int B, int feat, int apply_tanh,
+                   float* x_out, float* z_out, const float* act, int A, void* X_out,
+                   curla_stream_t stream);
 int curla_ln_bwd(const float* dz_a, const float* dz_b, const float* x_in, const float* gamma,
                  int B, int feat, float* dx_f32, void* dx_bf16, float* scratch, float* dgamma,
                  float* dbeta, float* dbias_fc, curla_stream_t stream);
@@ -109,6 +123,18 @@ int curla_head_bwd(const float* dOut, const float* W, const void* H, int B, int 
 int curla_head_wgrad(const float* dOut, const void* H, int B, int hid, int No, float* dW,
                      float* db, curla_stream_t stream);
 int curla_colsum_bf16(const void* dH, int B, int hid, float* db, curla_stream_t stream);
+/* nb heads of one shape per launch (Q1 || Q2); bsP = stride of every parameter(-gradient) pointer */
+int curla_head_fwd_batched(const void* H, int ldh, const float* W, const float* bias, int B, int hid,
+                           int No, float* out, int nb, long long bsH, long long bsP, long long bsOut,
+                           curla_stream_t stream);
+int curla_head_bwd_batched(const float* dOut, const float* W, const void* H, int B, int hid, int No,
+                           void* dH, int nb, long long bsDOut, long long bsP, long long bsH,
+                           long long bsDH, curla_stream_t stream);
+int curla_head_wgrad_batched(const float* dOut, const void* H, int B, int hid, int No, float* dW,
+                             float* db, int nb, long long bsDOut, long long bsH, long long bsP,
+                             curla_stream_t stream);
+int curla_colsum_bf16_batched(const void* dH, int B, int hid, float* db, int nb, long long bsDH,
+                              long long bsP, curla_stream_t stream);
 int curla_policy_fwd(const float* t, const float* noise_in, unsigned long long seed,
                      unsigned long long offset, int B, int A, float ls_min, float ls_max,
                      int compute_pi, int compute_log_pi, float* mu, float* pi, float* log_pi,
