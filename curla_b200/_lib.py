@@ -49,6 +49,8 @@ SIGNATURES = {
     'curla_conv_dgrad': (_i, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_wgrad_workspace_floats': (c_ll, [_i]),
     'curla_conv_wgrad': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, _f, _i, _i, _i, _i, _i, _i, _i, c_vp]),
+    'curla_conv_wgrad_partial': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, _i, _i, _i, _i, _i, _i, c_vp, c_vp]),
+    'curla_conv_wgrad_reduce_multi': (_i, [_i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'curla_gemm_bf16': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,
                              c_ll, _i, c_ll, _f, c_vp]),
     'curla_gemm_bf16_seg': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp, _i, c_vp,

@@ -239,6 +239,35 @@ k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
     }
 }
 
+// Same reduction for up to 4 layers in one launch (blockIdx.y = layer): the engine defers the
+// second stage of every layer of a backward pass to a single kernel after the last dgrad.
+struct WgReduceJob { const float* partial; int nparts, ntaps, CP, Cin, s2d; float scale; float* dW; float* db; };
+struct WgReduceJobs { WgReduceJob j[4]; };
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_reduce_multi(WgReduceJobs jobs) {
+    __shared__ float red[8][33];
+    const WgReduceJob& J = jobs.j[blockIdx.y];
+    const int per = J.ntaps * J.CP * 32 + 32;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    if (blockIdx.x * 32 >= per) return;
+    float s = 0.f;
+    if (i < per)
+        for (int c = threadIdx.y; c < J.nparts; c += 8) s += J.partial[(long long)c * per + i];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || i >= per) return;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) s += red[r][threadIdx.x];
+    if (i >= J.ntaps * J.CP * 32) { J.db[i - J.ntaps * J.CP * 32] = s; return; }
+    const int co = i & 31, ci = (i >> 5) % J.CP, t = (i >> 5) / J.CP;
+    if (!J.s2d) {
+        if (ci < J.Cin) J.dW[((long long)co * J.Cin + ci) * 9 + t] = s * J.scale;
+    } else {
+        const int c = ci >> 2, ky = 2 * (t >> 1) + ((ci >> 1) & 1), kx = 2 * (t & 1) + (ci & 1);
+        if (c < J.Cin && ky < 3 && kx < 3) J.dW[((long long)co * J.Cin + c) * 9 + ky * 3 + kx] = s * J.scale;
+    }
+}
+
 template <int CP, int GR, int NDX>
 static int launch_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
                         float* workspace, int B, int pitch, int S, int Hv, int Wv, int* grid_out,
@@ -282,6 +311,41 @@ using namespace curla;
 extern "C" long long curla_conv_wgrad_workspace_floats(int first_layer) {
     const long long per = first_layer ? (4 * 48 * 32 + 32) : (9 * 32 * 32 + 32);
     return per * (long long)(sm_count() * 2);
+}
+
+// First stage only: per-CTA partials into `workspace` (curla_conv_wgrad_workspace_floats);
+// *nparts_out = number of partial slices written.  Finish with curla_conv_wgrad_reduce_multi.
+extern "C" int curla_conv_wgrad_partial(const void* in, long long in_sstride, const void* dy,
+                                        long long dy_sstride, float* workspace, int B, int pitch,
+                                        int S, int Hv, int Wv, int first_layer, int* nparts_out,
+                                        cudaStream_t stream) {
+    if (first_layer) {
+        if (launch_wgrad<48, 2, 2>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, nparts_out, stream)) return -1;
+    } else {
+        if (launch_wgrad<32, 3, 3>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, nparts_out, stream)) return -1;
+    }
+    return check_launch("conv_wgrad");
+}
+
+// Deterministic second stage of n <= 4 layers in one launch.  Per layer l: workspace[l],
+// nparts[l], first_layer[l] (selects the 2x2 space-to-depth tap mapping), Cin[l], scale[l],
+// dW[l] (OIHW fp32), db[l] (32 floats).
+extern "C" int curla_conv_wgrad_reduce_multi(int n, float* const* workspace, const int* nparts,
+                                             const int* first_layer, const int* Cin,
+                                             const float* scale, float* const* dW, float* const* db,
+                                             cudaStream_t stream) {
+    CURLA_CHECK(n >= 1 && n <= 4, "conv_wgrad_reduce_multi: 1..4 layers");
+    WgReduceJobs jobs;
+    int per_max = 0;
+    for (int l = 0; l < n; ++l) {
+        WgReduceJob& J = jobs.j[l];
+        J.partial = workspace[l]; J.nparts = nparts[l]; J.ntaps = first_layer[l] ? 4 : 9; J.CP = first_layer[l] ? 48 : 32;
+        J.Cin = Cin[l]; J.s2d = first_layer[l] ? 1 : 0; J.scale = scale[l]; J.dW = dW[l]; J.db = db[l];
+        const int per = J.ntaps * J.CP * 32 + 32;
+        per_max = per > per_max ? per : per_max;
+    }
+    k_conv_wgrad_reduce_multi<<<dim3(cdiv(per_max, 32), n), dim3(32, 8), 0, stream>>>(jobs);
+    return check_launch("conv_wgrad_reduce");
 }
 
 // dW (OIHW fp32, Cin real channels), db[32].  Hv/Wv = valid dims of dY (this layer's OUTPUT).

@@ -134,6 +134,7 @@ struct curla_agent {
     bf16 *s2d_obs, *s2d_next, *s2d_pos, *actA[4], *actB[4], *dact[4];
     long long act_sstride, s2d_sstride;
     float *fc_partial, *wgrad_ws, *curl_ws, *ln_scratch;
+    long long wgrad_ws_stride;
     TailBuf t_p1, t_p2, t_p3, t_p4, t_p5, t_p7;
     MlpBuf m_p1, m_p2q[2], m_p3q[2], m_p4, m_p5q[2];
     float *t_out1, *t_out4, *a_next, *logpi_next, *mu_scratch, *pi4, *logpi4, *ls4, *noise4, *ls1;
@@ -348,7 +349,8 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->fc_partial = b.w<float>("fc_partial", DT_F32, {a->fc_splits, B, 64});
     {
         long long w1 = curla_conv_wgrad_workspace_floats(1), w2 = curla_conv_wgrad_workspace_floats(0);
-        a->wgrad_ws = b.w<float>("wgrad_ws", DT_F32, {w1 > w2 ? w1 : w2});
+        a->wgrad_ws = b.w<float>("wgrad_ws", DT_F32, {4, w1 > w2 ? w1 : w2});   // one slice per conv layer
+        a->wgrad_ws_stride = w1 > w2 ? w1 : w2;
     }
     a->curl_ws = b.w<float>("curl_ws", DT_F32, {curla_curl_workspace_floats(B, Bg)});
     a->ln_scratch = b.w<float>("ln_scratch", DT_F32, {2, B, 64});
@@ -568,14 +570,26 @@ struct Run {
                                           a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f,
                                           a->Kfc / 4, (long long)a->S * 8, 4, st));
         set_launch_tag(nullptr);
+        // wgrad first stages interleaved with the dgrad chain; all four deterministic second
+        // stages run as ONE launch at the end (nothing before the optimizer reads dW)
+        int nparts[4] = {0, 0, 0, 0};
+        auto ws = [&](int l) { return a->wgrad_ws + (long long)l * a->wgrad_ws_stride; };
         for (int i = 3; i >= 1 && ok(); --i) {
-            chk(curla_conv_wgrad(acts[i - 1], a->act_sstride, a->dact[i], a->act_sstride, a->wgrad_ws, g(e.conv_w[i]),
-                                 g(e.conv_b[i]), 1.f, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 32, 0, st));
+            chk(curla_conv_wgrad_partial(acts[i - 1], a->act_sstride, a->dact[i], a->act_sstride, ws(i), B, a->pitch, a->S,
+                                         a->Ho[i], a->Wo[i], 0, &nparts[i], st));
             if (ok()) chk(curla_conv_dgrad(a->dact[i], a->act_sstride, Sh(convs->conv[i]), acts[i - 1], a->dact[i - 1],
                                            a->act_sstride, B, a->pitch, a->S, a->Ho[i - 1], a->Wo[i - 1], st));
         }
-        if (ok()) chk(curla_conv_wgrad(s2d, a->s2d_sstride, a->dact[0], a->act_sstride, a->wgrad_ws, g(e.conv_w[0]),
-                                       g(e.conv_b[0]), 1.0f / 255.0f, B, a->pitch, a->S, a->Ho[0], a->Wo[0], a->cfg.C, 1, st));
+        if (ok()) chk(curla_conv_wgrad_partial(s2d, a->s2d_sstride, a->dact[0], a->act_sstride, ws(0), B, a->pitch, a->S,
+                                               a->Ho[0], a->Wo[0], 1, &nparts[0], st));
+        if (ok()) {
+            float* wsp[4] = {ws(0), ws(1), ws(2), ws(3)};
+            const int first[4] = {1, 0, 0, 0}, cin[4] = {a->cfg.C, 32, 32, 32};
+            const float sc[4] = {1.0f / 255.0f, 1.f, 1.f, 1.f};
+            float* dWp[4]; float* dbp[4];
+            for (int l = 0; l < 4; ++l) { dWp[l] = g(e.conv_w[l]); dbp[l] = g(e.conv_b[l]); }
+            chk(curla_conv_wgrad_reduce_multi(4, wsp, nparts, first, cin, sc, dWp, dbp, st));
+        }
     }
 };
 

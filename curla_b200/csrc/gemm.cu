@@ -36,6 +36,7 @@ struct GemmArgs {
     // Batched problems (Q1 || Q2 of the critic: same shapes, different weights): blockIdx.z is
     // the batch index (split-K and batching are mutually exclusive); element strides.
     int batch; long long bsA, bsB, bsC, bsBias, bsMask;
+    int vec_c;                // host: bf16 output (and mask) rows are 16-byte addressable -> staged epilogue
 };
 
 // i / seg_len through a float reciprocal: exact here because i is a multiple of 2 (columns)
@@ -118,8 +119,19 @@ k_gemm(GemmArgs p) {
     // The epilogue's ReLU-mask words are fetched now, behind the operand loads already in
     // flight, so their DRAM latency is not serialised after the MMAs (fc dgrad: K = 64 only).
     const bf16* __restrict__ maskp = p.mask ? p.mask + bz * p.bsMask : nullptr;
-    uint32_t mk[2][2][4];
-    if (maskp) {
+    uint32_t mkw[16];          // staged epilogue: chunk i -> words 4i..4i+3; direct epilogue: [(mt*2+h)*4 + nt]
+    if (maskp && p.vec_c) {
+        // staged epilogue: thread owns 16-byte chunks c = tid + 128*i of the 64 x 64 tile (row c>>3, chunk c&7)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tid + i * 128, m = m0 + (c >> 3), n = n0 + (c & 7) * 8;
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (m < p.M && n < p.n_store)
+                t = __ldg(reinterpret_cast<const uint4*>(
+                    maskp + (long long)m * p.ldmask + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4))));
+            mkw[4 * i] = t.x; mkw[4 * i + 1] = t.y; mkw[4 * i + 2] = t.z; mkw[4 * i + 3] = t.w;
+        }
+    } else if (maskp) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -128,9 +140,9 @@ k_gemm(GemmArgs p) {
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const int n = n0 + wn * 32 + nt * 8 + (lane & 3) * 2;
-                    mk[mt][h][nt] = 0u;
+                    mkw[(mt * 2 + h) * 4 + nt] = 0u;
                     if (m < p.M && n < p.n_store)
-                        mk[mt][h][nt] = __ldg(reinterpret_cast<const uint32_t*>(
+                        mkw[(mt * 2 + h) * 4 + nt] = __ldg(reinterpret_cast<const uint32_t*>(
                             maskp + (long long)m * p.ldmask + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4))));
                 }
             }
@@ -180,6 +192,52 @@ k_gemm(GemmArgs p) {
     float* Cf = (float*)p.C + (long long)sz * p.split_stride + bz * p.bsC;
     bf16* Cb = (bf16*)p.C + bz * p.bsC;
     const float* __restrict__ biasp = p.bias ? p.bias + bz * p.bsBias : nullptr;
+    if (p.vec_c) {
+        // bf16 output through shared memory: the tile is written back as 16-byte chunks, 128
+        // contiguous bytes per row (and the mask is read the same way) instead of 4-byte pieces
+        constexpr int CP_ = BN + 8;                       // padded row: conflict-free 16-byte reads
+        bf16* sC = reinterpret_cast<bf16*>(smem);
+        __syncthreads();                                  // every warp is done with the operand stages
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = wm * 32 + mt * 16 + h * 8 + gq;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int cl = wn * 32 + nt * 8 + q * 2, n = n0 + cl;
+                    float v0 = acc[mt][nt][h * 2] * p.alpha, v1 = acc[mt][nt][h * 2 + 1] * p.alpha;
+                    if (biasp && n < p.n_store) { v0 += biasp[n]; v1 += (n + 1 < p.n_store) ? biasp[n + 1] : 0.f; }
+                    if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                    *reinterpret_cast<uint32_t*>(sC + r * CP_ + cl) = pack_bf16x2(v0, v1);
+                }
+            }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tid + i * 128, r = c >> 3, m = m0 + r, n = n0 + (c & 7) * 8;
+            if (m >= p.M || n >= p.n_store) continue;
+            uint4 v = *reinterpret_cast<const uint4*>(sC + r * CP_ + (c & 7) * 8);
+            if (maskp) {
+                auto keep = [](uint32_t val, uint32_t mw) {
+                    const float2 mv = unpack_bf16x2(mw);
+                    return (mv.x > 0.f ? val & 0x0000FFFFu : 0u) | (mv.y > 0.f ? val & 0xFFFF0000u : 0u);
+                };
+                v.x = keep(v.x, mkw[4 * i]); v.y = keep(v.y, mkw[4 * i + 1]); v.z = keep(v.z, mkw[4 * i + 2]); v.w = keep(v.w, mkw[4 * i + 3]);
+            }
+            bf16* dst = Cb + (long long)m * p.ldc + seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+            if (n + 8 <= p.n_store) {
+                *reinterpret_cast<uint4*>(dst) = v;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t w = k < 2 ? v.x : (k < 4 ? v.y : (k < 6 ? v.z : v.w));
+                    if (n + k < p.n_store) reinterpret_cast<uint16_t*>(dst)[k] = (uint16_t)(w >> ((k & 1) * 16));
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -195,7 +253,7 @@ k_gemm(GemmArgs p) {
                 if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                 const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
                 if (maskp) {
-                    const float2 mv = unpack_bf16x2(mk[mt][h][nt]);
+                    const float2 mv = unpack_bf16x2(mkw[(mt * 2 + h) * 4 + nt]);
                     v0 = mv.x > 0.f ? v0 : 0.f;
                     v1 = mv.y > 0.f ? v1 : 0.f;
                 }
@@ -277,6 +335,8 @@ static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream)
     const int zs = cdiv(p.K, p.k_per_split);
     dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.batch > 1 ? p.batch : zs);
     p.seg_inv = p.seg_mask ? 1.0f / (float)p.seg_len : 0.f;
+    p.vec_c = p.out_bf16 && p.ldc % 8 == 0 && p.bsC % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+              (!p.mask || (p.ldmask % 8 == 0 && p.bsMask % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0));
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
         case 3: k_gemm<true, true, false><<<grid, 128, 0, stream>>>(p); break;
         case 1: k_gemm<true, false, false><<<grid, 128, 0, stream>>>(p); break;

@@ -15,26 +15,32 @@ constexpr int FP = 64;   // padded feature width of every [B][FP] fp32 / bf16 ro
 
 // ------------------------------------------------------------------ LayerNorm fwd
 // x = sum_s partial[s][b][:] + bias ; z = LN(x)*gamma + beta ; optional tanh.
-// Saves x (pre-norm) for the backward.  One warp per row, lane owns cols lane, lane+32.
+// Saves x (pre-norm) for the backward.  One CTA per row: 4 split groups x 64 columns sum the
+// split-K partials of the fc GEMM (fixed order => deterministic), then warp 0 normalises
+// (lane owns cols lane, lane+32).
 __global__ void __launch_bounds__(256)
 k_ln_fwd(const float* __restrict__ partial, int nsplit, long long split_stride,
          const float* __restrict__ bias, const float* __restrict__ gamma,
          const float* __restrict__ beta, int B, int feat, int apply_tanh,
          float* __restrict__ x_out, float* __restrict__ z_out,
          const float* __restrict__ act, int A, bf16* __restrict__ X_out) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= B) return;
+    __shared__ float s_x[4][FP];
+    const int row = blockIdx.x;
+    {
+        const int c = threadIdx.x & 63, sg = threadIdx.x >> 6;
+        float s = 0.f;
+        if (c < feat)
+            for (int k = sg; k < nsplit; k += 4) s += partial[k * split_stride + (long long)row * FP + c];
+        s_x[sg][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     float x[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         const int c = lane + e * 32;
-        float s = 0.f;
-        if (c < feat) {
-            for (int k = 0; k < nsplit; ++k) s += partial[k * split_stride + (long long)row * FP + c];
-            s += bias[c];
-        }
-        x[e] = s;
+        x[e] = c < feat ? ((s_x[0][c] + s_x[1][c]) + (s_x[2][c] + s_x[3][c])) + bias[c] : 0.f;
     }
     const float mean = warp_sum(x[0] + x[1]) / feat;
     float d0 = lane < feat ? x[0] - mean : 0.f, d1 = lane + 32 < feat ? x[1] - mean : 0.f;
@@ -407,8 +413,8 @@ extern "C" int curla_ln_fwd_x(const float* partial, int nsplit, long long split_
                               int feat, int apply_tanh, float* x_out, float* z_out,
                               const float* act, int A, void* X_out, cudaStream_t stream) {
     CURLA_CHECK(feat <= FP && feat + A <= FP, "ln_fwd: feature_dim (+ action_dim) > 64 unsupported");
-    k_ln_fwd<<<cdiv(B, 8), 256, 0, stream>>>(partial, nsplit, split_stride, bias, gamma, beta, B,
-                                             feat, apply_tanh, x_out, z_out, act, A, (bf16*)X_out);
+    k_ln_fwd<<<B, 256, 0, stream>>>(partial, nsplit, split_stride, bias, gamma, beta, B, feat, apply_tanh,
+                                    x_out, z_out, act, A, (bf16*)X_out);
     return check_launch("ln_fwd");
 }
 

@@ -78,6 +78,16 @@ int curla_conv_wgrad(const void* in, long long in_sstride, const void* dy, long 
                      float* workspace, float* dW, float* db, float scale, int B, int pitch,
                      int S, int Hv, int Wv, int Cin, int first_layer, curla_stream_t stream);
 
+/* two-stage form: per-CTA partials for one layer, then ONE deterministic reduction launch for
+ * up to four layers (the engine defers every layer's second stage to the end of a backward) */
+int curla_conv_wgrad_partial(const void* in, long long in_sstride, const void* dy,
+                             long long dy_sstride, float* workspace, int B, int pitch, int S,
+                             int Hv, int Wv, int first_layer, int* nparts_out,
+                             curla_stream_t stream);
+int curla_conv_wgrad_reduce_multi(int n, float* const* workspace, const int* nparts,
+                                  const int* first_layer, const int* Cin, const float* scale,
+                                  float* const* dW, float* const* db, curla_stream_t stream);
+
 /* ---- K7/K9: bf16 tensor-core GEMM  (encoder.py:98; curl_sac.py:70-74,129-133) ----------- */
 int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C,
                     long long ldc, int M, int N, int K, int layout, int n_store, int out_bf16,
