@@ -333,12 +333,23 @@ class _Host(object):
                       (s2d.shape[0] // c.batch) * s2d.shape[1], _lib.ptr(s2d), eng.stream())
         return s2d
 
+    INFER_BATCH = 512     # engine batch used for inference-only agents (eval.py, latent tools)
+
+    def _grow_for_inference(self, n):
+        """An agent that has not trained yet (eval.py / plot_tsne/*.py never call update) gets an
+        engine large enough to run batched inference in few launches; once training started the
+        engine batch is the replay batch and larger inputs are processed in chunks of it."""
+        c = self.engine.cfg
+        if n > c.batch and getattr(self, '_update_count', 1) == 0 and hasattr(self, '_make_engine'):
+            self._make_engine(batch=min(int(n), self.INFER_BATCH), frame_hw=(c.Hf, c.Wf))
+
     def encode(self, net, obs, apply_tanh=False):
-        eng = self.engine
-        c = eng.cfg
-        obs = torch.as_tensor(obs, device=eng.device)
+        obs = torch.as_tensor(obs, device=self.engine.device)
         if obs.dim() == 3:
             obs = obs.unsqueeze(0)
+        self._grow_for_inference(obs.shape[0])
+        eng = self.engine
+        c = eng.cfg
         assert tuple(obs.shape[1:]) == (c.C, c.H, c.W), 'encoder input %s != %s' % (
             tuple(obs.shape[1:]), (c.C, c.H, c.W))
         n = obs.shape[0]
@@ -347,6 +358,35 @@ class _Host(object):
             b1 = min(n, b0 + c.batch)
             s2d = self._stage(obs, b0, b1)
             with torch.cuda.device(eng.device):
+                _lib.check(eng.lib.curla_agent_encode(eng.h, net, _lib.ptr(s2d), b1 - b0, int(apply_tanh),
+                                                      _lib.ptr(out[b0:b1]), eng.stream()), 'encode')
+        return out[:, :c.feature_dim]
+
+    def encode_frames(self, net, frames, top=0, left=0, apply_tanh=False):
+        """Encoder forward straight from uint8 frames (N, C, Hf, Wf) resident on the device: the
+        fused gather+crop kernel takes the (top, left) window of every frame (the center crop of
+        augmentations.py:37-43 when the stored frames are larger than the encoder input), so no
+        float copy of the observations is ever made.  Batched form of latent_data.py:74-83."""
+        frames = torch.as_tensor(frames)
+        assert frames.dtype == torch.uint8 and frames.dim() == 4
+        self._grow_for_inference(frames.shape[0])
+        eng = self.engine
+        c = eng.cfg
+        frames = frames.to(eng.device).contiguous()
+        n, C_, Hf, Wf = frames.shape
+        assert C_ == c.C and top + c.H <= Hf and left + c.W <= Wf, 'frames %s do not contain a %dx%d window at (%d, %d)' % (
+            tuple(frames.shape), c.H, c.W, top, left)
+        out = torch.zeros((n, 64), dtype=torch.float32, device=eng.device)
+        s2d = eng.t['s2d.next']
+        stride = (s2d.shape[0] // c.batch) * s2d.shape[1]
+        idx = torch.arange(n, dtype=torch.int64, device=eng.device)
+        h1 = torch.full((c.batch,), int(top), dtype=torch.int64, device=eng.device)
+        w1 = torch.full((c.batch,), int(left), dtype=torch.int64, device=eng.device)
+        for b0 in range(0, n, c.batch):
+            b1 = min(n, b0 + c.batch)
+            with torch.cuda.device(eng.device):
+                _lib.call('curla_gather_crop_s2d', _lib.ptr(frames), c.C, Hf, Wf, _lib.ptr(idx[b0:b1]), _lib.ptr(h1),
+                          _lib.ptr(w1), b1 - b0, c.H, c.W, s2d.shape[1], stride, _lib.ptr(s2d), eng.stream())
                 _lib.check(eng.lib.curla_agent_encode(eng.h, net, _lib.ptr(s2d), b1 - b0, int(apply_tanh),
                                                       _lib.ptr(out[b0:b1]), eng.stream()), 'encode')
         return out[:, :c.feature_dim]
