@@ -110,16 +110,23 @@ def fill_replay(rb, seed=1):
 
 
 # ------------------------------------------------------------------ algorithmic work
-def conv_layer_work(B, layer):
-    """(flops, algorithmic bytes) of one forward launch of conv layer `layer` (1..3 = the
-    32->32 3x3 layers) at the 76x135 crop geometry: read the valid bf16 input once, write
-    the valid bf16 output once, weights once."""
-    ho = [37, 35, 33, 31]
-    wo = [67, 65, 63, 61]
-    hin, win, hout, wout = ho[layer - 1], wo[layer - 1], ho[layer], wo[layer]
-    flops = 2.0 * B * hout * wout * 32 * 288
-    byts = B * (hin * win + hout * wout) * 32 * 2 + 9 * 32 * 32 * 2
-    return flops, byts
+WORKLOADS = {
+    # BASELINE.json configs[1] (the metric's configuration) / configs[3] with --gpus 8
+    'curl_crop': dict(aug='random_crop', pixel_sac=False,
+                      what='CURL random-crop SAC update, train.py defaults'),
+    # configs[2]
+    'pixel_sac': dict(aug='identity', pixel_sac=True, what='Pixel SAC (--pixel_sac: identity 90x160, no contrastive head)'),
+    # configs[0]'s augmentation at the default batch (the reference times it on CPU at a small batch)
+    'curl_identity': dict(aug='identity', pixel_sac=False, what='CURL identity-augmentation update (90x160 encoder input)'),
+}
+
+
+def geometry(hw):
+    ho, wo = [(hw[0] - 3) // 2 + 1], [(hw[1] - 3) // 2 + 1]
+    for _ in range(3):
+        ho.append(ho[-1] - 2)
+        wo.append(wo[-1] - 2)
+    return ho, wo
 
 
 def run_ours(args, rank, world, device):
@@ -127,14 +134,16 @@ def run_ours(args, rank, world, device):
     torch.cuda.set_device(device)
     np.random.seed(12345)                    # identical global index stream on every rank
     torch.manual_seed(0)
-    aug = augmentations.make_augmentor('random_crop', FRAME[1:])
+    wl = WORKLOADS[args.workload]
+    aug = augmentations.make_augmentor(wl['aug'], FRAME[1:])
     Bg = args.batch * world
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
         rb = utils.ReplayBuffer(FRAME, ACTION, CAPACITY, Bg, device, aug)
     fill_replay(rb)
-    agent = curl_sac.CurlSacAgent((9, 76, 135), ACTION, device, aug, log_interval=10 ** 9, **HP)
+    agent = curl_sac.CurlSacAgent((9, *aug.output_shape), ACTION, device, aug, log_interval=10 ** 9,
+                                  pixel_sac=wl['pixel_sac'], **HP)
     L = NullLogger()
     step0 = 0
 
@@ -218,12 +227,15 @@ def run_ours(args, rank, world, device):
             prof[nm] = (int(cnt), float(tot))
         step0 += args.prof_steps
     return dict(ms_per_step=ms_per_step, launches=launches, clocks=clocks, e2e_s=e2e_s, h2d=h2d, d2h=d2h,
-                prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last)
+                prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last, obs_hw=tuple(aug.output_shape))
 
 
-def cpu_reference_updates(batch, steps, warmup, threads):
+def cpu_reference_updates(batch, steps, warmup, threads, workload='curl_crop'):
     """The oracle port of the reference's CPU update (torch fp32, oneDNN) on the host cores."""
     from oracle import curla_oracle as O
+    wl = WORKLOADS[workload]
+    crop = wl['aug'] == 'random_crop'
+    ohw = (76, 135) if crop else FRAME[1:]
     torch.set_num_threads(threads)
     rs = np.random.RandomState(1)
     cap = 64
@@ -231,23 +243,102 @@ def cpu_reference_updates(batch, steps, warmup, threads):
     actions = rs.uniform(-1, 1, size=(cap, 2)).astype(np.float32)
     rewards = rs.standard_normal(size=(cap, 1)).astype(np.float32)
     not_dones = (rs.uniform(size=(cap, 1)) > 0.01).astype(np.float32)
-    agent = O.OracleAgent((9, 76, 135), 2, hidden_dim=HP['hidden_dim'])
+    agent = O.OracleAgent((9, *ohw), 2, hidden_dim=HP['hidden_dim'], pixel_sac=wl['pixel_sac'])
     agent.init_random(0)
     np.random.seed(0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        d = O.draw_sample_indices(cap, 0, True, batch, 'random_crop', FRAME[1:], (76, 135))
+        d = O.draw_sample_indices(cap, 0, True, batch, wl['aug'], FRAME[1:], ohw)
         f = lambda a: torch.from_numpy(a).float()
-        obs = f(O.gather_crop(frames[0], d['idxs'], d['h1_obs'], d['w1_obs'], (76, 135)))
-        nxt = f(O.gather_crop(frames[1], d['idxs'], d['h1_next'], d['w1_next'], (76, 135)))
-        pos = f(O.gather_crop(frames[0], d['idxs'], d['h1_pos'], d['w1_pos'], (76, 135)))
+        if crop:
+            obs = f(O.gather_crop(frames[0], d['idxs'], d['h1_obs'], d['w1_obs'], ohw))
+            nxt = f(O.gather_crop(frames[1], d['idxs'], d['h1_next'], d['w1_next'], ohw))
+            pos = f(O.gather_crop(frames[0], d['idxs'], d['h1_pos'], d['w1_pos'], ohw))
+        else:
+            obs, nxt = f(O.gather(frames[0], d['idxs'])), f(O.gather(frames[1], d['idxs']))
+            pos = obs.clone()
         noise = torch.randn(2, batch, 2)
         agent.update(obs, torch.from_numpy(actions[d['idxs']]), torch.from_numpy(rewards[d['idxs']]), nxt,
                      torch.from_numpy(not_dones[d['idxs']]), pos, i, noise[0], noise[1])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return float(np.mean(times))
+
+
+def latent_sweep(args, rank, local):
+    """BASELINE.json configs[4]: encoder-only latent extraction over a synthetic episode set
+    (plot_tsne/latent_data.py:63-104), batch sweep.  One JSON line; `value` is the best batch."""
+    if rank != 0:
+        return
+    from curla_b200 import augmentations, curl_sac, latent
+    from oracle import curla_oracle as O
+    device = torch.device('cuda', local)
+    torch.cuda.set_device(device)
+    torch.manual_seed(0)
+    N = 20000                                    # latent_episodes.py:189 collects 20,000 observations
+    aug = augmentations.make_augmentor('random_crop', FRAME[1:])
+    agent = curl_sac.CurlSacAgent((9, *aug.output_shape), ACTION, device, aug, **HP)
+    g = torch.Generator(device=device).manual_seed(1)
+    frames = torch.empty((N, *FRAME), dtype=torch.uint8, device=device)          # 2.6 GB > L2
+    for s0 in range(0, N, 2000):
+        frames[s0:s0 + 2000] = torch.randint(0, 256, (min(2000, N - s0), *FRAME), device=device, dtype=torch.uint8, generator=g)
+    top, left = latent.center_window(FRAME[1:], tuple(aug.output_shape))
+    sweep = {}
+    for b in (1, 8, 64, 512):
+        agent.INFER_BATCH = b
+        agent._make_engine(batch=b, frame_hw=agent.image_shape)
+        n = min(N, max(b * 8, 256)) if b < 512 else N
+        for _ in range(max(args.warmup, 3)):
+            agent.encode_frames(0, frames[:min(n, 4 * b)], top, left)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        z = agent.encode_frames(0, frames[:n], top, left)
+        e1.record()
+        torch.cuda.synchronize()
+        sweep[str(b)] = {'obs_per_s': n / (e0.elapsed_time(e1) * 1e-3), 'observations': n}
+    # end to end through the public call with HOST frames: H2D of the uint8 frames + encoders + policy + Q + D2H
+    agent.INFER_BATCH = 512
+    agent._make_engine(batch=512, frame_hw=agent.image_shape)
+    host = frames[:4096].cpu().numpy()
+    latent.extract(agent, host[:1024])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = latent.extract(agent, host)
+    e2e_s = time.perf_counter() - t0
+    # CPU: the oracle port of agent.actor.encoder at batch 64 on the host cores (bounded sample)
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    o = O.OracleAgent((9, *aug.output_shape), 2, hidden_dim=HP['hidden_dim'])
+    o.init_random(0)
+    x = torch.from_numpy(host[:64, :, top:top + 76, left:left + 135].astype(np.float32))
+    with torch.no_grad():
+        O.encoder_forward(o.actor, 'encoder.', x)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            O.encoder_forward(o.actor, 'encoder.', x)
+        cpu_s = (time.perf_counter() - t0) / 4
+    best = max(sweep, key=lambda k: sweep[k]['obs_per_s'])
+    hbm, tf, how = peaks()
+    flops_obs = 134.01e6
+    line = {'metric': 'encoder_latent_obs_per_sec', 'value': sweep[best]['obs_per_s'], 'unit': 'obs/s', 'n_gpus': 1,
+            'steps': 1, 'warmup': max(args.warmup, 3), 'ms_per_step': 1e3 * sweep[best]['observations'] / sweep[best]['obs_per_s'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'encoder-only latent extraction (actor.encoder forward, center crop 90x160 -> 76x135) over %d '
+                                   'synthetic uint8 frames resident in HBM (2.6 GB, > L2); batch sweep' % N,
+                       'best_batch': int(best)},
+            'sweep': sweep,
+            'roofline': {'bound': 'tensor', 'achieved': sweep[best]['obs_per_s'] * flops_obs / 1e12, 'peak': tf, 'unit': 'TFLOP/s',
+                         'frac': sweep[best]['obs_per_s'] * flops_obs / 1e12 / tf, 'traffic': None, 'peak_source': how,
+                         'note': '134.0 MFLOP per observation (SURVEY 8d); N=32 conv taps cap the tensor pipe at 40 % (profiles/r01c_microbench.txt)'},
+            'e2e': {'value': len(host) / e2e_s, 'unit': 'obs/s', 'h2d_bytes_per_step': int(host.nbytes),
+                    'd2h_bytes_per_step': int(sum(v.nbytes for v in out.values())),
+                    'what': 'curla_b200.latent.extract(agent, host uint8 frames): latents + sampled actions + min-Q for 4096 observations'},
+            'cpu_baseline': {'value': 64 / cpu_s, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
+                             'sample': 'oracle port of actor.encoder forward (torch fp32 CPU), batch 64 x 4 passes'},
+            'gpu_launches': None}
+    print(json.dumps(line))
 
 
 def main():
@@ -260,15 +351,21 @@ def main():
     ap.add_argument('--prof-steps', type=int, default=4)
     ap.add_argument('--cpu-baseline-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='curl_crop', choices=sorted(WORKLOADS) + ['latent'],
+                    help='curl_crop = BASELINE.json configs[1] (default, the metric); pixel_sac = configs[2]; '
+                         'curl_identity = configs[0] at the default batch; latent = configs[4] (encoder-only sweep)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     cores = os.cpu_count()
-    config = {'workload': 'CURL random-crop SAC update, train.py defaults: per-GPU batch %d, frames 9x90x160 -> '
-                          'crop 9x76x135, hidden 1024, feature 50, 4x32 filters; synthetic replay of %d transitions '
-                          '(4.25 GB, > L2) resident in HBM' % (args.batch, CAPACITY),
+    if args.workload == 'latent':
+        return latent_sweep(args, rank, local)
+    wl = WORKLOADS[args.workload]
+    config = {'workload': '%s: per-GPU batch %d, frames 9x90x160%s, hidden 1024, feature 50, 4x32 filters; synthetic replay '
+                          'of %d transitions (4.25 GB, > L2) resident in HBM'
+                          % (wl['what'], args.batch, ' -> crop 9x76x135' if wl['aug'] == 'random_crop' else '', CAPACITY),
               'per_gpu_batch': args.batch, 'global_batch': args.batch * world,
               'parallelism': 'dp%d (grad all-reduce + all-gathered CURL keys)' % world,
               'l2': 'inputs larger than L2 (random replay rows from 4.25 GB; ~1.4 GB of activations per update)',
@@ -279,7 +376,7 @@ def main():
             return
         # bounded sample: a smaller batch of the same update, throughput in obs/s
         sample_b = 128
-        sec = cpu_reference_updates(sample_b, args.steps if args.steps <= 8 else 8, 1, cores)
+        sec = cpu_reference_updates(sample_b, args.steps if args.steps <= 8 else 8, 1, cores, args.workload)
         val = sample_b / sec
         line = {'impl': 'reference', 'metric': 'sac_curl_update_obs_per_sec', 'value': val, 'unit': 'obs/s',
                 'updates_per_s': val / args.batch, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -313,10 +410,11 @@ def main():
     hbm, tf, how = peaks()
     # per-kernel rooflines from the live CUDA-event profile (algorithmic bytes: DESIGN.md section 4);
     # the headline `roofline` entry is the kernel with the largest share of the update
-    ho, wo = [37, 35, 33, 31], [67, 65, 63, 61]
+    H_, W_ = r['obs_hw']
+    ho, wo = geometry((H_, W_))
     Bb = args.batch
     act = lambda l: Bb * ho[l] * wo[l] * 64                      # valid bf16 positions x 32 channels
-    s2d_bytes = Bb * 38 * 68 * 48 * 2
+    s2d_bytes = Bb * ((H_ + 1) // 2) * ((W_ + 1) // 2) * 48 * 2
     conv_flops = lambda l: 2.0 * Bb * ho[l] * wo[l] * 32 * (81 if l == 0 else 288)
     stacks = {'conv_fwd': 5, 'conv_dgrad': 2, 'conv_wgrad': 2}       # conv-stack passes per update pair avg
     table = {
@@ -330,7 +428,7 @@ def main():
                            bytes=s2d_bytes + act(0) + sum(act(l - 1) + act(l) for l in (1, 2, 3)),
                            flops=sum(conv_flops(l) for l in range(4))),
         'gather_s2d': dict(kernel='k_gather_s2d (replay gather + crop + u8->bf16 s2d)', launches=1,
-                           bytes=Bb * 9 * 76 * 135 + s2d_bytes, flops=0.0),
+                           bytes=Bb * 9 * H_ * W_ + s2d_bytes, flops=0.0),
         'adam_f32': dict(kernel='k_adam (fused multi-tensor Adam)', launches=None, bytes=None, flops=0.0),
     }
     traffic_db = {}
@@ -361,7 +459,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         sb = 128
-        sec = cpu_reference_updates(sb, args.cpu_baseline_steps, 1, cores)
+        sec = cpu_reference_updates(sb, args.cpu_baseline_steps, 1, cores, args.workload)
         cpu = {'value': sb / sec, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
                'sample': 'oracle port of the reference update (torch fp32 CPU), batch %d x %d updates after 1 warm-up'
                          % (sb, args.cpu_baseline_steps), 'updates_per_s_at_batch_%d' % args.batch: sb / sec / args.batch}

@@ -340,8 +340,9 @@ class _Host(object):
         engine large enough to run batched inference in few launches; once training started the
         engine batch is the replay batch and larger inputs are processed in chunks of it."""
         c = self.engine.cfg
-        if n > c.batch and getattr(self, '_update_count', 1) == 0 and hasattr(self, '_make_engine'):
-            self._make_engine(batch=min(int(n), self.INFER_BATCH), frame_hw=(c.Hf, c.Wf))
+        target = min(int(n), self.INFER_BATCH)
+        if target > c.batch and getattr(self, '_update_count', 1) == 0 and hasattr(self, '_make_engine'):
+            self._make_engine(batch=target, frame_hw=(c.Hf, c.Wf))
 
     def encode(self, net, obs, apply_tanh=False):
         obs = torch.as_tensor(obs, device=self.engine.device)
