@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256)
 k_color_jiggle(float* __restrict__ x, int n_images, int HW, const float* __restrict__ params,
                unsigned long long seed, unsigned long long offset, float c_rng, float s_rng, float h_rng,
                float p_apply, int order, float* __restrict__ params_out) {
+    pdl_grid_sync();
     const int img = blockIdx.y;
     float cf, sf, hf;
     bool apply;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256)
 k_noisy_cover(float* __restrict__ x, long long n4, int H, int W, int top, int bottom, float c0, float c1,
               float c2, float stdv, const float* __restrict__ noise_in, unsigned long long seed,
               unsigned long long offset) {
+    pdl_grid_sync();
     const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
     const long long e = i4 * 4;                     // W % 4 == 0: the 4 elements share (img, ch, y)
@@ -141,7 +143,7 @@ extern "C" int curla_color_jiggle(float* x, int n_images, int H, int W, const fl
     CURLA_CHECK(n_images > 0 && H > 0 && W > 0, "color_jiggle: bad shape");
     const int HW = H * W;
     dim3 grid(cdiv(HW, 256 * 4) > 0 ? cdiv(HW, 256 * 4) : 1, n_images);
-    k_color_jiggle<<<grid, 256, 0, stream>>>(x, n_images, HW, params, seed, offset, contrast, saturation, hue, p,
+    launch_k(k_color_jiggle, dim3(grid), dim3(256), 0, stream, x, n_images, HW, params, seed, offset, contrast, saturation, hue, p,
                                             order, params_out);
     return check_launch("color_jiggle");
 }
@@ -152,7 +154,7 @@ extern "C" int curla_noisy_cover(float* x, int n_images, int H, int W, int top, 
     CURLA_CHECK(n_images > 0 && H > 0 && W > 0 && W % 4 == 0, "noisy_cover: W must be a multiple of 4");
     CURLA_CHECK(((uintptr_t)x & 15) == 0, "noisy_cover: x must be 16-byte aligned");
     const long long n4 = (long long)n_images * 3 * H * W / 4;
-    k_noisy_cover<<<cdiv(n4, 256), 256, 0, stream>>>(x, n4, H, W, top, bottom, cover3_host[0], cover3_host[1],
+    launch_k(k_noisy_cover, dim3(cdiv(n4, 256)), dim3(256), 0, stream, x, n4, H, W, top, bottom, cover3_host[0], cover3_host[1],
                                                     cover3_host[2], stdv, noise_in, seed, offset);
     return check_launch("noisy_cover");
 }

@@ -22,6 +22,33 @@ void set_launch_tag(const char* tag);  // optional profiler label for the next l
         }                                              \
     } while (0)
 
+// ---------------------------------------------------------------- launches
+// Programmatic dependent launch (PDL): every kernel is launched with the programmatic stream
+// serialization attribute and starts with pdl_grid_sync(): griddepcontrol.wait blocks until the
+// previous kernel in the stream has completed and its writes are visible (so stream-order
+// semantics are unchanged), and griddepcontrol.launch_dependents lets the NEXT kernel's launch
+// and CTA scheduling overlap this kernel's execution instead of following its drain.  The
+// ~115 launches of one update are otherwise separated by a launch gap each.
+// CURLA_NO_PDL=1 falls back to plain stream serialization.
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_grid_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -46,6 +46,11 @@ struct TcGeom {
 };
 struct TcTaps { int off[9]; };
 
+// CURLA_TC_DEBUG & 64: per-CTA cycle counters of the MMA thread and the producer (timing
+// experiments only): [0] MMA wait tempty, [1] MMA wait full, [2] MMA issue, [3] producer wait
+// empty, [4] kernel total, [5] tiles, [6] epilogue warp 0 wait tfull, [7] epilogue warp 0 busy
+__device__ long long g_tc_dbg[160][8];
+
 // ---------------------------------------------------------------- the kernel
 // Warp-specialised, persistent, one CTA per SM:
 //   warps 0..15  epilogue   (two groups of 8 alternating tiles; TMEM -> registers -> bias/ReLU or ReLU-mask -> plane stores: a
@@ -109,6 +114,8 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // everything above is independent of earlier kernels; from here on we read their outputs
+    pdl_grid_sync();
     if (!DGRAD) {
         for (int i = tid; i < NTAPS * 32 * CH; i += kTcThreads) {
             const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
@@ -160,6 +167,8 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         };
         const int tstep = gridDim.x * kEpiGroups;
         const int tile0 = blockIdx.x + egroup * gridDim.x;
+        long long e_wait = 0;
+        const long long e_start = clock64();
         acc = egroup;                              // local tile j uses accumulator stage j % 4
         if (DGRAD) load_mask(tile0, xn);
         for (int tile = tile0; tile < g.total_tiles; tile += tstep) {
@@ -174,7 +183,9 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                 for (int c = 0; c < 4; ++c) xm[c] = xn[c];
                 load_mask(tile + tstep, xn);
             }
+            const long long e0 = clock64();
             mbar_wait(s_tfull + 8 * acc, acc_phase);
+            e_wait += clock64() - e0;
             tc_fence_after();
             uint32_t r[32];
             tmem_ld32(taddr0 + acc * (kTcSub * 32), r);
@@ -205,6 +216,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
             acc += kEpiGroups;
             if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
         }
+        if ((g.debug & 64) && tid == 0) { g_tc_dbg[blockIdx.x][6] = e_wait; g_tc_dbg[blockIdx.x][7] = clock64() - e_start - e_wait; }
     } else if (warp == kEpiAll) {
         // ================= MMA issuer
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -218,9 +230,15 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
             for (int ks = 0; ks < KS; ++ks)
                 a_off[t * KS + ks] = ((uint32_t)(2 * ks) * PS +
                                       (uint32_t)((g.debug & 8) ? ((taps.off[t] - g.min_off) & ~7) : (taps.off[t] - g.min_off)) * 16u) >> 4;
+        long long c_te = 0, c_fu = 0, c_is = 0, c_n = 0;
+        const long long c_start = clock64();
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            const long long c0 = clock64();
             mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            const long long c1 = clock64();
             mbar_wait(s_full + 8 * stage, phase);
+            const long long c2 = clock64();
+            c_te += c1 - c0; c_fu += c2 - c1; ++c_n;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
@@ -242,19 +260,27 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                 umma_commit(s_tfull + 8 * acc);       // accumulators complete
             }
             __syncwarp();
+            c_is += clock64() - c2;
             if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+        if ((g.debug & 64) && lane == 0) {
+            long long* d = g_tc_dbg[blockIdx.x];
+            d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n;
         }
     } else {
         // ================= producer: slab[c][0:rows][16 B] <- plane c rows [p0+min_off, +rows)
         uint32_t stage = 0, phase = 0;
+        long long c_pw = 0;
         const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
             const int b = tile / g.tiles_per_sample;
             const int p0 = (tile - b * g.tiles_per_sample) * TM;
             const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * 8;
             const uint32_t dst = s_slab0 + stage * slab_bytes;
+            const long long c0 = clock64();
             mbar_wait(s_empty + 8 * stage, phase ^ 1);
+            c_pw += clock64() - c0;
             if (elect_one()) {
                 const uint32_t bar = s_full + 8 * stage;
                 if (g.debug & 1) {
@@ -268,6 +294,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
             __syncwarp();
             if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
+        if ((g.debug & 64) && lane == 0) g_tc_dbg[blockIdx.x][3] = c_pw;
     }
     tc_fence_before();
     __syncthreads();
@@ -319,7 +346,7 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
     if (tc_set_smem(kern, smem)) return -1;
     const int cap = sm_count();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
-    kern<<<grid, kTcThreads, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
+    launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, (const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
                                              (const bf16*)relu_src, (bf16*)out, out_sstride, g, taps);
     return 0;
 }
@@ -327,6 +354,13 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
 }  // namespace curla
 
 using namespace curla;
+
+// timing experiments: copies the CURLA_TC_DEBUG&64 counters of `n` CTAs (8 int64 each) to the host
+extern "C" int curla_conv_debug_read(long long* out, int n) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 8 * (n < 160 ? n : 160));
+    CURLA_CHECK(e == cudaSuccess, "conv_debug_read: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 // Rows of zero padding the caller keeps in front of sample 0 and behind sample B-1 of every
 // activation buffer handed to the conv kernels (slabs read past the tile on both sides).

@@ -101,6 +101,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
                 make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
         }
     }
+    pdl_grid_sync();     // the prologue above touched no global memory
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(256)
 k_conv_wgrad_reduce(const float* __restrict__ partial, int nparts, int ntaps,
                     int CP, int Cin, int s2d, float scale,
                     float* __restrict__ dW, float* __restrict__ db) {
+    pdl_grid_sync();
     // block = 32 consecutive elements x 8 partial-slices; fixed summation tree => deterministic
     __shared__ float red[8][33];
     const int per = ntaps * CP * 32 + 32;
@@ -245,6 +247,7 @@ struct WgReduceJob { const float* partial; int nparts, ntaps, CP, Cin, s2d; floa
 struct WgReduceJobs { WgReduceJob j[4]; };
 __global__ void __launch_bounds__(256)
 k_conv_wgrad_reduce_multi(WgReduceJobs jobs) {
+    pdl_grid_sync();
     __shared__ float red[8][33];
     const WgReduceJob& J = jobs.j[blockIdx.y];
     const int per = J.ntaps * J.CP * 32 + 32;
@@ -299,7 +302,7 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }
     const int cap = sm_count();
     const int grid = g.total_runs < cap ? g.total_runs : cap;
-    kern<<<grid, kWgThreads, smem, stream>>>((const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride, workspace, g);
+    launch_k(kern, dim3(grid), dim3(kWgThreads), smem, stream, (const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride, workspace, g);
     *grid_out = grid;
     return 0;
 }
@@ -344,7 +347,7 @@ extern "C" int curla_conv_wgrad_reduce_multi(int n, float* const* workspace, con
         const int per = J.ntaps * J.CP * 32 + 32;
         per_max = per > per_max ? per : per_max;
     }
-    k_conv_wgrad_reduce_multi<<<dim3(cdiv(per_max, 32), n), dim3(32, 8), 0, stream>>>(jobs);
+    launch_k(k_conv_wgrad_reduce_multi, dim3(cdiv(per_max, 32), n), dim3(32, 8), 0, stream, jobs);
     return check_launch("conv_wgrad_reduce");
 }
 
@@ -358,12 +361,12 @@ extern "C" int curla_conv_wgrad(const void* in, long long in_sstride, const void
         if (launch_wgrad<48, 2, 2>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, &grid, stream)) return -1;
         if (check_launch("conv_wgrad")) return -1;
         const int per = 4 * 48 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 4, 48, Cin, 1, scale, dW, db);
+        launch_k(k_conv_wgrad_reduce, dim3(cdiv(per, 32)), dim3(32, 8), 0, stream, workspace, grid, 4, 48, Cin, 1, scale, dW, db);
     } else {
         if (launch_wgrad<32, 3, 3>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, &grid, stream)) return -1;
         if (check_launch("conv_wgrad")) return -1;
         const int per = 9 * 32 * 32 + 32;
-        k_conv_wgrad_reduce<<<cdiv(per, 32), dim3(32, 8), 0, stream>>>(workspace, grid, 9, 32, Cin, 0, scale, dW, db);
+        launch_k(k_conv_wgrad_reduce, dim3(cdiv(per, 32)), dim3(32, 8), 0, stream, workspace, grid, 9, 32, Cin, 0, scale, dW, db);
     }
     return check_launch("conv_wgrad_reduce");
 }

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256)
 k_sgemm_strided(const float* __restrict__ A, long long sam, long long sak,
                 const float* __restrict__ Bm, long long sbk, long long sbn,
                 float* __restrict__ C, long long ldc, int M, int N, int K) {
+    pdl_grid_sync();
     __shared__ float sA[32][33], sB[32][33];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256)
 k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const float* __restrict__ z_pos,
             int B, int Bg, int label0, float grad_scale, float* __restrict__ row_loss,
             float* __restrict__ dz_a, float* __restrict__ V, float* __restrict__ logits_copy) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) float s_dyn[];
     const int BgP = (Bg + 3) & ~3;                // row stride of the logits block (keeps s_za 16-byte aligned)
     float* s_log = s_dyn;                         // [R][BgP]
@@ -155,6 +157,7 @@ k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const fl
 __global__ void __launch_bounds__(256)
 k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const float* __restrict__ row_loss,
           int B, int feat, float* __restrict__ dW, float* __restrict__ loss_out) {
+    pdl_grid_sync();
     __shared__ float s_red[4][64];
     __shared__ float s_l[8];
     const int a = blockIdx.x, b = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -187,14 +190,14 @@ static int launch_curl_rows(const float* z_a, const float* U, const float* z_pos
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return -1; }
     }
-    kern<<<cdiv(B, R), 256, smem, st>>>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy);
+    launch_k(kern, dim3(cdiv(B, R)), dim3(256), smem, st, z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy);
     return check_launch("curl_rows");
 }
 
 static int sgemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk,
                  long long sbn, float* C, long long ldc, int M, int N, int K, cudaStream_t st) {
     dim3 grid(cdiv(N, 32), cdiv(M, 32));
-    k_sgemm_strided<<<grid, 256, 0, st>>>(A, sam, sak, Bm, sbk, sbn, C, ldc, M, N, K);
+    launch_k(k_sgemm_strided, dim3(grid), dim3(256), 0, st, A, sam, sak, Bm, sbk, sbn, C, ldc, M, N, K);
     return check_launch("curl_sgemm");
 }
 
@@ -234,6 +237,6 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
         default: rc = launch_curl_rows<1>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
     }
     if (rc) return -1;
-    k_curl_dw<<<feat, 256, 0, stream>>>(z_a, V, row_loss, B, feat, dW, loss_out);
+    launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, V, row_loss, B, feat, dW, loss_out);
     return check_launch("curl_dw");
 }

@@ -15,6 +15,7 @@
 
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -34,6 +35,11 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 static thread_local long long g_launches = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("CURLA_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
 
 // Optional CUDA-event profiler: one event after every launch on the engine's stream; the
 // interval between consecutive events is that launch's device time (single stream, so

@@ -24,6 +24,7 @@ k_gather_crop_f32(const uint8_t* __restrict__ frames, int C, int Hf, int Wf,
                   const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
                   const int64_t* __restrict__ w1, int B, int H, int W,
                   float* __restrict__ out) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const long long rows = (long long)B * C * H;
     long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -57,6 +58,7 @@ k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
              const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
              const int64_t* __restrict__ w1, int H, int W, int Hs, int Ws, int CP,
              long long out_sample_stride, bf16* __restrict__ out) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t s_raw[];
     const int b = blockIdx.y, yb = blockIdx.x;
     const long long fi = idxs ? idxs[b] : b;
@@ -111,6 +113,7 @@ k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
 // out[b][k] = src[idx[b]][k]   (actions / rewards / not_dones: utils.py:163-165)
 __global__ void k_gather_rows_f32(const float* __restrict__ src, const int64_t* __restrict__ idxs,
                                   int B, int K, float* __restrict__ out) {
+    pdl_grid_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * K) {
         const int b = i / K, k = i % K;
@@ -131,7 +134,7 @@ extern "C" int curla_gather_crop_f32(const uint8_t* frames, int C, int Hf, int W
     int grid = (int)((rows + wpb - 1) / wpb);
     const int cap = sm_count() * 32;
     if (grid > cap) grid = cap;
-    k_gather_crop_f32<<<grid, wpb * 32, 0, stream>>>(frames, C, Hf, Wf, idxs, h1, w1, B, H, W, out);
+    launch_k(k_gather_crop_f32, dim3(grid), dim3(wpb * 32), 0, stream, frames, C, Hf, Wf, idxs, h1, w1, B, H, W, out);
     return check_launch("gather_crop_f32");
 }
 
@@ -145,7 +148,7 @@ static int launch_s2d(const SrcT* frames, int C, int Hf, int Wf, const int64_t* 
     dim3 grid(Hs, B);
     const int V = 16 / (int)sizeof(SrcT);
     size_t smem = (size_t)2 * C * ((Wf + V - 1) / V * V + V) * sizeof(SrcT);
-    k_gather_s2d<SrcT><<<grid, 128, smem, stream>>>(frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
+    launch_k(k_gather_s2d<SrcT>, dim3(grid), dim3(128), smem, stream, frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
                                                     CP, out_sample_stride, out);
     return check_launch("gather_s2d");
 }
@@ -166,6 +169,6 @@ extern "C" int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, in
 
 extern "C" int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K,
                                      float* out, cudaStream_t stream) {
-    k_gather_rows_f32<<<cdiv((long long)B * K, 256), 256, 0, stream>>>(src, idxs, B, K, out);
+    launch_k(k_gather_rows_f32, dim3(cdiv((long long)B * K, 256)), dim3(256), 0, stream, src, idxs, B, K, out);
     return check_launch("gather_rows_f32");
 }

@@ -58,6 +58,7 @@ __device__ __forceinline__ uint32_t off128(int row, int chunk) {     // 128-byte
 template <bool A_KMAJOR, bool B_KMAJOR, bool SEG>
 __global__ void __launch_bounds__(128)
 k_gemm(GemmArgs p) {
+    pdl_grid_sync();
     __shared__ __align__(128) uint8_t smem[STAGES * (BM * BK * 2 + BN * BK * 2)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
@@ -338,14 +339,14 @@ static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream)
     p.vec_c = p.out_bf16 && p.ldc % 8 == 0 && p.bsC % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
               (!p.mask || (p.ldmask % 8 == 0 && p.bsMask % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0));
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
-        case 3: k_gemm<true, true, false><<<grid, 128, 0, stream>>>(p); break;
-        case 1: k_gemm<true, false, false><<<grid, 128, 0, stream>>>(p); break;
-        case 2: k_gemm<false, true, false><<<grid, 128, 0, stream>>>(p); break;
-        case 0: k_gemm<false, false, false><<<grid, 128, 0, stream>>>(p); break;
-        case 7: k_gemm<true, true, true><<<grid, 128, 0, stream>>>(p); break;
-        case 5: k_gemm<true, false, true><<<grid, 128, 0, stream>>>(p); break;
-        case 6: k_gemm<false, true, true><<<grid, 128, 0, stream>>>(p); break;
-        default: k_gemm<false, false, true><<<grid, 128, 0, stream>>>(p); break;
+        case 3: launch_k(k_gemm<true, true, false>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 1: launch_k(k_gemm<true, false, false>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 2: launch_k(k_gemm<false, true, false>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 0: launch_k(k_gemm<false, false, false>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 7: launch_k(k_gemm<true, true, true>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 5: launch_k(k_gemm<true, false, true>, dim3(grid), dim3(128), 0, stream, p); break;
+        case 6: launch_k(k_gemm<false, true, true>, dim3(grid), dim3(128), 0, stream, p); break;
+        default: launch_k(k_gemm<false, false, true>, dim3(grid), dim3(128), 0, stream, p); break;
     }
     return check_launch("gemm_bf16");
 }

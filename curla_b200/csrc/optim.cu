@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
        float* __restrict__ v, long long n, long long double_from, AdamHyper h, int t_host,
        const int* __restrict__ t_dev) {
+    pdl_grid_sync();
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const int t = t_dev ? *t_dev : t_host;
@@ -69,6 +70,7 @@ k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m
 // log_alpha is a float64 0-dim tensor (curl_sac.py:292); state[0]=m, state[1]=v.
 __global__ void k_adam_f64_scalar(double* p, const double* g, double* state, AdamHyper h,
                                   int t_host, const int* t_dev) {
+    pdl_grid_sync();
     if (threadIdx.x || blockIdx.x) return;
     const int t = t_dev ? *t_dev : t_host;
     double m = state[0], v = state[1];
@@ -86,6 +88,7 @@ __global__ void k_adam_f64_scalar(double* p, const double* g, double* state, Ada
 __global__ void __launch_bounds__(256)
 k_ema(float* __restrict__ tgt, const float* __restrict__ p, long long n, long long split,
       float tau_a, float omt_a, float tau_b, float omt_b) {
+    pdl_grid_sync();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     auto one = [&](float t, float q, long long i) {
@@ -119,6 +122,7 @@ struct PackTable {
 
 __global__ void __launch_bounds__(256)
 k_pack(const float* __restrict__ src_arena, bf16* __restrict__ dst_arena, PackTable tbl) {
+    pdl_grid_sync();
     const PackSeg s = tbl.seg[blockIdx.y];
     const float* src = src_arena + s.src_off;
     bf16* dst = dst_arena + s.dst_off;
@@ -193,7 +197,7 @@ extern "C" int curla_adam_f32(float* p, const float* g, float* m, float* v, long
                               double eps, int t_host, const int* t_dev, cudaStream_t stream) {
     if (n <= 0) return 0;
     AdamHyper h{lr, beta1, beta2, eps};
-    k_adam<<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, double_from, h, t_host, t_dev);
+    launch_k(k_adam, dim3(ew_grid(n)), dim3(256), 0, stream, p, g, m, v, n, double_from, h, t_host, t_dev);
     return check_launch("adam_f32");
 }
 
@@ -201,14 +205,14 @@ extern "C" int curla_adam_f64_scalar(double* p, const double* g, double* state, 
                                      double beta1, double beta2, double eps, int t_host,
                                      const int* t_dev, cudaStream_t stream) {
     AdamHyper h{lr, beta1, beta2, eps};
-    k_adam_f64_scalar<<<1, 32, 0, stream>>>(p, g, state, h, t_host, t_dev);
+    launch_k(k_adam_f64_scalar, dim3(1), dim3(32), 0, stream, p, g, state, h, t_host, t_dev);
     return check_launch("adam_f64_scalar");
 }
 
 extern "C" int curla_ema_f32(float* target, const float* p, long long n, long long split,
                              double tau_a, double tau_b, cudaStream_t stream) {
     if (n <= 0) return 0;
-    k_ema<<<ew_grid(n), 256, 0, stream>>>(target, p, n, split, (float)tau_a, (float)(1.0 - tau_a),
+    launch_k(k_ema, dim3(ew_grid(n)), dim3(256), 0, stream, target, p, n, split, (float)tau_a, (float)(1.0 - tau_a),
                                           (float)tau_b, (float)(1.0 - tau_b));
     return check_launch("ema_f32");
 }
@@ -231,7 +235,7 @@ extern "C" int curla_pack_shadows(const float* src_arena, void* dst_arena, const
         }
         long long gx = (maxn + 255) / 256;
         if (gx > 2048) gx = 2048;
-        k_pack<<<dim3((unsigned)gx, tbl.n), 256, 0, stream>>>(src_arena, (bf16*)dst_arena, tbl);
+        launch_k(k_pack, dim3((unsigned)gx, tbl.n), dim3(256), 0, stream, src_arena, (bf16*)dst_arena, tbl);
         if (check_launch("pack_shadows")) return -1;
     }
     return 0;

@@ -24,6 +24,7 @@ k_ln_fwd(const float* __restrict__ partial, int nsplit, long long split_stride,
          const float* __restrict__ beta, int B, int feat, int apply_tanh,
          float* __restrict__ x_out, float* __restrict__ z_out,
          const float* __restrict__ act, int A, bf16* __restrict__ X_out) {
+    pdl_grid_sync();
     __shared__ float s_x[4][FP];
     const int row = blockIdx.x;
     {
@@ -71,6 +72,7 @@ k_ln_bwd(const float* __restrict__ dz_a, const float* __restrict__ dz_b,
          const float* __restrict__ x_in, const float* __restrict__ gamma, int B, int feat,
          float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, float* __restrict__ dzsum,
          float* __restrict__ dzx) {
+    pdl_grid_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -110,6 +112,7 @@ k_ln_bwd(const float* __restrict__ dz_a, const float* __restrict__ dz_b,
 __global__ void __launch_bounds__(1024)
 k_colsum3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
           int B, int feat, float* __restrict__ oa, float* __restrict__ ob, float* __restrict__ oc) {
+    pdl_grid_sync();
     __shared__ float s[3][16][FP];
     const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
     float sa = 0.f, sb = 0.f, sc = 0.f;
@@ -131,6 +134,7 @@ k_colsum3(const float* __restrict__ a, const float* __restrict__ b, const float*
 // X[b][0:feat] = z, X[b][feat:feat+A] = act (optional), rest 0   (bf16 MLP input rows)
 __global__ void k_pack_x(const float* __restrict__ z, const float* __restrict__ act, int B,
                          int feat, int A, bf16* __restrict__ X) {
+    pdl_grid_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * FP) return;
     const int b = i / FP, c = i % FP;
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(256)
 k_head_fwd(const bf16* __restrict__ H, int ldh, const float* __restrict__ W,
            const float* __restrict__ bias, int B, int hid, int No, float* __restrict__ out,
            long long bsH, long long bsW, long long bsOut) {
+    pdl_grid_sync();
     H += blockIdx.y * bsH; W += blockIdx.y * bsW; bias += blockIdx.y * bsW; out += blockIdx.y * bsOut;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(256)
 k_head_bwd(const float* __restrict__ dOut, const float* __restrict__ W,
            const bf16* __restrict__ H, int B, int hid, int No, bf16* __restrict__ dH,
            long long bsDOut, long long bsW, long long bsH, long long bsDH) {
+    pdl_grid_sync();
     dOut += blockIdx.y * bsDOut; W += blockIdx.y * bsW; H += blockIdx.y * bsH; dH += blockIdx.y * bsDH;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * hid) return;
@@ -185,6 +191,7 @@ k_head_bwd(const float* __restrict__ dOut, const float* __restrict__ W,
 __global__ void __launch_bounds__(512)
 k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, int hid, int No,
              float* __restrict__ dW, float* __restrict__ db, long long bsDOut, long long bsH, long long bsW) {
+    pdl_grid_sync();
     dOut += blockIdx.y * bsDOut; H += blockIdx.y * bsH; dW += blockIdx.y * bsW; db += blockIdx.y * bsW;
     __shared__ float red[16][4][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -225,6 +232,7 @@ k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, 
 __global__ void __launch_bounds__(512)
 k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ db, long long bsDH,
               long long bsDb) {
+    pdl_grid_sync();
     dH += blockIdx.y * bsDH; db += blockIdx.y * bsDb;
     __shared__ float red[16][64];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -259,6 +267,7 @@ __global__ void k_policy_fwd(const float* __restrict__ t, const float* __restric
                              float* __restrict__ mu_out, float* __restrict__ pi_out,
                              float* __restrict__ log_pi_out, float* __restrict__ ls_out,
                              float* __restrict__ noise_out) {
+    pdl_grid_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float n[4] = {0.f, 0.f, 0.f, 0.f};
@@ -297,6 +306,7 @@ __global__ void k_policy_bwd(const float* __restrict__ dx1, const float* __restr
                              const float* __restrict__ noise, const float* __restrict__ pi_in,
                              const float* __restrict__ ls_in, int B, int A, float ls_min,
                              float ls_max, float* __restrict__ dt) {
+    pdl_grid_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float glp = *glogpi_ptr;
@@ -335,6 +345,7 @@ k_critic_loss(const float* __restrict__ tq1, const float* __restrict__ tq2,
               float discount, const float* __restrict__ q1, const float* __restrict__ q2, int B,
               float grad_scale, float* __restrict__ target_q, float* __restrict__ dq1,
               float* __restrict__ dq2, float* __restrict__ metrics) {
+    pdl_grid_sync();
     __shared__ float s_red[8];
     const float alpha = (float)exp(*log_alpha);
     float l = 0.f, rs = 0.f;
@@ -362,6 +373,7 @@ k_actor_loss(const float* __restrict__ log_pi, const float* __restrict__ q1,
              const double* __restrict__ log_alpha, float target_entropy, float grad_scale,
              float* __restrict__ dq1, float* __restrict__ dq2, float* __restrict__ glogpi,
              double* __restrict__ g_log_alpha, float* __restrict__ metrics) {
+    pdl_grid_sync();
     __shared__ float s_red[8];
     const double alpha_d = exp(*log_alpha);
     const float alpha = (float)alpha_d;
@@ -391,6 +403,7 @@ k_actor_loss(const float* __restrict__ log_pi, const float* __restrict__ q1,
 // out = a + b over n floats (sums the two Q heads' input gradients)
 __global__ void k_add2(const float* __restrict__ a, const float* __restrict__ b, long long n,
                        float* __restrict__ out) {
+    pdl_grid_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + b[i];
 }
@@ -413,7 +426,7 @@ extern "C" int curla_ln_fwd_x(const float* partial, int nsplit, long long split_
                               int feat, int apply_tanh, float* x_out, float* z_out,
                               const float* act, int A, void* X_out, cudaStream_t stream) {
     CURLA_CHECK(feat <= FP && feat + A <= FP, "ln_fwd: feature_dim (+ action_dim) > 64 unsupported");
-    k_ln_fwd<<<B, 256, 0, stream>>>(partial, nsplit, split_stride, bias, gamma, beta, B, feat, apply_tanh,
+    launch_k(k_ln_fwd, dim3(B), dim3(256), 0, stream, partial, nsplit, split_stride, bias, gamma, beta, B, feat, apply_tanh,
                                     x_out, z_out, act, A, (bf16*)X_out);
     return check_launch("ln_fwd");
 }
@@ -425,16 +438,16 @@ extern "C" int curla_ln_bwd(const float* dz_a, const float* dz_b, const float* x
                             cudaStream_t stream) {
     float* dzsum = scratch;
     float* dzx = scratch + (long long)B * FP;
-    k_ln_bwd<<<cdiv(B, 8), 256, 0, stream>>>(dz_a, dz_b, x_in, gamma, B, feat, dx_f32,
+    launch_k(k_ln_bwd, dim3(cdiv(B, 8)), dim3(256), 0, stream, dz_a, dz_b, x_in, gamma, B, feat, dx_f32,
                                              (bf16*)dx_bf16, dzsum, dzx);
     if (check_launch("ln_bwd")) return -1;
-    k_colsum3<<<1, 1024, 0, stream>>>(dzx, dzsum, dx_f32, B, feat, dgamma, dbeta, dbias_fc);
+    launch_k(k_colsum3, dim3(1), dim3(1024), 0, stream, dzx, dzsum, dx_f32, B, feat, dgamma, dbeta, dbias_fc);
     return check_launch("ln_bwd_params");
 }
 
 extern "C" int curla_pack_x(const float* z, const float* act, int B, int feat, int A, void* X,
                             cudaStream_t stream) {
-    k_pack_x<<<cdiv((long long)B * FP, 256), 256, 0, stream>>>(z, act, B, feat, A, (bf16*)X);
+    launch_k(k_pack_x, dim3(cdiv((long long)B * FP, 256)), dim3(256), 0, stream, z, act, B, feat, A, (bf16*)X);
     return check_launch("pack_x");
 }
 
@@ -445,7 +458,7 @@ extern "C" int curla_head_fwd_batched(const void* H, int ldh, const float* W, co
                                       int hid, int No, float* out, int nb, long long bsH, long long bsP,
                                       long long bsOut, cudaStream_t stream) {
     CURLA_CHECK(No <= 4 && hid % 2 == 0, "head_fwd: No<=4, even hidden");
-    k_head_fwd<<<dim3(cdiv(B, 8), nb), 256, 0, stream>>>((const bf16*)H, ldh, W, bias, B, hid, No, out, bsH, bsP, bsOut);
+    launch_k(k_head_fwd, dim3(cdiv(B, 8), nb), dim3(256), 0, stream, (const bf16*)H, ldh, W, bias, B, hid, No, out, bsH, bsP, bsOut);
     return check_launch("head_fwd");
 }
 extern "C" int curla_head_fwd(const void* H, int ldh, const float* W, const float* bias, int B,
@@ -456,7 +469,7 @@ extern "C" int curla_head_fwd(const void* H, int ldh, const float* W, const floa
 extern "C" int curla_head_bwd_batched(const float* dOut, const float* W, const void* H, int B, int hid,
                                       int No, void* dH, int nb, long long bsDOut, long long bsP,
                                       long long bsH, long long bsDH, cudaStream_t stream) {
-    k_head_bwd<<<dim3(cdiv((long long)B * hid, 256), nb), 256, 0, stream>>>(dOut, W, (const bf16*)H, B, hid, No,
+    launch_k(k_head_bwd, dim3(cdiv((long long)B * hid, 256), nb), dim3(256), 0, stream, dOut, W, (const bf16*)H, B, hid, No,
                                                                          (bf16*)dH, bsDOut, bsP, bsH, bsDH);
     return check_launch("head_bwd");
 }
@@ -468,7 +481,7 @@ extern "C" int curla_head_bwd(const float* dOut, const float* W, const void* H, 
 extern "C" int curla_head_wgrad_batched(const float* dOut, const void* H, int B, int hid, int No,
                                         float* dW, float* db, int nb, long long bsDOut, long long bsH,
                                         long long bsP, cudaStream_t stream) {
-    k_head_wgrad<<<dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream>>>(dOut, (const bf16*)H, B, hid, No, dW, db,
+    launch_k(k_head_wgrad, dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream, dOut, (const bf16*)H, B, hid, No, dW, db,
                                                                       bsDOut, bsH, bsP);
     return check_launch("head_wgrad");
 }
@@ -479,7 +492,7 @@ extern "C" int curla_head_wgrad(const float* dOut, const void* H, int B, int hid
 
 extern "C" int curla_colsum_bf16_batched(const void* dH, int B, int hid, float* db, int nb, long long bsDH,
                                          long long bsP, cudaStream_t stream) {
-    k_colsum_bf16<<<dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream>>>((const bf16*)dH, B, hid, db, bsDH, bsP);
+    launch_k(k_colsum_bf16, dim3(cdiv(hid, 64), nb), dim3(32, 16), 0, stream, (const bf16*)dH, B, hid, db, bsDH, bsP);
     return check_launch("colsum_bf16");
 }
 extern "C" int curla_colsum_bf16(const void* dH, int B, int hid, float* db, cudaStream_t stream) {
@@ -492,7 +505,7 @@ extern "C" int curla_policy_fwd(const float* t, const float* noise_in, unsigned 
                                 float* pi, float* log_pi, float* ls, float* noise_out,
                                 cudaStream_t stream) {
     CURLA_CHECK(A <= 4, "policy_fwd: action dim > 4 unsupported");
-    k_policy_fwd<<<cdiv(B, 128), 128, 0, stream>>>(t, noise_in, seed, offset, B, A, ls_min, ls_max,
+    launch_k(k_policy_fwd, dim3(cdiv(B, 128)), dim3(128), 0, stream, t, noise_in, seed, offset, B, A, ls_min, ls_max,
                                                    compute_pi, compute_log_pi, mu, pi, log_pi, ls,
                                                    noise_out);
     return check_launch("policy_fwd");
@@ -502,7 +515,7 @@ extern "C" int curla_policy_bwd(const float* dx1, const float* dx2, int feat, co
                                 const float* t, const float* noise, const float* pi,
                                 const float* ls, int B, int A, float ls_min, float ls_max,
                                 float* dt, cudaStream_t stream) {
-    k_policy_bwd<<<cdiv(B, 128), 128, 0, stream>>>(dx1, dx2, feat, glogpi, t, noise, pi, ls, B, A,
+    launch_k(k_policy_bwd, dim3(cdiv(B, 128)), dim3(128), 0, stream, dx1, dx2, feat, glogpi, t, noise, pi, ls, B, A,
                                                    ls_min, ls_max, dt);
     return check_launch("policy_bwd");
 }
@@ -512,7 +525,7 @@ extern "C" int curla_critic_loss(const float* tq1, const float* tq2, const float
                                  const double* log_alpha, float discount, const float* q1,
                                  const float* q2, int B, float grad_scale, float* target_q,
                                  float* dq1, float* dq2, float* metrics, cudaStream_t stream) {
-    k_critic_loss<<<1, 256, 0, stream>>>(tq1, tq2, logpi_next, reward, not_done, log_alpha, discount,
+    launch_k(k_critic_loss, dim3(1), dim3(256), 0, stream, tq1, tq2, logpi_next, reward, not_done, log_alpha, discount,
                                          q1, q2, B, grad_scale, target_q, dq1, dq2, metrics);
     return check_launch("critic_loss");
 }
@@ -522,13 +535,13 @@ extern "C" int curla_actor_loss(const float* log_pi, const float* q1, const floa
                                 float target_entropy, float grad_scale, float* dq1, float* dq2,
                                 float* glogpi, double* g_log_alpha, float* metrics,
                                 cudaStream_t stream) {
-    k_actor_loss<<<1, 256, 0, stream>>>(log_pi, q1, q2, ls, B, A, log_alpha, target_entropy,
+    launch_k(k_actor_loss, dim3(1), dim3(256), 0, stream, log_pi, q1, q2, ls, B, A, log_alpha, target_entropy,
                                         grad_scale, dq1, dq2, glogpi, g_log_alpha, metrics);
     return check_launch("actor_loss");
 }
 
 extern "C" int curla_add2(const float* a, const float* b, long long n, float* out,
                           cudaStream_t stream) {
-    k_add2<<<cdiv(n, 256), 256, 0, stream>>>(a, b, n, out);
+    launch_k(k_add2, dim3(cdiv(n, 256)), dim3(256), 0, stream, a, b, n, out);
     return check_launch("add2");
 }

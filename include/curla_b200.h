@@ -73,6 +73,8 @@ int curla_conv_fwd(const void* in, long long in_sstride, const void* wts, const 
 int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts, const void* x,
                      void* dx, long long dx_sstride, int B, int pitch, int S, int Hv, int Wv,
                      curla_stream_t stream);
+/* timing experiments (CURLA_TC_DEBUG=64): per-CTA cycle counters of the conv pipeline roles */
+int curla_conv_debug_read(long long* out, int n);
 long long curla_conv_wgrad_workspace_floats(int first_layer);
 int curla_conv_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
                      float* workspace, float* dW, float* db, float scale, int B, int pitch,

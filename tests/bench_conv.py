@@ -49,3 +49,14 @@ ts.sort()
 print('layer %d %s debug=%s stages=%s: median %.1f us  min %.1f us' % (
     layer, 'dgrad' if dgrad else 'fwd', os.environ.get('CURLA_TC_DEBUG', '0'), os.environ.get('CURLA_TC_STAGES', 'max'),
     ts[len(ts) // 2], ts[0]))
+
+if int(os.environ.get('CURLA_TC_DEBUG', '0')) & 64:
+    import ctypes as C
+    import numpy as np
+    buf = (C.c_longlong * (148 * 8))()
+    _lib.call('curla_conv_debug_read', buf, 148)
+    a = np.array(list(buf), dtype=np.int64).reshape(148, 8)
+    names = ['mma wait tempty', 'mma wait full', 'mma issue+sync', 'producer wait empty', 'mma loop total', 'tiles',
+             'epi w0 wait tfull', 'epi w0 busy']
+    for i, nme in enumerate(names):
+        print('   %-22s mean %9.0f  min %9d  max %9d clk' % (nme, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
