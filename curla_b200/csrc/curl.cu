@@ -19,7 +19,7 @@ namespace curla {
 __global__ void __launch_bounds__(256)
 k_sgemm_strided(const float* __restrict__ A, long long sam, long long sak,
                 const float* __restrict__ Bm, long long sbk, long long sbn,
-                float* __restrict__ C, long long ldc, int M, int N, int K) {
+                float* __restrict__ C, long long ldc, float* __restrict__ Ct, long long ldct, int M, int N, int K) {
     pdl_grid_sync();
     __shared__ float sA[32][33], sB[32][33];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -52,7 +52,10 @@ k_sgemm_strided(const float* __restrict__ A, long long sam, long long sak,
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int m = m0 + ty + i * 16, n = n0 + tx + j * 16;
-            if (m < M && n < N) C[m * ldc + n] = acc[i][j];
+            if (m < M && n < N) {
+                C[m * ldc + n] = acc[i][j];
+                if (Ct) Ct[n * ldct + m] = acc[i][j];
+            }
         }
 }
 
@@ -65,7 +68,8 @@ k_sgemm_strided(const float* __restrict__ A, long long sam, long long sak,
 // re-associated so that no [Bg][feat] intermediate and no strided pass over dl is needed).
 template <int R>
 __global__ void __launch_bounds__(256)
-k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const float* __restrict__ z_pos,
+k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const float* __restrict__ Ut,
+            const float* __restrict__ z_pos,
             int B, int Bg, int label0, float grad_scale, float* __restrict__ row_loss,
             float* __restrict__ dz_a, float* __restrict__ V, float* __restrict__ logits_copy) {
     pdl_grid_sync();
@@ -81,23 +85,42 @@ k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const fl
         s_za[t] = i < B ? z_a[(long long)i * 64 + (t & 63)] : 0.f;
     }
     __syncthreads();
-    // ---- logits[r][j] = z_a[i0+r] . U[j]
-    for (int j = tid; j < Bg; j += 256) {
-        float acc[R];
+    // ---- logits[r][j] = z_a[i0+r] . U[j].  Ut[k][j] makes consecutive lanes read consecutive j;
+    // a thread owns 4 consecutive j (one 16-byte load per k) and one half of the k range, so each
+    // shared-memory broadcast of z_a feeds four FMAs.
+    {
+        const int kh = tid >> 7;                                // k in [32*kh, 32*kh + 32)
+        const bool vec = (Bg & 3) == 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            // pass 0: half 0 stores its partial sums; pass 1: half 1 adds its own (fixed order => deterministic)
+            if (kh == pass)
+                for (int j4 = (tid & 127) * 4; j4 < Bg; j4 += 512) {
+                    float acc[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-        const float4* u4 = reinterpret_cast<const float4*>(U + (long long)j * 64);
-#pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
-            const float4 u = u4[k];
+                    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+#pragma unroll 8
+                    for (int k = kh * 32; k < kh * 32 + 32; ++k) {
+                        float4 u;
+                        const float* up = Ut + (long long)k * Bg + j4;
+                        if (vec) u = *reinterpret_cast<const float4*>(up);
+                        else { u.x = up[0]; u.y = j4 + 1 < Bg ? up[1] : 0.f; u.z = j4 + 2 < Bg ? up[2] : 0.f; u.w = j4 + 3 < Bg ? up[3] : 0.f; }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 a = *reinterpret_cast<const float4*>(s_za + r * 64 + k * 4);
-                acc[r] += a.x * u.x + a.y * u.y + a.z * u.z + a.w * u.w;
-            }
+                        for (int r = 0; r < R; ++r) {
+                            const float a = s_za[r * 64 + k];
+                            acc[r][0] += a * u.x; acc[r][1] += a * u.y; acc[r][2] += a * u.z; acc[r][3] += a * u.w;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (j4 + e < Bg) {
+                                float* d = s_log + (size_t)r * BgP + j4 + e;
+                                *d = pass ? *d + acc[r][e] : acc[r][e];
+                            }
+                }
+            __syncthreads();
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) s_log[(size_t)r * BgP + j] = acc[r];
     }
     __syncthreads();
     if (logits_copy)
@@ -128,6 +151,7 @@ k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const fl
     float dz[R], vv[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { dz[r] = 0.f; vv[r] = 0.f; }
+#pragma unroll 8
     for (int j = q; j < Bg; j += 4) {
         const float u = U[(long long)j * 64 + a], zp = z_pos[(long long)j * 64 + a];
 #pragma unroll
@@ -162,6 +186,7 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
     __shared__ float s_l[8];
     const int a = blockIdx.x, b = threadIdx.x & 63, q = threadIdx.x >> 6;
     float s = 0.f;
+#pragma unroll 8
     for (int i = q; i < B; i += 4) s += z_a[(long long)i * 64 + a] * V[(long long)i * 64 + b];
     s_red[q][b] = s;
     __syncthreads();
@@ -181,7 +206,7 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
 }
 
 template <int R>
-static int launch_curl_rows(const float* z_a, const float* U, const float* z_pos, int B, int Bg, int label0,
+static int launch_curl_rows(const float* z_a, const float* U, const float* Ut, const float* z_pos, int B, int Bg, int label0,
                             float grad_scale, float* row_loss, float* dz_a, float* V, float* logits_copy,
                             cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)R * ((Bg + 3) & ~3) + R * 64 + 8 * R * 64);
@@ -190,14 +215,14 @@ static int launch_curl_rows(const float* z_a, const float* U, const float* z_pos
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error("curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e)); return -1; }
     }
-    launch_k(kern, dim3(cdiv(B, R)), dim3(256), smem, st, z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy);
+    launch_k(kern, dim3(cdiv(B, R)), dim3(256), smem, st, z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy);
     return check_launch("curl_rows");
 }
 
 static int sgemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk,
-                 long long sbn, float* C, long long ldc, int M, int N, int K, cudaStream_t st) {
+                 long long sbn, float* C, long long ldc, float* Ct, long long ldct, int M, int N, int K, cudaStream_t st) {
     dim3 grid(cdiv(N, 32), cdiv(M, 32));
-    launch_k(k_sgemm_strided, dim3(grid), dim3(256), 0, st, A, sam, sak, Bm, sbk, sbn, C, ldc, M, N, K);
+    launch_k(k_sgemm_strided, dim3(grid), dim3(256), 0, st, A, sam, sak, Bm, sbk, sbn, C, ldc, Ct, ldct, M, N, K);
     return check_launch("curl_sgemm");
 }
 
@@ -206,8 +231,8 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 using namespace curla;
 
 extern "C" long long curla_curl_workspace_floats(int B, int Bg) {
-    // U [Bg][64] + V [B][64] + row_loss [B]
-    return (long long)Bg * 64 + (long long)B * 64 + B;
+    // U [Bg][64] + Ut [64][Bg] + V [B][64] + row_loss [B]
+    return 2LL * Bg * 64 + (long long)B * 64 + B;
 }
 
 // z_a [B][64] (local rows), z_pos [Bg][64] (all ranks' keys), W [feat][feat].
@@ -219,10 +244,12 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
                                   float* logits_copy, cudaStream_t stream) {
     CURLA_CHECK(feat <= 64 && B >= 1 && Bg >= B && label0 >= 0 && label0 + B <= Bg, "curl: bad shape");
     float* U = workspace;
-    float* V = U + (long long)Bg * 64;
+    float* Ut = U + (long long)Bg * 64;
+    float* V = Ut + (long long)Bg * 64;
     float* row_loss = V + (long long)B * 64;
-    // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace)
-    if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Bg, feat, feat, stream)) return -1;
+    // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace),
+    // written in both orientations: U for the gradient pass, Ut for the coalesced logits pass
+    if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Ut, Bg, Bg, feat, feat, stream)) return -1;
     // rows per CTA: as many as keep the [R][Bg] logits block in shared memory, while leaving
     // at least ~one CTA per SM
     const size_t cap = 200 * 1024 / sizeof(float);
@@ -231,10 +258,10 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
     CURLA_CHECK((size_t)R * (Bg + 3) + 9 * R * 64 <= cap, "curl: global batch %d does not fit shared memory", Bg);
     int rc;
     switch (R) {
-        case 8: rc = launch_curl_rows<8>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
-        case 4: rc = launch_curl_rows<4>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
-        case 2: rc = launch_curl_rows<2>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
-        default: rc = launch_curl_rows<1>(z_a, U, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        case 8: rc = launch_curl_rows<8>(z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        case 4: rc = launch_curl_rows<4>(z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        case 2: rc = launch_curl_rows<2>(z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
+        default: rc = launch_curl_rows<1>(z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
     }
     if (rc) return -1;
     launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, V, row_loss, B, feat, dW, loss_out);

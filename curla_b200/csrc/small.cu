@@ -116,6 +116,7 @@ k_colsum3(const float* __restrict__ a, const float* __restrict__ b, const float*
     __shared__ float s[3][16][FP];
     const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
     float sa = 0.f, sb = 0.f, sc = 0.f;
+#pragma unroll 8
     for (int r = rg; r < B; r += 16) {
         const long long o = (long long)r * FP + col;
         sa += a[o]; sb += b[o]; sc += c[o];
@@ -156,11 +157,30 @@ k_head_fwd(const bf16* __restrict__ H, int ldh, const float* __restrict__ W,
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = lane * 2; j < hid; j += 64) {
-        const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(H + (long long)row * ldh + j));
+    const bf16* hrow = H + (long long)row * ldh;
+    if ((hid & 7) == 0 && (ldh & 7) == 0 && ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W)) & 15) == 0) {
+        // 8 hidden units (one 16-byte load of H, two of each W row) per lane per step; the steps of
+        // a row are independent, so the compiler keeps all of their loads in flight
+#pragma unroll 4
+        for (int j = lane * 8; j < hid; j += 256) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(hrow + j);
+            const float2 h0 = unpack_bf16x2(hv.x), h1 = unpack_bf16x2(hv.y), h2 = unpack_bf16x2(hv.z), h3 = unpack_bf16x2(hv.w);
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
-            if (o < No) acc[o] += h.x * W[o * hid + j] + h.y * W[o * hid + j + 1];
+            for (int o = 0; o < 4; ++o)
+                if (o < No) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(W + o * hid + j);
+                    const float4 w1 = *reinterpret_cast<const float4*>(W + o * hid + j + 4);
+                    acc[o] += h0.x * w0.x + h0.y * w0.y + h1.x * w0.z + h1.y * w0.w +
+                              h2.x * w1.x + h2.y * w1.y + h3.x * w1.z + h3.y * w1.w;
+                }
+        }
+    } else {
+        for (int j = lane * 2; j < hid; j += 64) {
+            const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(hrow + j));
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < No) acc[o] += h.x * W[o * hid + j] + h.y * W[o * hid + j + 1];
+        }
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o)
@@ -198,6 +218,7 @@ k_head_wgrad(const float* __restrict__ dOut, const bf16* __restrict__ H, int B, 
     const int j = (blockIdx.x * 32 + tx) * 2;
     float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     if (j < hid) {
+#pragma unroll 8
         for (int b = ty; b < B; b += 16) {
             const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(H + (long long)b * hid + j));
 #pragma unroll
@@ -239,6 +260,7 @@ k_colsum_bf16(const bf16* __restrict__ dH, int B, int hid, float* __restrict__ d
     const int j = (blockIdx.x * 32 + tx) * 2;
     float s0 = 0.f, s1 = 0.f;
     if (j < hid) {
+#pragma unroll 8
         for (int b = ty; b < B; b += 16) {
             const float2 h = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dH + (long long)b * hid + j));
             s0 += h.x; s1 += h.y;

@@ -439,6 +439,69 @@ class _Host(object):
         return getattr(self, '_noise_seed', 0x5eed)
 
 
+class _ActionGraph(object):
+    """The B=1 action path of train.py:418 / eval.py:78 (curl_sac.py:330-347) as ONE captured CUDA
+    graph with pinned-host input and output: H2D of the observation (+ policy noise), the fused
+    gather/center-crop -> space-to-depth kernel, the actor encoder (4 tcgen05 conv launches, fc
+    split-K GEMM, LayerNorm), the trunk + tanh-Gaussian head, D2H of (mu, pi).  One graph launch
+    and one stream sync per environment step instead of ~15 launches and three blocking copies.
+    The graph replays on the caller's current stream, so it is ordered after any update in flight
+    (it shares the engine's inference scratch buffers)."""
+
+    def __init__(self, agent, in_shape, in_dtype, top, left, sample):
+        eng = agent.engine
+        c = eng.cfg
+        dev = eng.device
+        A = c.action_dim
+        self.engine, self.A, self.sample = eng, A, sample
+        self.h_in = torch.empty(in_shape, dtype=in_dtype).pin_memory()
+        self.h_noise = torch.zeros((1, A), dtype=torch.float32).pin_memory()
+        self.h_out = torch.zeros((2, A), dtype=torch.float32).pin_memory()
+        self.d_in = torch.zeros(in_shape, dtype=in_dtype, device=dev)
+        self.d_noise = torch.zeros((1, A), dtype=torch.float32, device=dev)
+        self.d_out = torch.zeros((2, A), dtype=torch.float32, device=dev)     # row 0 = mu, row 1 = pi
+        self.d_ls = torch.zeros((1, A), dtype=torch.float32, device=dev)
+        self.d_z = torch.zeros((1, 64), dtype=torch.float32, device=dev)
+        self.idx = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.h1 = torch.full((1,), int(top), dtype=torch.int64, device=dev)
+        self.w1 = torch.full((1,), int(left), dtype=torch.int64, device=dev)
+        s2d = eng.t['s2d.next']
+        self.s2d, self.stride = s2d, (s2d.shape[0] // c.batch) * s2d.shape[1]
+        self._run()                                   # eager warm-up (function attributes, lazy loading)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run()
+
+    def _run(self):
+        eng = self.engine
+        c = eng.cfg
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self.d_noise.copy_(self.h_noise, non_blocking=True)
+        with torch.cuda.device(eng.device):
+            if self.d_in.dtype == torch.uint8:
+                _lib.call('curla_gather_crop_s2d', _lib.ptr(self.d_in), c.C, self.d_in.shape[1], self.d_in.shape[2],
+                          _lib.ptr(self.idx), _lib.ptr(self.h1), _lib.ptr(self.w1), 1, c.H, c.W, self.s2d.shape[1],
+                          self.stride, _lib.ptr(self.s2d), eng.stream())
+            else:
+                _lib.call('curla_f32_to_s2d', _lib.ptr(self.d_in), c.C, c.H, c.W, 1, self.s2d.shape[1], self.stride,
+                          _lib.ptr(self.s2d), eng.stream())
+            _lib.check(eng.lib.curla_agent_encode(eng.h, 0, _lib.ptr(self.s2d), 1, 0, _lib.ptr(self.d_z), eng.stream()),
+                       'encode')
+            _lib.check(eng.lib.curla_agent_actor_head(
+                eng.h, _lib.ptr(self.d_z), 1, _lib.ptr(self.d_noise), 0, 0, int(self.sample), 0, _lib.ptr(self.d_out[0]),
+                _lib.ptr(self.d_out[1]) if self.sample else None, None, _lib.ptr(self.d_ls), eng.stream()), 'actor_head')
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def __call__(self, obs):
+        np.copyto(self.h_in.numpy(), obs, casting='unsafe')
+        if self.sample:
+            torch.randn(self.h_noise.shape, out=self.h_noise)       # fresh policy noise (curl_sac.py:97)
+        self.graph.replay()
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return self.h_out[1 if self.sample else 0].numpy().copy()
+
+
 class _StandaloneEncoderHost(_Host):
     """Private engine behind a bare CNNEncoder(...) (encoder.py:132-169 style use)."""
 
@@ -535,6 +598,7 @@ class CurlSacAgent(_Host):
         critic0 = _InitCritic(obs_shape, action_shape, hidden_dim, encoder_feature_dim, num_layers, num_filters)
         _InitCritic(obs_shape, action_shape, hidden_dim, encoder_feature_dim, num_layers, num_filters)  # target: RNG parity
         self.engine = None
+        self._act_graphs = {}
         self._make_engine(batch=1, frame_hw=self.image_shape)
 
         self.actor = Actor(self, obs_shape, action_shape, hidden_dim, encoder_feature_dim, actor_log_std_min,
@@ -576,6 +640,7 @@ class CurlSacAgent(_Host):
                 pass
             eng._steps = getattr(old, '_steps', None)
         self.engine = eng
+        self._engine_gen = getattr(self, '_engine_gen', 0) + 1      # invalidates captured action graphs
         if self.world > 1:
             self._init_comm()
 
@@ -607,19 +672,50 @@ class CurlSacAgent(_Host):
     def alpha(self):
         return self.log_alpha.exp()
 
+    def _act(self, obs, sample, crop):
+        """Graph-captured B=1 action path.  uint8 observations (what FrameStack yields) go to the device
+        as bytes and are center-cropped by the gather kernel; other dtypes take the float route."""
+        obs = np.asarray(obs)
+        if crop and tuple(obs.shape[-2:]) != self.image_shape:
+            if obs.dtype == np.uint8:
+                top, left = (obs.shape[-2] - self.image_shape[0]) // 2, (obs.shape[-1] - self.image_shape[1]) // 2
+            else:
+                obs, top, left = self.augmentor.evaluation_augmentation(obs), 0, 0      # augmentations.py:37-43
+        else:
+            top, left = 0, 0
+        if obs.dtype != np.uint8:
+            obs = obs.astype(np.float32, copy=False)
+        assert obs.shape[0] == self.obs_shape[0] and obs.shape[-2] - top >= self.image_shape[0] and \
+            obs.shape[-1] - left >= self.image_shape[1], 'observation %s does not fit the encoder input %s' % (
+                obs.shape, self.obs_shape)
+        key = (self._engine_gen, obs.shape, obs.dtype.str, top, left, bool(sample))
+        g = self._act_graphs.get(key)
+        if g is None:
+            for k in [k for k in self._act_graphs if k[0] != self._engine_gen]:
+                del self._act_graphs[k]                  # engine re-created: its buffers are gone
+            in_dtype = torch.uint8 if obs.dtype == np.uint8 else torch.float32
+            g = self._act_graphs[key] = _ActionGraph(self, tuple(obs.shape), in_dtype, top, left, sample)
+        return g(obs)
+
     def select_action(self, obs):
-        with torch.no_grad():
-            obs = torch.FloatTensor(np.ascontiguousarray(obs)).to(self.device).unsqueeze(0)
-            mu, _, _, _ = self.actor(obs, compute_pi=False, compute_log_pi=False)
-            return mu.cpu().data.numpy().flatten()
+        """curl_sac.py:330-336: tanh(mu) of one observation (already encoder-sized)."""
+        if os.environ.get('CURLA_NO_GRAPH') == '1':
+            with torch.no_grad():
+                obs = torch.FloatTensor(np.ascontiguousarray(obs)).to(self.device).unsqueeze(0)
+                mu, _, _, _ = self.actor(obs, compute_pi=False, compute_log_pi=False)
+                return mu.cpu().data.numpy().flatten()
+        return self._act(obs, sample=False, crop=False)
 
     def sample_action(self, obs):
-        if obs.shape[-2:] != self.image_shape:
-            obs = self.augmentor.evaluation_augmentation(obs)
-        with torch.no_grad():
-            obs = torch.FloatTensor(np.ascontiguousarray(obs)).to(self.device).unsqueeze(0)
-            mu, pi, _, _ = self.actor(obs, compute_log_pi=False)
-            return pi.cpu().data.numpy().flatten()
+        """curl_sac.py:338-347: center-crop if needed, then a sample of the tanh-Gaussian policy."""
+        if os.environ.get('CURLA_NO_GRAPH') == '1':
+            if obs.shape[-2:] != self.image_shape:
+                obs = self.augmentor.evaluation_augmentation(obs)
+            with torch.no_grad():
+                obs = torch.FloatTensor(np.ascontiguousarray(obs)).to(self.device).unsqueeze(0)
+                mu, pi, _, _ = self.actor(obs, compute_log_pi=False)
+                return pi.cpu().data.numpy().flatten()
+        return self._act(obs, sample=True, crop=True)
 
     def update(self, replay_buffer, L, step, only_cpc=False, _phases=0):
         """One whole SAC+CURL update (curl_sac.py:426-451) as a single engine call.

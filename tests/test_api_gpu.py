@@ -164,6 +164,35 @@ def test_batched_latent_extraction_matches_per_observation_oracle():
     assert agent.engine.cfg.batch == n
 
 
+def test_graph_action_path_equals_eager_path(monkeypatch):
+    """The captured-graph B=1 path (uint8 frame in, center crop on the device) returns what the
+    eager module-call path returns for the same observation."""
+    cfg, run, agent, rb = _agent('crop90x160')
+    rs = np.random.RandomState(4)
+    for _ in range(3):
+        frame = rs.randint(0, 256, size=(9, 90, 160)).astype(np.uint8)
+        a_graph = agent.select_action(frame[:, 7:83, 12:147])                 # uint8, encoder-sized
+        a_f32 = agent.select_action(frame[:, 7:83, 12:147].astype(np.float32))
+        monkeypatch.setenv('CURLA_NO_GRAPH', '1')
+        a_eager = agent.select_action(frame[:, 7:83, 12:147].astype(np.float32))
+        monkeypatch.delenv('CURLA_NO_GRAPH')
+        assert np.array_equal(a_graph, a_f32) and np.array_equal(a_graph, a_eager)
+    # the cropping route: sample_action on a stored-size frame with zero noise == select_action on its center crop
+    frame = rs.randint(0, 256, size=(9, 90, 160)).astype(np.uint8)
+    import torch as _t
+    real_randn = _t.randn
+    monkeypatch.setattr(_t, 'randn', lambda *a, out=None, **k: out.zero_() if out is not None else real_randn(*a, **k))
+    s0 = agent.sample_action(frame)
+    monkeypatch.setattr(_t, 'randn', real_randn)
+    assert np.allclose(s0, agent.select_action(frame[:, 7:83, 12:147]), atol=1e-6)
+    # graphs survive an engine re-creation (first update changes the engine batch)
+    agent.update(rb, T.NullLogger(), 0)
+    a1 = agent.select_action(frame[:, 7:83, 12:147])
+    monkeypatch.setenv('CURLA_NO_GRAPH', '1')
+    a2 = agent.select_action(frame[:, 7:83, 12:147].astype(np.float32))
+    assert np.array_equal(a1, a2)
+
+
 def test_sample_action_is_stochastic_select_is_not():
     cfg, run, agent, rb = _agent('crop90x160')
     frame = np.random.RandomState(0).randint(0, 256, size=(9, 90, 160)).astype(np.uint8)
