@@ -335,7 +335,7 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
     { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
     g.plane_bytes = g.plane_rows * 16 + ((g.debug & 16) ? 64 : 0);
     const size_t slab = (size_t)CH * g.plane_bytes;
-    const size_t budget = 200 * 1024;
+    const size_t budget = 190 * 1024;      // leaves room for one 32 KB GEMM CTA of the side stream next to a conv CTA
     int stages = (int)((budget - fixed) / slab);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { set_last_error("conv_tc: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }

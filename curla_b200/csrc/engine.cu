@@ -137,9 +137,12 @@ struct curla_agent {
     float* P; bf16* Sh; float* G; float* Ad; uint8_t* Wk;
     bool bound;
     // workspace pointers
-    bf16 *s2d_obs, *s2d_next, *s2d_pos, *actA[4], *actB[4], *dact[4];
+    bf16 *s2d_obs, *s2d_next, *s2d_pos, *actA[4], *actB[4], *actC[4], *dact[4];
     long long act_sstride, s2d_sstride;
-    float *fc_partial, *wgrad_ws, *curl_ws, *ln_scratch;
+    float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch;
+    // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
+    // there while the main stream already runs the next pass's conv stack
+    cudaStream_t side; cudaEvent_t ev[4]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     long long wgrad_ws_stride;
     TailBuf t_p1, t_p2, t_p3, t_p4, t_p5, t_p7;
     MlpBuf m_p1, m_p2q[2], m_p3q[2], m_p4, m_p5q[2];
@@ -343,6 +346,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     for (int i = 0; i < 4; ++i) {
         a->actA[i] = b.w<bf16>("actA." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
         a->actB[i] = b.w<bf16>("actB." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
+        a->actC[i] = b.w<bf16>("actC." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
         a->dact[i] = b.w<bf16>("dact." + std::to_string(i), DT_BF16, {R, 32}, PADR * 32, PADR * 32);
     }
     {   // split-K for the fc forward: ~4 CTAs of 64x64 tiles per SM (bytes in flight, not FLOPs, bound it)
@@ -353,6 +357,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
         a->fc_splits = curla_gemm_effective_splits(a->Kfc, sp);
     }
     a->fc_partial = b.w<float>("fc_partial", DT_F32, {a->fc_splits, B, 64});
+    a->fc_partial2 = b.w<float>("fc_partial2", DT_F32, {a->fc_splits, B, 64});
     {
         long long w1 = curla_conv_wgrad_workspace_floats(1), w2 = curla_conv_wgrad_workspace_floats(0);
         a->wgrad_ws = b.w<float>("wgrad_ws", DT_F32, {4, w1 > w2 ? w1 : w2});   // one slice per conv layer
@@ -423,10 +428,17 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
     a->last_launches = 0;
     a->nccl_lib = nullptr; a->comm = nullptr;
+    a->side = nullptr; a->side_state = 0;
     return a;
 }
 
-extern "C" void curla_agent_destroy(curla_agent* a) { delete a; }
+extern "C" void curla_agent_destroy(curla_agent* a) {
+    if (a && a->side_state == 1) {
+        for (auto& e : a->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(a->side);
+    }
+    delete a;
+}
 extern "C" long long curla_agent_arena_bytes(const curla_agent* a, int which) {
     return (which >= 0 && which < CURLA_ARENA_COUNT) ? a->arena_bytes[which] : -1;
 }
@@ -451,8 +463,8 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
     const uintptr_t base = (uintptr_t)a->Wk;
     auto rb = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(base + (uintptr_t)p); };
     rb(a->s2d_obs); rb(a->s2d_next); rb(a->s2d_pos);
-    for (int i = 0; i < 4; ++i) { rb(a->actA[i]); rb(a->actB[i]); rb(a->dact[i]); }
-    rb(a->fc_partial); rb(a->wgrad_ws); rb(a->curl_ws); rb(a->ln_scratch);
+    for (int i = 0; i < 4; ++i) { rb(a->actA[i]); rb(a->actB[i]); rb(a->actC[i]); rb(a->dact[i]); }
+    rb(a->fc_partial); rb(a->fc_partial2); rb(a->wgrad_ws); rb(a->curl_ws); rb(a->ln_scratch);
     TailBuf* tb[] = {&a->t_p1, &a->t_p2, &a->t_p3, &a->t_p4, &a->t_p5, &a->t_p7};
     for (auto t : tb) { rb(t->fc_out); rb(t->z); }
     MlpBuf* mb[] = {&a->m_p1, &a->m_p2q[0], &a->m_p2q[1], &a->m_p3q[0], &a->m_p3q[1], &a->m_p4, &a->m_p5q[0], &a->m_p5q[1]};
@@ -495,15 +507,16 @@ struct Run {
     }
     // fc (split-K) + bias + LayerNorm
     void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
-              const float* act = nullptr, bf16* X_out = nullptr) {
+              const float* act = nullptr, bf16* X_out = nullptr, float* partial = nullptr) {
         if (!ok()) return;
+        if (!partial) partial = a->fc_partial;
         set_launch_tag("gemm_fc_fwd");
-        chk(curla_gemm_bf16_seg(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, a->fc_partial, 64, B, 64, a->Kfc,
+        chk(curla_gemm_bf16_seg(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, partial, 64, B, 64, a->Kfc,
                                 3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f,
                                 a->Kfc / 4, (long long)a->S * 8, 1, st));
         set_launch_tag(nullptr);
         if (!ok()) return;
-        chk(curla_ln_fwd_x(a->fc_partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
+        chk(curla_ln_fwd_x(partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
                            a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, act, act ? a->cfg.action_dim : 0, X_out, st));
     }
     // nb MLPs of one shape in one launch each (nb = 2: the critic's Q1 || Q2 on the shared input
@@ -703,6 +716,22 @@ extern "C" int curla_profile_read(char* buf, int cap) {
     return n;
 }
 
+// Side stream (created lazily: needs the CUDA context of the caller's device).  CURLA_STREAMS=1
+// keeps everything on the caller's stream; so does the CUDA-event profiler (per-kernel times
+// are only meaningful when launches are serialised).
+static cudaStream_t side_stream(curla_agent* a, cudaStream_t st) {
+    if (a->side_state == 0) {
+        const char* e = getenv("CURLA_STREAMS");
+        a->side_state = -1;
+        if (!(e && e[0] == '1') && cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking) == cudaSuccess) {
+            bool okev = true;
+            for (auto& ev : a->ev) okev = okev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+            if (okev) a->side_state = 1;
+        }
+    }
+    return (a->side_state == 1 && !g_prof.on) ? a->side : st;
+}
+
 // ================================================================== the update
 extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
     CURLA_CHECK(a->bound, "agent not bound");
@@ -740,20 +769,33 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     bool have_p5 = false;
     if (do_critic) {
         // ---------------- update_critic (curl_sac.py:349-371)
+        // The tail of each pass (fc split-K GEMM, LayerNorm, MLP heads: latency-bound kernels that
+        // fill a fraction of the GPU) runs on the side stream while the main stream already runs
+        // the next pass's conv stack; fork/join with events, no host synchronisation.
+        const cudaStream_t ss = side_stream(a, st);
+        const bool forked = ss != st;
+        Run r2{a, ss};
+        auto fork = [&](int k) { if (forked) { cudaEventRecord(a->ev[k], st); cudaStreamWaitEvent(ss, a->ev[k], 0); } };
         // F1: actor(next_obs) -> a', log_pi'
         r.conv_stack(a->s2d_next, a->enc_critic, a->s_critic, a->actB);
-        r.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X);
-        r.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
-        if (r.ok()) r.chk(curla_policy_fwd(a->t_out1, u->noise_next, u->seed, u->offset * 2, B, A, (float)c.log_std_min,
-                                           (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, st));
+        fork(0);
+        r2.rc = r.rc;
+        r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
+        r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
+        if (r2.ok()) r2.chk(curla_policy_fwd(a->t_out1, u->noise_next, u->seed, u->offset * 2, B, A, (float)c.log_std_min,
+                                             (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, ss));
         // F2: critic_target(next_obs, a')
-        r.conv_stack(a->s2d_next, a->enc_target, a->s_target, a->actB);
-        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X);
-        r.mlp_fwd_n(a->m_p2q[0].X, a->q_target, a->sq_target, a->m_p2q, 2, B);
+        bf16* const* act2 = forked ? a->actC : a->actB;      // F1's tail may still be reading actB[3]
+        r.conv_stack(a->s2d_next, a->enc_target, a->s_target, act2);
+        fork(1);
+        r2.tail(act2[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X, a->fc_partial2);
+        r2.mlp_fwd_n(a->m_p2q[0].X, a->q_target, a->sq_target, a->m_p2q, 2, B);
         // F3: critic(obs, action)
         r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
         r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p3, B, 0, a->act_b, a->m_p3q[0].X);
         r.mlp_fwd_n(a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, B);
+        if (forked) { cudaEventRecord(a->ev[2], ss); cudaStreamWaitEvent(st, a->ev[2], 0); }
+        r.chk(r2.rc);
         if (r.ok()) r.chk(curla_critic_loss(a->tq[0], a->tq[1], a->logpi_next, a->rew_b, a->nd_b, a->log_alpha, (float)c.discount,
                                             a->q3[0], a->q3[1], B, gs, a->target_q, a->dq[0], a->dq[1], a->metrics, st));
         // backward
@@ -806,13 +848,21 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
 
     if (do_cpc) {
         // ---------------- update_cpc (curl_sac.py:406-423)
-        if (!have_p5) {   // F6: anchor through the current critic encoder
+        const cudaStream_t ss = side_stream(a, st);
+        const bool forked = ss != st && !have_p5;
+        if (!have_p5) {   // F6: anchor through the current critic encoder (its tail on the side stream)
             r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
-            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B);
+            Run r2{a, forked ? ss : st};
+            r2.rc = r.rc;
+            if (forked) { cudaEventRecord(a->ev[3], st); cudaStreamWaitEvent(ss, a->ev[3], 0); }
+            r2.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, nullptr, nullptr, forked ? a->fc_partial2 : nullptr);
+            if (forked) cudaEventRecord(a->ev[2], ss);
+            r.chk(r2.rc);
         }
         // F7: keys through the (post-EMA) target encoder, no grad
         r.conv_stack(s2d_pos, a->enc_target, a->s_target, a->actB);
         r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
+        if (forked) cudaStreamWaitEvent(st, a->ev[2], 0);
         const float* zpos = a->t_p7.z;
         if (c.world > 1 && r.ok()) {
             CURLA_CHECK(a->comm, "update: world>1 but no communicator");
