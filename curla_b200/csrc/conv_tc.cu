@@ -114,28 +114,34 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // everything above is independent of earlier kernels; from here on we read their outputs
-    pdl_grid_sync();
-    if (!DGRAD) {
-        for (int i = tid; i < NTAPS * 32 * CH; i += kTcThreads) {
-            const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
-            cp_async16(s_w + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
-        }
-        if (tid < 32) reinterpret_cast<float*>(smem + 256)[tid] = bias[tid];
-    } else {
-        // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
-        for (int i = tid; i < NTAPS * 32 * CP; i += kTcThreads) {
-            const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
-            reinterpret_cast<bf16*>(smem + kSmemHdr)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
-        }
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_proxy_async();          // generic-proxy writes of the weights -> visible to the tensor core
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();              // barriers initialised, TMEM address published
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 192);
+    // everything above is independent of earlier kernels; from here on we read their outputs
+    pdl_grid_sync();
+    // The producer warp goes straight to its loop (its first bulk copies overlap the weight
+    // staging below); the other 17 warps stage the weights and meet on named barrier 1.
+    constexpr int kStageThreads = kTcThreads - 32;
+    if (warp != kEpiAll + 1) {
+        if (!DGRAD) {
+            for (int i = tid; i < NTAPS * 32 * CH; i += kStageThreads) {
+                const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
+                cp_async16(s_w + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
+            }
+            if (tid < 32) reinterpret_cast<float*>(smem + 256)[tid] = bias[tid];
+        } else {
+            // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
+            for (int i = tid; i < NTAPS * 32 * CP; i += kStageThreads) {
+                const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
+                reinterpret_cast<bf16*>(smem + kSmemHdr)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();      // generic-proxy writes of the weights -> visible to the tensor core
+        asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+    }
 
     if (warp < kEpiAll) {
         // ================= epilogue: one output position per thread per tile
