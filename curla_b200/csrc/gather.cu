@@ -121,6 +121,18 @@ __global__ void k_gather_rows_f32(const float* __restrict__ src, const int64_t* 
     }
 }
 
+// ReplayBuffer.add (utils.py:120-128): one staged transition vec = [action[na] | reward | not_done]
+// written to row `row` of the three fp32 ring arrays.
+__global__ void k_scatter_transition(const float* __restrict__ vec, int na, long long row,
+                                     float* __restrict__ actions, float* __restrict__ rewards,
+                                     float* __restrict__ not_dones) {
+    pdl_grid_sync();
+    const int t = threadIdx.x;
+    if (t < na) actions[row * na + t] = vec[t];
+    else if (t == na) rewards[row] = vec[na];
+    else if (t == na + 1) not_dones[row] = vec[na + 1];
+}
+
 }  // namespace curla
 
 using namespace curla;
@@ -171,4 +183,11 @@ extern "C" int curla_gather_rows_f32(const float* src, const int64_t* idxs, int 
                                      float* out, cudaStream_t stream) {
     launch_k(k_gather_rows_f32, dim3(cdiv((long long)B * K, 256)), dim3(256), 0, stream, src, idxs, B, K, out);
     return check_launch("gather_rows_f32");
+}
+
+extern "C" int curla_scatter_transition(const float* vec, int na, long long row, float* actions,
+                                        float* rewards, float* not_dones, cudaStream_t stream) {
+    CURLA_CHECK(na >= 1 && na <= 62 && row >= 0, "scatter_transition: bad shape");
+    launch_k(k_scatter_transition, dim3(1), dim3(64), 0, stream, vec, na, row, actions, rewards, not_dones);
+    return check_launch("scatter_transition");
 }

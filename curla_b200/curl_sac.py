@@ -619,6 +619,7 @@ class CurlSacAgent(_Host):
         self.engine.refresh_shadows()
 
         self._update_count = 0
+        self._metrics_host = None
         self._noise_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         self._noise_override = None      # tests inject (noise_next, noise_cur)
         self._arange = None
@@ -785,7 +786,11 @@ class CurlSacAgent(_Host):
                 m = m.clone()
                 torch.distributed.all_reduce(m)
                 m /= self.world
-            m = m.cpu().numpy()
+            if self._metrics_host is None:
+                self._metrics_host = torch.empty(m.shape, dtype=m.dtype).pin_memory()
+            self._metrics_host.copy_(m, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            m = self._metrics_host.numpy()
             L.log('train/batch_reward', float(m[0]) if not only_cpc else float(reward_for_log()), step)
             if not only_cpc:
                 L.log('train_critic/loss', float(m[1]), step)

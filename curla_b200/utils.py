@@ -115,6 +115,11 @@ class ReplayBuffer(object):
         self._idx_slot = 0
         self._idx_events = [None, None]
         self._add_event = None
+        # numpy views of the pinned staging buffers (host-side writes without tensor indexing overhead)
+        self._np_obs = self._stage_obs.numpy()
+        self._np_vec = self._stage_vec.numpy()
+        self._np_idx = self._stage_idx.numpy()
+        self._dev_vec = torch.zeros_like(self._stage_vec, device=self.device)
 
         self.idx = 0
         self.last_save = 0
@@ -122,22 +127,27 @@ class ReplayBuffer(object):
 
     # -- ingest (utils.py:120-128) -----------------------------------------------
     def add(self, obs, action, reward, next_obs, done):
+        """One transition from host numpy into the HBM ring: two pinned-staged async H2D copies for
+        the frame stacks and one 16-byte copy + one scatter kernel for action / reward / not_done."""
         if self._add_event is not None:
             self._add_event.synchronize()        # staging buffers are free again
         na = self.actions.shape[1]
-        self._stage_obs[0].copy_(torch.as_tensor(np.asarray(obs)))
-        self._stage_obs[1].copy_(torch.as_tensor(np.asarray(next_obs)))
-        self._stage_vec[:na] = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(-1))
-        self._stage_vec[na] = float(reward)
-        self._stage_vec[na + 1] = float(not done)
+        np.copyto(self._np_obs[0], obs, casting='unsafe')
+        np.copyto(self._np_obs[1], next_obs, casting='unsafe')
+        v = self._np_vec
+        v[:na] = np.asarray(action, dtype=np.float32).reshape(-1)
+        v[na] = reward
+        v[na + 1] = float(not done)
         i = self.idx
         self.obses[i].copy_(self._stage_obs[0], non_blocking=True)
         self.next_obses[i].copy_(self._stage_obs[1], non_blocking=True)
-        vec = self._stage_vec.to(self.device, non_blocking=True)
-        self.actions[i].copy_(vec[:na])
-        self.rewards[i].copy_(vec[na:na + 1])
-        self.not_dones[i].copy_(vec[na + 1:na + 2])
-        self._add_event = torch.cuda.Event()
+        self._dev_vec.copy_(self._stage_vec, non_blocking=True)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.call('curla_scatter_transition', _lib.ptr(self._dev_vec), na, i, _lib.ptr(self.actions),
+                      _lib.ptr(self.rewards), _lib.ptr(self.not_dones), st)
+        if self._add_event is None:
+            self._add_event = torch.cuda.Event()
         self._add_event.record(torch.cuda.current_stream(self.device))
 
         self.idx = (self.idx + 1) % self.capacity
@@ -149,23 +159,24 @@ class ReplayBuffer(object):
         upload the draws as one int64 block.  Returns (dict of host arrays, device [7,B])
         with rows idxs, h1_obs, w1_obs, h1_next, w1_next, h1_pos, w1_pos."""
         B = self.batch_size
-        if self._idx_events[self._idx_slot] is not None:
-            self._idx_events[self._idx_slot].synchronize()   # pinned slot no longer in flight
-        host = self._stage_idx[self._idx_slot]
+        ev = self._idx_events[self._idx_slot]
+        if ev is not None:
+            ev.synchronize()                                  # pinned slot no longer in flight
+        host = self._np_idx[self._idx_slot]
         d = {}
         d['idxs'] = np.random.randint(0, self.capacity if self.full else self.idx, size=B)
-        host[0].copy_(torch.from_numpy(d['idxs']))
+        host[0] = d['idxs']
         if isinstance(self.augmentor, augmentations.RandomCrop):
             for r, name in enumerate(('obs', 'next', 'pos')):
                 h1, w1 = self.augmentor.draw_offsets(B, self.obs_shape[1:])
                 d['h1_' + name], d['w1_' + name] = h1, w1
-                host[1 + 2 * r].copy_(torch.from_numpy(h1))
-                host[2 + 2 * r].copy_(torch.from_numpy(w1))
+                host[1 + 2 * r] = h1
+                host[2 + 2 * r] = w1
         dev = self._dev_idx[self._idx_slot]
-        dev.copy_(host, non_blocking=True)
-        ev = torch.cuda.Event()
+        dev.copy_(self._stage_idx[self._idx_slot], non_blocking=True)
+        if ev is None:
+            ev = self._idx_events[self._idx_slot] = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        self._idx_events[self._idx_slot] = ev
         self._idx_slot ^= 1
         return d, dev
 

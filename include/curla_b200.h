@@ -44,6 +44,9 @@ int curla_gather_crop_s2d(const uint8_t* frames, int C, int Hf, int Wf, const in
 int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
                      long long out_sample_stride, void* out, curla_stream_t stream);
 /* actions / rewards / not_dones rows (utils.py:163-165) */
+/* ReplayBuffer.add (utils.py:120-128): vec = [action[na] | reward | not_done] -> ring row */
+int curla_scatter_transition(const float* vec, int na, long long row, float* actions,
+                             float* rewards, float* not_dones, curla_stream_t stream);
 int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
                           curla_stream_t stream);
 
