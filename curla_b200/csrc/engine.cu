@@ -782,7 +782,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         r2.rc = r.rc;
         r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
         r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
-        if (r2.ok()) r2.chk(curla_policy_fwd(a->t_out1, u->noise_next, u->seed, u->offset * 2, B, A, (float)c.log_std_min,
+        if (r2.ok()) r2.chk(curla_policy_fwd_rows(a->t_out1, u->noise_next, u->seed, u->offset * 2, c.rank * B, B, A, (float)c.log_std_min,
                                              (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, ss));
         // F2: critic_target(next_obs, a')
         bf16* const* act2 = forked ? a->actC : a->actB;      // F1's tail may still be reading actB[3]
@@ -816,7 +816,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
             r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B, 0, nullptr, a->m_p4.X);
             r.mlp_fwd_n(a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, B);
-            if (r.ok()) r.chk(curla_policy_fwd(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, B, A, (float)c.log_std_min,
+            if (r.ok()) r.chk(curla_policy_fwd_rows(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, c.rank * B, B, A, (float)c.log_std_min,
                                                (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4, a->ls4, a->noise4, st));
             r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
             have_p5 = true;

@@ -288,7 +288,7 @@ __global__ void k_policy_fwd(const float* __restrict__ t, const float* __restric
                              float ls_min, float ls_max, int compute_pi, int compute_log_pi,
                              float* __restrict__ mu_out, float* __restrict__ pi_out,
                              float* __restrict__ log_pi_out, float* __restrict__ ls_out,
-                             float* __restrict__ noise_out) {
+                             float* __restrict__ noise_out, int row0) {
     pdl_grid_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -297,7 +297,8 @@ __global__ void k_policy_fwd(const float* __restrict__ t, const float* __restric
         if (noise_in) {
             for (int k = 0; k < A; ++k) n[k] = noise_in[b * A + k];
         } else {
-            const uint4 r = philox4x32(make_uint4((uint32_t)b, (uint32_t)offset, (uint32_t)(offset >> 32), 0u),
+            // counter = GLOBAL row: a data-parallel shard draws exactly the rows of the global batch's noise
+            const uint4 r = philox4x32(make_uint4((uint32_t)(b + row0), (uint32_t)offset, (uint32_t)(offset >> 32), 0u),
                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
             const float2 g0 = box_muller(r.x, r.y), g1 = box_muller(r.z, r.w);
             n[0] = g0.x; n[1] = g0.y; n[2] = g1.x; n[3] = g1.y;
@@ -526,10 +527,21 @@ extern "C" int curla_policy_fwd(const float* t, const float* noise_in, unsigned 
                                 float ls_max, int compute_pi, int compute_log_pi, float* mu,
                                 float* pi, float* log_pi, float* ls, float* noise_out,
                                 cudaStream_t stream) {
+    return curla_policy_fwd_rows(t, noise_in, seed, offset, 0, B, A, ls_min, ls_max, compute_pi, compute_log_pi, mu, pi,
+                                 log_pi, ls, noise_out, stream);
+}
+
+// Same for rows [row0, row0 + B) of a larger (global) batch: the built-in Philox noise of local
+// row b is the noise global row row0 + b would get on a single GPU.
+extern "C" int curla_policy_fwd_rows(const float* t, const float* noise_in, unsigned long long seed,
+                                     unsigned long long offset, int row0, int B, int A, float ls_min,
+                                     float ls_max, int compute_pi, int compute_log_pi, float* mu,
+                                     float* pi, float* log_pi, float* ls, float* noise_out,
+                                     cudaStream_t stream) {
     CURLA_CHECK(A <= 4, "policy_fwd: action dim > 4 unsupported");
     launch_k(k_policy_fwd, dim3(cdiv(B, 128)), dim3(128), 0, stream, t, noise_in, seed, offset, B, A, ls_min, ls_max,
                                                    compute_pi, compute_log_pi, mu, pi, log_pi, ls,
-                                                   noise_out);
+                                                   noise_out, row0);
     return check_launch("policy_fwd");
 }
 

@@ -1,0 +1,87 @@
+"""Data-parallel equivalence check (not collected by pytest; needs >= 2 GPUs for the DP leg):
+
+    python tests/dp_equivalence.py > /tmp/dp1.json
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/dp_equivalence.py > /tmp/dp2.json
+    python tests/dp_equivalence.py --compare /tmp/dp1.json /tmp/dp2.json
+
+Both legs run the same GLOBAL batch (64) from the same numpy / Philox streams: one GPU with batch
+64, or G ranks with batch 64/G each (sharded indices and policy noise, all-gathered CURL keys,
+all-reduced gradients).  Logged losses and parameter checksums must agree to fp32 reduction-order
+noise amplified by Adam's sign-like first steps: the first critic loss agrees to
+~1e-4, later values to <1e-2 of max(|v|, 1) (mean-of-means == global mean for
+equal shards)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def run():
+    from curla_b200 import augmentations, curl_sac, utils
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    np.random.seed(321)
+    torch.manual_seed(5)
+    aug = augmentations.make_augmentor('random_crop', (90, 160))
+    rb = utils.ReplayBuffer((9, 90, 160), (2,), 256, 64, dev, aug)
+    g = torch.Generator(device=dev).manual_seed(1)
+    rb.obses.copy_(torch.randint(0, 256, rb.obses.shape, device=dev, dtype=torch.uint8, generator=g))
+    rb.next_obses.copy_(torch.randint(0, 256, rb.obses.shape, device=dev, dtype=torch.uint8, generator=g))
+    rb.actions.copy_(torch.rand(rb.actions.shape, device=dev, generator=g) * 2 - 1)
+    rb.rewards.copy_(torch.randn(rb.rewards.shape, device=dev, generator=g))
+    rb.not_dones.fill_(1.0)
+    rb.idx, rb.full = 0, True
+    agent = curl_sac.CurlSacAgent((9, 76, 135), (2,), dev, aug, hidden_dim=256, discount=0.99, init_temperature=0.1,
+                                  alpha_lr=1e-4, alpha_beta=0.5, critic_tau=0.01, encoder_tau=0.05, log_interval=1)
+
+    class L:
+        rows = []
+
+        def log(self, k, v, s):
+            self.rows.append((s, k, float(v)))
+
+    log = L()
+    for step in range(4):
+        agent.update(rb, log, step)
+    torch.cuda.synchronize()
+    t = agent.engine.t
+    sums = {k: float(t[k].double().abs().sum()) for k in ('critic.encoder.convs.0.weight', 'critic.encoder.fc.weight_canon',
+                                                           'critic.Q1.trunk.2.weight', 'actor.trunk.4.weight', 'CURL.W',
+                                                           'target.encoder.convs.3.weight')}
+    if rank == 0:
+        print(json.dumps({'world': world, 'rows': log.rows, 'sums': sums, 'log_alpha': float(t['log_alpha'])}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def compare(a, b):
+    A, B = [json.loads([l for l in open(p) if l.startswith('{')][-1]) for p in (a, b)]
+    worst = 0.0
+    for (s1, k1, v1), (s2, k2, v2) in zip(A['rows'], B['rows']):
+        assert (s1, k1) == (s2, k2)
+        err = abs(v1 - v2) / max(abs(v1), 1.0)
+        worst = max(worst, err)
+        print('%d %-28s %14.7f %14.7f  rel %.2e' % (s1, k1, v1, v2, err))
+    for k in A['sums']:
+        err = abs(A['sums'][k] - B['sums'][k]) / A['sums'][k]
+        worst = max(worst, err)
+        print('%-36s %.9e %.9e  rel %.2e' % (k, A['sums'][k], B['sums'][k], err))
+    print('log_alpha %.12f %.12f' % (A['log_alpha'], B['log_alpha']))
+    print('WORST relative difference: %.3e' % worst)
+    assert worst < 1e-2, 'data-parallel run diverges from the single-GPU run'
+    print('DP EQUIVALENCE OK (world %d vs %d)' % (A['world'], B['world']))
+
+
+if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == '--compare':
+        compare(sys.argv[2], sys.argv[3])
+    else:
+        run()
