@@ -250,11 +250,12 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
     // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace),
     // written in both orientations: U for the gradient pass, Ut for the coalesced logits pass
     if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Ut, Bg, Bg, feat, feat, stream)) return -1;
-    // rows per CTA: as many as keep the [R][Bg] logits block in shared memory, while leaving
-    // at least ~one CTA per SM
+    // rows per CTA: every CTA streams all of U and z_pos (Bg x 512 B) from L2, so the re-read
+    // traffic is (B / R) x that -- at a global batch of 4096 it is what bounds the kernel, and more
+    // rows per CTA beat more CTAs; at small Bg the kernel is latency-bound and wants >= ~1 CTA/SM.
     const size_t cap = 200 * 1024 / sizeof(float);
     int R = 8;
-    while (R > 1 && ((size_t)R * (Bg + 3) + 9 * R * 64 > cap || cdiv(B, R) < sm_count() / 2)) R >>= 1;
+    while (R > 1 && ((size_t)R * (Bg + 3) + 9 * R * 64 > cap || (Bg < 2048 && cdiv(B, R) < sm_count() / 2))) R >>= 1;
     CURLA_CHECK((size_t)R * (Bg + 3) + 9 * R * 64 <= cap, "curl: global batch %d does not fit shared memory", Bg);
     int rc;
     switch (R) {
