@@ -42,6 +42,7 @@ SIGNATURES = {
     'curla_gather_crop_s2d': (_i, [c_vp, _i, _i, _i, c_vp, c_vp, c_vp, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_f32_to_s2d': (_i, [c_vp, _i, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_scatter_transition': (_i, [c_vp, _i, c_ll, c_vp, c_vp, c_vp, c_vp]),
+    'curla_replay_add': (_i, [c_vp, c_vp, c_ll, c_vp, c_vp, _i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'curla_gather_rows_f32': (_i, [c_vp, c_vp, _i, _i, c_vp, c_vp]),
     'curla_color_jiggle': (_i, [c_vp, _i, _i, _i, c_vp, C.c_ulonglong, C.c_ulonglong, _f, _f, _f, _f, _i, c_vp, c_vp]),
     'curla_noisy_cover': (_i, [c_vp, _i, _i, _i, _i, _i, c_vp, _f, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp]),

@@ -14,6 +14,7 @@
 //                      planes [CP/8][S][8] per sample.
 //                      uint8 values are exact in bf16.
 #include "common.cuh"
+#include "../../include/curla_b200.h"
 
 namespace curla {
 
@@ -190,4 +191,19 @@ extern "C" int curla_scatter_transition(const float* vec, int na, long long row,
     CURLA_CHECK(na >= 1 && na <= 62 && row >= 0, "scatter_transition: bad shape");
     launch_k(k_scatter_transition, dim3(1), dim3(64), 0, stream, vec, na, row, actions, rewards, not_dones);
     return check_launch("scatter_transition");
+}
+
+// ReplayBuffer.add in one call (utils.py:120-128): two async H2D copies of the pinned frame
+// stacks into ring row `row`, one of the staged [action | reward | not_done] vector, and the
+// scatter kernel.  All pointers except the *_pinned ones are device pointers.
+extern "C" int curla_replay_add(const uint8_t* obs_pinned, const uint8_t* next_pinned, long long frame_bytes,
+                                const float* vec_pinned, float* vec_dev, int na, long long row,
+                                uint8_t* obses, uint8_t* next_obses, float* actions, float* rewards,
+                                float* not_dones, cudaStream_t stream) {
+    CURLA_CHECK(na >= 1 && na <= 62 && row >= 0 && frame_bytes > 0, "replay_add: bad shape");
+    cudaError_t e = cudaMemcpyAsync(obses + row * frame_bytes, obs_pinned, (size_t)frame_bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(next_obses + row * frame_bytes, next_pinned, (size_t)frame_bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vec_dev, vec_pinned, sizeof(float) * (na + 2), cudaMemcpyHostToDevice, stream);
+    CURLA_CHECK(e == cudaSuccess, "replay_add: %s", cudaGetErrorString(e));
+    return curla_scatter_transition(vec_dev, na, row, actions, rewards, not_dones, stream);
 }

@@ -619,6 +619,7 @@ class CurlSacAgent(_Host):
         self.engine.refresh_shadows()
 
         self._update_count = 0
+        self._ptr_cache = {}
         self._metrics_host = None
         self._noise_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         self._noise_override = None      # tests inject (noise_next, noise_cur)
@@ -739,14 +740,23 @@ class CurlSacAgent(_Host):
             self._ensure_engine(B, replay_buffer.obs_shape[1:])
             d, dev = replay_buffer.draw_indices()
             sl = dp.shard_slice(self.rank, self.world, Bg)
-            a.obses, a.next_obses = replay_buffer.obses.data_ptr(), replay_buffer.next_obses.data_ptr()
-            a.actions, a.rewards = replay_buffer.actions.data_ptr(), replay_buffer.rewards.data_ptr()
-            a.not_dones = replay_buffer.not_dones.data_ptr()
-            a.idxs = dev[0, sl].data_ptr()
+            # device pointers of this rank's slices of the [7][Bg] index block (two staging slots),
+            # computed once per (buffer, slot): 8 bytes per int64, row stride Bg
+            ck = (id(replay_buffer), dev.data_ptr(), sl.start)
+            ptrs = self._ptr_cache.get(ck)
+            if ptrs is None:
+                if len(self._ptr_cache) > 8:
+                    self._ptr_cache.clear()
+                base = dev.data_ptr() + 8 * sl.start
+                ptrs = self._ptr_cache[ck] = (
+                    replay_buffer.obses.data_ptr(), replay_buffer.next_obses.data_ptr(), replay_buffer.actions.data_ptr(),
+                    replay_buffer.rewards.data_ptr(), replay_buffer.not_dones.data_ptr(),
+                    [base + 8 * Bg * r for r in range(7)])
+            a.obses, a.next_obses, a.actions, a.rewards, a.not_dones = ptrs[:5]
+            rows = ptrs[5]
+            a.idxs = rows[0]
             if isinstance(replay_buffer.augmentor, augmentations.RandomCrop):
-                a.h1_obs, a.w1_obs = dev[1, sl].data_ptr(), dev[2, sl].data_ptr()
-                a.h1_next, a.w1_next = dev[3, sl].data_ptr(), dev[4, sl].data_ptr()
-                a.h1_pos, a.w1_pos = dev[5, sl].data_ptr(), dev[6, sl].data_ptr()
+                a.h1_obs, a.w1_obs, a.h1_next, a.w1_next, a.h1_pos, a.w1_pos = rows[1:7]
                 a.pos_is_obs = 0
             else:
                 a.pos_is_obs = 1

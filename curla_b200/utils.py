@@ -120,6 +120,7 @@ class ReplayBuffer(object):
         self._np_vec = self._stage_vec.numpy()
         self._np_idx = self._stage_idx.numpy()
         self._dev_vec = torch.zeros_like(self._stage_vec, device=self.device)
+        self._add_ptrs = None
 
         self.idx = 0
         self.last_save = 0
@@ -139,16 +140,19 @@ class ReplayBuffer(object):
         v[na] = reward
         v[na + 1] = float(not done)
         i = self.idx
-        self.obses[i].copy_(self._stage_obs[0], non_blocking=True)
-        self.next_obses[i].copy_(self._stage_obs[1], non_blocking=True)
-        self._dev_vec.copy_(self._stage_vec, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        if self._add_ptrs is None:
+            fb = int(np.prod(self.obs_shape))
+            self._add_ptrs = (self._stage_obs[0].data_ptr(), self._stage_obs[1].data_ptr(), fb, self._stage_vec.data_ptr(),
+                              self._dev_vec.data_ptr(), self.obses.data_ptr(), self.next_obses.data_ptr(),
+                              self.actions.data_ptr(), self.rewards.data_ptr(), self.not_dones.data_ptr())
+        p = self._add_ptrs
         with torch.cuda.device(self.device):
-            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.call('curla_scatter_transition', _lib.ptr(self._dev_vec), na, i, _lib.ptr(self.actions),
-                      _lib.ptr(self.rewards), _lib.ptr(self.not_dones), st)
+            _lib.call('curla_replay_add', p[0], p[1], p[2], p[3], p[4], na, i, p[5], p[6], p[7], p[8], p[9],
+                      C.c_void_p(stream.cuda_stream))
         if self._add_event is None:
             self._add_event = torch.cuda.Event()
-        self._add_event.record(torch.cuda.current_stream(self.device))
+        self._add_event.record(stream)
 
         self.idx = (self.idx + 1) % self.capacity
         self.full = self.full or self.idx == 0

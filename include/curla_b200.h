@@ -47,6 +47,11 @@ int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,
 /* ReplayBuffer.add (utils.py:120-128): vec = [action[na] | reward | not_done] -> ring row */
 int curla_scatter_transition(const float* vec, int na, long long row, float* actions,
                              float* rewards, float* not_dones, curla_stream_t stream);
+/* the whole add(): pinned host frames + staged vec -> ring row (H2D copies + scatter) */
+int curla_replay_add(const uint8_t* obs_pinned, const uint8_t* next_pinned, long long frame_bytes,
+                     const float* vec_pinned, float* vec_dev, int na, long long row, uint8_t* obses,
+                     uint8_t* next_obses, float* actions, float* rewards, float* not_dones,
+                     curla_stream_t stream);
 int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
                           curla_stream_t stream);
 
