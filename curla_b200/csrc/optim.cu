@@ -118,16 +118,19 @@ struct PackSeg {
 struct PackTable {
     int n;
     PackSeg seg[CURLA_MAX_PACK];
+    int blk0[CURLA_MAX_PACK + 1];     // first CTA of each segment (CTAs are dealt out in proportion to the work)
 };
 
 __global__ void __launch_bounds__(256)
 k_pack(const float* __restrict__ src_arena, bf16* __restrict__ dst_arena, PackTable tbl) {
     pdl_grid_sync();
-    const PackSeg s = tbl.seg[blockIdx.y];
+    int si = 0;
+    while (si + 1 < tbl.n && (int)blockIdx.x >= tbl.blk0[si + 1]) ++si;
+    const PackSeg s = tbl.seg[si];
     const float* src = src_arena + s.src_off;
     bf16* dst = dst_arena + s.dst_off;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)(tbl.blk0[si + 1] - tbl.blk0[si]) * blockDim.x;
+    long long i = (long long)((int)blockIdx.x - tbl.blk0[si]) * blockDim.x + threadIdx.x;
     if (s.kind == PACK_ROWS && (s.cols_pad & 7) == 0 && (s.dst_off & 7) == 0) {
         // 8 outputs (one 16-byte store) per thread; the big rows are the three fc weights (50 x Kfc -> 64 x Kfc)
         const int cpv = s.cols_pad >> 3;
@@ -223,7 +226,7 @@ extern "C" int curla_pack_shadows(const float* src_arena, void* dst_arena, const
     for (int base = 0; base < n; base += CURLA_MAX_PACK) {
         PackTable tbl;
         tbl.n = (n - base < CURLA_MAX_PACK) ? n - base : CURLA_MAX_PACK;
-        long long maxn = 1;
+        int nblk = 0;
         for (int i = 0; i < tbl.n; ++i) {
             const long long* r = segs + (long long)(base + i) * 7;
             PackSeg& s = tbl.seg[i];
@@ -231,11 +234,16 @@ extern "C" int curla_pack_shadows(const float* src_arena, void* dst_arena, const
             s.cols = (int)r[4]; s.rows_pad = (int)r[5]; s.cols_pad = (int)r[6];
             long long cnt = s.kind == PACK_ROWS ? (long long)s.rows_pad * s.cols_pad
                           : (s.kind == PACK_CONV ? 9LL : 4LL) * s.rows * s.cols_pad;
-            if (cnt > maxn) maxn = cnt;
+            // the vectorised row path moves 8 elements per thread; a CTA gets ~2 items per thread
+            const long long items = (s.kind == PACK_ROWS && (s.cols_pad & 7) == 0 && (s.dst_off & 7) == 0) ? cnt / 8 : cnt;
+            long long b = (items + 511) / 512;
+            if (b < 1) b = 1;
+            if (b > 2048) b = 2048;
+            tbl.blk0[i] = nblk;
+            nblk += (int)b;
         }
-        long long gx = (maxn + 255) / 256;
-        if (gx > 2048) gx = 2048;
-        launch_k(k_pack, dim3((unsigned)gx, tbl.n), dim3(256), 0, stream, src_arena, (bf16*)dst_arena, tbl);
+        tbl.blk0[tbl.n] = nblk;
+        launch_k(k_pack, dim3((unsigned)nblk), dim3(256), 0, stream, src_arena, (bf16*)dst_arena, tbl);
         if (check_launch("pack_shadows")) return -1;
     }
     return 0;

@@ -1,9 +1,9 @@
 """Data-parallel equivalence check (not collected by pytest; needs >= 2 GPUs for the DP leg):
 
-    python tests/dp_equivalence.py > /tmp/dp1.json
+    python tests/manual/dp_equivalence.py > /tmp/dp1.json
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 tests/dp_equivalence.py > /tmp/dp2.json
-    python tests/dp_equivalence.py --compare /tmp/dp1.json /tmp/dp2.json
+        --master-port 29533 tests/manual/dp_equivalence.py > /tmp/dp2.json
+    python tests/manual/dp_equivalence.py --compare /tmp/dp1.json /tmp/dp2.json
 
 Both legs run the same GLOBAL batch (64) from the same numpy / Philox streams: one GPU with batch
 64, or G ranks with batch 64/G each (sharded indices and policy noise, all-gathered CURL keys,
@@ -18,7 +18,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def run():
