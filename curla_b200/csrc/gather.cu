@@ -45,68 +45,68 @@ k_gather_crop_f32(const uint8_t* __restrict__ frames, int C, int Hf, int Wf,
 }
 
 // ------------------------------------------------------------------ s2d bf16 (channel planes)
-// One CTA per (sample b, s2d block-row yb).  The 2*C source rows are staged in shared memory
-// with 16-byte loads of WHOLE stored rows (a crop window at an arbitrary byte offset touches
-// every 32-byte sector of the row anyway), then every thread emits one 16-byte group of 8
-// s2d channels; consecutive threads write consecutive positions of one channel plane, so the
-// stores of a warp are 512 contiguous bytes.
+// One CTA per (sample b, output channel-chunk plane j).  Plane j holds s2d channels 8j..8j+7 =
+// input channels 2j and 2j+1 (x 2x2 sub-positions), so the CTA reads the crop rows of exactly
+// two stored channel planes -- each ONE contiguous run of H*Wf elements starting at row oy
+// (whole stored rows: a crop window at an arbitrary byte offset touches every 32-byte sector of a
+// row anyway) -- stages them in shared memory with 16-byte cp.async copies, and writes the whole
+// output plane [Hs*Ws][8] bf16 as one contiguous 16-bytes-per-thread stream.  Long contiguous
+// reads and writes keep DRAM pages open; the per-block-row version of this kernel moved the same
+// bytes in 160-byte pieces and ran at half the bandwidth.
 //   out[b][j][yb*Ws + xb][e]  with s2d channel ch = j*8 + e = c*4 + sy*2 + sx
 //                             = frame[idx[b]][c][oy + 2yb+sy][ox + 2xb+sx]
-// zero where 2yb+sy >= H, 2xb+sx >= W or ch >= 4C.  Plane stride = S positions (S*8 elements).
+// zero where 2yb+sy >= H, 2xb+sx >= W or c >= C.  Planes with 8j >= 4C are all zero and are
+// never written (the caller's buffer is zero-initialised): grid.x covers only the real planes.
 template <typename SrcT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
              const int64_t* __restrict__ idxs, const int64_t* __restrict__ h1,
              const int64_t* __restrict__ w1, int H, int W, int Hs, int Ws, int CP,
              long long out_sample_stride, bf16* __restrict__ out) {
     pdl_grid_sync();
     extern __shared__ __align__(16) uint8_t s_raw[];
-    const int b = blockIdx.y, yb = blockIdx.x;
+    const int b = blockIdx.y, j = blockIdx.x;
     const long long fi = idxs ? idxs[b] : b;
     const int oy = h1 ? (int)h1[b] : 0;
     const int ox = w1 ? (int)w1[b] : 0;
-    const int nrows = 2 * C;                       // r = c*2 + sy
     constexpr int V = 16 / (int)sizeof(SrcT);      // source elements per 16-byte vector
-    const int rowv = (Wf + V - 1) / V;             // vectors per staged row
-    const int rpitch = rowv * V + V;               // elements; +V keeps rows apart in the banks
-    SrcT* s_rows = reinterpret_cast<SrcT*>(s_raw);
+    const int plane_elems = H * Wf;                // staged run of one input channel
+    const int ppitch = (plane_elems + V - 1) / V * V + V;
+    SrcT* s_pl = reinterpret_cast<SrcT*>(s_raw);   // [2][ppitch]
+    const int c0 = 2 * j;
     const bool vec_ok = (Wf % V == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
-    if (vec_ok) {
-        for (int i = threadIdx.x; i < nrows * rowv; i += blockDim.x) {
-            const int r = i / rowv, v = i - r * rowv;
-            const int c = r >> 1, y = 2 * yb + (r & 1);
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (y < H)
-                val = *reinterpret_cast<const uint4*>(frames + ((fi * C + c) * Hf + (oy + y)) * (long long)Wf + v * V);
-            *reinterpret_cast<uint4*>(s_rows + r * rpitch + v * V) = val;
-        }
-    } else {
-        for (int i = threadIdx.x; i < nrows * Wf; i += blockDim.x) {
-            const int r = i / Wf, x = i - r * Wf;
-            const int c = r >> 1, y = 2 * yb + (r & 1);
-            s_rows[r * rpitch + x] = (y < H) ? frames[((fi * C + c) * Hf + (oy + y)) * (long long)Wf + x] : (SrcT)0;
+    for (int lp = 0; lp < 2; ++lp) {
+        const int c = c0 + lp;
+        if (c >= C) break;
+        const SrcT* src = frames + ((fi * C + c) * Hf + oy) * (long long)Wf;
+        if (vec_ok) {
+            const uint32_t s0 = smem_u32(s_pl + lp * ppitch);
+            for (int i = threadIdx.x; i < plane_elems / V; i += blockDim.x)
+                cp_async16(s0 + (uint32_t)(i * 16), src + (long long)i * V, 16);
+        } else {
+            for (int i = threadIdx.x; i < plane_elems; i += blockDim.x) s_pl[lp * ppitch + i] = src[i];
         }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
-    const int chunks = CP / 8;
     const long long S = (long long)Hs * Ws;
-    bf16* obase = out + b * out_sample_stride + (long long)yb * Ws * 8;
-    for (int i = threadIdx.x; i < Ws * chunks; i += blockDim.x) {
-        const int j = i / Ws, xb = i - j * Ws;
+    bf16* oplane = out + b * out_sample_stride + (long long)j * S * 8;
+    for (int p = threadIdx.x; p < Hs * Ws; p += blockDim.x) {
+        const int yb = p / Ws, xb = p - yb * Ws;
         uint32_t w[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {          // two s2d channels per 32-bit word: sx = 0, 1
-            const int ch = j * 8 + h * 2;       // = c*4 + sy*2 (+ sx)
-            const int c = ch >> 2, sy = (ch >> 1) & 1;
+        for (int h = 0; h < 4; ++h) {          // word h: input channel c0 + (h >> 1), sub-row sy = h & 1, sx = 0, 1
+            const int lp = h >> 1, sy = h & 1, y = 2 * yb + sy;
             float v0 = 0.f, v1 = 0.f;
-            if (c < C) {
-                const SrcT* rp = s_rows + (c * 2 + sy) * rpitch + ox + 2 * xb;
+            if (c0 + lp < C && y < H) {
+                const SrcT* rp = s_pl + lp * ppitch + y * Wf + ox + 2 * xb;
                 if (2 * xb < W) v0 = (float)rp[0];
                 if (2 * xb + 1 < W) v1 = (float)rp[1];
             }
             w[h] = pack_bf16x2(v0, v1);
         }
-        *reinterpret_cast<uint4*>(obase + (long long)j * S * 8 + (long long)xb * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(oplane + (long long)p * 8) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -158,10 +158,16 @@ static int launch_s2d(const SrcT* frames, int C, int Hf, int Wf, const int64_t* 
     CURLA_CHECK(B > 0 && H <= Hf && W <= Wf && CP % 8 == 0 && CP >= 4 * C, "gather_s2d: bad shape");
     const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
     CURLA_CHECK(out_sample_stride >= (long long)Hs * Ws * CP, "gather_s2d: sample stride too small");
-    dim3 grid(Hs, B);
+    const int real_planes = (4 * C + 7) / 8;        // planes beyond these are all zero: left untouched
+    dim3 grid(real_planes, B);
     const int V = 16 / (int)sizeof(SrcT);
-    size_t smem = (size_t)2 * C * ((Wf + V - 1) / V * V + V) * sizeof(SrcT);
-    launch_k(k_gather_s2d<SrcT>, dim3(grid), dim3(128), smem, stream, frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
+    const size_t smem = (size_t)2 * (((size_t)H * Wf + V - 1) / V * V + V) * sizeof(SrcT);
+    CURLA_CHECK(smem <= 220 * 1024, "gather_s2d: a %dx%d window of %zu-byte elements does not fit shared memory", H, Wf, sizeof(SrcT));
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_gather_s2d<SrcT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CURLA_CHECK(e == cudaSuccess, "gather_s2d: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    }
+    launch_k(k_gather_s2d<SrcT>, dim3(grid), dim3(256), smem, stream, frames, C, Hf, Wf, idxs, h1, w1, H, W, Hs, Ws,
                                                     CP, out_sample_stride, out);
     return check_launch("gather_s2d");
 }

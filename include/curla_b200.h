@@ -35,8 +35,10 @@ int curla_version(void);
 int curla_gather_crop_f32(const uint8_t* frames, int C, int Hf, int Wf, const int64_t* idxs,
                           const int64_t* h1, const int64_t* w1, int B, int H, int W,
                           float* out, curla_stream_t stream);
-/* same gather, written as the bf16 space-to-depth rows the conv stack consumes:
- * out[b][yb*Ws+xb][c*4+sy*2+sx], CP channels per row (>= 4C, multiple of 8).           */
+/* same gather, written as the bf16 space-to-depth channel planes the conv stack consumes:
+ * out[b][ch/8][yb*Ws+xb][ch%8] with ch = c*4+sy*2+sx, CP channels (>= 4C, multiple of 8).
+ * Planes that hold only padding channels (8j >= 4C) are NOT written: the caller provides a
+ * zero-initialised buffer once (the engine's arenas are).                                */
 int curla_gather_crop_s2d(const uint8_t* frames, int C, int Hf, int Wf, const int64_t* idxs,
                           const int64_t* h1, const int64_t* w1, int B, int H, int W, int CP,
                           long long out_sample_stride, void* out, curla_stream_t stream);
