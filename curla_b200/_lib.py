@@ -13,6 +13,11 @@ c_ll = C.c_longlong
 c_vp = C.c_void_p
 
 
+class ConvSeg(C.Structure):
+    """curla_conv_seg (include/curla_b200.h): one pass of a multi-pass conv launch."""
+    _fields_ = [('inp', c_vp), ('wts', c_vp), ('bias', c_vp), ('out', c_vp), ('B', C.c_int)]
+
+
 class AgentConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         'C', 'H', 'W', 'Hf', 'Wf', 'feature_dim', 'hidden_dim', 'action_dim', 'num_filters',
@@ -49,6 +54,7 @@ SIGNATURES = {
     'curla_conv_pad_rows': (_i, [_i]),
     'curla_conv_fwd': (_i, [c_vp, c_ll, c_vp, c_vp, _f, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_dgrad': (_i, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, _i, _i, _i, _i, _i, c_vp]),
+    'curla_conv_fwd_multi': (_i, [c_vp, _i, c_ll, _f, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_debug_read': (_i, [c_vp, _i]),
     'curla_conv_wgrad_workspace_floats': (c_ll, [_i]),
     'curla_conv_wgrad': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, _f, _i, _i, _i, _i, _i, _i, _i, c_vp]),

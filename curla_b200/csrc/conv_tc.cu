@@ -28,8 +28,10 @@
 // the ReLU mask of dgrad with 64-byte row stores).  See the kernel for the pipeline.
 #include "common.cuh"
 #include "tc.cuh"
+#include "../../include/curla_b200.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace curla {
 
@@ -41,22 +43,58 @@ struct TcGeom {
     int min_off;         // most negative tap shift
     int stages;          // slab ring depth (host: as many as fit in shared memory, <= 8)
     int plane_bytes;     // shared-memory stride between channel planes of a slab
+    float inv_tps, inv_pitch;   // 1/tiles_per_sample, 1/pitch: index divisions through a float reciprocal (exact for
+                         // these ranges: (i + 0.5) / d is never within float rounding of an integer)
     int debug;           // CURLA_TC_DEBUG bitmask (timing experiments only): 1 no loads, 2 no MMA, 4 no stores,
-                         // 8 tap shifts rounded to 8 rows (WRONG results: aligned core matrices), 16 plane skew +64 B
+                         // 8 tap shifts rounded to 8 rows (WRONG results: aligned core matrices), 16 plane skew +64 B,
+                         // 64 role cycle counters, 128 single MMA issuer warp
 };
 struct TcTaps { int off[9]; };
+// Up to three independent passes ("segments") of the same layer in one launch: tiles
+// [tile_end[s-1], tile_end[s]) belong to segment s, which has its own input/output buffers and
+// one of (at most) two weight sets staged in shared memory.  Unused tile_end entries hold the
+// total tile count.
+struct TcSegs {
+    const bf16* in[3];
+    bf16* out[3];
+    const bf16* wts[2];
+    const float* bias[2];
+    int tile_end[3];
+    int wsel[3];
+    int nw;
+};
+struct TileLoc { int seg, b, t; };
+__device__ __forceinline__ int tc_div(int i, float inv_d) { return __float2int_rd(((float)i + 0.5f) * inv_d); }
+__device__ __forceinline__ TileLoc tc_locate(const TcSegs& s, int tiles_per_sample, float inv_tps, int tile) {
+    int seg = 0, start = 0;
+    if (tile >= s.tile_end[0]) { seg = 1; start = s.tile_end[0]; }
+    if (tile >= s.tile_end[1]) { seg = 2; start = s.tile_end[1]; }
+    const int local = tile - start;
+    const int b = tc_div(local, inv_tps);
+    TileLoc l;
+    l.seg = seg; l.b = b; l.t = local - b * tiles_per_sample;
+    return l;
+}
+template <typename T>
+__device__ __forceinline__ T tc_pick(T const (&a)[3], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 
 // CURLA_TC_DEBUG & 64: per-CTA cycle counters of the MMA thread and the producer (timing
 // experiments only): [0] MMA wait tempty, [1] MMA wait full, [2] MMA issue, [3] producer wait
 // empty, [4] kernel total, [5] tiles, [6] epilogue warp 0 wait tfull, [7] epilogue warp 0 busy
-__device__ long long g_tc_dbg[160][8];
+//   [8] globaltimer (ns) at kernel entry, [9] at MMA loop start, [10] at MMA loop end, [11] at CTA exit
+__device__ long long g_tc_dbg[160][12];
+__device__ __forceinline__ long long tc_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------- the kernel
 // Warp-specialised, persistent, one CTA per SM:
 //   warps 0..15  epilogue   (two groups of 8 alternating tiles; TMEM -> registers -> bias/ReLU or ReLU-mask -> plane stores: a
 //                            warp writes 32 consecutive positions x 16 B = 512 contiguous bytes)
-//   warp  16     MMA issuer (one elected lane; 2 x NTAPS x CP/16 tcgen05.mma per tile)
-//   warp  17     producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
+//   warps 16,17  MMA issuers (one elected lane each, alternating tiles; 2 x NTAPS x CP/16 tcgen05.mma per tile)
+//   warp  18     producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
 //                            per tile, one per channel plane -- the global layout IS the
 //                            shared-memory operand layout -- completing on the stage's mbarrier)
 // Pipelines: full/empty per slab stage (producer <-> MMA), tfull/tempty per TMEM accumulator
@@ -69,29 +107,30 @@ constexpr int kEpiWarps = 4 * kTcSub;     // 8 warps drain one tile (2 sub-tiles
 constexpr int kEpiGroups = 2;             // two such groups alternate tiles: a warp's per-tile latency
                                           // (wait, TMEM load, math, stores) is hidden behind the other group
 constexpr int kEpiAll = kEpiWarps * kEpiGroups;      // 16
-constexpr int kTcThreads = (kEpiAll + 2) * 32;       // 576
+constexpr int kMmaWarps = 2;                         // two issuer warps alternate tiles (see the kernel)
+constexpr int kTcThreads = (kEpiAll + kMmaWarps + 1) * 32;       // 608
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 4;
 constexpr int kSmemHdr = 512;             // barriers + tmem ptr + bias
 
 template <int CP, int NTAPS, bool DGRAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ wts,   // [NTAPS][32][CP]
-          const float* __restrict__ bias, float scale, const bf16* __restrict__ relu_src,
-          bf16* __restrict__ out, long long out_sstride, TcGeom g, TcTaps taps) {
+k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights: [NTAPS][32][CP] per set
+          float scale, const bf16* __restrict__ relu_src, long long out_sstride, TcGeom g, TcTaps taps) {
     constexpr int CH = CP / 8, KS = CP / 16, TM = kTcSub * 128;
     constexpr uint32_t W_BYTES = NTAPS * CH * 512;
     constexpr uint32_t TMEM_COLS = kAccStages * kTcSub * 32;   // 256
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    // header: full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem ptr @192, bias @256
+    if ((g.debug & 64) && tid == 0) g_tc_dbg[blockIdx.x][8] = tc_gtime();
+    // header: full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem ptr @192, bias set 0 @256, set 1 @384
     const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 160;
     const uint32_t s_tptr = s_base + 192;
     const uint32_t s_w = s_base + kSmemHdr;
     const uint32_t PS = (uint32_t)g.plane_bytes;
     const uint32_t slab_bytes = CH * PS;
-    const uint32_t s_slab0 = s_w + W_BYTES;
+    const uint32_t s_slab0 = s_w + (uint32_t)sg.nw * W_BYTES;
     const int stages = g.stages;
     const long long plane = (long long)g.S * 8;      // elements between channel planes (in and out)
 
@@ -123,18 +162,21 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
     // The producer warp goes straight to its loop (its first bulk copies overlap the weight
     // staging below); the other 17 warps stage the weights and meet on named barrier 1.
     constexpr int kStageThreads = kTcThreads - 32;
-    if (warp != kEpiAll + 1) {
-        if (!DGRAD) {
-            for (int i = tid; i < NTAPS * 32 * CH; i += kStageThreads) {
-                const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
-                cp_async16(s_w + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
-            }
-            if (tid < 32) reinterpret_cast<float*>(smem + 256)[tid] = bias[tid];
-        } else {
-            // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
-            for (int i = tid; i < NTAPS * 32 * CP; i += kStageThreads) {
-                const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
-                reinterpret_cast<bf16*>(smem + kSmemHdr)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
+    if (warp != kEpiAll + kMmaWarps) {
+        for (int ws = 0; ws < sg.nw; ++ws) {
+            const bf16* __restrict__ wts = ws ? sg.wts[1] : sg.wts[0];
+            if (!DGRAD) {
+                for (int i = tid; i < NTAPS * 32 * CH; i += kStageThreads) {
+                    const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
+                    cp_async16(s_w + ws * W_BYTES + (uint32_t)(((t * CH + kc) * 32 + n) * 16), wts + ((t * 32 + n) * CP + kc * 8), 16);
+                }
+                if (tid < 32) reinterpret_cast<float*>(smem + 256 + ws * 128)[tid] = (ws ? sg.bias[1] : sg.bias[0])[tid];
+            } else {
+                // B[n=ci][k=co] = W_t[co][ci]: transpose while staging (once per persistent CTA)
+                for (int i = tid; i < NTAPS * 32 * CP; i += kStageThreads) {
+                    const int t = i / (32 * CP), rem = i - t * (32 * CP), co = rem / CP, ci = rem - co * CP;
+                    reinterpret_cast<bf16*>(smem + kSmemHdr + ws * W_BYTES)[((t * CH + (co >> 3)) * 32 + ci) * 8 + (co & 7)] = wts[i];
+                }
             }
         }
         cp_async_commit();
@@ -153,17 +195,18 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         // bias in registers: shared memory is saturated by the tensor core's operand reads
         float bz[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bz[i] = DGRAD ? 0.f : reinterpret_cast<const float*>(smem + 256)[i];
+        for (int i = 0; i < 32; ++i) bz[i] = 0.f;
+        int bz_set = -1;                           // weight set whose bias bz[] holds (reloaded when a CTA crosses into another set)
         // dgrad: the ReLU mask (X at the same position) is fetched one tile ahead so that its
         // DRAM latency never sits between an accumulator becoming ready and being drained
         uint4 xn[4];
         auto load_mask = [&](int tile_, uint4 (&dst)[4]) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
-            if (tile_ < g.total_tiles) {
-                const int b_ = tile_ / g.tiles_per_sample;
+            if (tile_ < g.total_tiles) {             // dgrad launches have one segment
+                const int b_ = tc_div(tile_, g.inv_tps);
                 const int p_ = (tile_ - b_ * g.tiles_per_sample) * TM + row_in_tile;
-                const int y_ = p_ / g.pitch, x_ = p_ - y_ * g.pitch;
+                const int y_ = tc_div(p_, g.inv_pitch), x_ = p_ - y_ * g.pitch;
                 if (y_ < g.Hv && x_ < g.Wv && p_ < g.S) {
                     const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
 #pragma unroll
@@ -174,24 +217,34 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         const int tstep = gridDim.x * kEpiGroups;
         const int tile0 = blockIdx.x + egroup * gridDim.x;
         long long e_wait = 0;
+        const bool edbg = (g.debug & 64) != 0;
         const long long e_start = clock64();
         acc = egroup;                              // local tile j uses accumulator stage j % 4
         if (DGRAD) load_mask(tile0, xn);
         for (int tile = tile0; tile < g.total_tiles; tile += tstep) {
-            const int b = tile / g.tiles_per_sample;
-            const int p = (tile - b * g.tiles_per_sample) * TM + row_in_tile;
-            const int y = p / g.pitch, x = p - y * g.pitch;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            const int p = tl.t * TM + row_in_tile;
+            const int y = tc_div(p, g.inv_pitch), x = p - y * g.pitch;
             const bool valid = (y < g.Hv) && (x < g.Wv);
-            const long long o = (long long)b * out_sstride + (long long)p * 8;   // + c*plane
+            bf16* __restrict__ out = tc_pick(sg.out, tl.seg);
+            const long long o = (long long)tl.b * out_sstride + (long long)p * 8;   // + c*plane
+            if (!DGRAD) {
+                const int ws = tc_pick(sg.wsel, tl.seg);
+                if (ws != bz_set) {
+                    bz_set = ws;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) bz[i] = reinterpret_cast<const float*>(smem + 256 + ws * 128)[i];
+                }
+            }
             uint4 xm[4];
             if (DGRAD) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) xm[c] = xn[c];
                 load_mask(tile + tstep, xn);
             }
-            const long long e0 = clock64();
+            const long long e0 = edbg ? clock64() : 0;
             mbar_wait(s_tfull + 8 * acc, acc_phase);
-            e_wait += clock64() - e0;
+            if (edbg) e_wait += clock64() - e0;
             tc_fence_after();
             uint32_t r[32];
             tmem_ld32(taddr0 + acc * (kTcSub * 32), r);
@@ -223,9 +276,18 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
             if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
         }
         if ((g.debug & 64) && tid == 0) { g_tc_dbg[blockIdx.x][6] = e_wait; g_tc_dbg[blockIdx.x][7] = clock64() - e_start - e_wait; }
-    } else if (warp == kEpiAll) {
-        // ================= MMA issuer
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    } else if (warp < kEpiAll + kMmaWarps) {
+        // ================= MMA issuers: warp mw takes the CTA's local tiles mw, mw + 2, ...
+        // Measured with one issuer (profiles/r01k_conv_roles.txt): a tile's 36 MMAs execute in
+        // ~1440 clk, but the issuing thread blocks while the MMA queue is full and then spends
+        // ~690 clk per tile on the commits, the two barrier waits and the tile bookkeeping before
+        // it can issue again -- the tensor pipe idled a third of the time.  With two issuers the
+        // other warp's MMAs are already queued while this one does its bookkeeping.
+        const int mw = warp - kEpiAll;
+        const int nmw = (g.debug & 128) ? 1 : kMmaWarps;
+        const bool dbg = (g.debug & 64) && mw == 0;
+        if (mw < nmw) {
+        uint32_t stage = (uint32_t)mw, phase = 0, acc = (uint32_t)mw, acc_phase = 0;
         // descriptors differ only in the 14-bit start-address field: precompute the field
         // offsets (16-byte units) once, add the stage base per tile
         const uint64_t a_hi = make_desc(0, PS, 128), b_hi = make_desc(0, 512, 128);
@@ -238,26 +300,33 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                                       (uint32_t)((g.debug & 8) ? ((taps.off[t] - g.min_off) & ~7) : (taps.off[t] - g.min_off)) * 16u) >> 4;
         long long c_te = 0, c_fu = 0, c_is = 0, c_n = 0;
         const long long c_start = clock64();
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-            const long long c0 = clock64();
+        if (dbg && lane == 0) g_tc_dbg[blockIdx.x][9] = tc_gtime();
+        const int valid_pos = g.Hv * g.pitch;
+        for (int tile = blockIdx.x + mw * gridDim.x; tile < g.total_tiles; tile += nmw * gridDim.x) {
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            // sub-tiles that start at or beyond the last valid output row hold no valid position:
+            // their MMAs are skipped (the epilogue writes exact zeros there whatever TMEM holds)
+            const int nsub = (tl.t * TM + 128 >= valid_pos) ? 1 : kTcSub;
+            const uint32_t w16 = (s_w + (uint32_t)tc_pick(sg.wsel, tl.seg) * W_BYTES) >> 4;
+            const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
+            const long long c0 = dbg ? clock64() : 0;
             mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
-            const long long c1 = clock64();
+            const long long c1 = dbg ? clock64() : 0;
             mbar_wait(s_full + 8 * stage, phase);
-            const long long c2 = clock64();
-            c_te += c1 - c0; c_fu += c2 - c1; ++c_n;
+            const long long c2 = dbg ? clock64() : 0;
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
                 if (!(g.debug & 2))
 #pragma unroll
                 for (int s = 0; s < kTcSub; ++s) {
+                    if (s >= nsub) break;
                     const uint32_t d = tmem_base + acc * (kTcSub * 32) + (uint32_t)(s * 32);
 #pragma unroll
                     for (int t = 0; t < NTAPS; ++t) {
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint64_t ad = a_hi | (uint64_t)((slab16 + (uint32_t)(s * 128) + a_off[t * KS + ks]) & 0x3FFFu);
-                            const uint64_t bd = b_hi | (uint64_t)(((s_w >> 4) + (uint32_t)((t * CH + 2 * ks) * 32)) & 0x3FFFu);
+                            const uint64_t bd = b_hi | (uint64_t)((w16 + (uint32_t)((t * CH + 2 * ks) * 32)) & 0x3FFFu);
                             if (t | ks) umma_bf16<1>(d, ad, bd); else umma_bf16<0>(d, ad, bd);
                         }
                     }
@@ -266,13 +335,16 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
                 umma_commit(s_tfull + 8 * acc);       // accumulators complete
             }
             __syncwarp();
-            c_is += clock64() - c2;
-            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            if (dbg) { c_te += c1 - c0; c_fu += c2 - c1; ++c_n; c_is += clock64() - c2; }
+            stage += (uint32_t)nmw;
+            if (stage >= (uint32_t)stages) { stage -= (uint32_t)stages; phase ^= 1; }
+            acc += (uint32_t)nmw;
+            if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
         }
-        if ((g.debug & 64) && lane == 0) {
+        if (dbg && lane == 0) {
             long long* d = g_tc_dbg[blockIdx.x];
-            d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n;
+            d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n; d[10] = tc_gtime();
+        }
         }
     } else {
         // ================= producer: slab[c][0:rows][16 B] <- plane c rows [p0+min_off, +rows)
@@ -280,13 +352,13 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         long long c_pw = 0;
         const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-            const int b = tile / g.tiles_per_sample;
-            const int p0 = (tile - b * g.tiles_per_sample) * TM;
-            const bf16* src = in + (long long)b * in_sstride + (long long)(p0 + g.min_off) * 8;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            const int p0 = tl.t * TM;
+            const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
             const uint32_t dst = s_slab0 + stage * slab_bytes;
-            const long long c0 = clock64();
+            const long long c0 = (g.debug & 64) ? clock64() : 0;
             mbar_wait(s_empty + 8 * stage, phase ^ 1);
-            c_pw += clock64() - c0;
+            if (g.debug & 64) c_pw += clock64() - c0;
             if (elect_one()) {
                 const uint32_t bar = s_full + 8 * stage;
                 if (g.debug & 1) {
@@ -308,6 +380,7 @@ k_conv_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restr
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                      : "memory");
+        if ((g.debug & 64) && lane == 0) g_tc_dbg[blockIdx.x][11] = tc_gtime();
     }
 }
 
@@ -320,6 +393,8 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     g.plane_rows = (g.slab_rows + 7) / 8 * 8;
     g.min_off = min_off;
     g.stages = 2;
+    g.inv_tps = 1.0f / (float)g.tiles_per_sample;
+    g.inv_pitch = 1.0f / (float)pitch;
     g.plane_bytes = g.plane_rows * 16;
     g.debug = 0;
     return g;
@@ -333,11 +408,10 @@ static int tc_set_smem(K kern, size_t bytes) {
 }
 
 template <int CP, int NTAPS, bool DGRAD>
-static int launch_tc(const void* in, long long in_sstride, const void* wts, const float* bias, float scale,
-                     const void* relu_src, void* out, long long out_sstride, TcGeom g, const TcTaps& taps,
-                     cudaStream_t stream) {
+static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const void* relu_src, long long out_sstride,
+                     TcGeom g, const TcTaps& taps, cudaStream_t stream) {
     constexpr int CH = CP / 8;
-    const size_t fixed = kSmemHdr + (size_t)NTAPS * CH * 512;
+    const size_t fixed = kSmemHdr + (size_t)sg.nw * NTAPS * CH * 512;
     { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
     g.plane_bytes = g.plane_rows * 16 + ((g.debug & 16) ? 64 : 0);
     const size_t slab = (size_t)CH * g.plane_bytes;
@@ -345,15 +419,45 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
     int stages = (int)((budget - fixed) / slab);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { set_last_error("conv_tc: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
+    // Even ring depth: issuer warp 0 then only ever touches the even stages' barriers and issuer 1
+    // the odd ones.  With an odd depth the two warps alternate on every full[] barrier, and a
+    // parity wait for phase n+1 passes spuriously while phase n is still incomplete (one warp a
+    // ring ahead of the other's bulk copies) -- observed as a trapped launch on the B200.
+    stages &= ~1;
     g.stages = stages;
-    { const char* e = getenv("CURLA_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) g.stages = atoi(e); }
+    { const char* e = getenv("CURLA_TC_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= stages) g.stages = atoi(e) & ~1; }
     const size_t smem = fixed + stages * slab;
     auto kern = k_conv_tc<CP, NTAPS, DGRAD>;
     if (tc_set_smem(kern, smem)) return -1;
     const int cap = sm_count();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
-    launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, (const bf16*)in, in_sstride, (const bf16*)wts, bias, scale,
-                                             (const bf16*)relu_src, (bf16*)out, out_sstride, g, taps);
+    launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, sg, in_sstride, scale, (const bf16*)relu_src, out_sstride, g, taps);
+    return 0;
+}
+
+// fills the segment table; total tiles -> g.total_tiles
+static int make_segs(const curla_conv_seg* segs, int nseg, TcGeom& g, TcSegs& sg) {
+    CURLA_CHECK(nseg >= 1 && nseg <= 3, "conv: 1..3 segments per launch (got %d)", nseg);
+    memset(&sg, 0, sizeof(sg));
+    int tiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        CURLA_CHECK(segs[s].B >= 1 && segs[s].in && segs[s].out && segs[s].wts, "conv: bad segment %d", s);
+        sg.in[s] = (const bf16*)segs[s].in;
+        sg.out[s] = (bf16*)segs[s].out;
+        int w = -1;
+        for (int k = 0; k < sg.nw; ++k) if (sg.wts[k] == (const bf16*)segs[s].wts && sg.bias[k] == segs[s].bias) w = k;
+        if (w < 0) {
+            CURLA_CHECK(sg.nw < 2, "conv: at most two distinct weight sets per launch");
+            w = sg.nw++;
+            sg.wts[w] = (const bf16*)segs[s].wts;
+            sg.bias[w] = segs[s].bias;
+        }
+        sg.wsel[s] = w;
+        tiles += segs[s].B * g.tiles_per_sample;
+        sg.tile_end[s] = tiles;
+    }
+    for (int s = nseg; s < 3; ++s) sg.tile_end[s] = tiles;
+    g.total_tiles = tiles;
     return 0;
 }
 
@@ -361,9 +465,9 @@ static int launch_tc(const void* in, long long in_sstride, const void* wts, cons
 
 using namespace curla;
 
-// timing experiments: copies the CURLA_TC_DEBUG&64 counters of `n` CTAs (8 int64 each) to the host
+// timing experiments: copies the CURLA_TC_DEBUG&64 counters of `n` CTAs (12 int64 each) to the host
 extern "C" int curla_conv_debug_read(long long* out, int n) {
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 8 * (n < 160 ? n : 160));
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 12 * (n < 160 ? n : 160));
     CURLA_CHECK(e == cudaSuccess, "conv_debug_read: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -374,22 +478,32 @@ extern "C" int curla_conv_pad_rows(int pitch) { return 128 * (kTcSub + 1) + 2 * 
 
 // layer 1: in = s2d bf16 [B][S][48]; layers 2..4: in = bf16 [B][S][32].  out bf16 [B][S][32].
 // Hv/Wv = valid output dims of this layer.
+extern "C" int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long long in_sstride, float scale,
+                                    long long out_sstride, int pitch, int S, int Hv, int Wv, int first_layer,
+                                    cudaStream_t stream) {
+    TcTaps taps;
+    TcSegs sg;
+    if (first_layer) {
+        for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
+        for (int t = 4; t < 9; ++t) taps.off[t] = 0;
+        TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, pitch + 1, 0);
+        if (make_segs(segs, nseg, g, sg)) return -1;
+        if (launch_tc<48, 4, false>(sg, in_sstride, scale, nullptr, out_sstride, g, taps, stream)) return -1;
+    } else {
+        for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
+        TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
+        if (make_segs(segs, nseg, g, sg)) return -1;
+        if (launch_tc<32, 9, false>(sg, in_sstride, scale, nullptr, out_sstride, g, taps, stream)) return -1;
+    }
+    return check_launch("conv_fwd");
+}
+
 extern "C" int curla_conv_fwd(const void* in, long long in_sstride, const void* wts,
                               const float* bias, float scale, void* out, long long out_sstride,
                               int B, int pitch, int S, int Hv, int Wv, int first_layer,
                               cudaStream_t stream) {
-    TcTaps taps;
-    if (first_layer) {
-        for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
-        for (int t = 4; t < 9; ++t) taps.off[t] = 0;
-        const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, pitch + 1, 0);
-        if (launch_tc<48, 4, false>(in, in_sstride, wts, bias, scale, nullptr, out, out_sstride, g, taps, stream)) return -1;
-    } else {
-        for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
-        const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
-        if (launch_tc<32, 9, false>(in, in_sstride, wts, bias, scale, nullptr, out, out_sstride, g, taps, stream)) return -1;
-    }
-    return check_launch("conv_fwd");
+    const curla_conv_seg seg = {in, wts, bias, out, B};
+    return curla_conv_fwd_multi(&seg, 1, in_sstride, scale, out_sstride, pitch, S, Hv, Wv, first_layer, stream);
 }
 
 // dX[P] = relu'(X[P]) * sum_t dY[P - off_t] . Wt^T ; Hv/Wv = valid dims of X (this layer's INPUT).
@@ -397,8 +511,11 @@ extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void
                                 const void* x, void* dx, long long dx_sstride, int B, int pitch,
                                 int S, int Hv, int Wv, cudaStream_t stream) {
     TcTaps taps;
+    TcSegs sg;
     for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
-    const TcGeom g = make_tc_geom(B, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
-    if (launch_tc<32, 9, true>(dy, dy_sstride, wts, nullptr, 1.f, x, dx, dx_sstride, g, taps, stream)) return -1;
+    TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
+    const curla_conv_seg seg = {dy, wts, nullptr, dx, B};
+    if (make_segs(&seg, 1, g, sg)) return -1;
+    if (launch_tc<32, 9, true>(sg, dy_sstride, 1.f, x, dx_sstride, g, taps, stream)) return -1;
     return check_launch("conv_dgrad");
 }

@@ -482,6 +482,16 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
 // ================================================================== launch helpers
 namespace {
 
+// CURLA_MERGE: how independent encoder passes share conv launches (results are bit-identical
+// in every mode).  0 = one launch per pass and layer; 1 = F1+F2 (both read next_obs) share
+// launches, F3 runs beside their tails, CURL anchor+key share launches; 2 (default) = F1+F2+F3
+// share launches as well.
+int merge_mode() {
+    static int m = -1;
+    if (m < 0) { const char* e = getenv("CURLA_MERGE"); m = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    return m;
+}
+
 struct Run {
     curla_agent* a;
     cudaStream_t st;
@@ -495,15 +505,34 @@ struct Run {
         if (!ok()) return;
         chk(curla_pack_shadows(a->P, a->Sh, segs.data(), (int)(segs.size() / 7), st));
     }
-    // conv stack forward: s2d input -> acts[0..3]
-    void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4]) {
-        if (!ok()) return;
+    // conv stack forward: s2d input -> acts[0..3].  Up to three independent passes (own input,
+    // weights and output buffers) run as ONE launch per layer (curla_conv_fwd_multi): 4 launches
+    // instead of 4 per pass, and no pipeline fill/drain between passes.  CURLA_MERGE=0 launches
+    // each pass separately (same results bit for bit).
+    struct Pass { const bf16* s2d; const EncP* e; const EncS* s; bf16* const* acts; };
+    void conv_stack_multi(const Pass* ps, int np) {
+        if (!ok() || np <= 0) return;
+        if (!merge_mode() && np > 1) {
+            for (int k = 0; k < np; ++k) conv_stack_multi(ps + k, 1);
+            return;
+        }
         const int B = a->cfg.batch;
-        chk(curla_conv_fwd(s2d, a->s2d_sstride, Sh(s.conv[0]), P(e.conv_b[0]), 1.0f / 255.0f, acts[0],
-                           a->act_sstride, B, a->pitch, a->S, a->Ho[0], a->Wo[0], 1, st));
-        for (int i = 1; i < 4 && ok(); ++i)
-            chk(curla_conv_fwd(acts[i - 1], a->act_sstride, Sh(s.conv[i]), P(e.conv_b[i]), 1.0f, acts[i],
-                               a->act_sstride, B, a->pitch, a->S, a->Ho[i], a->Wo[i], 0, st));
+        for (int i = 0; i < 4 && ok(); ++i) {
+            curla_conv_seg sg[3];
+            for (int k = 0; k < np; ++k) {
+                sg[k].in = i == 0 ? ps[k].s2d : ps[k].acts[i - 1];
+                sg[k].wts = Sh(ps[k].s->conv[i]);
+                sg[k].bias = P(ps[k].e->conv_b[i]);
+                sg[k].out = ps[k].acts[i];
+                sg[k].B = B;
+            }
+            chk(curla_conv_fwd_multi(sg, np, i == 0 ? a->s2d_sstride : a->act_sstride, i == 0 ? 1.0f / 255.0f : 1.0f,
+                                     a->act_sstride, a->pitch, a->S, a->Ho[i], a->Wo[i], i == 0, st));
+        }
+    }
+    void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4]) {
+        const Pass p = {s2d, &e, &s, acts};
+        conv_stack_multi(&p, 1);
     }
     // fc (split-K) + bias + LayerNorm
     void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
@@ -776,22 +805,47 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         const bool forked = ss != st;
         Run r2{a, ss};
         auto fork = [&](int k) { if (forked) { cudaEventRecord(a->ev[k], st); cudaStreamWaitEvent(ss, a->ev[k], 0); } };
-        // F1: actor(next_obs) -> a', log_pi'
-        r.conv_stack(a->s2d_next, a->enc_critic, a->s_critic, a->actB);
-        fork(0);
-        r2.rc = r.rc;
-        r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
-        r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
-        if (r2.ok()) r2.chk(curla_policy_fwd_rows(a->t_out1, u->noise_next, u->seed, u->offset * 2, c.rank * B, B, A, (float)c.log_std_min,
-                                             (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, ss));
-        // F2: critic_target(next_obs, a')
-        bf16* const* act2 = forked ? a->actC : a->actB;      // F1's tail may still be reading actB[3]
-        r.conv_stack(a->s2d_next, a->enc_target, a->s_target, act2);
-        fork(1);
-        r2.tail(act2[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X, a->fc_partial2);
-        r2.mlp_fwd_n(a->m_p2q[0].X, a->q_target, a->sq_target, a->m_p2q, 2, B);
-        // F3: critic(obs, action)
-        r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
+        const int mm = merge_mode();
+        // F1: actor(next_obs) -> a', log_pi';  F2: critic_target(next_obs, a');  F3: critic(obs, action)
+        bf16* const* act2 = (forked || mm) ? a->actC : a->actB;      // F1's tail may still be reading actB[3]
+        const Run::Pass p1 = {a->s2d_next, &a->enc_critic, &a->s_critic, a->actB};
+        const Run::Pass p2 = {a->s2d_next, &a->enc_target, &a->s_target, act2};
+        const Run::Pass p3 = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA};
+        auto tail1 = [&]() {
+            r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
+            r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
+            if (r2.ok()) r2.chk(curla_policy_fwd_rows(a->t_out1, u->noise_next, u->seed, u->offset * 2, c.rank * B, B, A, (float)c.log_std_min,
+                                                 (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, ss));
+        };
+        auto tail2 = [&]() {
+            r2.tail(act2[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X, a->fc_partial2);
+            r2.mlp_fwd_n(a->m_p2q[0].X, a->q_target, a->sq_target, a->m_p2q, 2, B);
+        };
+        if (mm == 0) {
+            r.conv_stack_multi(&p1, 1);
+            fork(0);
+            r2.rc = r.rc;
+            tail1();
+            r.conv_stack_multi(&p2, 1);
+            fork(1);
+            tail2();
+            r.conv_stack_multi(&p3, 1);
+        } else if (mm == 1) {
+            const Run::Pass ps[2] = {p1, p2};
+            r.conv_stack_multi(ps, 2);
+            fork(0);
+            r2.rc = r.rc;
+            tail1();
+            tail2();
+            r.conv_stack_multi(&p3, 1);
+        } else {
+            const Run::Pass ps[3] = {p1, p2, p3};
+            r.conv_stack_multi(ps, 3);
+            fork(0);
+            r2.rc = r.rc;
+            tail1();
+            tail2();
+        }
         r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p3, B, 0, a->act_b, a->m_p3q[0].X);
         r.mlp_fwd_n(a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, B);
         if (forked) { cudaEventRecord(a->ev[2], ss); cudaStreamWaitEvent(st, a->ev[2], 0); }
@@ -809,11 +863,44 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
                                          c.critic_lr, c.critic_beta, 0.999, 1e-8, ++a->t_critic, nullptr, st));
         r.pack(a->pack_critic);
     }
+    const int mm = merge_mode();
+    auto ema = [&]() {
+        // soft_update_params x3 (curl_sac.py:442-445): encoder tau on [0,n_enc), critic tau on Q1,Q2
+        if (r.ok()) r.chk(curla_ema_f32(a->P + a->off_target, a->P + a->off_critic, a->n_critic, a->n_enc, c.encoder_tau,
+                                        c.critic_tau, st));
+        r.pack(a->pack_target);
+    };
+    // The reference runs the EMA after the actor step (curl_sac.py:439-445); it reads the critic
+    // and writes the target only, neither of which the actor step touches, so running it first
+    // is the same computation -- and lets the post-EMA key pass F7 share conv launches with F4.
+    const bool ema_first = mm != 0;
+    if (do_sac && do_ema && ema_first) ema();
+    const cudaStream_t ss7 = do_cpc ? side_stream(a, st) : st;
+    const bool forked7 = ss7 != st;
+    const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA};    // F4 == F5 == F6 conv part
+    const Run::Pass p_key = {s2d_pos, &a->enc_target, &a->s_target, a->actB};          // F7
+    bool key_done = false, join7 = false;
+    // tail of one pass on the side stream (fc_partial2 is the side stream's split-K buffer)
+    auto side_tail = [&](const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t) {
+        Run r2{a, ss7};
+        r2.rc = r.rc;
+        if (forked7) { cudaEventRecord(a->ev[3], st); cudaStreamWaitEvent(ss7, a->ev[3], 0); }
+        r2.tail(act4, fc_shadow, e, t, B, 0, nullptr, nullptr, a->fc_partial2);
+        if (forked7) { cudaEventRecord(a->ev[2], ss7); join7 = true; }
+        r.chk(r2.rc);
+    };
     if (do_sac) {
         if (do_actor) {
             // ---------------- update_actor_and_alpha (curl_sac.py:373-404)
             // F4: conv_theta'(obs) shared by actor(obs), critic(obs, pi) and the CURL anchor
-            r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
+            if (mm && do_cpc) {
+                const Run::Pass ps[2] = {p_anchor, p_key};
+                r.conv_stack_multi(ps, 2);
+                side_tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7);   // keys: beside the actor step
+                key_done = true;
+            } else {
+                r.conv_stack_multi(&p_anchor, 1);
+            }
             r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B, 0, nullptr, a->m_p4.X);
             r.mlp_fwd_n(a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, B);
             if (r.ok()) r.chk(curla_policy_fwd_rows(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, c.rank * B, B, A, (float)c.log_std_min,
@@ -838,31 +925,27 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             if (r.ok()) r.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
                                                     1e-8, ++a->t_alpha, nullptr, st));
         }
-        if (do_ema) {
-            // soft_update_params x3 (curl_sac.py:442-445): encoder tau on [0,n_enc), critic tau on Q1,Q2
-            if (r.ok()) r.chk(curla_ema_f32(a->P + a->off_target, a->P + a->off_critic, a->n_critic, a->n_enc, c.encoder_tau,
-                                            c.critic_tau, st));
-            r.pack(a->pack_target);
-        }
+        if (do_ema && !ema_first) ema();
     }
 
     if (do_cpc) {
         // ---------------- update_cpc (curl_sac.py:406-423)
-        const cudaStream_t ss = side_stream(a, st);
-        const bool forked = ss != st && !have_p5;
-        if (!have_p5) {   // F6: anchor through the current critic encoder (its tail on the side stream)
-            r.conv_stack(a->s2d_obs, a->enc_critic, a->s_critic, a->actA);
-            Run r2{a, forked ? ss : st};
-            r2.rc = r.rc;
-            if (forked) { cudaEventRecord(a->ev[3], st); cudaStreamWaitEvent(ss, a->ev[3], 0); }
-            r2.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, nullptr, nullptr, forked ? a->fc_partial2 : nullptr);
-            if (forked) cudaEventRecord(a->ev[2], ss);
-            r.chk(r2.rc);
+        if (!have_p5) {
+            // F6: anchor through the current critic encoder (its tail on the side stream);
+            // F7: keys through the (post-EMA) target encoder, no grad
+            if (mm) {
+                const Run::Pass ps[2] = {p_anchor, p_key};
+                r.conv_stack_multi(ps, 2);
+            } else {
+                r.conv_stack_multi(&p_anchor, 1);
+            }
+            side_tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5);
         }
-        // F7: keys through the (post-EMA) target encoder, no grad
-        r.conv_stack(s2d_pos, a->enc_target, a->s_target, a->actB);
-        r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
-        if (forked) cudaStreamWaitEvent(st, a->ev[2], 0);
+        if (!key_done) {
+            if (!(mm && !have_p5)) r.conv_stack_multi(&p_key, 1);
+            r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
+        }
+        if (join7) cudaStreamWaitEvent(st, a->ev[2], 0);
         const float* zpos = a->t_p7.z;
         if (c.world > 1 && r.ok()) {
             CURLA_CHECK(a->comm, "update: world>1 but no communicator");

@@ -83,6 +83,21 @@ int curla_conv_fwd(const void* in, long long in_sstride, const void* wts, const 
 int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts, const void* x,
                      void* dx, long long dx_sstride, int B, int pitch, int S, int Hv, int Wv,
                      curla_stream_t stream);
+/* One launch for up to three independent encoder passes of the same layer (F1
+ * conv_theta(next_obs), F2 conv_target(next_obs), F3 conv_theta(obs) have no dependency on each
+ * other, nor have the CURL anchor and key passes): segment s maps in[s] -> out[s] with its own
+ * weights/bias (at most two DISTINCT weight pointers per call) and batch.  Same geometry,
+ * strides and scale for all segments.  Bitwise identical to nseg curla_conv_fwd calls.       */
+typedef struct curla_conv_seg {
+    const void* in;
+    const void* wts;
+    const float* bias;
+    void* out;
+    int B;
+} curla_conv_seg;
+int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long long in_sstride, float scale,
+                         long long out_sstride, int pitch, int S, int Hv, int Wv,
+                         int first_layer, curla_stream_t stream);
 /* timing experiments (CURLA_TC_DEBUG=64): per-CTA cycle counters of the conv pipeline roles */
 int curla_conv_debug_read(long long* out, int n);
 long long curla_conv_wgrad_workspace_floats(int first_layer);

@@ -53,10 +53,14 @@ print('layer %d %s debug=%s stages=%s: median %.1f us  min %.1f us' % (
 if int(os.environ.get('CURLA_TC_DEBUG', '0')) & 64:
     import ctypes as C
     import numpy as np
-    buf = (C.c_longlong * (148 * 8))()
+    buf = (C.c_longlong * (148 * 12))()
     _lib.call('curla_conv_debug_read', buf, 148)
-    a = np.array(list(buf), dtype=np.int64).reshape(148, 8)
+    a = np.array(list(buf), dtype=np.int64).reshape(148, 12)
     names = ['mma wait tempty', 'mma wait full', 'mma issue+sync', 'producer wait empty', 'mma loop total', 'tiles',
              'epi w0 wait tfull', 'epi w0 busy']
     for i, nme in enumerate(names):
         print('   %-22s mean %9.0f  min %9d  max %9d clk' % (nme, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
+    t0 = a[:, 8].min()
+    for i, nme in ((8, 'CTA entry'), (9, 'MMA loop start'), (10, 'MMA loop end'), (11, 'CTA exit')):
+        v = (a[:, i] - t0) / 1e3
+        print('   %-22s mean %8.2f  min %8.2f  max %8.2f us after the first CTA entry' % (nme, v.mean(), v.min(), v.max()))

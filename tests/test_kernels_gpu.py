@@ -124,6 +124,52 @@ def test_conv_forward(H, W, B):
         cur = bf16r(ours)                 # feed OUR stored activations to the next reference layer
 
 
+@pytest.mark.parametrize('H,W', [(76, 135), (90, 160)])
+def test_conv_forward_multi_segment(H, W):
+    """One launch over three passes (two weight sets, different batch sizes) == three launches, bit for bit."""
+    import ctypes as C
+    Bs = [3, 2, 4]
+    cases = [_conv_case(H, W, b, seed=10 + i) for i, b in enumerate(Bs)]
+    wsets = [cases[0][2:], cases[1][2:], cases[0][2:]]          # passes 0 and 2 share weights (F1 / F3)
+    singles, s2ds, keep = [], [], []
+    for (g, x, _, _), (ws, bs) in zip(cases, wsets):
+        s2d, acts, kp = _run_conv_stack(g, x, ws, bs)
+        singles.append(acts); s2ds.append(s2d); keep.append(kp)
+    wsh = [[pack_conv_w(ws[l], l == 0) for l in range(4)] for ws, _ in wsets[:2]]
+    bd = [[bs[l].to(DEV) for l in range(4)] for _, bs in wsets[:2]]
+    wsel = [0, 1, 0]
+    g0 = cases[0][0]
+    ins = s2ds
+    for l in range(4):
+        outs = []
+        segs = (_lib.ConvSeg * 3)()
+        for k in range(3):
+            full, out = cases[k][0].alloc(32)
+            out.fill_(-7.0)                                        # every position must be (re)written
+            keep.append(full); outs.append(out)
+            segs[k].inp = ins[k].data_ptr(); segs[k].wts = wsh[wsel[k]][l].data_ptr()
+            segs[k].bias = bd[wsel[k]][l].data_ptr(); segs[k].out = out.data_ptr(); segs[k].B = Bs[k]
+        _lib.call('curla_conv_fwd_multi', C.byref(segs), 3, g0.S * (g0.CP1 if l == 0 else 32),
+                  1.0 / 255.0 if l == 0 else 1.0, g0.S * 32, g0.pitch, g0.S, g0.Ho[l], g0.Wo[l], 1 if l == 0 else 0,
+                  stream())
+        torch.cuda.synchronize()
+        n = min(g0.S, -(-g0.Ho[l] * g0.pitch // 256) * 256)        # positions a launch writes per sample and plane
+        for k in range(3):
+            a = outs[k].view(torch.int16).view(Bs[k], 4, g0.S, 8)
+            b = singles[k][l].view(torch.int16).view(Bs[k], 4, g0.S, 8)
+            assert torch.equal(a[:, :, :n], b[:, :, :n]), (l, k)
+            a[:, :, n:] = 0                                        # never written: zero like the engine's arenas
+        ins = outs
+    # more than two distinct weight sets is refused
+    segs = (_lib.ConvSeg * 3)()
+    for k in range(3):
+        segs[k].inp = s2ds[k].data_ptr(); segs[k].wts = wsh[k % 2][0].data_ptr(); segs[k].bias = bd[k % 2][0].data_ptr() + 4 * (k == 2)
+        segs[k].out = outs[k].data_ptr(); segs[k].B = Bs[k]
+    with pytest.raises(_lib.CurlaError):
+        _lib.call('curla_conv_fwd_multi', C.byref(segs), 3, g0.S * g0.CP1, 1.0, g0.S * 32, g0.pitch, g0.S, g0.Ho[0],
+                  g0.Wo[0], 1, stream())
+
+
 @pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2)])
 def test_conv_backward(H, W, B):
     g, x, ws, bs = _conv_case(H, W, B, seed=1)
