@@ -43,6 +43,7 @@ struct TcGeom {
     int min_off;         // most negative tap shift
     int stages;          // slab ring depth (host: as many as fit in shared memory, <= 8)
     int plane_bytes;     // shared-memory stride between channel planes of a slab
+    int dynamic, ctr_slot;   // tiles handed out through an atomic counter (g_tc_ctr pair ctr_slot) instead of round robin
     float inv_tps, inv_pitch;   // 1/tiles_per_sample, 1/pitch: index divisions through a float reciprocal (exact for
                          // these ranges: (i + 0.5) / d is never within float rounding of an integer)
     int debug;           // CURLA_TC_DEBUG bitmask (timing experiments only): 1 no loads, 2 no MMA, 4 no stores,
@@ -81,8 +82,33 @@ __device__ __forceinline__ T tc_pick(T const (&a)[3], int i) { return i == 0 ? a
 // CURLA_TC_DEBUG & 64: per-CTA cycle counters of the MMA thread and the producer (timing
 // experiments only): [0] MMA wait tempty, [1] MMA wait full, [2] MMA issue, [3] producer wait
 // empty, [4] kernel total, [5] tiles, [6] epilogue warp 0 wait tfull, [7] epilogue warp 0 busy
-//   [8] globaltimer (ns) at kernel entry, [9] at MMA loop start, [10] at MMA loop end, [11] at CTA exit
-__device__ long long g_tc_dbg[160][12];
+//   [8] globaltimer (ns) at kernel entry, [9] at MMA loop start, [10] at MMA loop end, [11] at CTA exit, [12] %smid,
+//   [13] issuer warp 1: loop end (globaltimer), [14] issuer warp 1: issue+sync clk,
+//   [15] producer: waiting for a tile id (counter atomic), [16] producer: publishing + issuing the bulk copies, [17] producer loop total
+__device__ long long g_tc_dbg[160][20];
+// Dynamic tile scheduler: pairs {next tile, finished CTAs}; a launch takes the next pair of the
+// pool (host side, round robin) and its last CTA zeroes the pair again.
+constexpr int kCtrSlots = 256;
+__device__ int g_tc_ctr[2 * kCtrSlots];
+__device__ __forceinline__ int ld_volatile_s32(const void* p) { return *reinterpret_cast<const volatile int*>(p); }
+// Ring entry of local tile j: (j mod 1024) << 20 | (tile + 1); tile = -1 ends the stream.  ONE 32-bit
+// store publishes id and readiness together, so the producer needs no fence between "id" and
+// "count" stores -- a MEMBAR there also waits for its in-flight counter atomics (measured: the
+// producer then became the bottleneck).  Slots start as 0xFFFFFFFF (tag 4095: matches no j).
+// atomicAdd(p, 1) -- and the same atom.add / atom.inc written as inline PTX, even with a
+// clock-derived addend -- is compiled into a warp-aggregated sequence (vote, leader atomic, SHFL
+// of the result) whose SHFL consumes the result at once: the issuing thread waits out every
+// round trip.  An addend ptxas cannot prove warp-uniform (a volatile shared-memory load from a
+// per-lane address; the words all hold 1) keeps it a plain ATOMG whose result register is only
+// waited for where it is first read.
+__device__ __forceinline__ int atom_add_nonuniform(int* p, int addend) {
+    int old;
+    asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(addend) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t ring_entry(int j, int tile) { return ((uint32_t)(j & 0x3FF) << 20) | (uint32_t)(tile + 1); }
+__device__ __forceinline__ bool ring_ready(uint32_t e, int j) { return (e >> 20) == (uint32_t)(j & 0x3FF); }
+__device__ __forceinline__ int ring_tile(uint32_t e) { return (int)(e & 0xFFFFFu) - 1; }
 __device__ __forceinline__ long long tc_gtime() {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -97,6 +123,11 @@ __device__ __forceinline__ long long tc_gtime() {
 //   warp  18     producer   (one elected lane: CP/8 bulk copies cp.async.bulk global -> shared
 //                            per tile, one per channel plane -- the global layout IS the
 //                            shared-memory operand layout -- completing on the stage's mbarrier)
+// Tiles: the producer decides which tile is the CTA's local tile j (the first two round robin,
+// the rest from a global atomic counter: SMs drain tiles at visibly different rates -- the even
+// SM of a TPC ~14 % slower in an MMA-only run, profiles/r01l_conv_sm_imbalance.txt -- and a static
+// split waits for the slowest) and publishes it in a shared-memory ring before filling the slab;
+// two -1 entries end the stream (one per issuer warp / epilogue group).
 // Pipelines: full/empty per slab stage (producer <-> MMA), tfull/tempty per TMEM accumulator
 // stage (MMA <-> epilogue; 4 stages x 2 sub-tiles x 32 columns = 256 TMEM columns), so loads
 // of tile i+k, the MMAs of tile i+1 and the epilogue of tile i all run concurrently.
@@ -110,8 +141,9 @@ constexpr int kEpiAll = kEpiWarps * kEpiGroups;      // 16
 constexpr int kMmaWarps = 2;                         // two issuer warps alternate tiles (see the kernel)
 constexpr int kTcThreads = (kEpiAll + kMmaWarps + 1) * 32;       // 608
 constexpr int kMaxStages = 8;
-constexpr int kAccStages = 4;
-constexpr int kSmemHdr = 512;             // barriers + tmem ptr + bias
+constexpr int kAccStages = 4;            // 256 TMEM columns (8 stages = all 512 columns measured no faster)
+constexpr int kSmemHdr = 768;             // barriers + tmem ptr + bias + tile ring + 32 ones
+constexpr int kRing = 16;                 // published tile ids: local tile j -> slot j % 16 (deeper than slab + accumulator stages)
 
 template <int CP, int NTAPS, bool DGRAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -123,10 +155,16 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    if ((g.debug & 64) && tid == 0) g_tc_dbg[blockIdx.x][8] = tc_gtime();
-    // header: full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem ptr @192, bias set 0 @256, set 1 @384
-    const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 160;
-    const uint32_t s_tptr = s_base + 192;
+    if ((g.debug & 64) && tid == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_tc_dbg[blockIdx.x][8] = tc_gtime();
+        g_tc_dbg[blockIdx.x][12] = smid;
+    }
+    // header: full[8] @0, empty[8] @64, tfull[8] @128, tempty[8] @192, bias set 0 @256, set 1 @384,
+    //         tile ring[16] @512, tmem ptr @576, ones[32] @640 (see atom_add_nonuniform)
+    const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 192;
+    const uint32_t s_tptr = s_base + 576;
     const uint32_t s_w = s_base + kSmemHdr;
     const uint32_t PS = (uint32_t)g.plane_bytes;
     const uint32_t slab_bytes = CH * PS;
@@ -136,6 +174,8 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
 
     // ---- one-time setup: barriers, TMEM, weights, bias
     if (tid == 0) {
+        for (int i = 0; i < kRing; ++i) reinterpret_cast<volatile uint32_t*>(smem + 512)[i] = 0xFFFFFFFFu;
+        for (int i = 0; i < 32; ++i) reinterpret_cast<volatile int*>(smem + 640)[i] = 1;
         for (int i = 0; i < stages; ++i) {
             mbar_init(s_full + 8 * i, 1);
             mbar_init(s_empty + 8 * i, 1);
@@ -156,7 +196,7 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
     tc_fence_before();
     __syncthreads();              // barriers initialised, TMEM address published
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 192);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 576);
     // everything above is independent of earlier kernels; from here on we read their outputs
     pdl_grid_sync();
     // The producer warp goes straight to its loop (its first bulk copies overlap the weight
@@ -200,28 +240,32 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
         // dgrad: the ReLU mask (X at the same position) is fetched one tile ahead so that its
         // DRAM latency never sits between an accumulator becoming ready and being drained
         uint4 xn[4];
-        auto load_mask = [&](int tile_, uint4 (&dst)[4]) {
+        int xn_tile = -1;
+        auto load_mask = [&](int tile_, uint4 (&dst)[4]) {          // dgrad launches have one segment
 #pragma unroll
             for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
-            if (tile_ < g.total_tiles) {             // dgrad launches have one segment
-                const int b_ = tc_div(tile_, g.inv_tps);
-                const int p_ = (tile_ - b_ * g.tiles_per_sample) * TM + row_in_tile;
-                const int y_ = tc_div(p_, g.inv_pitch), x_ = p_ - y_ * g.pitch;
-                if (y_ < g.Hv && x_ < g.Wv && p_ < g.S) {
-                    const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
+            const int b_ = tc_div(tile_, g.inv_tps);
+            const int p_ = (tile_ - b_ * g.tiles_per_sample) * TM + row_in_tile;
+            const int y_ = tc_div(p_, g.inv_pitch), x_ = p_ - y_ * g.pitch;
+            if (y_ < g.Hv && x_ < g.Wv && p_ < g.S) {
+                const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(relu_src + o_ + c * plane);
-                }
+                for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(relu_src + o_ + c * plane);
             }
         };
-        const int tstep = gridDim.x * kEpiGroups;
-        const int tile0 = blockIdx.x + egroup * gridDim.x;
         long long e_wait = 0;
         const bool edbg = (g.debug & 64) != 0;
         const long long e_start = clock64();
-        acc = egroup;                              // local tile j uses accumulator stage j % 4
-        if (DGRAD) load_mask(tile0, xn);
-        for (int tile = tile0; tile < g.total_tiles; tile += tstep) {
+        acc = egroup;                              // local tile j uses accumulator stage j % kAccStages
+        for (int j = egroup;; j += kEpiGroups) {
+            uint32_t ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1)));
+            if (!ring_ready(ent, j)) {                          // not published yet (rare: the producer runs stages ahead)
+                const long long t0 = clock64();
+                while (!ring_ready(ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))), j))
+                    if (clock64() - t0 > (1ll << 31)) __trap();
+            }
+            const int tile = ring_tile(ent);
+            if (tile < 0) break;
             const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
             const int p = tl.t * TM + row_in_tile;
             const int y = tc_div(p, g.inv_pitch), x = p - y * g.pitch;
@@ -238,9 +282,20 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
             }
             uint4 xm[4];
             if (DGRAD) {
+                if (xn_tile == tile) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) xm[c] = xn[c];
-                load_mask(tile + tstep, xn);
+                    for (int c = 0; c < 4; ++c) xm[c] = xn[c];
+                } else {
+                    load_mask(tile, xm);
+                }
+                // this group's next tile, if the producer has published it already (it normally
+                // has: the producer runs a ring of slabs ahead): its mask is fetched now
+                xn_tile = -1;
+                const uint32_t e2 = (uint32_t)ld_volatile_s32(smem + 512 + 4 * ((j + kEpiGroups) & (kRing - 1)));
+                if (ring_ready(e2, j + kEpiGroups)) {
+                    xn_tile = ring_tile(e2);
+                    if (xn_tile >= 0) load_mask(xn_tile, xn);
+                }
             }
             const long long e0 = edbg ? clock64() : 0;
             mbar_wait(s_tfull + 8 * acc, acc_phase);
@@ -285,7 +340,7 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
         // other warp's MMAs are already queued while this one does its bookkeeping.
         const int mw = warp - kEpiAll;
         const int nmw = (g.debug & 128) ? 1 : kMmaWarps;
-        const bool dbg = (g.debug & 64) && mw == 0;
+        const bool dbg = (g.debug & 64) != 0;
         if (mw < nmw) {
         uint32_t stage = (uint32_t)mw, phase = 0, acc = (uint32_t)mw, acc_phase = 0;
         // descriptors differ only in the 14-bit start-address field: precompute the field
@@ -300,20 +355,22 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
                                       (uint32_t)((g.debug & 8) ? ((taps.off[t] - g.min_off) & ~7) : (taps.off[t] - g.min_off)) * 16u) >> 4;
         long long c_te = 0, c_fu = 0, c_is = 0, c_n = 0;
         const long long c_start = clock64();
-        if (dbg && lane == 0) g_tc_dbg[blockIdx.x][9] = tc_gtime();
+        if (dbg && lane == 0 && mw == 0) g_tc_dbg[blockIdx.x][9] = tc_gtime();
         const int valid_pos = g.Hv * g.pitch;
-        for (int tile = blockIdx.x + mw * gridDim.x; tile < g.total_tiles; tile += nmw * gridDim.x) {
+        for (int j = mw;; j += nmw) {
+            const long long c1 = dbg ? clock64() : 0;
+            mbar_wait(s_full + 8 * stage, phase);                  // slab filled, tile id published
+            const long long c2 = dbg ? clock64() : 0;
+            const int tile = ring_tile((uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))));
+            if (tile < 0) break;
             const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
             // sub-tiles that start at or beyond the last valid output row hold no valid position:
             // their MMAs are skipped (the epilogue writes exact zeros there whatever TMEM holds)
             const int nsub = (tl.t * TM + 128 >= valid_pos) ? 1 : kTcSub;
             const uint32_t w16 = (s_w + (uint32_t)tc_pick(sg.wsel, tl.seg) * W_BYTES) >> 4;
             const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
-            const long long c0 = dbg ? clock64() : 0;
             mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
-            const long long c1 = dbg ? clock64() : 0;
-            mbar_wait(s_full + 8 * stage, phase);
-            const long long c2 = dbg ? clock64() : 0;
+            const long long c3 = dbg ? clock64() : 0;
             tc_fence_after();
             if (elect_one()) {
                 if (!(g.debug & 2))
@@ -335,7 +392,7 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
                 umma_commit(s_tfull + 8 * acc);       // accumulators complete
             }
             __syncwarp();
-            if (dbg) { c_te += c1 - c0; c_fu += c2 - c1; ++c_n; c_is += clock64() - c2; }
+            if (dbg) { c_te += c3 - c2; c_fu += c2 - c1; ++c_n; c_is += clock64() - c3; }
             stage += (uint32_t)nmw;
             if (stage >= (uint32_t)stages) { stage -= (uint32_t)stages; phase ^= 1; }
             acc += (uint32_t)nmw;
@@ -343,36 +400,74 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
         }
         if (dbg && lane == 0) {
             long long* d = g_tc_dbg[blockIdx.x];
-            d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n; d[10] = tc_gtime();
+            if (mw == 0) { d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n; d[10] = tc_gtime(); }
+            else { d[13] = tc_gtime(); d[14] = c_is; }
         }
         }
     } else {
-        // ================= producer: slab[c][0:rows][16 B] <- plane c rows [p0+min_off, +rows)
+        const int one = ld_volatile_s32(smem + 640 + 4 * lane);       // 1, but not provably warp-uniform
+        if (lane == 0) {
+        // ================= producer (one thread): slab[c][0:rows][16 B] <- plane c rows [p0+min_off, +rows)
         uint32_t stage = 0, phase = 0;
-        long long c_pw = 0;
+        long long c_pw = 0, c_q = 0, c_cp = 0;
+        const long long c_p0 = clock64();
         const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
-            const int p0 = tl.t * TM;
-            const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
-            const uint32_t dst = s_slab0 + stage * slab_bytes;
-            const long long c0 = (g.debug & 64) ? clock64() : 0;
-            mbar_wait(s_empty + 8 * stage, phase ^ 1);
-            if (g.debug & 64) c_pw += clock64() - c0;
-            if (elect_one()) {
+        int* const ctr = g_tc_ctr + 2 * g.ctr_slot;
+        const int G = (int)gridDim.x;
+        // Tile queue of four FIXED registers (the loop is unrolled by four): slot u is consumed,
+        // then immediately re-armed with an atomic whose value is first read four tiles later, so
+        // up to four counter round trips (~1 us each under load) are in flight and none is waited
+        // for.  (A shifting queue q0 <- q1 <- q2 stalls on the register move of the youngest entry.)
+        int q[4];
+        // q[] holds tile - 2G (the raw counter value): adding the offset where the atomic is issued
+        // would consume its result -- and wait for it -- on the spot
+        q[0] = (int)blockIdx.x - 2 * G; q[1] = q[0] + G;
+        q[2] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[1] + G;
+        q[3] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[2] + G;
+        int sentinels = 0, j = 0;
+        while (sentinels < 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (sentinels >= 2) break;
+                const long long cq = (g.debug & 64) ? clock64() : 0;
+                const int tile = q[u] + 2 * G;
+                const bool real = tile < g.total_tiles;
+                const long long c0 = (g.debug & 64) ? clock64() + (real ? 0 : 1) : 0;      // (depends on the id: read after it arrived)
+                if (g.debug & 64) c_q += c0 - cq;
+                mbar_wait(s_empty + 8 * stage, phase ^ 1);
+                const long long c1 = (g.debug & 64) ? clock64() : 0;
+                if (g.debug & 64) c_pw += c1 - c0;
+                *reinterpret_cast<volatile uint32_t*>(smem + 512 + 4 * (j & (kRing - 1))) = ring_entry(j, real ? tile : -1);
                 const uint32_t bar = s_full + 8 * stage;
-                if (g.debug & 1) {
+                if (!real || (g.debug & 1)) {
                     mbar_arrive(bar);
                 } else {
+                    const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+                    const int p0 = tl.t * TM;
+                    const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
+                    const uint32_t dst = s_slab0 + stage * slab_bytes;
                     mbar_expect_tx(bar, bytes * CH);
 #pragma unroll
                     for (int c = 0; c < CH; ++c) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
                 }
+                if (g.debug & 64) c_cp += clock64() - c1;
+                ++j;
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+                if (!real) ++sentinels;                       // ids only grow: everything after is past the end too
+                else q[u] = g.dynamic ? atom_add_nonuniform(ctr, one) : tile + 2 * G;
             }
-            __syncwarp();
-            if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
         }
-        if ((g.debug & 64) && lane == 0) g_tc_dbg[blockIdx.x][3] = c_pw;
+        if (g.dynamic) {
+            // every tile this CTA will ever ask for has been asked for: the last CTA to get here
+            // re-arms the counter pair for the launch that takes it next
+            __threadfence();
+            if (atomicAdd(ctr + 1, 1) == G - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+        }
+        if (g.debug & 64) {
+            long long* d = g_tc_dbg[blockIdx.x];
+            d[3] = c_pw; d[15] = c_q; d[16] = c_cp; d[17] = clock64() - c_p0;
+        }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -393,6 +488,7 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     g.plane_rows = (g.slab_rows + 7) / 8 * 8;
     g.min_off = min_off;
     g.stages = 2;
+    g.dynamic = 0; g.ctr_slot = 0;
     g.inv_tps = 1.0f / (float)g.tiles_per_sample;
     g.inv_pitch = 1.0f / (float)pitch;
     g.plane_bytes = g.plane_rows * 16;
@@ -431,6 +527,12 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     if (tc_set_smem(kern, smem)) return -1;
     const int cap = sm_count();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
+    {   // dynamic tile hand-out once every CTA has more than its two round-robin tiles
+        static unsigned seq = 0;
+        const char* e = getenv("CURLA_TC_STATIC");
+        g.dynamic = (g.total_tiles > 2 * grid && !(e && e[0] == '1')) ? 1 : 0;
+        g.ctr_slot = g.dynamic ? (int)(seq++ % kCtrSlots) : 0;
+    }
     launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, sg, in_sstride, scale, (const bf16*)relu_src, out_sstride, g, taps);
     return 0;
 }
@@ -456,6 +558,7 @@ static int make_segs(const curla_conv_seg* segs, int nseg, TcGeom& g, TcSegs& sg
         tiles += segs[s].B * g.tiles_per_sample;
         sg.tile_end[s] = tiles;
     }
+    CURLA_CHECK(tiles < (1 << 20) - 1, "conv: %d tiles in one launch (limit 2^20 - 2)", tiles);
     for (int s = nseg; s < 3; ++s) sg.tile_end[s] = tiles;
     g.total_tiles = tiles;
     return 0;
@@ -465,9 +568,9 @@ static int make_segs(const curla_conv_seg* segs, int nseg, TcGeom& g, TcSegs& sg
 
 using namespace curla;
 
-// timing experiments: copies the CURLA_TC_DEBUG&64 counters of `n` CTAs (12 int64 each) to the host
+// timing experiments: copies the CURLA_TC_DEBUG&64 counters of `n` CTAs (20 int64 each) to the host
 extern "C" int curla_conv_debug_read(long long* out, int n) {
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 12 * (n < 160 ? n : 160));
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 20 * (n < 160 ? n : 160));
     CURLA_CHECK(e == cudaSuccess, "conv_debug_read: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -53,9 +53,11 @@ print('layer %d %s debug=%s stages=%s: median %.1f us  min %.1f us' % (
 if int(os.environ.get('CURLA_TC_DEBUG', '0')) & 64:
     import ctypes as C
     import numpy as np
-    buf = (C.c_longlong * (148 * 12))()
+    buf = (C.c_longlong * (148 * 20))()
     _lib.call('curla_conv_debug_read', buf, 148)
-    a = np.array(list(buf), dtype=np.int64).reshape(148, 12)
+    a = np.array(list(buf), dtype=np.int64).reshape(148, 20)
+    if os.environ.get('CURLA_TC_DUMP'):
+        np.save(os.environ['CURLA_TC_DUMP'], a)
     names = ['mma wait tempty', 'mma wait full', 'mma issue+sync', 'producer wait empty', 'mma loop total', 'tiles',
              'epi w0 wait tfull', 'epi w0 busy']
     for i, nme in enumerate(names):

@@ -124,6 +124,22 @@ def test_conv_forward(H, W, B):
         cur = bf16r(ours)                 # feed OUR stored activations to the next reference layer
 
 
+def test_conv_forward_dynamic_tiles_match_static(monkeypatch):
+    """More than two tiles per SM: tiles are handed out by an atomic counter.  Same bits as the
+    round-robin split, launch after launch (the counter pair re-arms itself)."""
+    g, x, ws, bs = _conv_case(76, 135, 48, seed=5)
+    assert 48 * -(-g.Ho[0] * g.pitch // 256) > 2 * torch.cuda.get_device_properties(0).multi_processor_count
+    monkeypatch.setenv('CURLA_TC_STATIC', '1')
+    _, ref, keep0 = _run_conv_stack(g, x, ws, bs)
+    torch.cuda.synchronize()
+    monkeypatch.setenv('CURLA_TC_STATIC', '0')
+    for _ in range(3):
+        _, acts, keep1 = _run_conv_stack(g, x, ws, bs)
+        torch.cuda.synchronize()
+        for l in range(4):
+            assert torch.equal(acts[l].view(torch.int16), ref[l].view(torch.int16)), l
+
+
 @pytest.mark.parametrize('H,W', [(76, 135), (90, 160)])
 def test_conv_forward_multi_segment(H, W):
     """One launch over three passes (two weight sets, different batch sizes) == three launches, bit for bit."""
