@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libcurla_b200.so')
 STAMP = os.path.join(HERE, 'build', 'stamp')
-SOURCES = ['engine.cu', 'gather.cu', 'gemm.cu', 'small.cu', 'curl.cu', 'optim.cu', 'augment.cu',
+SOURCES = ['engine.cu', 'gather.cu', 'gemm.cu', 'gemm_tc.cu', 'small.cu', 'curl.cu', 'optim.cu', 'augment.cu',
            'conv_tc.cu', 'conv_wgrad_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']

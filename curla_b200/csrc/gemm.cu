@@ -9,44 +9,18 @@
 // "Row" extents (the slow index of a stored matrix) may be ragged; contiguous extents
 // must be multiples of 8 elements (16-byte cp.async chunks, zero padded buffers).
 // 64x64x32 CTA tile, 4 warps, 4-stage cp.async pipeline, mma.sync m16n8k16 bf16->fp32.
+// Measured alternatives (tests/bench_gemm.py, profiles/r02a_gemm_tcgen05_vs_mma_sync.txt): every shape of
+// the update moves ~4-5 TB/s of operands through 16-byte cp.async (16-19 B/clk per SM).  A
+// tcgen05 kernel fed the same way (gemm_tc.cu) is 1.3-2x slower, and this kernel with one
+// 128-byte cp.async.bulk per operand row instead of cp.async is 1.5-2x slower still; the way
+// forward is whole-tile tensor-map TMA loads.
 #include "common.cuh"
+#include "gemm.cuh"
 #include "../../include/curla_b200.h"
 
 namespace curla {
 
 constexpr int BM = 64, BN = 64, BK = 32, STAGES = 4;
-
-struct GemmArgs {
-    const bf16* A; long long lda;
-    const bf16* B; long long ldb;
-    void* C; long long ldc;
-    int M, N, K;
-    int n_store;              // columns [0, n_store) are written
-    int out_bf16;             // 1: bf16 output, 0: fp32
-    const float* bias;        // per column, optional
-    int relu;
-    const bf16* mask; long long ldmask;   // optional: out = mask[m][n] > 0 ? v : 0
-    int k_per_split;          // multiple of BK; blockIdx.z selects the K range
-    long long split_stride;   // elements between split outputs (fp32 partials)
-    float alpha;
-    // Segmented contiguous index (the channel-plane activation layout of the conv stack,
-    // DESIGN.md section 3): index i of the chosen operand lives at (i / seg_len) * seg_stride +
-    // i % seg_len.  seg_mask: 1 = A's contiguous index, 2 = B's, 4 = C's and the mask's column.
-    int seg_len; long long seg_stride; int seg_mask; float seg_inv;
-    // Batched problems (Q1 || Q2 of the critic: same shapes, different weights): blockIdx.z is
-    // the batch index (split-K and batching are mutually exclusive); element strides.
-    int batch; long long bsA, bsB, bsC, bsBias, bsMask;
-    int vec_c;                // host: bf16 output (and mask) rows are 16-byte addressable -> staged epilogue
-};
-
-// i / seg_len through a float reciprocal: exact here because i is a multiple of 2 (columns)
-// or 8 (chunks) below 2^22 with only a handful of segments, so (i + 0.5) / seg_len is never
-// within float rounding of an integer.
-__device__ __forceinline__ long long seg_off(int i, int seg_len, long long seg_stride, float inv_len, bool on) {
-    if (!on) return i;
-    const int s = __float2int_rd(((float)i + 0.5f) * inv_len);
-    return (long long)s * seg_stride + (i - s * seg_len);
-}
 
 __device__ __forceinline__ uint32_t off64(int row, int chunk) {      // 64-byte rows
     return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
@@ -331,11 +305,18 @@ extern "C" int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, 
 }
 
 static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream) {
-    const int kt = cdiv(p.K, BK);
-    p.k_per_split = cdiv(kt, splits) * BK;
+    // K range of a split: a multiple of 64 (the tcgen05 kernel's K step; also fine for BK = 32),
+    // so that the number of partial slices does not depend on which kernel runs
+    const int kt = cdiv(p.K, 64);
+    p.k_per_split = cdiv(kt, splits) * 64;
     const int zs = cdiv(p.K, p.k_per_split);
     dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.batch > 1 ? p.batch : zs);
     p.seg_inv = p.seg_mask ? 1.0f / (float)p.seg_len : 0.f;
+    {
+        const int r = gemm_tc_try_launch(p, layout, zs, stream);
+        if (r < 0) return -1;
+        if (r > 0) return check_launch("gemm_bf16");
+    }
     p.vec_c = p.out_bf16 && p.ldc % 8 == 0 && p.bsC % 8 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
               (!p.mask || (p.ldmask % 8 == 0 && p.bsMask % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0));
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
@@ -353,7 +334,7 @@ static int gemm_launch(GemmArgs& p, int layout, int splits, cudaStream_t stream)
 
 // number of K splits curla_gemm_bf16 will actually launch for (K, splits)
 extern "C" int curla_gemm_effective_splits(int K, int splits) {
-    const int kt = cdiv(K, BK);
-    const int kps = cdiv(kt, splits) * BK;
+    const int kt = cdiv(K, 64);
+    const int kps = cdiv(kt, splits) * 64;
     return cdiv(K, kps);
 }

@@ -120,6 +120,8 @@ int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, 
                     long long ldc, int M, int N, int K, int layout, int n_store, int out_bf16,
                     const float* bias, int relu, const void* mask, long long ldmask, int splits,
                     long long split_stride, float alpha, curla_stream_t stream);
+/* timing experiments: clock counters of one thread of the tcgen05 GEMM (gemm_tc.cu) */
+int curla_gemm_tc_debug_read(long long* out8);
 /* same, with the contiguous index of A (seg_mask&1), B (&2) or C+mask columns (&4) split into
  * segments of seg_len elements seg_stride apart (channel-plane activations) */
 int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long ldb, void* C,

@@ -235,7 +235,8 @@ def test_conv_backward(H, W, B):
 
 # ------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize('layout', [3, 1, 2, 0])
-@pytest.mark.parametrize('M,N,K', [(70, 72, 96), (5, 64, 64), (130, 200, 40), (64, 64, 2048)])
+@pytest.mark.parametrize('M,N,K', [(70, 72, 96), (5, 64, 64), (130, 200, 40), (64, 64, 2048), (128, 64, 64), (300, 136, 200),
+                                   (512, 1024, 1024), (50, 4104, 136)])
 def test_gemm_layouts(layout, M, N, K):
     torch.manual_seed(layout * 100 + M)
     A = torch.randn(M, K, device=DEV)
@@ -255,6 +256,85 @@ def test_gemm_layouts(layout, M, N, K):
     _lib.call('curla_gemm_bf16', _lib.ptr(a), a.shape[1], _lib.ptr(b), b.shape[1], _lib.ptr(out), out.shape[1],
               M, N, K, layout, N, 0, None, 0, None, 0, 1, 0, 1.0, stream())
     assert rel_l2(out[:, :N], ref) < 2e-3, rel_l2(out[:, :N], ref)
+
+
+@pytest.mark.parametrize('case', ['mlp_fwd', 'mlp_dgrad', 'mlp_wgrad', 'mlp_wgrad_in', 'fc_fwd', 'fc_dgrad', 'fc_wgrad'])
+def test_gemm_tcgen05_matches_mma_sync(case, monkeypatch):
+    """The engine's GEMM call patterns at a batch that takes the tcgen05 kernel (gemm_tc.cu): same
+    call with CURLA_GEMM_TC=0 (mma.sync kernel) and =1, and against torch."""
+    torch.manual_seed(hash(case) % 1000)
+    Bn, hid = 200, 256
+    rnd = lambda *sh: torch.randn(*sh, device=DEV).to(torch.bfloat16)
+    seg_len, seg_stride, nseg = 1032, 1048, 4          # Kfc >= 4096: the few-row fc wgrad also takes the tcgen05 kernel
+    Kfc = seg_len * nseg
+
+    def scatter(x):
+        st = torch.full((x.shape[0], nseg * seg_stride), 3.0, device=DEV, dtype=x.dtype)
+        for s_ in range(nseg):
+            st[:, s_ * seg_stride:s_ * seg_stride + seg_len] = x[:, s_ * seg_len:(s_ + 1) * seg_len]
+        return st
+
+    def run(tc):
+        monkeypatch.setenv('CURLA_GEMM_TC', '1' if tc else '0')
+        if case == 'mlp_fwd':          # H2 = relu(H1 . W^T + b), Q1 || Q2 batched, bf16 out
+            H1, W, b = rnd(2, Bn, hid), rnd(2, hid, hid) * 0.1, torch.randn(2, hid, device=DEV)
+            out = torch.zeros(2, Bn, hid, device=DEV, dtype=torch.bfloat16)
+            _lib.call('curla_gemm_bf16_batched', _lib.ptr(H1), hid, _lib.ptr(W), hid, _lib.ptr(out), hid, Bn, hid, hid, 3, hid, 1,
+                      _lib.ptr(b), 1, None, 0, 1.0, 2, Bn * hid, hid * hid, Bn * hid, hid, 0, stream())
+            ref = torch.relu(torch.einsum('bmk,bnk->bmn', H1.float(), W.float()) + b[:, None, :])
+            return out.float(), ref, (H1, W, b)
+        if case == 'mlp_dgrad':        # dH1 = (H1 > 0) * dH2 . W, batched, bf16 out
+            dH2, W, H1 = rnd(2, Bn, hid), rnd(2, hid, hid) * 0.1, rnd(2, Bn, hid)
+            out = torch.zeros(2, Bn, hid, device=DEV, dtype=torch.bfloat16)
+            _lib.call('curla_gemm_bf16_batched', _lib.ptr(dH2), hid, _lib.ptr(W), hid, _lib.ptr(out), hid, Bn, hid, hid, 1, hid, 1,
+                      None, 0, _lib.ptr(H1), hid, 1.0, 2, Bn * hid, hid * hid, Bn * hid, 0, Bn * hid, stream())
+            ref = torch.einsum('bmk,bkn->bmn', dH2.float(), W.float()) * (H1.float() > 0)
+            return out.float(), ref, (dH2, W, H1)
+        if case == 'mlp_wgrad':        # dW[hid][hid] = dH2^T . H1, batched, fp32 out
+            dH2, H1 = rnd(2, Bn, hid), rnd(2, Bn, hid)
+            out = torch.zeros(2, hid, hid, device=DEV)
+            _lib.call('curla_gemm_bf16_batched', _lib.ptr(dH2), hid, _lib.ptr(H1), hid, _lib.ptr(out), hid, hid, hid, Bn, 0, hid, 0,
+                      None, 0, None, 0, 1.0, 2, Bn * hid, Bn * hid, hid * hid, 0, 0, stream())
+            return out, torch.einsum('bkm,bkn->bmn', dH2.float(), H1.float()), (dH2, H1)
+        if case == 'mlp_wgrad_in':     # dW0[hid][52] = dH1^T . X (X stored [B][64]), n_store 52, ldc 52
+            dH1, X = rnd(Bn, hid), rnd(Bn, 64)
+            out = torch.full((hid, 52), 9.0, device=DEV)
+            _lib.call('curla_gemm_bf16_batched', _lib.ptr(dH1), hid, _lib.ptr(X), 64, _lib.ptr(out), 52, hid, 64, Bn, 0, 52, 0,
+                      None, 0, None, 0, 1.0, 1, 0, 0, 0, 0, 0, stream())
+            return out, (dH1.float().t() @ X.float())[:, :52], (dH1, X)
+        act = rnd(Bn, Kfc)
+        act_s = scatter(act)
+        lds = act_s.shape[1]
+        W = rnd(64, Kfc) * 0.1
+        W[48:] = 0
+        if case == 'fc_fwd':           # split-K partials of z = act . W^T, A segmented
+            sp = _lib.load().curla_gemm_effective_splits(Kfc, 5)
+            part = torch.zeros(sp, Bn, 64, device=DEV)
+            _lib.call('curla_gemm_bf16_seg', _lib.ptr(act_s), lds, _lib.ptr(W), Kfc, _lib.ptr(part), 64, Bn, 64, Kfc, 3, 64, 0, None, 0,
+                      None, 0, sp, Bn * 64, 1.0, seg_len, seg_stride, 1, stream())
+            return part.sum(0), act.float() @ W.float().t(), (act_s, W)
+        dz = rnd(Bn, 64)
+        if case == 'fc_dgrad':         # dact = (act > 0) * dz . W, C and mask segmented, bf16 out
+            out = torch.full((Bn, lds), 5.0, device=DEV, dtype=torch.bfloat16)
+            _lib.call('curla_gemm_bf16_seg', _lib.ptr(dz), 64, _lib.ptr(W), Kfc, _lib.ptr(out), lds, Bn, Kfc, 64, 1, Kfc, 1, None, 0,
+                      _lib.ptr(act_s), lds, 1, 0, 1.0, seg_len, seg_stride, 4, stream())
+            want = scatter(((dz.float() @ W.float()) * (act.float() > 0)).to(torch.bfloat16)).float()
+            want[:, [c for c in range(lds) if c % seg_stride >= seg_len]] = 5.0      # gaps untouched
+            return out.float(), want, (dz, W, act_s)
+        # fc_wgrad: dW[48 (64)][Kfc] = dz^T . act, B segmented, fp32 out, M = 48 rows
+        out = torch.zeros(64, Kfc, device=DEV)
+        _lib.call('curla_gemm_bf16_seg', _lib.ptr(dz), 64, _lib.ptr(act_s), lds, _lib.ptr(out), Kfc, 48, Kfc, Bn, 0, Kfc, 0, None, 0,
+                  None, 0, 1, 0, 1.0, seg_len, seg_stride, 2, stream())
+        return out[:48], (dz.float().t() @ act.float())[:48], (dz, act_s)
+
+    st = torch.get_rng_state(), torch.cuda.get_rng_state()
+    a, ref, keep_a = run(False)
+    torch.set_rng_state(st[0]); torch.cuda.set_rng_state(st[1])
+    b, ref_b, keep_b = run(True)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, ref_b)
+    assert rel_l2(a, ref) < 6e-3 and rel_l2(b, ref) < 6e-3, (rel_l2(a, ref), rel_l2(b, ref))
+    assert rel_l2(b, a) < 3e-3, rel_l2(b, a)
 
 
 def test_gemm_epilogues_and_splitk():
