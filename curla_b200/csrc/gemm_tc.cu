@@ -1,309 +1,418 @@
 // K7/K9 on the 5th-generation tensor cores: the bf16 GEMM of gemm.cu for problems with at least
-// 128 rows -- the MLP trunks (encoder.py:98 -> curl_sac.py:70-74,129-133: 512 x 1024 x 1024) and the
-// encoder fc forward / dgrad / wgrad (512 x 64 x 67,456 and transposes) -- issued with tcgen05.mma,
-// accumulators in TMEM.  Same argument block, same four operand layouts, same epilogues
-// (alpha, bias, ReLU, ReLU mask, bf16 / fp32, split-K partials, batched, segmented operands).
+// 128 rows -- the MLP trunks (curl_sac.py:70-74,129-133: 512 x 1024 x 1024) and the encoder fc
+// forward / dgrad / wgrad (encoder.py:98: 512 x 64 x 67,456 and transposes) -- issued with
+// tcgen05.mma, accumulators in TMEM, operands brought in by tensor-map TMA loads.  Same argument
+// block, same four operand layouts and the same epilogues as gemm.cu (alpha, bias, ReLU, ReLU mask,
+// bf16 / fp32, split-K partials, batched, segmented operands), so gemm.cu stays the fallback for
+// small or unaligned problems.
 //
-// One CTA (256 threads) = one 128 x 64 output tile, K in steps of 64, four stages:
-//   * all threads copy the stage's operand tiles with 16-byte cp.async straight into the
-//     tensor core's canonical no-swizzle layouts (any row stride / segmented index in global
-//     memory; zero fill past the edges):
-//        K-major  operand (stored [rows][K]):  chunk (row r, 8-element K chunk kc) at kc*LBO + r*16
-//                 -> core matrix = 8 rows x 16 B, SBO = 128 B, LBO = rows*16 + 16
-//        MN-major operand (stored [K][cols]):  chunk (k, 8-column chunk c)        at c*SBO + k*16
-//                 -> LBO = 128 B (8 K rows), SBO = 64*16 + 16
-//     (the +16 makes the eight chunks a quarter-warp writes land in eight different bank groups);
-//   * cp.async.wait_group + fence.proxy.async + one __syncthreads per K step hand the stage to the
-//     async proxy; thread 0 then issues the step's four M=128 N=64 K=16 MMAs and commits them to
-//     the stage's mbarrier, which the copy of step k+3 into the same slot waits for;
-//   * after the last commit each warp reads 32 TMEM lanes x 32 columns (one output row per thread)
-//     and applies the epilogue with 16-byte stores.
-// An SS-mode MMA of this shape streams (128 + 64) rows x 32 B of operands from shared memory:
-// 48 clk per instruction (profiles/r01c_microbench.txt), 3,072 clk for K = 1024.
+// Why TMA: fed by 16-byte cp.async, both this kernel and gemm.cu top out near 20 B/clk per SM of
+// operand copies (LSU path; tests/bench_gemm.py, profiles/r02a_gemm_tcgen05_vs_mma_sync.txt) --
+// the tensor core idles.  One cp.async.bulk.tensor per operand tile and stage does not go
+// through the LSU.
+//
+// One CTA = one 128 x 64 output tile, K in steps of 64, up to four 24 KB stages:
+//   warp 0 (one lane)  producer: waits for the stage's `empty` mbarrier, arms `full` with the
+//                      stage's byte count and issues the tile loads.  Tiles land in the 128-byte
+//                      swizzled canonical layouts (cute/atom/mma_traits_sm100.hpp):
+//                        K-major  operand (stored [rows][K]):  box {64 k, rows}  -> [row][128 B], SBO = 1024
+//                        MN-major operand (stored [K][cols]):  box {64 cols, 64 k} -> [k][128 B], SBO = 1024,
+//                                                              LBO = 8192 between 64-column blocks
+//                      Out-of-range rows / K tails are zero-filled by the TMA unit.  Segmented
+//                      operands (channel-plane activations) are 3-D maps
+//                      {seg_len, segments, rows}: a box never leaves its segment.
+//   warp 1 (one lane)  MMA issuer: four M=128 N=64 K=16 MMAs per stage, tcgen05.commit -> `empty`.
+//   warps 2..5         epilogue: one output row per thread (TMEM lane), 64 columns, 16-byte stores.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <unordered_map>
 
 namespace curla {
 
 namespace {
 
-constexpr int TM = 128, TN = 64, TK = 64, TST = 4;
-constexpr uint32_t kLboA = TM * 16 + 16;      // K-major A: stride between 8-element K chunks
-constexpr uint32_t kSboA = TK * 16 + 16;      // MN-major A: stride between 8-row chunks
-constexpr uint32_t kLboB = TN * 16 + 16;      // K-major B
-constexpr uint32_t kSboB = TK * 16 + 16;      // MN-major B
-constexpr uint32_t kABytes = 16 * kSboA;      // 16,640 >= 8 * kLboA = 16,512
-constexpr uint32_t kBBytes = 8 * kLboB;       // 8,320 (both layouts)
-constexpr uint32_t kStageBytesTc = kABytes + kBBytes;      // 24,960 (multiple of 128)
-constexpr uint32_t kHdrTc = 128;              // freed[4] @0, done @32, tmem ptr @40
-constexpr uint32_t kSmemTc = kHdrTc + TST * kStageBytesTc;
+constexpr int TM = 128, TN = 64, TK = 64, kMaxSt = 4;
+constexpr uint32_t kABytes = TM * TK * 2, kBBytes = TN * TK * 2, kStageBytesTc = kABytes + kBBytes;   // 16 K + 8 K
+constexpr uint32_t kHdrTc = 1024;             // full[4] @0, empty[4] @32, done @64, tmem ptr @72; keeps the stages 1024-byte aligned
+constexpr int kTcGemmThreads = 192;
+
+struct TmaPlan {
+    int a_segk;            // A's K index is segmented: map {seg_len, segment, rows}
+    int b_segn;            // B's N index is segmented: map {seg_len, segment, K}; one N tile never leaves its segment
+    int per_seg;           // K steps per segment (a_segk) or N tiles per segment (b_segn)
+    int total_steps;       // a_segk: segments * per_seg
+    int nst;               // stages allocated
+};
 
 constexpr uint32_t idesc_tc(bool a_mn, bool b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
            ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
+// shared-memory matrix descriptor, 128-byte swizzle (layout type 2), version 1
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
 
-// timing experiments: clocks of thread 32 of CTA (0,0,0): [0] wait for the stage's copies, [1] fence + barrier,
-// [2] wait for the slot's MMAs, [3] issuing the next copies, [4] K loop total, [5] K steps, [6] kernel total
+// timing experiments: clocks of the MMA thread of CTA (0,0,0): [0] waiting for `full`, [1] issuing, [4] K loop, [5] K steps, [6] kernel
 __device__ long long g_gtc_dbg[8];
-constexpr int kTcGemmThreads = 256;          // 8 warps: all copy operands; the epilogue splits the 64 columns between warps 0-3 and 4-7
 
 template <bool A_KMAJOR, bool B_KMAJOR, bool SEG>
 __global__ void __launch_bounds__(kTcGemmThreads)
-k_gemm_tc(GemmArgs p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p, TmaPlan pl) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_freed = s_base, s_done = s_base + 32, s_tptr = s_base + 40;
+    const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72;
     const uint32_t s_stage0 = s_base + kHdrTc;
+    const long long t_start = clock64();
     if (tid == 0) {
-        for (int i = 0; i < TST; ++i) mbar_init(s_freed + 8 * i, 1);
+        for (int i = 0; i < kMaxSt; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
         mbar_init(s_done, 1);
         fence_mbar_init();
     }
-    if (warp == 0) {
+    if (warp == 2) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"((uint32_t)TN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int bz = p.batch > 1 ? blockIdx.z : 0, sz = p.batch > 1 ? 0 : blockIdx.z;
-    const bf16* __restrict__ Ap = p.A + bz * p.bsA;
-    const bf16* __restrict__ Bp = p.B + bz * p.bsB;
-    const int kbeg = sz * p.k_per_split;
-    int kend = kbeg + p.k_per_split;
-    if (kend > p.K) kend = p.K;
-    const int nk = (kend - kbeg + TK - 1) / TK;
-
-    // Per-thread copy plan, fixed for the whole K loop: 4 chunks of A and 2 of B per stage.
-    // Chunk c = tid + 256 i.  K-major operand: row = c / 8, K chunk = c % 8; MN-major operand:
-    // column chunk = c % (cols / 8), K row = c / (cols / 8).  Only the K coordinate moves.
-    const bf16* a_src[4]; uint32_t a_dst[4]; int a_k[4]; bool a_ok[4];
-    const bf16* b_src[2]; uint32_t b_dst[2]; int b_k[2]; bool b_ok[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = tid + i * kTcGemmThreads;
-        if (A_KMAJOR) {
-            const int r = c >> 3, kc = c & 7;
-            a_ok[i] = m0 + r < p.M; a_k[i] = kc * 8;
-            a_src[i] = Ap + (long long)(m0 + r) * p.lda;                 // + (segmented) K index
-            a_dst[i] = kc * kLboA + r * 16;
-        } else {
-            const int mc = c & 15, kk = c >> 4;
-            a_ok[i] = m0 + mc * 8 < p.M; a_k[i] = kk;
-            a_src[i] = Ap + seg_off(m0 + mc * 8, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1));   // + K * lda
-            a_dst[i] = mc * kSboA + kk * 16;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int c = tid + i * kTcGemmThreads;
-        if (B_KMAJOR) {
-            const int r = c >> 3, kc = c & 7;
-            b_ok[i] = n0 + r < p.N; b_k[i] = kc * 8;
-            b_src[i] = Bp + (long long)(n0 + r) * p.ldb;
-            b_dst[i] = kABytes + kc * kLboB + r * 16;
-        } else {
-            const int nc = c & 7, kk = c >> 3;
-            b_ok[i] = n0 + nc * 8 < p.N; b_k[i] = kk;
-            b_src[i] = Bp + seg_off(n0 + nc * 8, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2));
-            b_dst[i] = kABytes + nc * kSboB + kk * 16;
-        }
-    }
-    auto load_stage = [&](int kt, int st) {
-        const int k0 = kbeg + kt * TK;
-        const uint32_t sS = s_stage0 + st * kStageBytesTc;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = k0 + a_k[i];
-            const bool ok = a_ok[i] && k < kend;
-            const bf16* src = A_KMAJOR ? a_src[i] + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 1))
-                                       : a_src[i] + (long long)k * p.lda;
-            cp_async16(sS + a_dst[i], ok ? (const void*)src : (const void*)p.A, ok ? 16 : 0);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int k = k0 + b_k[i];
-            const bool ok = b_ok[i] && k < kend;
-            const bf16* src = B_KMAJOR ? b_src[i] + seg_off(k, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 2))
-                                       : b_src[i] + (long long)k * p.ldb;
-            cp_async16(sS + b_dst[i], ok ? (const void*)src : (const void*)p.B, ok ? 16 : 0);
-        }
-    };
-
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 40);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 72);
     pdl_grid_sync();              // everything above is independent of earlier kernels
 
-#pragma unroll
-    for (int s = 0; s < TST - 1; ++s) {
-        if (s < nk) load_stage(s, s);
-        cp_async_commit();
+    // ---- tile and K-step ranges
+    const int m0 = blockIdx.y * TM;
+    const int bz = p.batch > 1 ? blockIdx.z : 0, sz = p.batch > 1 ? 0 : blockIdx.z;
+    int n0, ncols = TN, bn_c0 = 0, bn_c1 = 0;
+    if (SEG && pl.b_segn) {
+        const int sg = blockIdx.x / pl.per_seg, j = blockIdx.x - sg * pl.per_seg;
+        n0 = sg * p.seg_len + j * TN;
+        ncols = p.seg_len - j * TN < TN ? p.seg_len - j * TN : TN;
+        bn_c0 = j * TN; bn_c1 = sg;
+    } else {
+        n0 = blockIdx.x * TN;
     }
-
-    // descriptor templates: K-major (lbo = K-chunk stride, sbo = 128); MN-major (lbo = 128 = eight K rows, sbo = chunk stride)
-    const uint64_t a_hi = A_KMAJOR ? make_desc(0, kLboA, 128) : make_desc(0, 128, kSboA);
-    const uint64_t b_hi = B_KMAJOR ? make_desc(0, kLboB, 128) : make_desc(0, 128, kSboB);
-    constexpr uint32_t kId = idesc_tc(!A_KMAJOR, !B_KMAJOR);
-
-    const bool dbg = tid == 32 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
-    long long d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-    const long long dl0 = clock64();
-    for (int kt = 0; kt < nk; ++kt) {
-        const long long c0 = dbg ? clock64() : 0;
-        cp_async_wait<TST - 2>();
-        const long long c1 = dbg ? clock64() : 0;
-        fence_proxy_async();          // this thread's cp.async writes -> visible to the tensor core
-        __syncthreads();              // ... and everybody else's
-        const long long c2 = dbg ? clock64() : 0;
-        const int st = kt % TST;
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t sA = s_stage0 + st * kStageBytesTc, sB = sA + kABytes;
-#pragma unroll
-            for (int ks = 0; ks < TK / 16; ++ks) {
-                const uint32_t ao = A_KMAJOR ? (uint32_t)(2 * ks) * kLboA : (uint32_t)ks * 256u;
-                const uint32_t bo = B_KMAJOR ? (uint32_t)(2 * ks) * kLboB : (uint32_t)ks * 256u;
-                const uint64_t ad = a_hi | (uint64_t)(((sA + ao) >> 4) & 0x3FFFu);
-                const uint64_t bd = b_hi | (uint64_t)(((sB + bo) >> 4) & 0x3FFFu);
-                umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | ks) != 0));
-            }
-            umma_commit(s_freed + 8 * st);        // slot reusable once these MMAs have read it
-        }
-        // stage kt + 3 goes into the slot of stage kt - 1: wait until its MMAs are done
-        const int nxt = kt + TST - 1;
-        long long c3 = c2;
-        if (nxt < nk) {
-            if (kt >= 1) mbar_wait(s_freed + 8 * ((kt - 1) % TST), (uint32_t)(((kt - 1) / TST) & 1));
-            c3 = dbg ? clock64() : 0;
-            load_stage(nxt, nxt % TST);
-        }
-        cp_async_commit();
-        if (dbg) { d0 += c1 - c0; d1 += c2 - c1; d2 += c3 - c2; d3 += clock64() - c3; }
+    int s_beg, s_end;
+    if (SEG && pl.a_segk) {
+        const int zs = p.batch > 1 ? 1 : (int)gridDim.z;
+        const int sps = (pl.total_steps + zs - 1) / zs;
+        s_beg = sz * sps;
+        s_end = s_beg + sps < pl.total_steps ? s_beg + sps : pl.total_steps;
+    } else {
+        const int kbeg = sz * p.k_per_split;
+        int kend = kbeg + p.k_per_split;
+        if (kend > p.K) kend = p.K;
+        s_beg = kbeg / TK;
+        s_end = (kend + TK - 1) / TK;
     }
-    if (dbg) { g_gtc_dbg[0] = d0; g_gtc_dbg[1] = d1; g_gtc_dbg[2] = d2; g_gtc_dbg[3] = d3; g_gtc_dbg[4] = clock64() - dl0; g_gtc_dbg[5] = nk; }
-    cp_async_wait<0>();
-    if (tid == 0) umma_commit(s_done);
-    mbar_wait(s_done, 0);
-    tc_fence_after();
+    const int nk = s_end > s_beg ? s_end - s_beg : 0;
+    const int nst = pl.nst;
 
-    // ---- epilogue: thread = output row m0 + 32 (warp % 4) + lane, 32 columns (warps 0-3: 0..31, warps 4-7: 32..63)
-    const int m = m0 + (warp & 3) * 32 + lane;
-    const int h = warp >> 2;
-    float* Cf = (float*)p.C + (long long)sz * p.split_stride + bz * p.bsC;
-    bf16* Cb = (bf16*)p.C + bz * p.bsC;
-    const float* __restrict__ biasp = p.bias ? p.bias + bz * p.bsBias : nullptr;
-    const bf16* __restrict__ maskp = p.mask ? p.mask + bz * p.bsMask : nullptr;
-    const bool f4 = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cf) & 15) == 0);
-    {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * 32), r);
-        if (m < p.M) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + h * 32 + j * 8;
-            if (n >= p.n_store) continue;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                v[e] = __uint_as_float(r[j * 8 + e]) * p.alpha;
-                if (biasp && n + e < p.n_store) v[e] += biasp[n + e];
-                if (p.relu) v[e] = fmaxf(v[e], 0.f);
-            }
-            const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
-            const bool whole = n + 8 <= p.n_store;
-            if (maskp) {
-                if (whole) {
-                    const uint4 mk = *reinterpret_cast<const uint4*>(maskp + (long long)m * p.ldmask + nc);
-                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 mv = unpack_bf16x2(mw[e]);
-                        v[2 * e] = mv.x > 0.f ? v[2 * e] : 0.f;
-                        v[2 * e + 1] = mv.y > 0.f ? v[2 * e + 1] : 0.f;
+    if (warp == 0) {
+        // ================= producer
+        if (lane == 0) {
+            const int za = p.bsA ? bz : 0, zb = p.bsB ? bz : 0;
+            uint32_t stage = 0, phase = 0;
+            for (int kt = 0; kt < nk; ++kt) {
+                const int step = s_beg + kt;
+                mbar_wait(s_empty + 8 * stage, phase ^ 1);
+                const uint32_t bar = s_full + 8 * stage;
+                const uint32_t dA = s_stage0 + stage * kStageBytesTc, dB = dA + kABytes;
+                mbar_expect_tx(bar, kStageBytesTc);
+                int kb = step * TK;                           // B's K coordinate (logical K)
+                if (A_KMAJOR) {
+                    if (SEG && pl.a_segk) {
+                        const int sg = step / pl.per_seg, j = step - sg * pl.per_seg;
+                        tma_load_3d(dA, &tmA, j * TK, sg, m0, bar);
+                        kb = sg * p.seg_len + j * TK;
+                    } else {
+                        tma_load_3d(dA, &tmA, step * TK, m0, za, bar);
                     }
                 } else {
-                    for (int e = 0; e < 8 && n + e < p.n_store; ++e)
-                        v[e] = __bfloat162float(maskp[(long long)m * p.ldmask + nc + e]) > 0.f ? v[e] : 0.f;
+                    tma_load_3d(dA, &tmA, m0, step * TK, za, bar);
+                    tma_load_3d(dA + kABytes / 2, &tmA, m0 + 64, step * TK, za, bar);
                 }
-            }
-            const long long o = (long long)m * p.ldc + nc;
-            if (p.out_bf16) {
-                if (whole) {
-                    *reinterpret_cast<uint4*>(Cb + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                } else {
-                    for (int e = 0; e < 8 && n + e < p.n_store; ++e) Cb[o + e] = __float2bfloat16(v[e]);
-                }
-            } else if (whole && f4) {
-                *reinterpret_cast<float4*>(Cf + o) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(Cf + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-                for (int e = 0; e < 8 && n + e < p.n_store; ++e) Cf[o + e] = v[e];
+                if (B_KMAJOR) tma_load_3d(dB, &tmB, kb, n0, zb, bar);
+                else if (SEG && pl.b_segn) tma_load_3d(dB, &tmB, bn_c0, bn_c1, step * TK, bar);
+                else tma_load_3d(dB, &tmB, n0, step * TK, zb, bar);
+                if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
             }
         }
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t kId = idesc_tc(!A_KMAJOR, !B_KMAJOR);
+            const bool dbg = (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+            long long d0 = 0, d1 = 0;
+            const long long dl0 = clock64();
+            uint32_t stage = 0, phase = 0;
+            for (int kt = 0; kt < nk; ++kt) {
+                const long long c0 = dbg ? clock64() : 0;
+                mbar_wait(s_full + 8 * stage, phase);
+                const long long c1 = dbg ? clock64() : 0;
+                tc_fence_after();
+                const uint32_t sA = s_stage0 + stage * kStageBytesTc, sB = sA + kABytes;
+#pragma unroll
+                for (int ks = 0; ks < TK / 16; ++ks) {
+                    // K-major: 16 k = 32 bytes further along the swizzled 128-byte rows; MN-major: 16 k rows = 2048 bytes
+                    const uint64_t ad = A_KMAJOR ? desc_sw128(sA + ks * 32, 16, 1024) : desc_sw128(sA + ks * 2048, kABytes / 2, 1024);
+                    const uint64_t bd = B_KMAJOR ? desc_sw128(sB + ks * 32, 16, 1024) : desc_sw128(sB + ks * 2048, kBBytes, 1024);
+                    umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | ks) != 0));
+                }
+                umma_commit(s_empty + 8 * stage);            // slot free once these MMAs have read it
+                if (dbg) { d0 += c1 - c0; d1 += clock64() - c1; }
+                if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(s_done);
+            if (dbg) { g_gtc_dbg[0] = d0; g_gtc_dbg[1] = d1; g_gtc_dbg[4] = clock64() - dl0; g_gtc_dbg[5] = nk; }
+        }
+    } else {
+        // ================= epilogue: thread = output row m0 + 32 (warp % 4) + lane, 64 columns in two TMEM loads
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        float* Cf = (float*)p.C + (long long)sz * p.split_stride + bz * p.bsC;
+        bf16* Cb = (bf16*)p.C + bz * p.bsC;
+        const float* __restrict__ biasp = p.bias ? p.bias + bz * p.bsBias : nullptr;
+        const bf16* __restrict__ maskp = p.mask ? p.mask + bz * p.bsMask : nullptr;
+        const bool f4 = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cf) & 15) == 0);
+        const bool bias_al = (reinterpret_cast<uintptr_t>(biasp) & 15) == 0;
+        mbar_wait(s_done, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = h * 32 + j * 8;                  // column inside the tile
+                const int n = n0 + c;
+                int lim = p.n_store - n;                       // columns of this chunk that exist
+                if (ncols - c < lim) lim = ncols - c;
+                if (lim <= 0) continue;
+                float v[8], bv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bv[e] = 0.f;
+                if (biasp) {
+                    if (lim >= 8 && bias_al) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + n)), b1 = __ldg(reinterpret_cast<const float4*>(biasp + n + 4));
+                        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (e < lim) bv[e] = biasp[n + e];
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = (nk > 0 ? __uint_as_float(r[j * 8 + e]) : 0.f) * p.alpha + bv[e];
+                    if (p.relu) v[e] = fmaxf(v[e], 0.f);
+                }
+                const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+                const bool whole = lim >= 8;
+                if (maskp) {
+                    if (whole) {
+                        const uint4 mk = *reinterpret_cast<const uint4*>(maskp + (long long)m * p.ldmask + nc);
+                        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 mv = unpack_bf16x2(mw[e]);
+                            v[2 * e] = mv.x > 0.f ? v[2 * e] : 0.f;
+                            v[2 * e + 1] = mv.y > 0.f ? v[2 * e + 1] : 0.f;
+                        }
+                    } else {
+                        for (int e = 0; e < lim; ++e)
+                            v[e] = __bfloat162float(maskp[(long long)m * p.ldmask + nc + e]) > 0.f ? v[e] : 0.f;
+                    }
+                }
+                const long long o = (long long)m * p.ldc + nc;
+                if (p.out_bf16) {
+                    if (whole) {
+                        *reinterpret_cast<uint4*>(Cb + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    } else {
+                        for (int e = 0; e < lim; ++e) Cb[o + e] = __float2bfloat16(v[e]);
+                    }
+                } else if (whole && f4) {
+                    *reinterpret_cast<float4*>(Cf + o) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(Cf + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                    for (int e = 0; e < lim; ++e) Cf[o + e] = v[e];
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (dbg) g_gtc_dbg[6] = clock64() - dl0;
-    if (warp == 0) {
+    if (tid == 32 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) g_gtc_dbg[6] = clock64() - t_start;
+    if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TN) : "memory");
     }
 }
 
+// ---------------------------------------------------------------- tensor maps (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+struct TmKey {
+    const void* ptr; unsigned long long d[3], s[2]; unsigned b[3]; unsigned pad;
+    bool operator==(const TmKey& o) const { return memcmp(this, &o, sizeof(TmKey)) == 0; }
+};
+struct TmKeyHash {
+    size_t operator()(const TmKey& k) const {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+        size_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmKey); ++i) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
+};
+// 3-D bf16 map, 128-byte swizzle, zero fill; cached (the update's operands live at fixed addresses)
+const CUtensorMap* get_map(const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                           unsigned long long s1_bytes, unsigned long long s2_bytes, unsigned b0, unsigned b1, unsigned b2) {
+    static thread_local std::unordered_map<TmKey, CUtensorMap, TmKeyHash> cache;
+    TmKey k;
+    memset(&k, 0, sizeof(k));
+    k.ptr = ptr; k.d[0] = d0; k.d[1] = d1; k.d[2] = d2; k.s[0] = s1_bytes; k.s[1] = s2_bytes; k.b[0] = b0; k.b[1] = b1; k.b[2] = b2;
+    auto it = cache.find(k);
+    if (it != cache.end()) return &it->second;
+    if (cache.size() > 4096) cache.clear();
+    CUtensorMap tm;
+    const cuuint64_t gd[3] = {d0, d1, d2};
+    const cuuint64_t gs[2] = {s1_bytes, s2_bytes};
+    const cuuint32_t bx[3] = {b0, b1, b2};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gd, gs, bx, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) dims %llu x %llu x %llu strides %llu, %llu box %u x %u x %u",
+                       (int)r, d0, d1, d2, s1_bytes, s2_bytes, b0, b1, b2);
+        return nullptr;
+    }
+    return &cache.emplace(k, tm).first->second;
+}
+
 template <bool AK, bool BK_, bool SG>
-int launch_one(const GemmArgs& p, dim3 grid, cudaStream_t stream) {
+int launch_one(const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& p, const TmaPlan& pl, dim3 grid, cudaStream_t stream) {
     auto kern = k_gemm_tc<AK, BK_, SG>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTc);
-        if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%u): %s", kSmemTc, cudaGetErrorString(e)); return -1; }
+        const int mx = (int)(kHdrTc + kMaxSt * kStageBytesTc);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%d): %s", mx, cudaGetErrorString(e)); return -1; }
         attr = true;
     }
-    // short K loops never refill a slot: only the stages they fill are allocated (fc dgrad, K = 64:
-    // one 25 KB stage, eight CTAs per SM instead of two)
-    const int nk = cdiv(p.k_per_split < p.K ? p.k_per_split : p.K, TK);
-    const uint32_t smem = kHdrTc + (uint32_t)(nk < TST ? nk : TST) * kStageBytesTc;
-    launch_k(kern, grid, dim3(kTcGemmThreads), smem, stream, p);
+    const uint32_t smem = kHdrTc + (uint32_t)pl.nst * kStageBytesTc;
+    launch_k(kern, grid, dim3(kTcGemmThreads), smem, stream, *ta, *tb, p, pl);
     return 1;
 }
 
 }  // namespace
 
 int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t stream) {
-    // Off unless CURLA_GEMM_TC=1 (read per call: the tests compare both kernels).  Fed by 16-byte
-    // cp.async this kernel is bound by the LSU path (~21 B/clk per SM of operand copies, see
-    // tests/bench_gemm.py / profiles/r02a_gemm_tcgen05_vs_mma_sync.txt), not by the tensor core, and
-    // is slower than gemm.cu's bulk-copy ring on every shape of the update; it needs tensor-map
-    // TMA loads (128-byte swizzled tiles) before it can replace it.
+    // CURLA_GEMM_TC (read per call: the tests compare both kernels): 0 = never, 2 = whenever the
+    // shape is supported, default = where it measured faster than gemm.cu (tests/bench_gemm.py,
+    // profiles/r02d_gemm_tma_vs_mma_sync.txt).  One CTA per output tile pays ~3 us of fixed cost
+    // (TMEM allocation, descriptor fetch, first load), so short K loops (fc dgrad: one step) and
+    // tall-skinny problems made of thousands of small tiles (fc wgrad) stay with gemm.cu until
+    // this kernel loops over tiles.
     const char* env = getenv("CURLA_GEMM_TC");
-    if (!(env && env[0] == '1')) return 0;
-    // at least one full tile of rows, or a long streaming problem with few rows (fc wgrad: 50 x 67,456 x B)
-    if (p.M < TM && !(p.N >= 4096 && p.K >= 128)) return 0;
+    if (env && env[0] == '0') return 0;
+    const bool force = env && env[0] == '2';
+    if (p.M < TM && !(p.N >= 4096 && p.K >= 128)) return 0;      // at least one full tile of rows, or fc wgrad (forced only)
+    if (!force) {
+        const int steps = cdiv(p.k_per_split < p.K ? p.k_per_split : p.K, TK);
+        if (p.M < TM || !(steps >= 12 || (steps >= 8 && p.N >= 128))) return 0;
+    }
+    const bool ak = layout & 1, bk = layout & 2;
+    // supported segment patterns: none; A's K (fc fwd, both K-major); B's N (fc wgrad, both MN-major);
+    // C / mask columns (fc dgrad: epilogue only)
+    if (p.seg_mask && !((p.seg_mask == 1 && ak && bk) || (p.seg_mask == 2 && !ak && !bk) || p.seg_mask == 4)) return 0;
+    if (p.seg_mask && (p.seg_len % 8 || p.seg_stride % 8 || p.batch > 1)) return 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(p.A) || !al16(p.B) || p.lda % 8 || p.ldb % 8 || p.bsA % 8 || p.bsB % 8 || p.K % 8) return 0;
     // 16-byte epilogue accesses: bf16 rows (and mask rows) must be 16-byte addressable
-    const uintptr_t cptr = reinterpret_cast<uintptr_t>(p.C);
-    if (p.out_bf16 && !(p.ldc % 8 == 0 && p.bsC % 8 == 0 && (cptr & 15) == 0)) return 0;
-    if (p.mask && !(p.ldmask % 8 == 0 && p.bsMask % 8 == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)) return 0;
-    if ((p.seg_mask & 4) && p.seg_len % 8 != 0) return 0;
-    dim3 grid(cdiv(p.N, TN), cdiv(p.M, TM), p.batch > 1 ? p.batch : splits);
+    if (p.out_bf16 && !(p.ldc % 8 == 0 && p.bsC % 8 == 0 && al16(p.C))) return 0;
+    if (p.mask && !(p.ldmask % 8 == 0 && p.bsMask % 8 == 0 && al16(p.mask))) return 0;
+    if (!encode_fn()) return 0;
+
+    const int nb = p.batch > 1 ? p.batch : 1;
+    auto r8 = [](long long x) { return (unsigned long long)((x + 7) / 8 * 8); };
+    TmaPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    const CUtensorMap *ta, *tb;
+    int nsteps = cdiv(p.k_per_split < p.K ? p.k_per_split : p.K, TK);
+    unsigned gx = (unsigned)cdiv(p.N, TN);
+    // an operand shared between the batched problems (stride 0) gets a 1-deep batch dimension
+    auto bdim = [&](long long bs) { return (unsigned long long)(bs ? nb : 1); };
+    auto bstr = [&](long long bs, unsigned long long rows, long long ld) { return (unsigned long long)(bs ? bs : (long long)rows * ld) * 2ull; };
+    if (p.seg_mask == 1) {
+        const int nseg = cdiv(p.K, p.seg_len);
+        pl.a_segk = 1; pl.per_seg = cdiv(p.seg_len, TK); pl.total_steps = nseg * pl.per_seg;
+        ta = get_map(p.A, (unsigned long long)p.seg_len, (unsigned long long)nseg, (unsigned long long)p.M,
+                     (unsigned long long)p.seg_stride * 2, (unsigned long long)p.lda * 2, TK, 1, TM);
+        nsteps = cdiv(pl.total_steps, splits);
+    } else if (ak) {
+        ta = get_map(p.A, (unsigned long long)p.K, (unsigned long long)p.M, bdim(p.bsA), (unsigned long long)p.lda * 2,
+                     bstr(p.bsA, (unsigned long long)p.M, p.lda), TK, TM, 1);
+    } else {
+        ta = get_map(p.A, r8(p.M), (unsigned long long)p.K, bdim(p.bsA), (unsigned long long)p.lda * 2,
+                     bstr(p.bsA, (unsigned long long)p.K, p.lda), 64, TK, 1);
+    }
+    if (p.seg_mask == 2) {
+        const int nseg = cdiv(p.N, p.seg_len);
+        pl.b_segn = 1; pl.per_seg = cdiv(p.seg_len, TN);
+        gx = (unsigned)(nseg * pl.per_seg);
+        tb = get_map(p.B, (unsigned long long)p.seg_len, (unsigned long long)nseg, (unsigned long long)p.K,
+                     (unsigned long long)p.seg_stride * 2, (unsigned long long)p.ldb * 2, TN, 1, TK);
+    } else if (bk) {
+        tb = get_map(p.B, (unsigned long long)p.K, (unsigned long long)p.N, bdim(p.bsB), (unsigned long long)p.ldb * 2,
+                     bstr(p.bsB, (unsigned long long)p.N, p.ldb), TK, TN, 1);
+    } else {
+        tb = get_map(p.B, r8(p.N), (unsigned long long)p.K, bdim(p.bsB), (unsigned long long)p.ldb * 2,
+                     bstr(p.bsB, (unsigned long long)p.K, p.ldb), TN, TK, 1);
+    }
+    if (!ta || !tb) return -1;
+    pl.nst = nsteps < kMaxSt ? (nsteps < 1 ? 1 : nsteps) : kMaxSt;
+    dim3 grid(gx, cdiv(p.M, TM), p.batch > 1 ? p.batch : splits);
     if (grid.y > 65535 || grid.z > 65535) return 0;
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
-        case 3: return launch_one<true, true, false>(p, grid, stream);
-        case 1: return launch_one<true, false, false>(p, grid, stream);
-        case 2: return launch_one<false, true, false>(p, grid, stream);
-        case 0: return launch_one<false, false, false>(p, grid, stream);
-        case 7: return launch_one<true, true, true>(p, grid, stream);
-        case 5: return launch_one<true, false, true>(p, grid, stream);
-        case 6: return launch_one<false, true, true>(p, grid, stream);
-        default: return launch_one<false, false, true>(p, grid, stream);
+        case 3: return launch_one<true, true, false>(ta, tb, p, pl, grid, stream);
+        case 1: return launch_one<true, false, false>(ta, tb, p, pl, grid, stream);
+        case 2: return launch_one<false, true, false>(ta, tb, p, pl, grid, stream);
+        case 0: return launch_one<false, false, false>(ta, tb, p, pl, grid, stream);
+        case 7: return launch_one<true, true, true>(ta, tb, p, pl, grid, stream);
+        case 5: return launch_one<true, false, true>(ta, tb, p, pl, grid, stream);
+        case 6: return launch_one<false, true, true>(ta, tb, p, pl, grid, stream);
+        default: return launch_one<false, false, true>(ta, tb, p, pl, grid, stream);
     }
 }
 

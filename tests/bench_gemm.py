@@ -53,7 +53,7 @@ cases = {
 }
 for name, fn in cases.items():
     res = []
-    for tc in ('1', '0'):
+    for tc in ('2', '0'):
         os.environ['CURLA_GEMM_TC'] = tc
         for _ in range(3):
             fn()
@@ -69,10 +69,10 @@ for name, fn in cases.items():
             ts.append(e0.elapsed_time(e1) * 1e3 / 4)
         ts.sort()
         res.append(ts[len(ts) // 2])
-        if tc == '1':
+        if tc == '2':
             import ctypes as C
             buf = (C.c_longlong * 8)()
             _lib.call('curla_gemm_tc_debug_read', buf)
             dbg = list(buf)
-    print('%-48s tcgen05 %7.1f us   mma.sync %7.1f us   | CTA0 clk: wait copies %d, fence+barrier %d, wait MMAs %d, issue copies %d, '
-          'loop %d (%d steps), kernel %d' % (name, res[0], res[1], *dbg[:7]))
+    print('%-48s tcgen05 %7.1f us   mma.sync %7.1f us   | MMA thread of CTA 0, clk: wait full %d, issue %d, K loop %d (%d steps), kernel %d'
+          % (name, res[0], res[1], dbg[0], dbg[1], dbg[4], dbg[5], dbg[6]))

@@ -275,7 +275,7 @@ def test_gemm_tcgen05_matches_mma_sync(case, monkeypatch):
         return st
 
     def run(tc):
-        monkeypatch.setenv('CURLA_GEMM_TC', '1' if tc else '0')
+        monkeypatch.setenv('CURLA_GEMM_TC', '2' if tc else '0')        # 2 = every supported shape
         if case == 'mlp_fwd':          # H2 = relu(H1 . W^T + b), Q1 || Q2 batched, bf16 out
             H1, W, b = rnd(2, Bn, hid), rnd(2, hid, hid) * 0.1, torch.randn(2, hid, device=DEV)
             out = torch.zeros(2, Bn, hid, device=DEV, dtype=torch.bfloat16)
