@@ -43,6 +43,8 @@ struct TcGeom {
     int min_off;         // most negative tap shift
     int stages;          // slab ring depth (host: as many as fit in shared memory, <= 8)
     int plane_bytes;     // shared-memory stride between channel planes of a slab
+    int zero_planes;         // trailing channel planes of the input that are all zero (conv-1: 4C = 36 real channels of 48):
+                             // never loaded, their shared-memory planes are zeroed once
     int dynamic, ctr_slot;   // tiles handed out through an atomic counter (g_tc_ctr pair ctr_slot) instead of round robin
     float inv_tps, inv_pitch;   // 1/tiles_per_sample, 1/pitch: index divisions through a float reciprocal (exact for
                          // these ranges: (i + 0.5) / d is never within float rounding of an integer)
@@ -219,9 +221,16 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
                 }
             }
         }
+        if (g.zero_planes > 0) {
+            const int per = g.zero_planes * (int)(PS / 16);            // 16-byte words per stage
+            for (int i = tid; i < stages * per; i += kStageThreads) {
+                const int st = i / per, w = i - st * per;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(s_slab0 + st * slab_bytes + (CH - g.zero_planes) * PS + w * 16), "r"(0) : "memory");
+            }
+        }
         cp_async_commit();
         cp_async_wait<0>();
-        fence_proxy_async();      // generic-proxy writes of the weights -> visible to the tensor core
+        fence_proxy_async();      // generic-proxy writes of the weights (and zero planes) -> visible to the tensor core
         asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
     }
 
@@ -446,9 +455,11 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
                     const int p0 = tl.t * TM;
                     const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
                     const uint32_t dst = s_slab0 + stage * slab_bytes;
-                    mbar_expect_tx(bar, bytes * CH);
+                    const int chl = CH - g.zero_planes;
+                    mbar_expect_tx(bar, bytes * chl);
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
+                    for (int c = 0; c < CH; ++c)
+                        if (c < chl) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
                 }
                 if (g.debug & 64) c_cp += clock64() - c1;
                 ++j;
@@ -488,7 +499,7 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     g.plane_rows = (g.slab_rows + 7) / 8 * 8;
     g.min_off = min_off;
     g.stages = 2;
-    g.dynamic = 0; g.ctr_slot = 0;
+    g.dynamic = 0; g.ctr_slot = 0; g.zero_planes = 0;
     g.inv_tps = 1.0f / (float)g.tiles_per_sample;
     g.inv_pitch = 1.0f / (float)pitch;
     g.plane_bytes = g.plane_rows * 16;
@@ -590,6 +601,10 @@ extern "C" int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long l
         for (int t = 0; t < 4; ++t) taps.off[t] = (t >> 1) * pitch + (t & 1);
         for (int t = 4; t < 9; ++t) taps.off[t] = 0;
         TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, pitch + 1, 0);
+        if (first_layer > 1) {                    // number of real s2d channels: whole planes above it are zero
+            CURLA_CHECK(first_layer <= 48, "conv_fwd: first_layer = %d real channels (max 48)", first_layer);
+            g.zero_planes = (48 - first_layer) / 8;
+        }
         if (make_segs(segs, nseg, g, sg)) return -1;
         if (launch_tc<48, 4, false>(sg, in_sstride, scale, nullptr, out_sstride, g, taps, stream)) return -1;
     } else {

@@ -527,7 +527,7 @@ struct Run {
                 sg[k].B = B;
             }
             chk(curla_conv_fwd_multi(sg, np, i == 0 ? a->s2d_sstride : a->act_sstride, i == 0 ? 1.0f / 255.0f : 1.0f,
-                                     a->act_sstride, a->pitch, a->S, a->Ho[i], a->Wo[i], i == 0, st));
+                                     a->act_sstride, a->pitch, a->S, a->Ho[i], a->Wo[i], i == 0 ? 4 * a->cfg.C : 0, st));
         }
     }
     void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4]) {

@@ -87,7 +87,9 @@ int curla_conv_dgrad(const void* dy, long long dy_sstride, const void* wts, cons
  * conv_theta(next_obs), F2 conv_target(next_obs), F3 conv_theta(obs) have no dependency on each
  * other, nor have the CURL anchor and key passes): segment s maps in[s] -> out[s] with its own
  * weights/bias (at most two DISTINCT weight pointers per call) and batch.  Same geometry,
- * strides and scale for all segments.  Bitwise identical to nseg curla_conv_fwd calls.       */
+ * strides and scale for all segments.  Bitwise identical to nseg curla_conv_fwd calls.
+ * first_layer: 0 = layers 2..4; 1 = the space-to-depth first layer; > 1 = first layer whose input
+ * has that many real channels (4*C): channel planes above it hold zeros and are not read.   */
 typedef struct curla_conv_seg {
     const void* in;
     const void* wts;

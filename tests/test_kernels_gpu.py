@@ -166,8 +166,8 @@ def test_conv_forward_multi_segment(H, W):
             segs[k].inp = ins[k].data_ptr(); segs[k].wts = wsh[wsel[k]][l].data_ptr()
             segs[k].bias = bd[wsel[k]][l].data_ptr(); segs[k].out = out.data_ptr(); segs[k].B = Bs[k]
         _lib.call('curla_conv_fwd_multi', C.byref(segs), 3, g0.S * (g0.CP1 if l == 0 else 32),
-                  1.0 / 255.0 if l == 0 else 1.0, g0.S * 32, g0.pitch, g0.S, g0.Ho[l], g0.Wo[l], 1 if l == 0 else 0,
-                  stream())
+                  1.0 / 255.0 if l == 0 else 1.0, g0.S * 32, g0.pitch, g0.S, g0.Ho[l], g0.Wo[l], 36 if l == 0 else 0,
+                  stream())                                        # 36 real s2d channels: the all-zero plane is not read
         torch.cuda.synchronize()
         n = min(g0.S, -(-g0.Ho[l] * g0.pitch // 256) * 256)        # positions a launch writes per sample and plane
         for k in range(3):
