@@ -45,7 +45,9 @@ constexpr int kTcGemmThreads = 192;
 struct TmaPlan {
     int a_segk;            // A's K index is segmented: map {seg_len, segment, rows}
     int b_segn;            // B's N index is segmented: map {seg_len, segment, K}; one N tile never leaves its segment
-    int per_seg;           // K steps per segment (a_segk) or N tiles per segment (b_segn)
+    int a_segm;            // A's M index is segmented (MN-major A): map {seg_len, segment, K}; one M tile never leaves its segment
+    int c_trans;           // store element (m, n) at C[n * ldc + m] (the problem was launched with its operands swapped)
+    int per_seg;           // K steps per segment (a_segk) or N / M tiles per segment (b_segn / a_segm)
     int total_steps;       // a_segk: segments * per_seg
     int nst;               // stages allocated
 };
@@ -95,7 +97,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     pdl_grid_sync();              // everything above is independent of earlier kernels
 
     // ---- tile and K-step ranges
-    const int m0 = blockIdx.y * TM;
+    int m0 = blockIdx.y * TM, mrows = TM, am_c0 = 0, am_c1 = 0;
+    if (SEG && pl.a_segm) {
+        const int sg = blockIdx.y / pl.per_seg, j = blockIdx.y - sg * pl.per_seg;
+        m0 = sg * p.seg_len + j * TM;
+        mrows = p.seg_len - j * TM < TM ? p.seg_len - j * TM : TM;
+        am_c0 = j * TM; am_c1 = sg;
+    }
     const int bz = p.batch > 1 ? blockIdx.z : 0, sz = p.batch > 1 ? 0 : blockIdx.z;
     int n0, ncols = TN, bn_c0 = 0, bn_c1 = 0;
     if (SEG && pl.b_segn) {
@@ -142,6 +150,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     } else {
                         tma_load_3d(dA, &tmA, step * TK, m0, za, bar);
                     }
+                } else if (SEG && pl.a_segm) {
+                    tma_load_3d(dA, &tmA, am_c0, am_c1, step * TK, bar);
+                    tma_load_3d(dA + kABytes / 2, &tmA, am_c0 + 64, am_c1, step * TK, bar);
                 } else {
                     tma_load_3d(dA, &tmA, m0, step * TK, za, bar);
                     tma_load_3d(dA + kABytes / 2, &tmA, m0 + 64, step * TK, za, bar);
@@ -183,7 +194,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else {
         // ================= epilogue: thread = output row m0 + 32 (warp % 4) + lane, 64 columns in two TMEM loads
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
+        const int mr = q * 32 + lane;                          // row inside the tile
+        const int m = m0 + mr;
         float* Cf = (float*)p.C + (long long)sz * p.split_stride + bz * p.bsC;
         bf16* Cb = (bf16*)p.C + bz * p.bsC;
         const float* __restrict__ biasp = p.bias ? p.bias + bz * p.bsBias : nullptr;
@@ -195,8 +207,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
+            __syncwarp();                                         // lanes re-converge before the warp-collective TMEM load
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
-            if (m >= p.M) continue;
+            if (m >= p.M || mr >= mrows) continue;
+            if (pl.c_trans) {
+                // operands were swapped: this thread's row is a COLUMN of the caller's fp32 matrix, so a
+                // warp writes 32 consecutive floats per column (no alpha / bias / mask on this path)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int n = n0 + h * 32 + c;
+                    if (n < p.n_store) Cf[(long long)n * p.ldc + m] = nk > 0 ? __uint_as_float(r[c]) * p.alpha : 0.f;
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int c = h * 32 + j * 8;                  // column inside the tile
@@ -261,6 +284,166 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- one K step, many N tiles per CTA
+// fc dgrad (encoder.py:98 backward): dact[B][67,456] = (act > 0) * dfc[B][64] . Wfc[64][67,456] -- K = 64 is a
+// single step, the work is the epilogue (16 KB of mask in, 16 KB of bf16 out per 128 x 64 tile).  One CTA
+// per tile pays its fixed cost 4,216 times; here a CTA keeps its A tile (128 rows of dfc) resident and
+// walks over a contiguous range of N tiles: producer warp (B tiles through a 4-deep ring), MMA warp
+// (4 MMAs per tile into one of four TMEM accumulators), four epilogue groups of four warps taking
+// tiles round robin.  An epilogue warp owns 32 rows x 64 columns: TMEM -> registers (one row per lane)
+// -> bf16 -> its private shared-memory patch -> read back as 16-byte chunks with eight lanes per
+// row, so that mask loads and stores are 4 rows x 128 contiguous bytes per instruction (one row
+// per lane = 32 scattered 16-byte pieces per instruction measured 85-100 us instead of ~50).
+constexpr int kNlThreads = 18 * 32;      // producer, MMA, 4 groups x 4 epilogue warps
+constexpr int kNlAcc = 4;
+constexpr uint32_t kNlPatch = 32 * 144;  // one warp's 32 rows x (128 + 16) bytes
+constexpr uint32_t kNlSmem = kHdrTc + kABytes + 4 * kBBytes + 16 * kNlPatch;
+
+template <bool SEG>
+__global__ void __launch_bounds__(kNlThreads, 1)
+k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p, int tiles_n) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    // header: b_full[4] @0, b_empty[4] @32, tfull[4] @64, tempty[4] @96, a_full @128, tmem ptr @136
+    const uint32_t s_bfull = s_base, s_bempty = s_base + 32, s_tfull = s_base + 64, s_tempty = s_base + 96;
+    const uint32_t s_afull = s_base + 128, s_tptr = s_base + 136;
+    const uint32_t sA = s_base + kHdrTc, sB0 = sA + kABytes, sP0 = sB0 + 4 * kBBytes;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(s_bfull + 8 * i, 1); mbar_init(s_bempty + 8 * i, 1); }
+        for (int i = 0; i < kNlAcc; ++i) { mbar_init(s_tfull + 8 * i, 1); mbar_init(s_tempty + 8 * i, 4); }
+        mbar_init(s_afull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"((uint32_t)(kNlAcc * TN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 136);
+    pdl_grid_sync();
+
+    const int m0 = blockIdx.y * TM;
+    // a CTA walks over a CONTIGUOUS range of N tiles: every row's 128-byte pieces are then touched in address order
+    const int per = (tiles_n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_first = (int)blockIdx.x * per;
+    const int my_tiles = tiles_n - t_first < per ? (tiles_n - t_first > 0 ? tiles_n - t_first : 0) : per;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(s_afull, kABytes);
+            tma_load_3d(sA, &tmA, 0, m0, 0, s_afull);
+            uint32_t stage = 0, phase = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                mbar_wait(s_bempty + 8 * stage, phase ^ 1);
+                mbar_expect_tx(s_bfull + 8 * stage, kBBytes);
+                tma_load_3d(sB0 + stage * kBBytes, &tmB, (t_first + i) * TN, 0, 0, s_bfull + 8 * stage);
+                if (++stage == 4) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t kId = idesc_tc(false, true);          // A K-major, B MN-major
+            mbar_wait(s_afull, 0);
+            uint32_t stage = 0, phase = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
+                mbar_wait(s_bfull + 8 * stage, phase);
+                mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t sB = sB0 + stage * kBBytes;
+#pragma unroll
+                for (int ks = 0; ks < TK / 16; ++ks)
+                    umma_bf16_rt(tmem_base + acc * TN, desc_sw128(sA + ks * 32, 16, 1024), desc_sw128(sB + ks * 2048, kBBytes, 1024), kId,
+                                 (uint32_t)(ks != 0));
+                umma_commit(s_bempty + 8 * stage);
+                umma_commit(s_tfull + 8 * acc);
+                if (++stage == 4) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue group g (tiles i with i % 4 == g); warp = TMEM lane quarter q = rows 32q .. 32q+31
+        const int g = (warp - 2) >> 2, q = warp & 3;
+        const uint32_t patch = sP0 + (uint32_t)(warp - 2) * kNlPatch;
+        bf16* __restrict__ Cb = (bf16*)p.C;
+        const bf16* __restrict__ maskp = p.mask;
+        // read-back / global access pattern: pass t (0..7): row 4t + lane / 8 of the warp's 32, 16-byte chunk lane % 8
+        const int cr = lane >> 3, cc = lane & 7;
+        uint4 mk[8];
+        auto load_mask = [&](int i) {
+            const int n = (t_first + i) * TN + cc * 8;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                mk[t] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // "keep" when there is no mask
+                const int m = m0 + q * 32 + t * 4 + cr;
+                if (maskp && m < p.M && n + 8 <= p.n_store)
+                    mk[t] = *reinterpret_cast<const uint4*>(maskp + (long long)m * p.ldmask +
+                                                            seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4)));
+            }
+        };
+        if (g < my_tiles) load_mask(g);
+        for (int i = g; i < my_tiles; i += kNlAcc) {
+            const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
+            mbar_wait(s_tfull + 8 * acc, acc_phase);
+            __syncwarp();                                         // lanes re-converge before the warp-collective TMEM loads
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + (uint32_t)(h * 32), r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[e] = pack_bf16x2(__uint_as_float(r[j * 8 + 2 * e]) * p.alpha, __uint_as_float(r[j * 8 + 2 * e + 1]) * p.alpha);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(patch + lane * 144 + (h * 4 + j) * 16), "r"(w[0]), "r"(w[1]),
+                                 "r"(w[2]), "r"(w[3]) : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tempty + 8 * acc);
+            const int n = (t_first + i) * TN + cc * 8;
+            const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int row = t * 4 + cr, m = m0 + q * 32 + row;
+                uint4 v;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(patch + row * 144 + cc * 16));
+                if (m >= p.M || n >= p.n_store) continue;
+                const long long o = (long long)m * p.ldc + nc;
+                if (n + 8 <= p.n_store) {
+                    auto keep = [](uint32_t val, uint32_t mw) {
+                        const float2 mv = unpack_bf16x2(mw);
+                        return (mv.x > 0.f ? val & 0x0000FFFFu : 0u) | (mv.y > 0.f ? val & 0xFFFF0000u : 0u);
+                    };
+                    v.x = keep(v.x, mk[t].x); v.y = keep(v.y, mk[t].y); v.z = keep(v.z, mk[t].z); v.w = keep(v.w, mk[t].w);
+                    *reinterpret_cast<uint4*>(Cb + o) = v;
+                } else {
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    for (int e = 0; e < p.n_store - n; ++e) {
+                        uint16_t x = (uint16_t)(w[e >> 1] >> ((e & 1) * 16));
+                        if (maskp && !(__bfloat162float(maskp[(long long)m * p.ldmask + nc + e]) > 0.f)) x = 0;
+                        reinterpret_cast<uint16_t*>(Cb + o)[e] = x;
+                    }
+                }
+            }
+            __syncwarp();                                         // the patch is rewritten by the next tile
+            if (i + kNlAcc < my_tiles) load_mask(i + kNlAcc);     // lands while the other three groups work
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kNlAcc * TN)) : "memory");
     }
 }
 
@@ -337,6 +520,9 @@ int launch_one(const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& p, 
 
 }  // namespace
 
+static int tc_swapped_wgrad(const GemmArgs& p, cudaStream_t stream);
+static int tc_nloop(const GemmArgs& p, cudaStream_t stream);
+
 int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t stream) {
     // CURLA_GEMM_TC (read per call: the tests compare both kernels): 0 = never, 2 = whenever the
     // shape is supported, default = where it measured faster than gemm.cu (tests/bench_gemm.py,
@@ -347,6 +533,19 @@ int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t s
     const char* env = getenv("CURLA_GEMM_TC");
     if (env && env[0] == '0') return 0;
     const bool force = env && env[0] == '2';
+    // fc wgrad: dW[feat <= 64][N] = A^T . B with B's N index segmented, fp32.  Launched with the operands
+    // swapped (M' = N in tiles of 128, N' = feat), so the big operand streams once through full tiles.
+    if (layout == 0 && p.seg_mask == 2 && p.M <= TN && p.N >= 4096 && p.K >= 128 && !p.out_bf16 && !p.bias && !p.mask &&
+        !p.relu && p.batch <= 1 && splits == 1 && p.n_store == p.N) {
+        const int r = tc_swapped_wgrad(p, stream);
+        if (r) return r;
+    }
+    // fc dgrad: one K step, thousands of N tiles, bf16 out (+ ReLU mask): the N-loop kernel
+    if (layout == 1 && p.K <= TK && p.N >= 4096 && p.M >= TM && p.out_bf16 && !p.bias && !p.relu && p.batch <= 1 && splits == 1 &&
+        (p.seg_mask == 0 || p.seg_mask == 4)) {
+        const int r = tc_nloop(p, stream);
+        if (r) return r;
+    }
     if (p.M < TM && !(p.N >= 4096 && p.K >= 128)) return 0;      // at least one full tile of rows, or fc wgrad (forced only)
     if (!force) {
         const int steps = cdiv(p.k_per_split < p.K ? p.k_per_split : p.K, TK);
@@ -414,6 +613,56 @@ int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t s
         case 6: return launch_one<false, true, true>(ta, tb, p, pl, grid, stream);
         default: return launch_one<false, false, true>(ta, tb, p, pl, grid, stream);
     }
+}
+
+static int tc_nloop(const GemmArgs& p, cudaStream_t stream) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(p.A) || !al16(p.B) || !al16(p.C) || p.lda % 8 || p.ldb % 8 || p.ldc % 8 || p.K % 8 || !encode_fn()) return 0;
+    if (p.mask && (!al16(p.mask) || p.ldmask % 8)) return 0;
+    if (p.seg_mask && (p.seg_len % 8 || p.seg_stride % 8)) return 0;
+    const CUtensorMap* ta = get_map(p.A, (unsigned long long)p.K, (unsigned long long)p.M, 1ull, (unsigned long long)p.lda * 2,
+                                    (unsigned long long)p.M * p.lda * 2, TK, TM, 1);
+    const CUtensorMap* tb = get_map(p.B, (unsigned long long)((p.N + 7) / 8 * 8), (unsigned long long)p.K, 1ull,
+                                    (unsigned long long)p.ldb * 2, (unsigned long long)p.K * p.ldb * 2, TN, TK, 1);
+    if (!ta || !tb) return -1;
+    const int tiles_n = cdiv(p.N, TN), mt = cdiv(p.M, TM);
+    int strips = cdiv(sm_count(), mt);                     // one CTA per SM
+    if (strips > tiles_n) strips = tiles_n;
+    if (mt > 65535) return 0;
+    static bool attr[2] = {false, false};
+    const int sg = p.seg_mask ? 1 : 0;
+    if (!attr[sg]) {
+        cudaError_t e = sg ? cudaFuncSetAttribute(k_gemm_tc_nloop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNlSmem)
+                           : cudaFuncSetAttribute(k_gemm_tc_nloop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNlSmem);
+        if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%u): %s", kNlSmem, cudaGetErrorString(e)); return -1; }
+        attr[sg] = true;
+    }
+    if (sg) launch_k(k_gemm_tc_nloop<true>, dim3(strips, mt), dim3(kNlThreads), kNlSmem, stream, *ta, *tb, p, tiles_n);
+    else launch_k(k_gemm_tc_nloop<false>, dim3(strips, mt), dim3(kNlThreads), kNlSmem, stream, *ta, *tb, p, tiles_n);
+    return 1;
+}
+
+static int tc_swapped_wgrad(const GemmArgs& p, cudaStream_t stream) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (!al16(p.A) || !al16(p.B) || p.lda % 8 || p.ldb % 8 || p.K % 8 || p.seg_len % 8 || p.seg_stride % 8 || !encode_fn()) return 0;
+    GemmArgs q = p;
+    q.A = p.B; q.lda = p.ldb; q.B = p.A; q.ldb = p.lda;
+    q.M = p.N; q.N = p.M; q.n_store = p.M;                  // rows = the caller's columns, columns = the caller's rows
+    q.k_per_split = (p.K + TK - 1) / TK * TK;
+    TmaPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    const int nseg = cdiv(p.N, p.seg_len);
+    pl.a_segm = 1; pl.c_trans = 1; pl.per_seg = cdiv(p.seg_len, TM);
+    const CUtensorMap* ta = get_map(q.A, (unsigned long long)p.seg_len, (unsigned long long)nseg, (unsigned long long)p.K,
+                                    (unsigned long long)p.seg_stride * 2, (unsigned long long)q.lda * 2, 64, 1, TK);
+    const CUtensorMap* tb = get_map(q.B, (unsigned long long)((p.M + 7) / 8 * 8), (unsigned long long)p.K, 1ull,
+                                    (unsigned long long)q.ldb * 2, (unsigned long long)p.K * q.ldb * 2, TN, TK, 1);
+    if (!ta || !tb) return -1;
+    const int nsteps = cdiv(p.K, TK);
+    pl.nst = nsteps < kMaxSt ? nsteps : kMaxSt;
+    dim3 grid(1, nseg * pl.per_seg, 1);
+    if (grid.y > 65535) return 0;
+    return launch_one<false, false, true>(ta, tb, q, pl, grid, stream);
 }
 
 }  // namespace curla
