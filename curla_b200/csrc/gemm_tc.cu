@@ -204,76 +204,110 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool bias_al = (reinterpret_cast<uintptr_t>(biasp) & 15) == 0;
         mbar_wait(s_done, 0);
         tc_fence_after();
+        if (pl.c_trans) {
+            // operands were swapped: this thread's row is a COLUMN of the caller's fp32 matrix, so a
+            // warp writes 32 consecutive floats per column (no bias / mask on this path)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            __syncwarp();                                         // lanes re-converge before the warp-collective TMEM load
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
-            if (m >= p.M || mr >= mrows) continue;
-            if (pl.c_trans) {
-                // operands were swapped: this thread's row is a COLUMN of the caller's fp32 matrix, so a
-                // warp writes 32 consecutive floats per column (no alpha / bias / mask on this path)
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                __syncwarp();                                     // lanes re-converge before the warp-collective TMEM load
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
+                if (m >= p.M || mr >= mrows) continue;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const int n = n0 + h * 32 + c;
                     if (n < p.n_store) Cf[(long long)n * p.ldc + m] = nk > 0 ? __uint_as_float(r[c]) * p.alpha : 0.f;
                 }
-                continue;
             }
+        } else {
+            // Phase 1: one row per lane (the TMEM layout): alpha, bias, ReLU in fp32 -> this warp's patch of
+            // shared memory (the operand stages are free: every MMA has completed), rows 272 bytes apart.
+            // Phase 2: read back as 16-byte chunks with 8 (bf16 out) or 16 (fp32 out) lanes per row, so
+            // that mask loads and stores are whole 128 / 256-byte row pieces per instruction (one row
+            // per lane = 32 scattered 16-byte pieces per instruction: measured 2-3x slower, see the N-loop kernel).
+            const uint32_t patch = s_stage0 + (uint32_t)q * (32 * 272);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = h * 32 + j * 8;                  // column inside the tile
-                const int n = n0 + c;
-                int lim = p.n_store - n;                       // columns of this chunk that exist
-                if (ncols - c < lim) lim = ncols - c;
-                if (lim <= 0) continue;
-                float v[8], bv[8];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) bv[e] = 0.f;
-                if (biasp) {
-                    if (lim >= 8 && bias_al) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(biasp + n)), b1 = __ldg(reinterpret_cast<const float4*>(biasp + n + 4));
-                        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-                    } else {
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + h * 32 + j * 4;
+                    float v[4], bv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (biasp) {
+                        if (bias_al && n + 4 <= p.n_store) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(biasp + n));
+                            bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) if (e < lim) bv[e] = biasp[n + e];
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    v[e] = (nk > 0 ? __uint_as_float(r[j * 8 + e]) : 0.f) * p.alpha + bv[e];
-                    if (p.relu) v[e] = fmaxf(v[e], 0.f);
-                }
-                const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
-                const bool whole = lim >= 8;
-                if (maskp) {
-                    if (whole) {
-                        const uint4 mk = *reinterpret_cast<const uint4*>(maskp + (long long)m * p.ldmask + nc);
-                        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 mv = unpack_bf16x2(mw[e]);
-                            v[2 * e] = mv.x > 0.f ? v[2 * e] : 0.f;
-                            v[2 * e + 1] = mv.y > 0.f ? v[2 * e + 1] : 0.f;
+                            for (int e = 0; e < 4; ++e) if (n + e < p.n_store) bv[e] = biasp[n + e];
                         }
-                    } else {
-                        for (int e = 0; e < lim; ++e)
-                            v[e] = __bfloat162float(maskp[(long long)m * p.ldmask + nc + e]) > 0.f ? v[e] : 0.f;
                     }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = (nk > 0 ? __uint_as_float(r[j * 4 + e]) : 0.f) * p.alpha + bv[e];
+                        if (p.relu) v[e] = fmaxf(v[e], 0.f);
+                    }
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(patch + lane * 272 + (h * 32 + j * 4) * 4), "f"(v[0]), "f"(v[1]),
+                                 "f"(v[2]), "f"(v[3]) : "memory");
                 }
-                const long long o = (long long)m * p.ldc + nc;
-                if (p.out_bf16) {
-                    if (whole) {
+            }
+            __syncwarp();
+            if (p.out_bf16) {
+                const int cr = lane >> 3, cc = lane & 7;
+                const int c = cc * 8, n = n0 + c;
+                int lim = p.n_store - n;
+                if (ncols - c < lim) lim = ncols - c;
+                const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int row = t * 4 + cr, mm = m0 + q * 32 + row;
+                    float4 a, b;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(patch + row * 272 + c * 4));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(patch + row * 272 + c * 4 + 16));
+                    if (mm >= p.M || q * 32 + row >= mrows || lim <= 0) continue;
+                    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    const long long o = (long long)mm * p.ldc + nc;
+                    if (lim >= 8) {
+                        if (maskp) {
+                            const uint4 mk = *reinterpret_cast<const uint4*>(maskp + (long long)mm * p.ldmask + nc);
+                            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 mv = unpack_bf16x2(mw[e]);
+                                v[2 * e] = mv.x > 0.f ? v[2 * e] : 0.f;
+                                v[2 * e + 1] = mv.y > 0.f ? v[2 * e + 1] : 0.f;
+                            }
+                        }
                         *reinterpret_cast<uint4*>(Cb + o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     } else {
-                        for (int e = 0; e < lim; ++e) Cb[o + e] = __float2bfloat16(v[e]);
+                        for (int e = 0; e < lim; ++e) {
+                            float x = v[e];
+                            if (maskp) x = __bfloat162float(maskp[(long long)mm * p.ldmask + nc + e]) > 0.f ? x : 0.f;
+                            Cb[o + e] = __float2bfloat16(x);
+                        }
                     }
-                } else if (whole && f4) {
-                    *reinterpret_cast<float4*>(Cf + o) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(Cf + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-                    for (int e = 0; e < lim; ++e) Cf[o + e] = v[e];
+                }
+            } else {
+                const int cr = lane >> 4, cc = lane & 15;
+                const int c = cc * 4, n = n0 + c;
+                int lim = p.n_store - n;
+                if (ncols - c < lim) lim = ncols - c;
+                const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int row = t * 2 + cr, mm = m0 + q * 32 + row;
+                    float4 a;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(patch + row * 272 + c * 4));
+                    if (mm >= p.M || q * 32 + row >= mrows || lim <= 0) continue;
+                    float v[4] = {a.x, a.y, a.z, a.w};
+                    if (maskp)
+                        for (int e = 0; e < 4 && e < lim; ++e)
+                            v[e] = __bfloat162float(maskp[(long long)mm * p.ldmask + nc + e]) > 0.f ? v[e] : 0.f;
+                    const long long o = (long long)mm * p.ldc + nc;
+                    if (lim >= 4 && f4) *reinterpret_cast<float4*>(Cf + o) = make_float4(v[0], v[1], v[2], v[3]);
+                    else for (int e = 0; e < 4 && e < lim; ++e) Cf[o + e] = v[e];
                 }
             }
         }
@@ -513,7 +547,8 @@ int launch_one(const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& p, 
         if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%d): %s", mx, cudaGetErrorString(e)); return -1; }
         attr = true;
     }
-    const uint32_t smem = kHdrTc + (uint32_t)pl.nst * kStageBytesTc;
+    uint32_t smem = kHdrTc + (uint32_t)pl.nst * kStageBytesTc;
+    if (smem < kHdrTc + 4 * 32 * 272) smem = kHdrTc + 4 * 32 * 272;        // the epilogue's four 32-row fp32 patches reuse the stages
     launch_k(kern, grid, dim3(kTcGemmThreads), smem, stream, *ta, *tb, p, pl);
     return 1;
 }
