@@ -418,7 +418,10 @@ def main():
     ho, wo = geometry((H_, W_))
     Bb = args.batch
     act = lambda l: Bb * ho[l] * wo[l] * 64                      # valid bf16 positions x 32 channels
-    s2d_bytes = Bb * ((H_ + 1) // 2) * ((W_ + 1) // 2) * 48 * 2
+    # space-to-depth input: 4*9 = 36 real channels live in five 8-channel planes (the sixth plane of the 48-channel
+    # operand is all zero: never written by the gather, never read by conv-1)
+    s2d_bytes = Bb * ((H_ + 1) // 2) * ((W_ + 1) // 2) * 40 * 2
+    kfc = ho[3] * ((W_ + 1) // 2) * 32                             # fc input in the pitch layout (67,456 for the crop)
     conv_flops = lambda l: 2.0 * Bb * ho[l] * wo[l] * 32 * (81 if l == 0 else 288)
     table = {
         'conv_fwd': dict(kernel='k_conv_tc<fwd> (tcgen05 conv forward, 4 layers)', launches=4,
@@ -432,6 +435,12 @@ def main():
                            flops=sum(conv_flops(l) for l in range(4))),
         'gather_s2d': dict(kernel='k_gather_s2d (replay gather + crop + u8->bf16 s2d)', launches=1,
                            bytes=Bb * 9 * H_ * W_ + s2d_bytes, flops=0.0),
+        'gemm_fc_fwd': dict(kernel='k_gemm_tc (tcgen05 + TMA, encoder fc forward, split-K)', launches=1,
+                            bytes=Bb * kfc * 2 + 64 * kfc * 2, flops=2.0 * Bb * 64 * kfc),
+        'gemm_fc_dgrad': dict(kernel='k_gemm_tc_nloop (tcgen05 + TMA, encoder fc dgrad + ReLU mask)', launches=1,
+                              bytes=2 * Bb * kfc * 2 + 64 * kfc * 2, flops=2.0 * Bb * 64 * kfc),
+        'gemm_fc_wgrad': dict(kernel='k_gemm_tc (tcgen05 + TMA, encoder fc wgrad, swapped operands)', launches=1,
+                              bytes=Bb * kfc * 2 + 50 * kfc * 4, flops=2.0 * Bb * 64 * kfc),
         'adam_f32': dict(kernel='k_adam (fused multi-tensor Adam)', launches=None, bytes=None, flops=0.0),
     }
     traffic_db = {}
