@@ -5,7 +5,7 @@
 //   encoder.py:77-90     CNNEncoder.forward_conv
 //   curl_sac.py:367,417  loss.backward() through the conv layers
 //
-// Same data layout as conv.cu: NHWC bf16 activations with a fixed row
+// Data layout: channel-plane bf16 activations with a fixed row
 // pitch, so a 3x3 valid conv over the flattened position index P is
 //     out[P][0:32] = sum_t in[P + off_t][0:CP] . W_t          (off_t = dy*pitch + dx)
 // i.e. nine GEMMs whose A operand is the SAME matrix shifted by off_t rows.
@@ -20,12 +20,14 @@
 // slab, no im2col, no data movement, any shift (only 16-byte alignment is required when no
 // swizzle is used).  Weights use the same layout [tap][chunk][32 n][8 k].
 //
-// One persistent CTA per SM over tiles of 256 positions, warp-specialised (producer warps fill
-// a ring of slabs with cp.async; one elected thread issues 2*NTAPS*(CP/16) MMAs of
-// M=128, N=32, K=16, bf16 -> fp32 per tile into double-buffered TMEM accumulators;
-// tcgen05.commit arrives on mbarriers; eight epilogue warps pull their 32 TMEM lanes with
-// tcgen05.ld -- one output position per thread, 32 channels -- and apply scale+bias+ReLU or
-// the ReLU mask of dgrad with 64-byte row stores).  See the kernel for the pipeline.
+// One persistent CTA per SM over tiles of 256 positions, warp-specialised: a producer thread
+// hands out tiles (atomic counter) and fills a ring of slabs with one cp.async.bulk per channel
+// plane; two issuer warps alternate tiles, each issuing 2*NTAPS*(CP/16) MMAs of M=128, N=32,
+// K=16, bf16 -> fp32 into one of four TMEM accumulators; tcgen05.commit arrives on mbarriers;
+// two groups of eight epilogue warps pull their 32 TMEM lanes with tcgen05.ld -- one output
+// position per thread, 32 channels -- and apply scale+bias+ReLU or the ReLU mask of dgrad; a
+// warp stores 32 consecutive positions x 16 B = 512 contiguous bytes per channel plane.  Up to
+// three independent passes (own input / output / weight set) share one launch.  See the kernel.
 #include "common.cuh"
 #include "tc.cuh"
 #include "../../include/curla_b200.h"
