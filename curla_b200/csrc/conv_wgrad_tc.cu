@@ -42,6 +42,7 @@ struct WgGeom {
     int runs_per_sample, total_runs;
     int kwin;              // 16-position K windows per image row = ceil((Wv + NDX - 1) / 16)
     int dyr;               // rows of a staged dy plane (>= pitch + NDX - 1, >= kwin*16), zero outside the copy
+    int nst;               // pipeline stages (2..4): more, shorter stages keep more of the fill latency covered
 };
 
 constexpr int kWgThreads = 6 * 32;      // 4 epilogue warps + MMA + producer
@@ -62,8 +63,9 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    // header: full[2] @0, empty[2] @16, done @32, tmem ptr @40
-    const uint32_t s_full = s_base, s_empty = s_base + 16, s_done = s_base + 32, s_tptr = s_base + 40;
+    // header: full[4] @0, empty[4] @32, done @64, tmem ptr @72
+    const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72;
+    const int nst = g.nst;
     const uint32_t PS = (uint32_t)g.pitch * 16u;                       // one plane of one image row
     const uint32_t slot_bytes = CPL * PS;
     const int slots = g.R + GR - 1;
@@ -75,7 +77,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     const long long plane = (long long)g.S * 8;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
         mbar_init(s_done, 1);
         fence_mbar_init();
     }
@@ -88,11 +90,11 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     }
     // every byte the tensor core may touch must be finite (junk rows are multiplied by exact
     // zeros of dy, and 0 * NaN would poison a useful accumulator row): clear both stages once
-    for (uint32_t i = tid; i < (2 * stage_bytes) / 16; i += kWgThreads)
+    for (uint32_t i = tid; i < ((uint32_t)nst * stage_bytes) / 16; i += kWgThreads)
         reinterpret_cast<uint4*>(smem + 128)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     // constant parts of both stages: ones-planes (bf16 1.0); the tail of every dy plane stays zero
-    for (int st = 0; st < 2; ++st) {
+    for (int st = 0; st < nst; ++st) {
         uint8_t* sb = smem + 128 + (size_t)st * stage_bytes;
         const int ones16 = slots * g.pitch;                              // 16-byte rows of ones
         for (int i = tid; i < ones16; i += kWgThreads) {
@@ -106,7 +108,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 40);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 72);
     const int my_runs = g.total_runs > (int)blockIdx.x ? (g.total_runs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 5) {
@@ -138,8 +140,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
                                      src_d + c * plane + (long long)r * g.pitch * 8, PS, bar);
             }
             __syncwarp();
-            stage ^= 1;
-            if (stage == 0) phase ^= 1;
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 4) {
         // ================= MMA issuer
@@ -165,8 +166,7 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
             }
             accum = 1;
             __syncwarp();
-            stage ^= 1;
-            if (stage == 0) phase ^= 1;
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit(s_done);
         __syncwarp();
@@ -283,20 +283,24 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     g.dyr = (g.dyr + 7) / 8 * 8;
     const size_t PS = (size_t)pitch * 16, DYB = (size_t)g.dyr * 16;
     const size_t budget = 225 * 1024 - 256;
+    // CURLA_WG_STAGES (timing experiments): ring depth 2..4; R = the most dy rows per stage that fit
+    int nst = 2;
+    { const char* e = getenv("CURLA_WG_STAGES"); if (e && e[0] >= '2' && e[0] <= '4') nst = e[0] - '0'; }
     int R = 0;
     for (int r = 1; r <= 16; ++r) {
         const size_t stage = (((size_t)(r + GR - 1) * CPL * PS + (size_t)r * 4 * NDX * DYB) + 127) & ~(size_t)127;
         // the junk chunks of the last row (up to chunk 15) must stay inside the stage: reads reach
         // slot r-1 + ceil(16 / CPL) planes, covered by the dy region behind the A slots
-        if (2 * stage <= budget) R = r;
+        if ((size_t)nst * stage <= budget) R = r;
     }
     if (R < 1) { set_last_error("conv_wgrad: pitch %d does not fit shared memory", pitch); return -1; }
     if (R > Hv) R = Hv;
     g.R = R;
+    g.nst = nst;
     g.runs_per_sample = cdiv(Hv, R);
     g.total_runs = B * g.runs_per_sample;
     const size_t stage = (((size_t)(R + GR - 1) * CPL * PS + (size_t)R * 4 * NDX * DYB) + 127) & ~(size_t)127;
-    const size_t smem = 128 + 2 * stage;
+    const size_t smem = 128 + (size_t)nst * stage;
     auto kern = k_conv_wgrad_tc<CP, GR, NDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }

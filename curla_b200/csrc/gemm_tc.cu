@@ -94,6 +94,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 72);
+    if (tid == 0) {               // the tensor maps are kernel parameters: fetch them while waiting for the previous kernel
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
     pdl_grid_sync();              // everything above is independent of earlier kernels
 
     // ---- tile and K-step ranges
@@ -361,6 +365,10 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 136);
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
     pdl_grid_sync();
 
     const int m0 = blockIdx.y * TM;
