@@ -3,7 +3,7 @@
  * The reference (paulvantieghem/curla) is pure Python/PyTorch and has no FFI; the
  * boundary it exposes for this path is the Python API of curl_sac.py / encoder.py /
  * utils.py / augmentations.py.  This header is the C ABI the Python host side
- * (curla_b200/*.py, via ctypes) binds; every entry point cites the reference
+ * (the curla_b200 Python package, via ctypes) binds; every entry point cites the reference
  * code it replaces (paths relative to the reference repo root).  INTEGRATION.md shows the
  * ctypes stubs a maintainer of the reference would add.
  *

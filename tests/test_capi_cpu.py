@@ -30,6 +30,28 @@ def test_header_symbols_exported(lib):
     assert lib.curla_version() >= 100
 
 
+def test_header_is_plain_c_and_structs_match_ctypes(tmp_path):
+    """include/curla_b200.h compiles as C99 (the boundary is a C ABI) and the structs the Python side
+    mirrors with ctypes have the same size and field offsets."""
+    import subprocess
+    from curla_b200 import _lib
+    src = tmp_path / 'probe.c'
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "curla_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(curla_conv_seg), offsetof(curla_conv_seg, in), offsetof(curla_conv_seg, wts),\n'
+        '         offsetof(curla_conv_seg, bias), offsetof(curla_conv_seg, out), offsetof(curla_conv_seg, B));\n'
+        '  printf("%zu %zu\\n", sizeof(curla_agent_config), sizeof(curla_update_args));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / 'probe'
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    vals = [int(v) for v in out]
+    cs = _lib.ConvSeg
+    assert vals[:6] == [C.sizeof(cs), cs.inp.offset, cs.wts.offset, cs.bias.offset, cs.out.offset, cs.B.offset]
+    assert vals[6] == C.sizeof(_lib.AgentConfig) and vals[7] == C.sizeof(_lib.UpdateArgs)
+
+
 def test_engine_layout_host_side(lib):
     """curla_agent_create is pure host code: check the memory plan without a GPU."""
     from curla_b200 import _lib
