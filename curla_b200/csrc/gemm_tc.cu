@@ -135,8 +135,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int nst = pl.nst;
 
     if (warp == 0) {
-        // ================= producer
-        if (lane == 0) {
+        // ================= producer (the whole warp runs the loop, one elected lane issues: a loop confined to
+        // lane 0 makes the compiler wrap every TMA / MMA instruction in an elect loop over the active lanes)
+        {
             const int za = p.bsA ? bz : 0, zb = p.bsB ? bz : 0;
             uint32_t stage = 0, phase = 0;
             for (int kt = 0; kt < nk; ++kt) {
@@ -144,6 +145,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 mbar_wait(s_empty + 8 * stage, phase ^ 1);
                 const uint32_t bar = s_full + 8 * stage;
                 const uint32_t dA = s_stage0 + stage * kStageBytesTc, dB = dA + kABytes;
+                if (elect_one()) {
                 mbar_expect_tx(bar, kStageBytesTc);
                 int kb = step * TK;                           // B's K coordinate (logical K)
                 if (A_KMAJOR) {
@@ -164,14 +166,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (B_KMAJOR) tma_load_3d(dB, &tmB, kb, n0, zb, bar);
                 else if (SEG && pl.b_segn) tma_load_3d(dB, &tmB, bn_c0, bn_c1, step * TK, bar);
                 else tma_load_3d(dB, &tmB, n0, step * TK, zb, bar);
+                }
+                __syncwarp();
                 if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer
-        if (lane == 0) {
+        {
             constexpr uint32_t kId = idesc_tc(!A_KMAJOR, !B_KMAJOR);
-            const bool dbg = (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+            const bool dbg = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0;
             long long d0 = 0, d1 = 0;
             const long long dl0 = clock64();
             uint32_t stage = 0, phase = 0;
@@ -181,18 +185,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const long long c1 = dbg ? clock64() : 0;
                 tc_fence_after();
                 const uint32_t sA = s_stage0 + stage * kStageBytesTc, sB = sA + kABytes;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < TK / 16; ++ks) {
-                    // K-major: 16 k = 32 bytes further along the swizzled 128-byte rows; MN-major: 16 k rows = 2048 bytes
-                    const uint64_t ad = A_KMAJOR ? desc_sw128(sA + ks * 32, 16, 1024) : desc_sw128(sA + ks * 2048, kABytes / 2, 1024);
-                    const uint64_t bd = B_KMAJOR ? desc_sw128(sB + ks * 32, 16, 1024) : desc_sw128(sB + ks * 2048, kBBytes, 1024);
-                    umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | ks) != 0));
+                    for (int ks = 0; ks < TK / 16; ++ks) {
+                        // K-major: 16 k = 32 bytes further along the swizzled 128-byte rows; MN-major: 16 k rows = 2048 bytes
+                        const uint64_t ad = A_KMAJOR ? desc_sw128(sA + ks * 32, 16, 1024) : desc_sw128(sA + ks * 2048, kABytes / 2, 1024);
+                        const uint64_t bd = B_KMAJOR ? desc_sw128(sB + ks * 32, 16, 1024) : desc_sw128(sB + ks * 2048, kBBytes, 1024);
+                        umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | ks) != 0));
+                    }
+                    umma_commit(s_empty + 8 * stage);        // slot free once these MMAs have read it
                 }
-                umma_commit(s_empty + 8 * stage);            // slot free once these MMAs have read it
+                __syncwarp();
                 if (dbg) { d0 += c1 - c0; d1 += clock64() - c1; }
                 if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
             }
-            umma_commit(s_done);
+            if (elect_one()) umma_commit(s_done);
+            __syncwarp();
             if (dbg) { g_gtc_dbg[0] = d0; g_gtc_dbg[1] = d1; g_gtc_dbg[4] = clock64() - dl0; g_gtc_dbg[5] = nk; }
         }
     } else {
@@ -378,36 +386,42 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int my_tiles = tiles_n - t_first < per ? (tiles_n - t_first > 0 ? tiles_n - t_first : 0) : per;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // (whole-warp loops with one elected lane issuing, as in k_gemm_tc)
+        if (elect_one()) {
             mbar_expect_tx(s_afull, kABytes);
             tma_load_3d(sA, &tmA, 0, m0, 0, s_afull);
-            uint32_t stage = 0, phase = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                mbar_wait(s_bempty + 8 * stage, phase ^ 1);
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            mbar_wait(s_bempty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(s_bfull + 8 * stage, kBBytes);
                 tma_load_3d(sB0 + stage * kBBytes, &tmB, (t_first + i) * TN, 0, 0, s_bfull + 8 * stage);
-                if (++stage == 4) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == 4) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t kId = idesc_tc(false, true);          // A K-major, B MN-major
-            mbar_wait(s_afull, 0);
-            uint32_t stage = 0, phase = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
-                mbar_wait(s_bfull + 8 * stage, phase);
-                mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t sB = sB0 + stage * kBBytes;
+        constexpr uint32_t kId = idesc_tc(false, true);          // A K-major, B MN-major
+        mbar_wait(s_afull, 0);
+        uint32_t stage = 0, phase = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
+            mbar_wait(s_bfull + 8 * stage, phase);
+            mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t sB = sB0 + stage * kBBytes;
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < TK / 16; ++ks)
                     umma_bf16_rt(tmem_base + acc * TN, desc_sw128(sA + ks * 32, 16, 1024), desc_sw128(sB + ks * 2048, kBBytes, 1024), kId,
                                  (uint32_t)(ks != 0));
                 umma_commit(s_bempty + 8 * stage);
                 umma_commit(s_tfull + 8 * acc);
-                if (++stage == 4) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == 4) { stage = 0; phase ^= 1; }
         }
     } else {
         // ================= epilogue group g (tiles i with i % 4 == g); warp = TMEM lane quarter q = rows 32q .. 32q+31
