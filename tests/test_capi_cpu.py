@@ -52,6 +52,21 @@ def test_header_is_plain_c_and_structs_match_ctypes(tmp_path):
     assert vals[6] == C.sizeof(_lib.AgentConfig) and vals[7] == C.sizeof(_lib.UpdateArgs)
 
 
+def test_host_only_helpers(lib):
+    """Pure host functions of the C ABI (no GPU): split-K ranges are multiples of 64 -- the K step of the
+    tcgen05 GEMM -- so the number of partial slices the engine allocates does not depend on which GEMM
+    kernel runs; the conv padding covers a slab's halo."""
+    for K, sp in ((67456, 74), (4096, 7), (64, 3), (88768, 74), (1000, 1), (8, 5)):
+        z = lib.curla_gemm_effective_splits(K, sp)
+        steps = -(-K // 64)
+        per = -(-steps // sp)
+        assert z == -(-steps // per) and 1 <= z <= sp, (K, sp, z)
+        assert (z - 1) * per * 64 < K <= z * per * 64            # every slice non-empty, K covered
+    assert lib.curla_gemm_effective_splits(67456, 74) == 71      # the encoder fc forward at train.py defaults
+    for pitch in (32, 42, 68, 80):
+        assert lib.curla_conv_pad_rows(pitch) >= 256 + 2 * pitch + 2
+
+
 def test_engine_layout_host_side(lib):
     """curla_agent_create is pure host code: check the memory plan without a GPU."""
     from curla_b200 import _lib
