@@ -524,7 +524,9 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
     g.plane_bytes = g.plane_rows * 16 + ((g.debug & 16) ? 64 : 0);
     const size_t slab = (size_t)CH * g.plane_bytes;
-    const size_t budget = 190 * 1024;      // leaves room for one 32 KB GEMM CTA of the side stream next to a conv CTA
+    // shared-memory budget of the slab ring (CURLA_TC_SMEM_KB, timing experiments: 64..225)
+    size_t budget = 190 * 1024;
+    { const char* e = getenv("CURLA_TC_SMEM_KB"); if (e && atoi(e) >= 64 && atoi(e) <= 225) budget = (size_t)atoi(e) * 1024; }
     int stages = (int)((budget - fixed) / slab);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { set_last_error("conv_tc: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
