@@ -13,8 +13,11 @@ the update is data parallel: per-GPU batch stays 512 (weak scaling), the global 
 `value` is observations/s through the update over all ranks (= global batch * updates/s;
 `updates_per_s` is printed beside it).
 
-One JSON line on stdout (rank 0).  --impl reference times the oracle port of the
-reference's CPU update on the host cores (the reference is pure Python; kind "port").
+One JSON line on stdout (rank 0).  --impl reference times the reference's OWN update (the
+unmodified modules shipped under baseline/_ref by build(), imported through oracle/shims) on
+the host cores at the same batch / replay capacity for the real step count (kind "reference";
+the oracle port only if those files are absent).  --impl reference_cuda is the informational
+"PyTorch eager on the B200" baseline of the same unmodified code.
 """
 import argparse
 import json
@@ -231,37 +234,103 @@ def run_ours(args, rank, world, device):
                 prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last, obs_hw=tuple(aug.output_shape))
 
 
-def cpu_reference_updates(batch, steps, warmup, threads, workload='curl_crop'):
-    """The oracle port of the reference's CPU update (torch fp32, oneDNN) on the host cores."""
+def fill_host_replay(rb, seed=1):
+    """SURVEY 8(d) synthetic fill of a host-numpy replay (the reference's ReplayBuffer): uniform uint8
+    frames (torch.randint per chunk: the values are not the measured thing, the 4.25 GB footprint is)."""
+    g = torch.Generator().manual_seed(seed)
+    n = rb.capacity
+    for s0 in range(0, n, 512):
+        e = min(n, s0 + 512)
+        rb.obses[s0:e] = torch.randint(0, 256, (e - s0, *FRAME), dtype=torch.uint8, generator=g).numpy()
+        rb.next_obses[s0:e] = torch.randint(0, 256, (e - s0, *FRAME), dtype=torch.uint8, generator=g).numpy()
+    rs = np.random.RandomState(seed)
+    rb.actions[:] = rs.uniform(-1, 1, size=rb.actions.shape).astype(np.float32)
+    rb.rewards[:] = rs.standard_normal(size=rb.rewards.shape).astype(np.float32)
+    rb.not_dones[:] = (rs.uniform(size=rb.not_dones.shape) > 0.01).astype(np.float32)
+    rb.idx, rb.full = 0, True
+
+
+def reference_updates(batch, steps, warmup, threads, workload='curl_crop', device='cpu', tf32=False):
+    """Seconds per update of the reference's OWN CurlSacAgent.update (curl_sac.py:426-451), sample_cpc
+    included, at the benchmarked configuration: batch `batch`, host replay of CAPACITY transitions,
+    train.py defaults.  kind 'reference' = the unmodified reference modules (/root/reference, or their
+    verbatim copies under baseline/_ref/ on the GPU box) imported through the three import shims of
+    oracle/shims; kind 'port' = the oracle restatement, only when neither is present.
+    Returns (seconds per update, kind)."""
+    from oracle import make_golden as MG
+    wl = WORKLOADS[workload]
+    torch.set_num_threads(threads)
+    ref_dir = MG.reference_dir()
+    if ref_dir is None:
+        if device != 'cpu':
+            raise SystemExit('reference modules not found (baseline/_ref): the CUDA baseline needs the reference itself')
+        return port_updates(batch, steps, warmup, workload), 'port'
+    import contextlib
+    import io
+    ref_utils, ref_aug, ref_sac, _ = MG.import_reference(ref_dir)
+    dev = torch.device(device)
+    if dev.type == 'cuda':
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    with contextlib.redirect_stdout(io.StringIO()):
+        aug = ref_aug.make_augmentor(wl['aug'], FRAME[1:])
+        rb = ref_utils.ReplayBuffer(FRAME, ACTION, CAPACITY, batch, dev, aug)
+    fill_host_replay(rb)
+    ref_utils.set_seed_everywhere(0)
+    agent = ref_sac.CurlSacAgent((9, *aug.output_shape), ACTION, dev, aug, log_interval=10 ** 9,
+                                 pixel_sac=wl['pixel_sac'], **HP)
+    L = NullLogger()
+    sync = (lambda: torch.cuda.synchronize()) if dev.type == 'cuda' else (lambda: None)
+    step = 2                                  # even start; never a multiple of log_interval
+    for _ in range(warmup):
+        agent.update(rb, L, step)
+        step += 1
+    if step % 2:
+        agent.update(rb, L, step)
+        step += 1
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        agent.update(rb, L, step)
+        step += 1
+    sync()
+    return (time.perf_counter() - t0) / steps, 'reference'
+
+
+def port_updates(batch, steps, warmup, workload='curl_crop'):
+    """Fallback when the reference modules are absent: the oracle port, same batch / capacity."""
     from oracle import curla_oracle as O
     wl = WORKLOADS[workload]
     crop = wl['aug'] == 'random_crop'
     ohw = (76, 135) if crop else FRAME[1:]
-    torch.set_num_threads(threads)
-    rs = np.random.RandomState(1)
-    cap = 64
-    frames = rs.randint(0, 256, size=(2, cap, *FRAME), dtype=np.uint8)
-    actions = rs.uniform(-1, 1, size=(cap, 2)).astype(np.float32)
-    rewards = rs.standard_normal(size=(cap, 1)).astype(np.float32)
-    not_dones = (rs.uniform(size=(cap, 1)) > 0.01).astype(np.float32)
+
+    class _RB:
+        capacity = CAPACITY
+    rb = _RB()
+    rb.obses = np.empty((CAPACITY, *FRAME), dtype=np.uint8)
+    rb.next_obses = np.empty((CAPACITY, *FRAME), dtype=np.uint8)
+    rb.actions = np.empty((CAPACITY, 2), dtype=np.float32)
+    rb.rewards = np.empty((CAPACITY, 1), dtype=np.float32)
+    rb.not_dones = np.empty((CAPACITY, 1), dtype=np.float32)
+    fill_host_replay(rb)
     agent = O.OracleAgent((9, *ohw), 2, hidden_dim=HP['hidden_dim'], pixel_sac=wl['pixel_sac'])
     agent.init_random(0)
     np.random.seed(0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        d = O.draw_sample_indices(cap, 0, True, batch, wl['aug'], FRAME[1:], ohw)
+        d = O.draw_sample_indices(CAPACITY, 0, True, batch, wl['aug'], FRAME[1:], ohw)
         f = lambda a: torch.from_numpy(a).float()
         if crop:
-            obs = f(O.gather_crop(frames[0], d['idxs'], d['h1_obs'], d['w1_obs'], ohw))
-            nxt = f(O.gather_crop(frames[1], d['idxs'], d['h1_next'], d['w1_next'], ohw))
-            pos = f(O.gather_crop(frames[0], d['idxs'], d['h1_pos'], d['w1_pos'], ohw))
+            obs = f(O.gather_crop(rb.obses, d['idxs'], d['h1_obs'], d['w1_obs'], ohw))
+            nxt = f(O.gather_crop(rb.next_obses, d['idxs'], d['h1_next'], d['w1_next'], ohw))
+            pos = f(O.gather_crop(rb.obses, d['idxs'], d['h1_pos'], d['w1_pos'], ohw))
         else:
-            obs, nxt = f(O.gather(frames[0], d['idxs'])), f(O.gather(frames[1], d['idxs']))
+            obs, nxt = f(O.gather(rb.obses, d['idxs'])), f(O.gather(rb.next_obses, d['idxs']))
             pos = obs.clone()
         noise = torch.randn(2, batch, 2)
-        agent.update(obs, torch.from_numpy(actions[d['idxs']]), torch.from_numpy(rewards[d['idxs']]), nxt,
-                     torch.from_numpy(not_dones[d['idxs']]), pos, i, noise[0], noise[1])
+        agent.update(obs, torch.from_numpy(rb.actions[d['idxs']]), torch.from_numpy(rb.rewards[d['idxs']]), nxt,
+                     torch.from_numpy(rb.not_dones[d['idxs']]), pos, 2 + i, noise[0], noise[1])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return float(np.mean(times))
@@ -350,7 +419,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=4)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference_cuda'])
+    ap.add_argument('--tf32', type=int, default=0, help='--impl reference_cuda: allow TF32 in cuDNN/cuBLAS (informational baseline)')
     ap.add_argument('--batch', type=int, default=BATCH, help='per-GPU batch (default: train.py default 512)')
     ap.add_argument('--prof-steps', type=int, default=4)
     ap.add_argument('--cpu-baseline-steps', type=int, default=4)
@@ -375,21 +445,28 @@ def main():
               'l2': 'inputs larger than L2 (random replay rows from 4.25 GB; ~1.4 GB of activations per update)',
               'precision': 'bf16 operands, fp32 accumulate, fp32 master weights/Adam/EMA/LN/losses'}
 
-    if args.impl == 'reference':
+    if args.impl in ('reference', 'reference_cuda'):
         if rank != 0:
             return
-        # bounded sample: a smaller batch of the same update, throughput in obs/s
-        sample_b = 128
-        sec = cpu_reference_updates(sample_b, args.steps if args.steps <= 8 else 8, 1, cores, args.workload)
-        val = sample_b / sec
-        line = {'impl': 'reference', 'metric': 'sac_curl_update_obs_per_sec', 'value': val, 'unit': 'obs/s',
-                'updates_per_s': val / args.batch, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': sec * 1e3 * args.batch / sample_b, 'higher_is_better': True, 'scaling': 'weak',
+        # the reference's own update at the SAME configuration (batch, capacity, hyper-parameters) for the
+        # REAL step count: K full updates after W warm-ups (about 1.4 s each on 16 host cores)
+        cuda = args.impl == 'reference_cuda'
+        if cuda and not torch.cuda.is_available():
+            raise SystemExit('--impl reference_cuda needs a CUDA device')
+        sec, kind = reference_updates(args.batch, args.steps, args.warmup, cores, args.workload,
+                                      device='cuda' if cuda else 'cpu', tf32=bool(args.tf32))
+        val = args.batch / sec
+        what = ('unmodified reference CurlSacAgent.update + ReplayBuffer.sample_cpc (baseline/_ref via oracle/shims)'
+                if kind == 'reference' else 'oracle port of the reference update (reference modules absent)')
+        where = ('PyTorch %s eager on cuda:0 (cuDNN/cuBLAS), allow_tf32=%s, host replay + H2D per update as the reference does'
+                 % (torch.__version__, bool(args.tf32))) if cuda else 'torch fp32 CPU, %d threads' % cores
+        line = {'impl': args.impl, 'metric': 'sac_curl_update_obs_per_sec', 'value': val, 'unit': 'obs/s',
+                'updates_per_s': 1.0 / sec, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': val, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
-                                 'sample': 'oracle port of the reference update (torch fp32 CPU, %d threads), batch %d '
-                                           'x %d updates of the same config; ms_per_step scaled to batch %d'
-                                           % (cores, sample_b, min(args.steps, 8), args.batch)},
+                'cpu_baseline': {'value': val, 'unit': 'obs/s', 'cores': cores, 'kind': kind,
+                                 'sample': '%s; %s; batch %d, replay capacity %d, %d timed updates after %d warm-ups'
+                                           % (what, where, args.batch, CAPACITY, args.steps, args.warmup)},
                 'e2e': {'value': val, 'unit': 'obs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return
@@ -476,11 +553,14 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        sb = 128
-        sec = cpu_reference_updates(sb, args.cpu_baseline_steps, 1, cores, args.workload)
-        cpu = {'value': sb / sec, 'unit': 'obs/s', 'cores': cores, 'kind': 'port',
-               'sample': 'oracle port of the reference update (torch fp32 CPU), batch %d x %d updates after 1 warm-up'
-                         % (sb, args.cpu_baseline_steps), 'updates_per_s_at_batch_%d' % args.batch: sb / sec / args.batch}
+        # bounded sample of the SAME workload: the reference's own update at the full batch and replay
+        # capacity, a few updates (about 1.4 s each on 16 cores)
+        sec, kind = reference_updates(args.batch, args.cpu_baseline_steps, 1, cores, args.workload)
+        cpu = {'value': args.batch / sec, 'unit': 'obs/s', 'cores': cores, 'kind': kind,
+               'sample': '%s, torch fp32 CPU %d threads: batch %d, replay capacity %d, %d updates after 1 warm-up'
+                         % ('unmodified reference update (baseline/_ref)' if kind == 'reference' else 'oracle port of the reference update',
+                            cores, args.batch, CAPACITY, args.cpu_baseline_steps),
+               'updates_per_s': 1.0 / sec}
     line = {'metric': 'sac_curl_update_obs_per_sec', 'value': value, 'unit': 'obs/s', 'updates_per_s': ups,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',

@@ -102,6 +102,22 @@ class _InitCritic(nn.Module):
         self.apply(weight_init)
 
 
+def initial_state(obs_shape, action_shape, hidden_dim, feature_dim, num_layers=4, num_filters=32):
+    """(actor_sd, critic_sd, W) drawn from the torch global RNG in the reference constructor's
+    order (curl_sac.py:275-317): Actor, Critic, Critic (target: its draws are discarded by the
+    copy at :287 but advance the stream), then CURL.W = torch.rand (:192).  The actor's conv
+    entries are the critic's (tie at :290).  CPU only; tests/test_capi_cpu.py pins it against
+    fingerprints of the reference's own freshly constructed agent (tests/golden/init_seed0.npz)."""
+    actor0 = _InitActor(obs_shape, action_shape, hidden_dim, feature_dim, num_layers, num_filters)
+    critic0 = _InitCritic(obs_shape, action_shape, hidden_dim, feature_dim, num_layers, num_filters)
+    _InitCritic(obs_shape, action_shape, hidden_dim, feature_dim, num_layers, num_filters)
+    W = torch.rand(feature_dim, feature_dim)
+    critic_sd = {k: v.detach().clone() for k, v in critic0.state_dict().items()}
+    actor_sd = {k: v.detach().clone() for k, v in actor0.state_dict().items()}
+    actor_sd.update({k: v.clone() for k, v in critic_sd.items() if k.startswith('encoder.convs.')})
+    return actor_sd, critic_sd, W
+
+
 # ---------------------------------------------------------------------------------
 # module-like views on the engine's tensors
 # ---------------------------------------------------------------------------------
@@ -594,9 +610,8 @@ class CurlSacAgent(_Host):
         encoder.out_dim_for(obs_shape, num_layers)     # raises NotImplementedError like the reference
 
         # initial weights: same constructors / RNG order as the reference (CPU, one-off)
-        actor0 = _InitActor(obs_shape, action_shape, hidden_dim, encoder_feature_dim, num_layers, num_filters)
-        critic0 = _InitCritic(obs_shape, action_shape, hidden_dim, encoder_feature_dim, num_layers, num_filters)
-        _InitCritic(obs_shape, action_shape, hidden_dim, encoder_feature_dim, num_layers, num_filters)  # target: RNG parity
+        actor_sd0, critic_sd0, W0 = initial_state(obs_shape, action_shape, hidden_dim, encoder_feature_dim,
+                                                  num_layers, num_filters)
         self.engine = None
         self._act_graphs = {}
         self._make_engine(batch=1, frame_hw=self.image_shape)
@@ -607,21 +622,21 @@ class CurlSacAgent(_Host):
                              num_layers, num_filters)
         self.critic_target = Critic(self, 'target', 2, obs_shape, action_shape, hidden_dim,
                                     encoder_feature_dim, num_layers, num_filters)
-        self.critic.load_state_dict(critic0.state_dict())
-        asd = actor0.state_dict()
-        asd.update({k: v for k, v in self.critic.state_dict().items() if k.startswith('encoder.convs.')})
-        self.actor.load_state_dict(asd)                                   # tied convs: curl_sac.py:290
+        self.critic.load_state_dict(critic_sd0)
+        self.actor.load_state_dict(actor_sd0)                             # tied convs: curl_sac.py:290
         self.critic_target.load_state_dict(self.critic.state_dict())     # curl_sac.py:287
         self.engine.t['log_alpha'].fill_(float(np.log(init_temperature)))  # curl_sac.py:292
         self.CURL = CURL(self, obs_shape, encoder_feature_dim, self.critic, self.critic_target,
                          output_type='continuous')
-        self.engine.t['CURL.W'].copy_(torch.rand(encoder_feature_dim, encoder_feature_dim))   # curl_sac.py:192
+        self.engine.t['CURL.W'].copy_(W0)                                 # curl_sac.py:192
         self.engine.refresh_shadows()
 
         self._update_count = 0
         self._ptr_cache = {}
         self._metrics_host = None
-        self._noise_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        # Philox key of the policy noise: derived from the torch seed WITHOUT drawing from the global
+        # stream, so the stream stands where the reference's does after construction
+        self._noise_seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x5EED) & ((1 << 63) - 1)
         self._noise_override = None      # tests inject (noise_next, noise_cur)
         self._arange = None
         self.train()

@@ -474,6 +474,7 @@ class OracleAgent:
         self.actor_opt.step()
         self.alpha_opt.zero_grad()
         alpha_loss = (self.alpha * (-log_pi - self.target_entropy).detach()).mean()
+        self.metrics['alpha'] = float(self.alpha.detach())            # logged before the step: curl_sac.py:400-402
         alpha_loss.backward()
         self.alpha_opt.step()
         self.metrics.update(actor_loss=float(actor_loss.detach()),

@@ -22,14 +22,43 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get('CURLA_REFERENCE', '/root/reference')
 
 
-def import_reference():
+REF_FILES = ('curl_sac.py', 'encoder.py', 'utils.py', 'augmentations.py')     # the hot path's four modules
+REF_SHIP = os.path.join(os.path.dirname(HERE), 'baseline', '_ref')            # git-ignored; travels to the GPU box
+
+
+def reference_dir():
+    """Where the UNMODIFIED reference modules can be imported from: /root/reference in the build
+    container, else the verbatim copies `ship_reference()` left under baseline/_ref/ (the GPU box
+    has no /root/reference).  None when neither exists."""
+    for d in (REF, REF_SHIP):
+        if all(os.path.isfile(os.path.join(d, f)) for f in REF_FILES):
+            return d
+    return None
+
+
+def ship_reference():
+    """Build-container step (called by __graft_entry__.build): copy the four reference modules,
+    byte for byte, to baseline/_ref/ so that `bench.py --impl reference` can time the reference's
+    OWN update on the GPU box's host cores.  The directory is git-ignored: reference sources never
+    enter the repository history."""
+    import shutil
+    if not all(os.path.isfile(os.path.join(REF, f)) for f in REF_FILES):
+        return None
+    os.makedirs(REF_SHIP, exist_ok=True)
+    for f in REF_FILES:
+        shutil.copyfile(os.path.join(REF, f), os.path.join(REF_SHIP, f))
+    return REF_SHIP
+
+
+def import_reference(ref_dir=None):
+    ref_dir = ref_dir or REF
     sys.path.insert(0, os.path.join(HERE, 'shims'))
-    sys.path.insert(0, REF)
+    sys.path.insert(0, ref_dir)
     import utils as ref_utils            # noqa: E402
     import augmentations as ref_aug      # noqa: E402
     import curl_sac as ref_sac           # noqa: E402
     import encoder as ref_enc            # noqa: E402
-    assert ref_sac.__file__.startswith(REF), ref_sac.__file__
+    assert os.path.realpath(ref_sac.__file__).startswith(os.path.realpath(ref_dir)), ref_sac.__file__
     return ref_utils, ref_aug, ref_sac, ref_enc
 
 
@@ -157,14 +186,41 @@ def run_scenario(name, cfg, ref_utils, ref_aug, ref_sac):
     return out
 
 
+INIT_CASES = {
+    # name -> (seed, obs_shape, hidden): fingerprints of a FRESHLY CONSTRUCTED reference agent
+    # (curl_sac.py:271-317) -- pins the product's init-RNG order (curla_b200.curl_sac.initial_state)
+    'init_seed0': (0, (9, 76, 135), 64),
+    'init_seed3_identity': (3, (9, 90, 160), 32),
+}
+
+
+def run_init(seed, obs_shape, hidden, ref_utils, ref_aug, ref_sac):
+    from . import scenario as S
+    ref_utils.set_seed_everywhere(seed)
+    augmentor = ref_aug.make_augmentor('identity', obs_shape[1:])
+    agent = ref_sac.CurlSacAgent(obs_shape, (S.ACTION_DIM,), torch.device('cpu'), augmentor,
+                                 hidden_dim=hidden, **S.HP)
+    out = {}
+    for net, mod in (('actor', agent.actor), ('critic', agent.critic), ('target', agent.critic_target)):
+        for k, v in mod.state_dict().items():
+            out['param/' + net + '.' + k] = S.summarize(v)
+    out['param/W'] = S.summarize(agent.CURL.W)
+    out['param/log_alpha'] = np.array([float(agent.log_alpha)])
+    out['next_rand'] = torch.rand(4).numpy()        # where the torch stream stands afterwards
+    return out
+
+
 def main():
     ref_utils, ref_aug, ref_sac, _ = import_reference()
     from . import scenario as S
     gold_dir = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
     os.makedirs(gold_dir, exist_ok=True)
-    names = sys.argv[1:] or list(S.SCENARIOS)
+    names = sys.argv[1:] or list(S.SCENARIOS) + list(INIT_CASES)
     for name in names:
-        out = run_scenario(name, S.SCENARIOS[name], ref_utils, ref_aug, ref_sac)
+        if name in INIT_CASES:
+            out = run_init(*INIT_CASES[name], ref_utils, ref_aug, ref_sac)
+        else:
+            out = run_scenario(name, S.SCENARIOS[name], ref_utils, ref_aug, ref_sac)
         path = os.path.join(gold_dir, name + '.npz')
         np.savez_compressed(path, **out)
         print('wrote', path, '%d arrays' % len(out), '%.1f KB' % (os.path.getsize(path) / 1024))

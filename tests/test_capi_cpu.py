@@ -122,3 +122,32 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.CurlaError):
         utils.ReplayBuffer((9, 90, 160), (2,), 8, 4, torch.device('cpu'),
                            augmentations.IdentityAugmentation((90, 160)))
+
+
+@pytest.mark.parametrize('case', ['init_seed0', 'init_seed3_identity'])
+def test_init_rng_matches_reference(case):
+    """The product draws its initial weights from the torch global RNG in the reference
+    constructor's order (curl_sac.py:271-317: Actor, Critic, target Critic, CURL.W): for a given
+    seed every initial tensor equals the reference's freshly constructed agent
+    (tests/golden/init_*.npz, written by oracle/make_golden.py from the unmodified reference),
+    and the stream stands at the same place afterwards."""
+    import numpy as np
+    import torch
+    from curla_b200 import curl_sac, utils
+    from oracle import scenario as S
+    from oracle.make_golden import INIT_CASES
+    seed, obs_shape, hidden = INIT_CASES[case]
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', case + '.npz'))
+    utils.set_seed_everywhere(seed)
+    actor_sd, critic_sd, W = curl_sac.initial_state(obs_shape, (S.ACTION_DIM,), hidden, S.FEATURE_DIM)
+    after = torch.rand(4).numpy()
+    n = 0
+    for net, sd in (('actor', actor_sd), ('critic', critic_sd), ('target', critic_sd)):
+        for k, v in sd.items():
+            assert np.array_equal(S.summarize(v), gold['param/%s.%s' % (net, k)]), (net, k)
+            n += 1
+    assert n == 3 * 12 + 6 + 12 + 12                        # every tensor of the three state dicts
+    assert {k for k in gold.files if k.startswith('param/actor.')} == {'param/actor.' + k for k in actor_sd}
+    assert np.array_equal(S.summarize(W), gold['param/W'])
+    assert np.array_equal(after, gold['next_rand'])
+    assert float(gold['param/log_alpha'][0]) == float(np.log(S.HP['init_temperature']))

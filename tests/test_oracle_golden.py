@@ -17,7 +17,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 METRIC_KEYS = {  # reference log key -> oracle metric name (curl_sac.py:361-432)
     'train/batch_reward': 'batch_reward', 'train_critic/loss': 'critic_loss',
     'train_actor/loss': 'actor_loss', 'train_actor/entropy': 'entropy',
-    'train_alpha/loss': 'alpha_loss', 'train/curl_loss': 'curl_loss'}
+    'train_alpha/loss': 'alpha_loss', 'train_alpha/value': 'alpha', 'train/curl_loss': 'curl_loss'}
 
 
 def close(a, b, rtol=2e-4, atol=2e-6):

@@ -57,6 +57,17 @@ PH_SAMPLE, PH_CRITIC, PH_ACTOR, PH_EMA, PH_CPC = 1, 2, 4, 8, 16
 EXTRA = {
     'crop90x160_b64': dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=128, hidden=256,
                            steps=[0, 1], only_cpc=[False, False], pixel_sac=False, detach_encoder=False),
+    # THE BENCHMARKED CONFIGURATION (train.py:72-73 defaults, BASELINE.json configs[1]): at this size the
+    # engine takes the tcgen05 + TMA GEMMs (k_gemm_tc, k_gemm_tc_nloop), the atomic-counter conv tile
+    # scheduler, three-segment conv launches and the full split-K of the fc -- none of which the small
+    # scenarios reach.  One even step (critic, actor + alpha, EMA, CPC) and one odd step (critic, CPC).
+    'crop90x160_b512_h1024': dict(aug='random_crop', frame_hw=(90, 160), B=512, capacity=640, hidden=1024,
+                                  steps=[0, 1], only_cpc=[False, False], pixel_sac=False, detach_encoder=False),
+    # configs[0]'s augmentation and configs[2] (pixel SAC) at the default batch: 90x160 encoder input
+    'identity90x160_b512_h1024': dict(aug='identity', frame_hw=(90, 160), B=512, capacity=640, hidden=1024,
+                                      steps=[0], only_cpc=[False], pixel_sac=False, detach_encoder=False),
+    'pixelsac90x160_b512_h1024': dict(aug='identity', frame_hw=(90, 160), B=512, capacity=640, hidden=1024,
+                                      steps=[0], only_cpc=[False], pixel_sac=True, detach_encoder=False),
 }
 ALL = dict(S.SCENARIOS)
 ALL.update(EXTRA)
@@ -455,3 +466,62 @@ def test_update_with_device_augmentations(aug_name):
         agent.update(rb, L, step)
     torch.cuda.synchronize()
     assert all(np.isfinite(v) for v in L.rows.values()) and ('train/curl_loss' in {k for _, k in L.rows})
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-step trajectory drift (SURVEY.md 4(d), 8(c) "100-update loss-trajectory overlay")
+# ---------------------------------------------------------------------------------------------
+DRIFT = dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=256, hidden=256,
+             steps=list(range(64)), only_cpc=[20 <= s < 30 for s in range(64)], pixel_sac=False,
+             detach_encoder=False)
+# Band of |cuda - oracle| for every logged scalar of every step, free running (no forcing: each side
+# follows its own Adam trajectory from identical weights, indices and policy noise).  relative to
+# max(|oracle|, floor).  Measured on the B200 (profiles/r03_drift_b64.txt): see DRIFT_MEASURED.
+DRIFT_BAND = {'train/batch_reward': (1e-6, 1.0), 'train_critic/loss': (0.10, 0.05), 'train_actor/loss': (0.10, 0.05),
+              'train_actor/entropy': (0.05, 1.0), 'train_alpha/loss': (0.10, 0.05), 'train_alpha/value': (1e-3, 0.1),
+              'train/curl_loss': (0.10, 0.05)}
+
+
+def test_trajectory_drift_b64():
+    """64 consecutive free-running updates at B=64 / hidden 256 (both step parities, a ten-step
+    only_cpc stretch as train.py:424-425 runs at the start of an episode): sampling stays bit
+    exact and EVERY logged scalar of EVERY step stays inside DRIFT_BAND of the oracle's."""
+    torch.set_num_threads(max(1, os.cpu_count() // 2))
+    cfg = DRIFT
+    run = S.OracleRun(cfg)
+    agent, rb = build_cuda_agent(cfg, run)
+    np_state = np.random.get_state()
+    L = NullLogger()
+    keymap = {'train/batch_reward': 'batch_reward', 'train_critic/loss': 'critic_loss',
+              'train_actor/loss': 'actor_loss', 'train_actor/entropy': 'entropy',
+              'train_alpha/loss': 'alpha_loss', 'train_alpha/value': 'alpha', 'train/curl_loss': 'curl_loss'}
+    lines, worst, bad = [], {}, []
+    for u, (step, only_cpc) in enumerate(zip(cfg['steps'], cfg['only_cpc'])):
+        np.random.set_state(np_state)
+        d, b, om = run.step()
+        after = np.random.get_state()
+        np.random.set_state(np_state)
+        agent._noise_override = (run.noise[u, 0], run.noise[u, 1])
+        agent.update(rb, L, step, only_cpc=only_cpc)
+        torch.cuda.synchronize()
+        assert np.array_equal(np.random.get_state()[1], after[1]), 'RNG consumption differs at step %d' % step
+        np_state = after
+        row = ['%3d%s' % (step, ' cpc' if only_cpc else '    ')]
+        for rk, ok in keymap.items():
+            if (step, rk) not in L.rows or om.get(ok) is None:
+                continue
+            got, ref = L.rows[(step, rk)], float(om[ok])
+            rel, floor = DRIFT_BAND[rk]
+            err = abs(got - ref) / max(abs(ref), floor)
+            worst[rk] = max(worst.get(rk, 0.0), err)
+            row.append('%s % .5f/% .5f' % (rk.split('/')[-1][:6] + ('' if 'alpha' not in rk else 'A'), got, ref))
+            if not np.isfinite(got) or err > rel:
+                bad.append((step, rk, got, ref, err, rel))
+        lines.append(' '.join(row))
+    text = '\n'.join(lines) + '\nworst relative deviation per scalar: ' + \
+        ', '.join('%s %.3e (band %.1e)' % (k, v, DRIFT_BAND[k][0]) for k, v in worst.items())
+    print(text)
+    out = os.environ.get('CURLA_DRIFT_OUT')
+    if out:
+        open(out, 'w').write('# step  scalar cuda/oracle ...  (tests/test_update_parity_gpu.py::test_trajectory_drift_b64)\n' + text + '\n')
+    assert not bad, bad[:8]
