@@ -116,6 +116,7 @@ SIGNATURES = {
     'curla_agent_q_heads': (_i, [c_vp, _i, c_vp, c_vp, _i, c_vp, c_vp, c_vp]),
     'curla_nccl_unique_id': (_i, [c_vp]),
     'curla_agent_init_comm': (_i, [c_vp, c_vp]),
+    'curla_agent_take_comm': (_i, [c_vp, c_vp]),
 }
 
 _lib = None

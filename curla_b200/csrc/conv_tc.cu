@@ -35,6 +35,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace curla {
 
 struct TcGeom {
@@ -509,6 +513,25 @@ static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, in
     return g;
 }
 
+// Counter pairs are handed out per (device, stream): launches on one stream are serialised (the next
+// kernel asks for tiles only after griddepcontrol.wait, i.e. after the previous one has re-armed its
+// pair), so a stream cycles through its own group of four pairs and two engines on different streams
+// or devices of one process never share one.  g_tc_ctr itself exists once per device.
+static int next_ctr_slot(cudaStream_t stream) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, std::pair<int, unsigned>> groups;     // -> (group, sequence)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = groups.find({dev, stream});
+    if (it == groups.end()) {
+        int used = 0;
+        for (auto& kv : groups) if (kv.first.first == dev) ++used;
+        it = groups.emplace(std::make_pair(dev, stream), std::make_pair(used % (kCtrSlots / 4), 0u)).first;
+    }
+    return it->second.first * 4 + (int)(it->second.second++ & 3u);
+}
+
 template <typename K>
 static int tc_set_smem(K kern, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -543,10 +566,9 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     const int cap = sm_count();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
     {   // dynamic tile hand-out once every CTA has more than its two round-robin tiles
-        static unsigned seq = 0;
         const char* e = getenv("CURLA_TC_STATIC");
         g.dynamic = (g.total_tiles > 2 * grid && !(e && e[0] == '1')) ? 1 : 0;
-        g.ctr_slot = g.dynamic ? (int)(seq++ % kCtrSlots) : 0;
+        g.ctr_slot = g.dynamic ? next_ctr_slot(stream) : 0;
     }
     launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, sg, in_sstride, scale, (const bf16*)relu_src, out_sstride, g, taps);
     return 0;

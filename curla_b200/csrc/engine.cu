@@ -64,7 +64,9 @@ struct Profiler {
         marks.push_back({what, e});
     }
 };
-static Profiler g_prof;
+// per host thread: an agent is driven by one thread (include/curla_b200.h: thread-compatible), so two
+// engines driven by two threads profile independently
+static thread_local Profiler g_prof;
 void profile_mark(const char* what) { if (g_prof.on) g_prof.mark(what); }
 
 static thread_local const char* g_tag = nullptr;
@@ -432,11 +434,14 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     return a;
 }
 
+static void destroy_comm(curla_agent* a);
 extern "C" void curla_agent_destroy(curla_agent* a) {
-    if (a && a->side_state == 1) {
+    if (!a) return;
+    if (a->side_state == 1) {
         for (auto& e : a->ev) cudaEventDestroy(e);
         cudaStreamDestroy(a->side);
     }
+    destroy_comm(a);
     delete a;
 }
 extern "C" long long curla_agent_arena_bytes(const curla_agent* a, int which) {
@@ -510,13 +515,13 @@ struct Run {
     // instead of 4 per pass, and no pipeline fill/drain between passes.  CURLA_MERGE=0 launches
     // each pass separately (same results bit for bit).
     struct Pass { const bf16* s2d; const EncP* e; const EncS* s; bf16* const* acts; };
-    void conv_stack_multi(const Pass* ps, int np) {
+    void conv_stack_multi(const Pass* ps, int np, int B = 0) {
         if (!ok() || np <= 0) return;
         if (!merge_mode() && np > 1) {
-            for (int k = 0; k < np; ++k) conv_stack_multi(ps + k, 1);
+            for (int k = 0; k < np; ++k) conv_stack_multi(ps + k, 1, B);
             return;
         }
-        const int B = a->cfg.batch;
+        if (B <= 0) B = a->cfg.batch;
         for (int i = 0; i < 4 && ok(); ++i) {
             curla_conv_seg sg[3];
             for (int k = 0; k < np; ++k) {
@@ -530,9 +535,9 @@ struct Run {
                                      a->act_sstride, a->pitch, a->S, a->Ho[i], a->Wo[i], i == 0 ? 4 * a->cfg.C : 0, st));
         }
     }
-    void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4]) {
+    void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4], int B = 0) {
         const Pass p = {s2d, &e, &s, acts};
-        conv_stack_multi(&p, 1);
+        conv_stack_multi(&p, 1, B);
     }
     // fc (split-K) + bias + LayerNorm
     void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
@@ -651,6 +656,7 @@ struct NcclApi {
     nccl_allgather_t all_gather = nullptr;
     nccl_getid_t get_id = nullptr;
     void* init_rank = nullptr;
+    int (*comm_destroy)(void*) = nullptr;
     const char* (*err_str)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -666,6 +672,7 @@ int load_nccl() {
     g_nccl.all_gather = (nccl_allgather_t)dlsym(g_nccl.lib, "ncclAllGather");
     g_nccl.get_id = (nccl_getid_t)dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.init_rank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.comm_destroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.err_str = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
     CURLA_CHECK(g_nccl.all_reduce && g_nccl.all_gather && g_nccl.get_id && g_nccl.init_rank, "nccl: missing symbols");
     return 0;
@@ -682,6 +689,23 @@ int all_reduce(curla_agent* a, void* buf, size_t n, int dt, cudaStream_t st) {
 
 }  // namespace
 
+static void destroy_comm(curla_agent* a) {
+    if (a->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(a->comm);
+    a->comm = nullptr;
+}
+
+// Hands the NCCL communicator of `from` (an engine being replaced: same rank / world, another batch
+// size) to `to`.  Not a collective: a rank may re-create its engine on its own (curl_sac.py
+// _grow_for_inference) without the other ranks taking part.
+extern "C" int curla_agent_take_comm(curla_agent* to, curla_agent* from) {
+    CURLA_CHECK(to && from && to != from, "take_comm: bad handles");
+    CURLA_CHECK(to->cfg.world == from->cfg.world && to->cfg.rank == from->cfg.rank, "take_comm: rank/world differ");
+    destroy_comm(to);
+    to->comm = from->comm;
+    from->comm = nullptr;
+    return 0;
+}
+
 extern "C" int curla_nccl_unique_id(void* out128) {
     if (load_nccl()) return -1;
     const int r = g_nccl.get_id(out128);
@@ -691,6 +715,7 @@ extern "C" int curla_nccl_unique_id(void* out128) {
 extern "C" int curla_agent_init_comm(curla_agent* a, const void* id128) {
     if (a->cfg.world == 1) return 0;
     if (load_nccl()) return -1;
+    destroy_comm(a);
     struct Id { char b[128]; } id;
     memcpy(&id, id128, 128);
     typedef int (*init_t)(void**, int, Id, int);
@@ -979,11 +1004,7 @@ extern "C" int curla_agent_encode(curla_agent* a, int net, const void* obs_s2d, 
     const EncP& e = net == 0 ? a->enc_actor : (net == 1 ? a->enc_critic : a->enc_target);
     const EncS& s = net == 2 ? a->s_target : a->s_critic;
     const long long fc = net == 0 ? a->s_actor_fc : (net == 1 ? a->s_critic.fc : a->s_target.fc);
-    // conv_stack uses cfg.batch tiles; run it on the first B samples only
-    const int saveB = a->cfg.batch;
-    a->cfg.batch = B;
-    r.conv_stack((const bf16*)obs_s2d, e, s, a->actB);
-    a->cfg.batch = saveB;
+    r.conv_stack((const bf16*)obs_s2d, e, s, a->actB, B);      // the first B samples only
     TailBuf t{a->t_p1.fc_out, z_out};
     r.tail(a->actB[3], fc, e, t, B, apply_tanh);
     return r.rc;

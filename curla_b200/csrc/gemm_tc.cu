@@ -542,7 +542,6 @@ const CUtensorMap* get_map(const void* ptr, unsigned long long d0, unsigned long
     k.ptr = ptr; k.d[0] = d0; k.d[1] = d1; k.d[2] = d2; k.s[0] = s1_bytes; k.s[1] = s2_bytes; k.b[0] = b0; k.b[1] = b1; k.b[2] = b2;
     auto it = cache.find(k);
     if (it != cache.end()) return &it->second;
-    if (cache.size() > 4096) cache.clear();
     CUtensorMap tm;
     const cuuint64_t gd[3] = {d0, d1, d2};
     const cuuint64_t gs[2] = {s1_bytes, s2_bytes};
@@ -556,18 +555,37 @@ const CUtensorMap* get_map(const void* ptr, unsigned long long d0, unsigned long
                        (int)r, d0, d1, d2, s1_bytes, s2_bytes, b0, b1, b2);
         return nullptr;
     }
+    // A launch looks up two maps and keeps both pointers: nothing cached is ever freed (unordered_map
+    // nodes do not move on rehash).  Once the cache is full -- a process walking over thousands of
+    // distinct operand addresses -- further maps are built uncached in a small ring of slots, more than
+    // one launch uses.
+    if (cache.size() >= 4096) {
+        static thread_local CUtensorMap overflow[8];
+        static thread_local unsigned next = 0;
+        CUtensorMap* slot = &overflow[next++ % 8];
+        *slot = tm;
+        return slot;
+    }
     return &cache.emplace(k, tm).first->second;
+}
+
+// cudaFuncSetAttribute is per device: one flag per (kernel instantiation, device)
+bool attr_needed(bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
 }
 
 template <bool AK, bool BK_, bool SG>
 int launch_one(const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& p, const TmaPlan& pl, dim3 grid, cudaStream_t stream) {
     auto kern = k_gemm_tc<AK, BK_, SG>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (attr_needed(attr)) {
         const int mx = (int)(kHdrTc + kMaxSt * kStageBytesTc);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%d): %s", mx, cudaGetErrorString(e)); return -1; }
-        attr = true;
     }
     uint32_t smem = kHdrTc + (uint32_t)pl.nst * kStageBytesTc;
     if (smem < kHdrTc + 4 * 32 * 272) smem = kHdrTc + 4 * 32 * 272;        // the epilogue's four 32-row fp32 patches reuse the stages
@@ -686,13 +704,12 @@ static int tc_nloop(const GemmArgs& p, cudaStream_t stream) {
     int strips = cdiv(sm_count(), mt);                     // one CTA per SM
     if (strips > tiles_n) strips = tiles_n;
     if (mt > 65535) return 0;
-    static bool attr[2] = {false, false};
+    static bool attr2[2][64] = {};
     const int sg = p.seg_mask ? 1 : 0;
-    if (!attr[sg]) {
+    if (attr_needed(attr2[sg])) {
         cudaError_t e = sg ? cudaFuncSetAttribute(k_gemm_tc_nloop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNlSmem)
                            : cudaFuncSetAttribute(k_gemm_tc_nloop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNlSmem);
         if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%u): %s", kNlSmem, cudaGetErrorString(e)); return -1; }
-        attr[sg] = true;
     }
     if (sg) launch_k(k_gemm_tc_nloop<true>, dim3(strips, mt), dim3(kNlThreads), kNlSmem, stream, *ta, *tb, p, tiles_n);
     else launch_k(k_gemm_tc_nloop<false>, dim3(strips, mt), dim3(kNlThreads), kNlSmem, stream, *ta, *tb, p, tiles_n);

@@ -122,16 +122,27 @@ def initial_state(obs_shape, action_shape, hidden_dim, feature_dim, num_layers=4
 # module-like views on the engine's tensors
 # ---------------------------------------------------------------------------------
 class _Linear(object):
+    """nn.Linear look-alike on engine tensors.  `.weight.grad` / `.bias.grad` (what
+    Logger.log_param reads, logger.py:155-162) are views of the gradient bucket of the last update."""
+
     def __init__(self, host, prefix):
         self._host, self._prefix = host, prefix
 
+    def _param(self, name):
+        eng = self._host.engine
+        t = eng.t[self._prefix + name]
+        g = eng.grad_view(self._prefix + name)
+        if g is not None:
+            t.grad = g
+        return t
+
     @property
     def weight(self):
-        return self._host.engine.t[self._prefix + 'weight']
+        return self._param('weight')
 
     @property
     def bias(self):
-        return self._host.engine.t[self._prefix + 'bias']
+        return self._param('bias')
 
 
 class _Trunk(object):
@@ -653,13 +664,21 @@ class CurlSacAgent(_Host):
                 eng.arenas[i].copy_(old.arenas[i])
             for k in ('log_alpha', 'adam.log_alpha'):
                 eng.t[k].copy_(old.t[k])
-            for k in ('t_critic', 't_actor', 't_alpha', 't_cpc'):
-                pass
-            eng._steps = getattr(old, '_steps', None)
+            # the Adam step counters live on the host side of the engine: without them the new engine
+            # would restart bias correction at t = 1 on warm moments
+            steps = (C.c_int * 4)()
+            _lib.check(eng.lib.curla_agent_get_opt_steps(old.h, steps), 'get_opt_steps')
+            _lib.check(eng.lib.curla_agent_set_opt_steps(eng.h, steps[0], steps[1], steps[2], steps[3]), 'set_opt_steps')
         self.engine = eng
         self._engine_gen = getattr(self, '_engine_gen', 0) + 1      # invalidates captured action graphs
         if self.world > 1:
-            self._init_comm()
+            if old is not None and getattr(self, '_comm_ready', False):
+                # same rank, same world: the communicator moves to the new engine (no collective, so a
+                # single rank may grow its engine for inference on its own)
+                _lib.check(eng.lib.curla_agent_take_comm(eng.h, old.h), 'take_comm')
+            else:
+                self._init_comm()
+                self._comm_ready = True
 
     def _init_comm(self):
         uid = dp.nccl_unique_id(self.engine.lib) if self.rank == 0 else b''
@@ -705,6 +724,11 @@ class CurlSacAgent(_Host):
         assert obs.shape[0] == self.obs_shape[0] and obs.shape[-2] - top >= self.image_shape[0] and \
             obs.shape[-1] - left >= self.image_shape[1], 'observation %s does not fit the encoder input %s' % (
                 obs.shape, self.obs_shape)
+        if not crop and tuple(obs.shape) != self.obs_shape:
+            # select_action does not crop (curl_sac.py:330-336): the reference fails at the fc layer on
+            # any other shape; never encode a silent top-left window
+            raise ValueError('select_action: observation %s is not the encoder input %s (center-crop it with '
+                             'augmentor.evaluation_augmentation first)' % (tuple(obs.shape), self.obs_shape))
         key = (self._engine_gen, obs.shape, obs.dtype.str, top, left, bool(sample))
         g = self._act_graphs.get(key)
         if g is None:
@@ -828,8 +852,60 @@ class CurlSacAgent(_Host):
             if not self.pixel_sac and step % self.cpc_update_freq == 0:
                 L.log('train/curl_loss', float(m[6]), step)
         if self.log_param_hist_imgs:
+            self._log_taps(L, step, only_cpc)
+
+    def _log_taps(self, L, step, only_cpc):
+        """--log_param_hist_imgs (curl_sac.py:370-371, 394-395): critic.log right after the critic step,
+        actor.log right after the actor step.  The whole update is ONE engine call here, so both run at
+        its end -- with the same content: the Q trunks and their gradients are not touched by the actor
+        / CURL phases, nor the actor trunk by the CURL phase; `outputs` holds what the reference's
+        modules hold at their log call (Q(obs, action) of update_critic, pre-tanh mu and std of
+        actor(obs)).  Afterwards the dicts are left as the reference leaves them at the end of update()."""
+        if only_cpc and not (not self.pixel_sac and step % self.cpc_update_freq == 0):
+            return
+        t = self.engine.t
+        A = self.action_shape[0]
+        did_actor = (not only_cpc) and step % self.actor_update_freq == 0
+        if not only_cpc:
+            self.critic.outputs['q1'] = t['p3.q1.out'].clone()
+            self.critic.outputs['q2'] = t['p3.q2.out'].clone()
             self.critic.log(L, step)
-            self.actor.log(L, step)
+            if did_actor:
+                self.actor.outputs['mu'] = t['p4.trunk.out'][:, :A].clone()
+                self.actor.outputs['std'] = t['log_std'].exp()
+                self.actor.log(L, step)
+                self.critic.outputs['q1'] = t['p5.q1.out'].clone()      # critic(obs, pi): the last critic forward
+                self.critic.outputs['q2'] = t['p5.q2.out'].clone()
+        self._fill_encoder_outputs(only_cpc, did_actor)
+
+    def _fill_encoder_outputs(self, only_cpc, did_actor):
+        """encoder.outputs as the reference's modules hold them after update() (encoder.py:79-108):
+        obs / conv1..4 / fc / ln of each encoder's LAST forward.  Decoded lazily from the engine's
+        activation buffers; only under --log_param_hist_imgs."""
+        eng = self.engine
+        t = eng.t
+        fd = eng.cfg.feature_dim
+        do_cpc = not self.pixel_sac
+        enc = self.critic.encoder
+        if do_cpc or did_actor or not only_cpc:
+            # the critic encoder's last pass ran on obs (F3, or F4 = F5 = F6) into actA
+            for l in range(4):
+                enc.outputs['conv%d' % (l + 1)] = eng.act_nchw('actA', l)
+            tail = 'p5' if (do_cpc or did_actor) else 'p3'
+            enc.outputs['fc'] = t[tail + '.fc_out'][:, :fd].clone()
+            enc.outputs['ln'] = t[tail + '.z'][:, :fd].clone()
+        if do_cpc:
+            tgt = self.critic_target.encoder
+            for l in range(4):
+                tgt.outputs['conv%d' % (l + 1)] = eng.act_nchw('actB', l)
+            tgt.outputs['fc'] = t['p7.fc_out'][:, :fd].clone()
+            tgt.outputs['ln'] = t['p7.z'][:, :fd].clone()
+        if did_actor:
+            aenc = self.actor.encoder
+            for l in range(4):
+                aenc.outputs['conv%d' % (l + 1)] = enc.outputs['conv%d' % (l + 1)]      # tied convs, same obs
+            aenc.outputs['fc'] = t['p4.fc_out'][:, :fd].clone()
+            aenc.outputs['ln'] = t['p4.z'][:, :fd].clone()
 
     def save(self, model_dir, augmentation, step):
         cpu = lambda sd: {k: v.detach().cpu() for k, v in sd.items()}

@@ -49,16 +49,29 @@ class _ParamView(object):
     def __init__(self, owner, prefix, is_fc=False):
         self._owner, self._prefix, self._is_fc = owner, prefix, is_fc
 
+    def _key(self, name):
+        k = self._prefix + name
+        if k.startswith('actor.encoder.convs.'):           # tied to the critic's (curl_sac.py:290)
+            k = 'critic' + k[len('actor'):]
+        return k
+
+    def _with_grad(self, t, key, conv=lambda x: x):
+        g = self._owner._engine().grad_view(key)           # what Logger.log_param reads (logger.py:155-162)
+        if g is not None:
+            t.grad = conv(g)
+        return t
+
     @property
     def weight(self):
         eng = self._owner._engine()
         if self._is_fc:
-            return eng.fc_to_torch(eng.t[self._prefix + 'weight_canon'])
-        return eng.t[self._prefix + 'weight']
+            k = self._key('weight_canon')
+            return self._with_grad(eng.fc_to_torch(eng.t[k]), k, eng.fc_to_torch)
+        return self._with_grad(eng.t[self._key('weight')], self._key('weight'))
 
     @property
     def bias(self):
-        return self._owner._engine().t[self._prefix + 'bias']
+        return self._with_grad(self._owner._engine().t[self._key('bias')], self._key('bias'))
 
 
 class CNNEncoder(object):
@@ -105,6 +118,11 @@ class CNNEncoder(object):
         keys = ['convs.%d.%s' % (i, k) for i in range(self.num_layers) for k in ('weight', 'bias')]
         keys += ['fc.weight_canon', 'fc.bias', 'ln.weight', 'ln.bias']
         return [eng.t[self._param_key(k)] for k in keys]
+
+    def _after_param_write(self):
+        """fp32 masters were written from outside the engine (utils.soft_update_params on two
+        encoders, utils.py:37-41): rebuild the bf16 kernel-layout shadows."""
+        self._engine().refresh_shadows()
 
     def _param_key(self, k):
         # the actor's conv layers ARE the critic's (tied, curl_sac.py:290)

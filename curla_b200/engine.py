@@ -77,6 +77,42 @@ class Engine:
     def last_launches(self):
         return self.lib.curla_agent_last_launches(self.h)
 
+    # -- gradients of the last update, as views of the flat gradient buckets -------------
+    def grad_view(self, key, bucket=None):
+        """View of the gradient bucket that mirrors parameter `key` (same shape as the parameter):
+        critic.* -> grad.critic (or grad.cpc with bucket='cpc': the CURL step's encoder gradient),
+        actor.* -> grad.actor, CURL.W -> grad.cpc.  None for parameters that never receive one
+        (target.*).  Valid until the next update overwrites the bucket."""
+        arena, off, shape, _ = self.info[key]
+        if arena != 0:
+            return None
+        n, o = int(np.prod(shape)), off // 4
+        base = lambda k: self.info[k][1] // 4
+        if key == 'CURL.W':
+            return self.t['grad.cpc'][0:n].view(shape)
+        if key.startswith('critic.'):
+            if bucket == 'cpc':
+                if not key.startswith('critic.encoder.'):
+                    return None
+                b0 = base('CURL.W')
+                return self.t['grad.cpc'][o - b0:o - b0 + n].view(shape)
+            b0 = base('critic.encoder.convs.0.weight')
+            return self.t['grad.critic'][o - b0:o - b0 + n].view(shape)
+        if key.startswith('actor.'):
+            b0 = base('actor.encoder.fc.weight_canon')
+            return self.t['grad.actor'][o - b0:o - b0 + n].view(shape)
+        return None
+
+    def act_nchw(self, buf, layer, n=None):
+        """Decode a conv-stack activation buffer ('actA.<l>' ...: channel planes [B][4][S][8] bf16) into
+        the reference's NCHW float tensor of layer `layer`'s valid output (encoder.py:81-87)."""
+        c = self.cfg
+        Hs, pitch = (c.H + 1) // 2, (c.W + 1) // 2
+        ho, wo = (c.H - 3) // 2 + 1 - 2 * layer, (c.W - 3) // 2 + 1 - 2 * layer
+        B = c.batch if n is None else n
+        v = self.t['%s.%d' % (buf, layer)][:B * Hs * pitch].view(B, 4, Hs, pitch, 8)[:, :, :ho, :wo, :]
+        return v.permute(0, 1, 4, 2, 3).reshape(B, 32, ho, wo).float()
+
     # -- canonical <-> PyTorch layout of the encoder fc weight ---------------------
     def fc_geometry(self):
         """(feat, Ho, Wo, pitch, planes): canon is [feat][planes][Ho*pitch][8] -- the K order in

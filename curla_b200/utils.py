@@ -252,6 +252,27 @@ class ReplayBuffer(object):
                 dst[start:end].copy_(torch.as_tensor(src))
             self.idx = end
 
+    def sample_proprio(self):
+        """utils.py:130-142: un-augmented (obs, action, reward, next_obs, not_done); dead code in the
+        reference (no caller), kept for API completeness."""
+        B = self.batch_size
+        idxs = np.random.randint(0, self.capacity if self.full else self.idx, size=B)
+        dev = torch.from_numpy(idxs).to(self.device)
+        hw = self.obs_shape[1:]
+        obses = self._gather_f32(self.obses, dev, None, None, hw)
+        next_obses = self._gather_f32(self.next_obses, dev, None, None, hw)
+        return obses, self._gather_rows(self.actions, dev), self._gather_rows(self.rewards, dev), next_obses, \
+            self._gather_rows(self.not_dones, dev)
+
+    def __getitem__(self, idx):
+        """utils.py:218-233: ONE random transition as host numpy (the argument is ignored, as in the
+        reference); dead code there, kept for API completeness."""
+        i = int(np.random.randint(0, self.capacity if self.full else self.idx, size=1)[0])
+        obs, next_obs = self.obses[i].cpu().numpy(), self.next_obses[i].cpu().numpy()
+        if self.transform:
+            obs, next_obs = self.transform(obs), self.transform(next_obs)
+        return obs, self.actions[i].cpu().numpy(), self.rewards[i].cpu().numpy(), next_obs, self.not_dones[i].cpu().numpy()
+
     def __len__(self):
         return self.capacity
 

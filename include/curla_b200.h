@@ -311,6 +311,9 @@ int curla_agent_q_heads(curla_agent* a, int net, const float* z, const float* ac
 /* data-parallel plumbing: NCCL communicator shared by all collectives of the update */
 int curla_nccl_unique_id(void* out128);
 int curla_agent_init_comm(curla_agent* a, const void* id128);
+/* hand `from`'s communicator to `to` (an engine re-created with another batch size on the same
+ * rank); not a collective.  curla_agent_destroy destroys a communicator the agent still owns. */
+int curla_agent_take_comm(curla_agent* to, curla_agent* from);
 
 #ifdef __cplusplus
 }

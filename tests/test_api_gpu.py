@@ -302,3 +302,151 @@ def test_train_py_learner_loop_with_stub_env():
     only = [s for (s, k) in L.rows if k == 'train/curl_loss']
     crit = [s for (s, k) in L.rows if k == 'train_critic/loss']
     assert len(only) == 30 and 0 < len(crit) < 30             # CPC every update, SAC only outside the warm-up steps
+
+
+# ------------------------------------------------------------------ logging taps (--log_param_hist_imgs)
+class _RecordingLogger(T.NullLogger):
+    """The part of logger.Logger the update touches under --log_param_hist_imgs: log_histogram and
+    log_param exactly as logger.py:155-173 reads its arguments (.weight.data, .weight.grad.data, ...)."""
+
+    def __init__(self):
+        super().__init__()
+        self.hist = {}
+
+    def log_histogram(self, key, histogram, step):
+        assert key.startswith('train') or key.startswith('eval')
+        self.hist[(step, key)] = histogram.detach().float().cpu().clone()
+
+    def log_param(self, key, param, step):
+        self.log_histogram(key + '_w', param.weight.data, step)
+        if hasattr(param.weight, 'grad') and param.weight.grad is not None:
+            self.log_histogram(key + '_w_g', param.weight.grad.data, step)
+        if hasattr(param, 'bias'):
+            self.log_histogram(key + '_b', param.bias.data, step)
+            if hasattr(param.bias, 'grad') and param.bias.grad is not None:
+                self.log_histogram(key + '_b_g', param.bias.grad.data, step)
+
+
+def test_log_param_hist_imgs_taps():
+    """curl_sac.py:370-371,394-395 + curl_sac.py:112-121,171-180: with log_param_hist_imgs the update logs
+    the critic's q1/q2 outputs, the actor's mu/std and weight / bias / GRADIENT histograms of every trunk
+    layer, on steps that are multiples of LOG_FREQ.  Values are checked against the oracle's teacher-free
+    first update (identical weights before the first optimizer step)."""
+    from curla_b200 import curl_sac
+    cfg = dict(S.SCENARIOS['crop90x160'])
+    run = S.OracleRun(cfg)
+    agent, rb = T.build_cuda_agent(cfg, run)
+    agent.log_param_hist_imgs = True
+    L = _RecordingLogger()
+    st = np.random.get_state()
+    d, b, om = run.step()
+    np.random.set_state(st)
+    agent._noise_override = (run.noise[0, 0], run.noise[0, 1])
+    agent.update(rb, L, 0)
+    torch.cuda.synchronize()
+    keys = {k for (s_, k) in L.hist if s_ == 0}
+    expect = {'train_critic/q1_hist', 'train_critic/q2_hist', 'train_actor/mu_hist', 'train_actor/std_hist'}
+    for i in range(3):
+        for q in ('q1', 'q2'):
+            expect |= {'train_critic/%s_fc%d_%s' % (q, i, sfx) for sfx in ('w', 'w_g', 'b', 'b_g')}
+        expect |= {'train_actor/fc%d_%s' % (i + 1, sfx) for sfx in ('w', 'w_g', 'b', 'b_g')}
+    assert keys == expect, (sorted(keys - expect), sorted(expect - keys))
+    o = run.agent
+    h = lambda k: L.hist[(0, k)]
+    assert T.rel_l2(h('train_critic/q1_hist'), o.dbg['q1']) < 2e-2               # Q(obs, action) of update_critic
+    g_ref = o.dbg['critic_grads']
+    assert h('train_critic/q1_fc1_w_g').shape == g_ref['Q1.trunk.2.weight'].shape
+    assert T.rel_l2(h('train_critic/q1_fc1_w_g'), g_ref['Q1.trunk.2.weight']) < 4e-1     # TOL_SMALL: B=4 scenario
+    assert T.rel_l2(h('train_critic/q2_fc2_b_g'), g_ref['Q2.trunk.4.bias']) < 4e-1
+    assert torch.equal(h('train_critic/q1_fc0_w'), agent.critic.Q1.trunk[0].weight.cpu())  # weights AFTER the step
+    assert T.rel_l2(h('train_actor/fc2_w_g'), o.dbg['actor_grads']['trunk.2.weight']) < 4e-1
+    assert h('train_actor/std_hist').shape == (cfg['B'], 2) and float(h('train_actor/std_hist').min()) > 0
+    # outputs dicts as the reference's modules hold them after update(): critic(obs, pi) ran last
+    assert torch.equal(agent.critic.outputs['q1'], agent.engine.t['p5.q1.out'])
+    enc_out = agent.critic.encoder.outputs
+    assert tuple(enc_out['conv4'].shape) == (cfg['B'], 32, 31, 61) and tuple(enc_out['ln'].shape) == (cfg['B'], 50)
+    assert T.rel_l2(enc_out['ln'], o.dbg['z_a']) < 5e-2
+    # an odd step that is a multiple of nothing logs nothing; LOG_FREQ gates the histograms
+    n = len(L.hist)
+    agent.update(rb, L, 1)
+    assert len(L.hist) == n and curl_sac.LOG_FREQ == 25_000
+
+
+def test_engine_recreation_keeps_optimizer_state():
+    """Re-creating the engine mid-run (the stored frame size changes: fused ReplayBuffer path -> float
+    path) must carry the Adam step counters with the moments: the run continues bit-identically."""
+    cfg = dict(S.SCENARIOS['crop90x160'])
+    run = S.OracleRun(cfg)
+    a1, rb1 = T.build_cuda_agent(cfg, run)
+    a2, rb2 = T.build_cuda_agent(cfg, run)
+    L = T.NullLogger()
+    st = np.random.get_state()
+    for u in range(4):
+        for agent, rb in ((a1, rb1), (a2, rb2)):
+            np.random.set_state(st)
+            agent._noise_override = (run.noise[u % 2, 0], run.noise[u % 2, 1])
+            if agent is a2 and u == 2:
+                c = agent.engine.cfg
+                agent._make_engine(c.batch, (c.Hf + 2, c.Wf + 2))        # any other geometry: new engine
+                agent._make_engine(c.batch, (c.Hf - 2, c.Wf - 2))        # ... and back (2 hand-overs)
+            agent.update(rb, L, u)
+            after = np.random.get_state()
+        st = after
+    torch.cuda.synchronize()
+    steps1, steps2 = (torch.zeros(4, dtype=torch.int32).numpy() for _ in range(2))
+    import ctypes as C
+    a1.engine.lib.curla_agent_get_opt_steps(a1.engine.h, steps1.ctypes.data_as(C.POINTER(C.c_int)))
+    a2.engine.lib.curla_agent_get_opt_steps(a2.engine.h, steps2.ctypes.data_as(C.POINTER(C.c_int)))
+    assert list(steps1) == list(steps2) == [4, 2, 2, 4]
+    p1, p2 = a1.engine.arenas[0].view(torch.float32), a2.engine.arenas[0].view(torch.float32)
+    assert torch.equal(p1, p2), float((p1 - p2).abs().max())
+
+
+def test_soft_update_params_on_encoders_refreshes_kernel_weights():
+    """utils.soft_update_params(agent.critic.encoder, agent.critic_target.encoder, tau) -- the reference
+    idiom (curl_sac.py:443-445) -- must reach the bf16 kernel-layout copies the forward reads."""
+    from curla_b200 import utils
+    cfg, run, agent, rb = _agent('crop90x160')
+    sd = agent.critic.state_dict()
+    agent.critic.load_state_dict({k: (v * 1.25 if k.startswith('encoder.') else v) for k, v in sd.items()})
+    obs = torch.from_numpy(np.random.RandomState(2).randint(0, 256, size=(3, *run.obs_shape)).astype(np.float32)).to(DEV)
+    before = agent.critic_target.encoder(obs).clone()
+    utils.soft_update_params(agent.critic.encoder, agent.critic_target.encoder, 0.5)
+    after = agent.critic_target.encoder(obs)
+    assert not torch.equal(before, after)
+    tgt = {k: v.cpu() for k, v in agent.critic_target.state_dict().items()}
+    for k, v in sd.items():
+        if k.startswith('encoder.'):
+            assert torch.allclose(tgt[k], (0.5 * 1.25 + 0.5) * v.cpu(), rtol=1e-6, atol=1e-7), k
+    with torch.no_grad():
+        z_ref = O.encoder_forward(tgt, 'encoder.', obs.cpu())
+    assert T.rel_l2(after, z_ref) < 2e-2
+
+
+def test_select_action_rejects_uncropped_observation():
+    cfg, run, agent, rb = _agent('crop90x160')
+    frame = np.zeros((9, 90, 160), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        agent.select_action(frame)                       # the reference fails at the fc layer (curl_sac.py:330-336)
+    assert agent.sample_action(frame).shape == (2,)      # sample_action center-crops (curl_sac.py:340-341)
+
+
+def test_replay_sample_proprio_and_getitem():
+    from curla_b200 import augmentations, utils
+    hw, cap, B = (90, 160), 8, 3
+    aug = augmentations.make_augmentor('identity', hw)
+    rb = utils.ReplayBuffer((9, *hw), (2,), cap, B, DEV, aug)
+    arrays = S.make_replay_arrays(cap, hw)
+    for dst, src in zip((rb.obses, rb.next_obses, rb.actions, rb.rewards, rb.not_dones), arrays):
+        dst.copy_(torch.from_numpy(src))
+    rb.idx, rb.full = 0, True
+    np.random.seed(3)
+    obs, act, rew, nxt, nd = rb.sample_proprio()
+    idxs = np.random.RandomState(3).randint(0, cap, size=B)
+    assert np.array_equal(obs.cpu().numpy(), arrays[0][idxs].astype(np.float32))
+    assert np.array_equal(nxt.cpu().numpy(), arrays[1][idxs].astype(np.float32))
+    assert np.array_equal(act.cpu().numpy(), arrays[2][idxs]) and np.array_equal(nd.cpu().numpy(), arrays[4][idxs])
+    np.random.seed(4)
+    o1, a1, r1, n1, d1 = rb[123]
+    i = np.random.RandomState(4).randint(0, cap, size=1)[0]
+    assert np.array_equal(o1, arrays[0][i]) and np.array_equal(n1, arrays[1][i]) and np.array_equal(a1, arrays[2][i])

@@ -57,6 +57,11 @@ PH_SAMPLE, PH_CRITIC, PH_ACTOR, PH_EMA, PH_CPC = 1, 2, 4, 8, 16
 EXTRA = {
     'crop90x160_b64': dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=128, hidden=256,
                            steps=[0, 1], only_cpc=[False, False], pixel_sac=False, detach_encoder=False),
+    # eight consecutive teacher-forced updates (both step parities twice, an only_cpc step): the three Adam
+    # states of the critic encoder, their step counters and the EMA over >= 4 steps
+    'crop90x160_b64_8steps': dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=128, hidden=256,
+                                  steps=list(range(8)), only_cpc=[False, False, False, True, False, False, False, False],
+                                  pixel_sac=False, detach_encoder=False),
     # THE BENCHMARKED CONFIGURATION (train.py:72-73 defaults, BASELINE.json configs[1]): at this size the
     # engine takes the tcgen05 + TMA GEMMs (k_gemm_tc, k_gemm_tc_nloop), the atomic-counter conv tile
     # scheduler, three-segment conv launches and the full split-K of the fc -- none of which the small
@@ -474,12 +479,30 @@ def test_update_with_device_augmentations(aug_name):
 DRIFT = dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=256, hidden=256,
              steps=list(range(64)), only_cpc=[20 <= s < 30 for s in range(64)], pixel_sac=False,
              detach_encoder=False)
-# Band of |cuda - oracle| for every logged scalar of every step, free running (no forcing: each side
-# follows its own Adam trajectory from identical weights, indices and policy noise).  relative to
-# max(|oracle|, floor).  Measured on the B200 (profiles/r03_drift_b64.txt): see DRIFT_MEASURED.
-DRIFT_BAND = {'train/batch_reward': (1e-6, 1.0), 'train_critic/loss': (0.10, 0.05), 'train_actor/loss': (0.10, 0.05),
-              'train_actor/entropy': (0.05, 1.0), 'train_alpha/loss': (0.10, 0.05), 'train_alpha/value': (1e-3, 0.1),
+# Band of |cuda - oracle| / max(|oracle|, floor) for every logged scalar of every step, free running (no
+# forcing: each side follows its own Adam trajectory from identical weights, indices and policy
+# noise).  name -> (relative band, floor).  The scenario starts from the REFERENCE'S OWN INITIALISATION
+# (curl_sac.py:38-54 through curla_b200.curl_sac.initial_state, pinned by tests/golden/init_*.npz) on
+# the SURVEY 8(d) synthetic replay: from dense He-random weights the same 64 steps are chaotic -- the
+# fp32 oracle started from weights perturbed by 2e-3 relative (the size of one bf16 operand rounding)
+# is 40 % off in critic loss by step 5 -- whereas from the reference init that perturbed oracle stays
+# within 4 % (critic), 0.15 (actor loss), 0.2 (entropy), 0.01 (alpha loss), 5 % (CURL loss).  The bands
+# are about three times that natural divergence.
+DRIFT_BAND = {'train/batch_reward': (1e-6, 1.0), 'train_critic/loss': (0.15, 0.05), 'train_actor/loss': (0.30, 1.0),
+              'train_actor/entropy': (0.20, 3.0), 'train_alpha/loss': (0.10, 0.3), 'train_alpha/value': (1e-3, 0.1),
               'train/curl_loss': (0.10, 0.05)}
+
+
+def reference_init_run(cfg, seed=0):
+    """OracleRun whose weights are the reference's own initialisation for `seed` (both sides load the
+    same state dicts; the sampling stream is re-seeded afterwards)."""
+    from curla_b200 import curl_sac, utils
+    run = S.OracleRun(cfg)
+    utils.set_seed_everywhere(seed)
+    run.state_dicts = curl_sac.initial_state(run.obs_shape, (S.ACTION_DIM,), cfg['hidden'], S.FEATURE_DIM)
+    run.agent.load_state(*run.state_dicts)
+    np.random.seed(S.SAMPLING_SEED)
+    return run
 
 
 def test_trajectory_drift_b64():
@@ -488,7 +511,7 @@ def test_trajectory_drift_b64():
     exact and EVERY logged scalar of EVERY step stays inside DRIFT_BAND of the oracle's."""
     torch.set_num_threads(max(1, os.cpu_count() // 2))
     cfg = DRIFT
-    run = S.OracleRun(cfg)
+    run = reference_init_run(cfg)
     agent, rb = build_cuda_agent(cfg, run)
     np_state = np.random.get_state()
     L = NullLogger()
