@@ -18,6 +18,17 @@ class ConvSeg(C.Structure):
     _fields_ = [('inp', c_vp), ('wts', c_vp), ('bias', c_vp), ('out', c_vp), ('B', C.c_int)]
 
 
+class GatherSeg(C.Structure):
+    """curla_gather_seg: one stream of a multi-stream gather launch."""
+    _fields_ = [('frames', c_vp), ('h1', c_vp), ('w1', c_vp), ('out', c_vp)]
+
+
+class GatherRows(C.Structure):
+    """curla_gather_rows: the batch's action / reward / not_done rows gathered by the same launch."""
+    _fields_ = [('actions', c_vp), ('rewards', c_vp), ('not_dones', c_vp), ('out_actions', c_vp),
+                ('out_rewards', c_vp), ('out_not_dones', c_vp), ('action_dim', C.c_int)]
+
+
 class AgentConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         'C', 'H', 'W', 'Hf', 'Wf', 'feature_dim', 'hidden_dim', 'action_dim', 'num_filters',
@@ -45,6 +56,7 @@ SIGNATURES = {
     'curla_version': (_i, []),
     'curla_gather_crop_f32': (_i, [c_vp, _i, _i, _i, c_vp, c_vp, c_vp, _i, _i, _i, c_vp, c_vp]),
     'curla_gather_crop_s2d': (_i, [c_vp, _i, _i, _i, c_vp, c_vp, c_vp, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
+    'curla_gather_crop_s2d_multi': (_i, [c_vp, _i, c_vp, _i, _i, _i, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_f32_to_s2d': (_i, [c_vp, _i, _i, _i, _i, _i, c_ll, c_vp, c_vp]),
     'curla_scatter_transition': (_i, [c_vp, _i, c_ll, c_vp, c_vp, c_vp, c_vp]),
     'curla_replay_add': (_i, [c_vp, c_vp, c_ll, c_vp, c_vp, _i, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -13,6 +13,8 @@
 // the update's FLOPs at the default batch).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace curla {
 
 // C[m][n] = sum_k A(m,k) * B(k,n), arbitrary element strides.  32x32 tile, 16x16 threads.
@@ -205,6 +207,252 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
     }
 }
 
+// ------------------------------------------------------------------ tensor-core path
+// The B x Bg bilinear contraction and its two gradient contractions on the tensor cores
+// (mma.sync m16n8k16, bf16 operands, fp32 accumulate).  The reference computes them in fp32
+// (curl_sac.py:211-222) and logits of magnitude ~30 sit in an exp(), so every fp32 operand x is split
+// into hi = bf16(x), lo = bf16(x - hi) and a product is  a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (three
+// MMAs; the dropped lo.lo term is 2^-18 relative): fp32-level results (tests: 1e-4 against torch fp32).
+//
+// Work unit = one warp: 16 local rows x 64 key columns.  A CTA is 8 warps = the same 16 rows x 512
+// columns; grid (B/16 row blocks, Bg/512 column blocks), so a global batch of 4096 keys spreads over
+// 8x more CTAs instead of one CTA streaming all of U per row block.  Softmax needs whole rows, hence
+// two passes over the same logits (recomputed bit-identically, they are 0.03 % of the update's FLOPs):
+//   k_curl_tc<0>: logits tile -> per (64-column tile, row) partial (max, sum exp) -> pstat, label logit
+//   k_curl_tc<1>: logits tile again, global (max, sum) from pstat, dl = (softmax - onehot) * grad_scale
+//                 kept in registers -- the m16n8 accumulator fragment of two adjacent column tiles IS the
+//                 m16k16 A fragment of the next MMA -- then dz_a += dl . U, V += dl . z_pos; the 8 warps
+//                 are summed in shared memory in a fixed order and written as per-column-block partials
+//   k_curl_reduce: sums the column-block partials (fixed order: deterministic), per-row loss
+// Operands are prepared once per update by k_curl_prep as bf16 hi/lo arrays in the two orientations
+// the B fragments want: Uk[j][k] (logits) and UT[a][j], ZT[a][j] (gradients).
+__device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_bf16x2(x - hf.x, y - hf.y);
+}
+__device__ __forceinline__ uint32_t ldg_u32(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+
+// U, z_pos: fp32 [Bg][64].  Uk_*: bf16 [BgP][64]; UT_*, ZT_*: bf16 [64][BgP]; rows j >= Bg are zero.
+__global__ void __launch_bounds__(256)
+k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, int BgP,
+            bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_lo, bf16* __restrict__ UT_hi, bf16* __restrict__ UT_lo,
+            bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_lo) {
+    pdl_grid_sync();
+    __shared__ float su[32][65], sz[32][65];
+    const int j0 = blockIdx.x * 32;
+    for (int t = threadIdx.x; t < 2048; t += 256) {
+        const int jj = t >> 6, k = t & 63, j = j0 + jj;
+        const float u = j < Bg ? U[(long long)j * 64 + k] : 0.f;
+        const float z = j < Bg ? z_pos[(long long)j * 64 + k] : 0.f;
+        su[jj][k] = u; sz[jj][k] = z;
+        const bf16 h = __float2bfloat16_rn(u);
+        Uk_hi[(long long)j * 64 + k] = h;
+        Uk_lo[(long long)j * 64 + k] = __float2bfloat16_rn(u - __bfloat162float(h));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2048; t += 256) {
+        const int a = t >> 5, jj = t & 31;
+        const long long o = (long long)a * BgP + j0 + jj;
+        const float u = su[jj][a], z = sz[jj][a];
+        const bf16 uh = __float2bfloat16_rn(u), zh = __float2bfloat16_rn(z);
+        UT_hi[o] = uh; UT_lo[o] = __float2bfloat16_rn(u - __bfloat162float(uh));
+        ZT_hi[o] = zh; ZT_lo[o] = __float2bfloat16_rn(z - __bfloat162float(zh));
+    }
+}
+
+struct CurlTc {
+    const float* z_a;                          // [B][64] fp32
+    const bf16 *Uk_hi, *Uk_lo, *UT_hi, *UT_lo, *ZT_hi, *ZT_lo;
+    float* pstat;                              // [NT][Bp][2]  (max, sum exp) per 64-column tile
+    float* lab_logit;                          // [Bp]
+    float* pdz; float* pV;                     // [NCB][Bp][64] column-block partials (NCB > 1), else dz_a / V directly
+    float* logits_copy;                        // optional [B][Bg]
+    int B, Bg, BgP, Bp, NT, label0;
+    float grad_scale;
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_curl_tc(const CurlTc p) {
+    pdl_grid_sync();
+    extern __shared__ __align__(16) float s_red[];            // PASS 1: [8 warps][2][16][64]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * 16;
+    const int jw = (blockIdx.y * 8 + warp) * 64;              // this warp's 64 key columns
+    const bool active = jw < p.BgP;
+    const int rowA = r0 + g, rowB = r0 + g + 8;
+    float lg[8][4];
+    if (active) {
+        // ---- A = z_a rows (hi / lo), all of K = 64 in registers
+        uint32_t a_hi[4][4], a_lo[4][4];
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int row = (h & 1) ? rowB : rowA, k = kt * 16 + 2 * t + (h >> 1) * 8;
+                float2 v = make_float2(0.f, 0.f);
+                if (row < p.B) v = *reinterpret_cast<const float2*>(p.z_a + (long long)row * 64 + k);
+                split_bf16(v.x, v.y, a_hi[kt][h], a_lo[kt][h]);
+            }
+        }
+        // ---- logits[16][64] = z_a . U^T : 8 column tiles of 8
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            lg[nt][0] = lg[nt][1] = lg[nt][2] = lg[nt][3] = 0.f;
+            const long long rowoff = (long long)(jw + nt * 8 + g) * 64 + 2 * t;
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) {
+                const uint32_t bh0 = ldg_u32(p.Uk_hi + rowoff + kt * 16), bh1 = ldg_u32(p.Uk_hi + rowoff + kt * 16 + 8);
+                const uint32_t bl0 = ldg_u32(p.Uk_lo + rowoff + kt * 16), bl1 = ldg_u32(p.Uk_lo + rowoff + kt * 16 + 8);
+                mma_bf16(lg[nt], a_hi[kt][0], a_hi[kt][1], a_hi[kt][2], a_hi[kt][3], bh0, bh1);
+                mma_bf16(lg[nt], a_lo[kt][0], a_lo[kt][1], a_lo[kt][2], a_lo[kt][3], bh0, bh1);
+                mma_bf16(lg[nt], a_hi[kt][0], a_hi[kt][1], a_hi[kt][2], a_hi[kt][3], bl0, bl1);
+            }
+        }
+    }
+    const int labA = p.label0 + rowA, labB = p.label0 + rowB;
+    if (PASS == 0) {
+        if (!active) return;
+        float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = jw + nt * 8 + 2 * t + e;
+                if (j < p.Bg) {
+                    mA = fmaxf(mA, lg[nt][e]); mB = fmaxf(mB, lg[nt][2 + e]);
+                    if (j == labA && rowA < p.B) p.lab_logit[rowA] = lg[nt][e];
+                    if (j == labB && rowB < p.B) p.lab_logit[rowB] = lg[nt][2 + e];
+                    if (p.logits_copy) {
+                        if (rowA < p.B) p.logits_copy[(long long)rowA * p.Bg + j] = lg[nt][e];
+                        if (rowB < p.B) p.logits_copy[(long long)rowB * p.Bg + j] = lg[nt][2 + e];
+                    }
+                }
+            }
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1)); mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+        float sA = 0.f, sB = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = jw + nt * 8 + 2 * t + e;
+                if (j < p.Bg) { sA += expf(lg[nt][e] - mA); sB += expf(lg[nt][2 + e] - mB); }
+            }
+        sA += __shfl_xor_sync(0xffffffffu, sA, 1); sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+        sB += __shfl_xor_sync(0xffffffffu, sB, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+        if (t == 0) {
+            float* ps = p.pstat + ((long long)(jw >> 6) * p.Bp) * 2;
+            ps[rowA * 2] = mA; ps[rowA * 2 + 1] = sA;
+            ps[rowB * 2] = mB; ps[rowB * 2 + 1] = sB;
+        }
+    } else {
+        float dz[8][4], vv[8][4];
+#pragma unroll
+        for (int na = 0; na < 8; ++na)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { dz[na][e] = 0.f; vv[na][e] = 0.f; }
+        if (active) {
+            // ---- global row statistics from the per-tile partials (fixed order)
+            float MA = -INFINITY, MB = -INFINITY;
+            for (int st = 0; st < p.NT; ++st) {
+                MA = fmaxf(MA, p.pstat[((long long)st * p.Bp + rowA) * 2]);
+                MB = fmaxf(MB, p.pstat[((long long)st * p.Bp + rowB) * 2]);
+            }
+            float SA = 0.f, SB = 0.f;
+            for (int st = 0; st < p.NT; ++st) {
+                const float* qa = p.pstat + ((long long)st * p.Bp + rowA) * 2;
+                const float* qb = p.pstat + ((long long)st * p.Bp + rowB) * 2;
+                SA += qa[1] * expf(qa[0] - MA);
+                SB += qb[1] * expf(qb[0] - MB);
+            }
+            const float iA = 1.f / SA, iB = 1.f / SB;
+            const float gA = rowA < p.B ? p.grad_scale : 0.f, gB = rowB < p.B ? p.grad_scale : 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = jw + nt * 8 + 2 * t + e;
+                    const bool ok = j < p.Bg;
+                    lg[nt][e] = ok ? (expf(lg[nt][e] - MA) * iA - (j == labA ? 1.f : 0.f)) * gA : 0.f;
+                    lg[nt][2 + e] = ok ? (expf(lg[nt][2 + e] - MB) * iB - (j == labB ? 1.f : 0.f)) * gB : 0.f;
+                }
+            // ---- dz_a[16][64] += dl . U ; V[16][64] += dl . z_pos   (k = j: 4 steps of 16 columns)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                uint32_t dh[4], dlo[4];
+                split_bf16(lg[2 * m][0], lg[2 * m][1], dh[0], dlo[0]);
+                split_bf16(lg[2 * m][2], lg[2 * m][3], dh[1], dlo[1]);
+                split_bf16(lg[2 * m + 1][0], lg[2 * m + 1][1], dh[2], dlo[2]);
+                split_bf16(lg[2 * m + 1][2], lg[2 * m + 1][3], dh[3], dlo[3]);
+#pragma unroll
+                for (int na = 0; na < 8; ++na) {
+                    const long long off = (long long)(na * 8 + g) * p.BgP + jw + m * 16 + 2 * t;
+                    const uint32_t uh0 = ldg_u32(p.UT_hi + off), uh1 = ldg_u32(p.UT_hi + off + 8);
+                    const uint32_t ul0 = ldg_u32(p.UT_lo + off), ul1 = ldg_u32(p.UT_lo + off + 8);
+                    mma_bf16(dz[na], dh[0], dh[1], dh[2], dh[3], uh0, uh1);
+                    mma_bf16(dz[na], dlo[0], dlo[1], dlo[2], dlo[3], uh0, uh1);
+                    mma_bf16(dz[na], dh[0], dh[1], dh[2], dh[3], ul0, ul1);
+                    const uint32_t zh0 = ldg_u32(p.ZT_hi + off), zh1 = ldg_u32(p.ZT_hi + off + 8);
+                    const uint32_t zl0 = ldg_u32(p.ZT_lo + off), zl1 = ldg_u32(p.ZT_lo + off + 8);
+                    mma_bf16(vv[na], dh[0], dh[1], dh[2], dh[3], zh0, zh1);
+                    mma_bf16(vv[na], dlo[0], dlo[1], dlo[2], dlo[3], zh0, zh1);
+                    mma_bf16(vv[na], dh[0], dh[1], dh[2], dh[3], zl0, zl1);
+                }
+            }
+        }
+        // ---- the CTA's 8 warps (8 x 64 columns) summed in a fixed order
+        float* mine = s_red + (size_t)warp * 2048;
+#pragma unroll
+        for (int na = 0; na < 8; ++na) {
+            const int a = na * 8 + 2 * t;
+            *reinterpret_cast<float2*>(mine + g * 64 + a) = make_float2(dz[na][0], dz[na][1]);
+            *reinterpret_cast<float2*>(mine + (g + 8) * 64 + a) = make_float2(dz[na][2], dz[na][3]);
+            *reinterpret_cast<float2*>(mine + 1024 + g * 64 + a) = make_float2(vv[na][0], vv[na][1]);
+            *reinterpret_cast<float2*>(mine + 1024 + (g + 8) * 64 + a) = make_float2(vv[na][2], vv[na][3]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2048; i += 256) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += s_red[(size_t)w * 2048 + i];
+            const int which = i >> 10, rem = i & 1023, row = r0 + (rem >> 6);
+            float* dst = which ? p.pV : p.pdz;
+            if (gridDim.y > 1) dst[((long long)blockIdx.y * p.Bp + row) * 64 + (rem & 63)] = sum;
+            else if (row < p.B) dst[(long long)row * 64 + (rem & 63)] = sum;
+        }
+    }
+}
+
+// row_loss[i] = log(sum_j exp(l_ij - M_i)) - (l_i,label - M_i); with more than one column block also
+// dz_a / V = sum over the column-block partials (fixed order).
+__global__ void __launch_bounds__(256)
+k_curl_reduce(const float* __restrict__ pstat, const float* __restrict__ lab_logit, const float* __restrict__ pdz,
+              const float* __restrict__ pV, int B, int Bp, int NT, int NCB, float* __restrict__ row_loss,
+              float* __restrict__ dz_a, float* __restrict__ V) {
+    pdl_grid_sync();
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 6), a = threadIdx.x & 63;
+    if (i >= B) return;
+    if (NCB > 1) {
+        float sd = 0.f, sv = 0.f;
+        for (int cb = 0; cb < NCB; ++cb) {
+            sd += pdz[((long long)cb * Bp + i) * 64 + a];
+            sv += pV[((long long)cb * Bp + i) * 64 + a];
+        }
+        dz_a[(long long)i * 64 + a] = sd;
+        V[(long long)i * 64 + a] = sv;
+    }
+    if (a == 0) {
+        float M = -INFINITY, S = 0.f;
+        for (int st = 0; st < NT; ++st) M = fmaxf(M, pstat[((long long)st * Bp + i) * 2]);
+        for (int st = 0; st < NT; ++st) S += pstat[((long long)st * Bp + i) * 2 + 1] * expf(pstat[((long long)st * Bp + i) * 2] - M);
+        row_loss[i] = logf(S) - (lab_logit[i] - M);
+    }
+}
+
 template <int R>
 static int launch_curl_rows(const float* z_a, const float* U, const float* Ut, const float* z_pos, int B, int Bg, int label0,
                             float grad_scale, float* row_loss, float* dz_a, float* V, float* logits_copy,
@@ -230,10 +478,25 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 
 using namespace curla;
 
-extern "C" long long curla_curl_workspace_floats(int B, int Bg) {
-    // U [Bg][64] + Ut [64][Bg] + V [B][64] + row_loss [B]
-    return 2LL * Bg * 64 + (long long)B * 64 + B;
+namespace {
+struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, total; };
+CurlPlan curl_plan(int B, int Bg) {
+    CurlPlan c;
+    c.BgP = (Bg + 63) / 64 * 64; c.Bp = (B + 15) / 16 * 16;
+    c.NT = c.BgP / 64; c.NCB = (c.NT + 7) / 8;
+    long long o = 2LL * Bg * 64 + (long long)B * 64 + B;       // U, Ut, V, row_loss (the CUDA-core path's layout)
+    o = (o + 3) / 4 * 4;
+    c.off_bf16 = o; o += 6 * c.BgP * 64 / 2;                   // six bf16 [BgP x 64] arrays
+    c.off_pstat = o; o += c.NT * c.Bp * 2;
+    c.off_lab = o; o += c.Bp;
+    c.off_pdz = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
+    c.off_pV = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
+    c.total = o;
+    return c;
 }
+}  // namespace
+
+extern "C" long long curla_curl_workspace_floats(int B, int Bg) { return curl_plan(B, Bg).total; }
 
 // z_a [B][64] (local rows), z_pos [Bg][64] (all ranks' keys), W [feat][feat].
 // Outputs: loss_out (mean over the LOCAL rows), dz_a [B][64], dW [feat][feat] (local
@@ -250,6 +513,44 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
     // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace),
     // written in both orientations: U for the gradient pass, Ut for the coalesced logits pass
     if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Ut, Bg, Bg, feat, feat, stream)) return -1;
+    {   // tensor-core path (default); CURLA_CURL_TC=0 keeps the CUDA-core rows kernel (A/B, tests)
+        const char* e = getenv("CURLA_CURL_TC");
+        if (!(e && e[0] == '0')) {
+            const CurlPlan cp = curl_plan(B, Bg);
+            bf16* hb = reinterpret_cast<bf16*>(workspace + cp.off_bf16);
+            const long long n = cp.BgP * 64;
+            CurlTc t;
+            t.z_a = z_a;
+            t.Uk_hi = hb; t.Uk_lo = hb + n; t.UT_hi = hb + 2 * n; t.UT_lo = hb + 3 * n; t.ZT_hi = hb + 4 * n; t.ZT_lo = hb + 5 * n;
+            t.pstat = workspace + cp.off_pstat; t.lab_logit = workspace + cp.off_lab;
+            t.pdz = cp.NCB > 1 ? workspace + cp.off_pdz : dz_a;
+            t.pV = cp.NCB > 1 ? workspace + cp.off_pV : V;
+            t.logits_copy = logits_copy;
+            t.B = B; t.Bg = Bg; t.BgP = (int)cp.BgP; t.Bp = (int)cp.Bp; t.NT = (int)cp.NT; t.label0 = label0; t.grad_scale = grad_scale;
+            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, Bg, (int)cp.BgP,
+                     hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n);
+            if (check_launch("curl_prep")) return -1;
+            const dim3 grid((unsigned)(cp.Bp / 16), (unsigned)cp.NCB);
+            launch_k(k_curl_tc<0>, grid, dim3(256), 0, stream, t);
+            if (check_launch("curl_rows")) return -1;
+            const size_t smem = sizeof(float) * 8 * 2048;
+            static bool attr[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 64 && !attr[dev]) {
+                cudaError_t e2 = cudaFuncSetAttribute(k_curl_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                CURLA_CHECK(e2 == cudaSuccess, "curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e2));
+                attr[dev] = true;
+            }
+            launch_k(k_curl_tc<1>, grid, dim3(256), smem, stream, t);
+            if (check_launch("curl_rows")) return -1;
+            launch_k(k_curl_reduce, dim3(cdiv(B, 4)), dim3(256), 0, stream, (const float*)t.pstat, (const float*)t.lab_logit,
+                     (const float*)t.pdz, (const float*)t.pV, B, (int)cp.Bp, (int)cp.NT, (int)cp.NCB, row_loss, dz_a, V);
+            if (check_launch("curl_reduce")) return -1;
+            launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, V, row_loss, B, feat, dW, loss_out);
+            return check_launch("curl_dw");
+        }
+    }
     // rows per CTA: every CTA streams all of U and z_pos (Bg x 512 B) from L2, so the re-read
     // traffic is (B / R) x that -- at a global batch of 4096 it is what bounds the kernel, and more
     // rows per CTA beat more CTAs; at small Bg the kernel is latency-bound and wants >= ~1 CTA/SM.

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <type_traits>
@@ -145,6 +146,9 @@ struct curla_agent {
     // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
     // there while the main stream already runs the next pass's conv stack
     cudaStream_t side; cudaEvent_t ev[4]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
+    // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
+    // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
+    cudaStream_t comm_st; cudaEvent_t cev[6]; int comm_state;
     long long wgrad_ws_stride;
     TailBuf t_p1, t_p2, t_p3, t_p4, t_p5, t_p7;
     MlpBuf m_p1, m_p2q[2], m_p3q[2], m_p4, m_p5q[2];
@@ -431,6 +435,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->last_launches = 0;
     a->nccl_lib = nullptr; a->comm = nullptr;
     a->side = nullptr; a->side_state = 0;
+    a->comm_st = nullptr; a->comm_state = 0;
     return a;
 }
 
@@ -440,6 +445,10 @@ extern "C" void curla_agent_destroy(curla_agent* a) {
     if (a->side_state == 1) {
         for (auto& e : a->ev) cudaEventDestroy(e);
         cudaStreamDestroy(a->side);
+    }
+    if (a->comm_state == 1) {
+        for (auto& e : a->cev) cudaEventDestroy(e);
+        cudaStreamDestroy(a->comm_st);
     }
     destroy_comm(a);
     delete a;
@@ -604,7 +613,8 @@ struct Run {
     }
     // LayerNorm + fc backward (+ conv stack backward when conv==true)
     void enc_bwd(const float* dz_a, const float* dz_b, const TailBuf& t, const EncP& e, long long fc_shadow,
-                 const EncS* convs, bf16* const acts[4], const bf16* s2d, float* gbase, long long pbase, bool conv) {
+                 const EncS* convs, bf16* const acts[4], const bf16* s2d, float* gbase, long long pbase, bool conv,
+                 const std::function<void()>& after_fc_wgrad = nullptr) {
         if (!ok()) return;
         const int B = a->cfg.batch, feat = a->cfg.feature_dim;
         auto g = [&](long long poff) { return gbase + (poff - pbase); };
@@ -616,6 +626,9 @@ struct Run {
                                           a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f,
                                           a->Kfc / 4, (long long)a->S * 8, 2, st));
         set_launch_tag(nullptr);
+        // everything of this bucket except the conv-layer gradients is final here (data parallel: its
+        // all-reduce + Adam start now, beside the conv backward below)
+        if (after_fc_wgrad && ok()) after_fc_wgrad();
         if (!conv) return;
         // d(act4) = relu'(act4) * dfc . Wfc
         set_launch_tag("gemm_fc_dgrad");
@@ -786,6 +799,22 @@ static cudaStream_t side_stream(curla_agent* a, cudaStream_t st) {
     return (a->side_state == 1 && !g_prof.on) ? a->side : st;
 }
 
+// Communication stream (created lazily, world > 1 only).  CURLA_COMM_OVERLAP=0 keeps the collectives
+// and the optimizer steps on the caller's stream, in line (so does the CUDA-event profiler).
+static cudaStream_t comm_stream(curla_agent* a, cudaStream_t st) {
+    if (a->cfg.world == 1) return st;
+    if (a->comm_state == 0) {
+        const char* e = getenv("CURLA_COMM_OVERLAP");
+        a->comm_state = -1;
+        if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&a->comm_st, cudaStreamNonBlocking) == cudaSuccess) {
+            bool okev = true;
+            for (auto& ev : a->cev) okev = okev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+            if (okev) a->comm_state = 1;
+        }
+    }
+    return (a->comm_state == 1 && !g_prof.on) ? a->comm_st : st;
+}
+
 // ================================================================== the update
 extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
     CURLA_CHECK(a->bound, "agent not bound");
@@ -795,6 +824,20 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     const long long launches0 = g_launches;
     if (g_prof.on) { g_prof.stream = st; g_prof.mark("__begin__"); }
     Run r{a, st};
+    const cudaStream_t cs = comm_stream(a, st);
+    const bool overlap = cs != st;                 // world > 1: bucket slices are reduced + stepped on cs
+    bool actor_pending = false;
+    // [split, n) of a bucket on the communication stream: all-reduce, then Adam on the reduced slice
+    auto reduce_step = [&](int ev_fork, float* pbase, float* gbase, float* m, float* v, long long from, long long to,
+                           long long double_from, double lr, double beta, int t) {
+        if (!r.ok()) return;
+        cudaEventRecord(a->cev[ev_fork], st);
+        cudaStreamWaitEvent(cs, a->cev[ev_fork], 0);
+        r.chk(all_reduce(a, gbase + from, (size_t)(to - from), NCCL_F32, cs));
+        const long long df = double_from > from ? double_from - from : 0;
+        if (r.ok()) r.chk(curla_adam_f32(pbase + from, gbase + from, m + from, v + from, to - from, df, lr, beta, 0.999, 1e-8, t,
+                                         nullptr, cs));
+    };
     const int ph = u->phases ? u->phases : CURLA_PHASE_ALL;
     const bool do_sac = !u->only_cpc;
     const bool do_critic = do_sac && (ph & CURLA_PHASE_CRITIC);
@@ -810,14 +853,28 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     };
     const bool do_sample = (ph & CURLA_PHASE_SAMPLE) != 0;
     const bool want_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
-    if (do_sample) stage(u->obs_f32, u->obses, u->h1_obs, u->w1_obs, a->s2d_obs);
     const bf16* s2d_pos = u->pos_is_obs ? a->s2d_obs : a->s2d_pos;
-    if (do_sample && want_cpc && !u->pos_is_obs) stage(u->pos_f32, u->obses, u->h1_pos, u->w1_pos, a->s2d_pos);
-    if (do_sample && do_sac) {
-        stage(u->next_f32, u->next_obses, u->h1_next, u->w1_next, a->s2d_next);
-        if (r.ok()) r.chk(curla_gather_rows_f32(u->actions, u->idxs, B, A, a->act_b, st));
-        if (r.ok()) r.chk(curla_gather_rows_f32(u->rewards, u->idxs, B, 1, a->rew_b, st));
-        if (r.ok()) r.chk(curla_gather_rows_f32(u->not_dones, u->idxs, B, 1, a->nd_b, st));
+    const bool need_pos = want_cpc && !u->pos_is_obs;
+    if (do_sample && !u->obs_f32 && !(need_pos && u->pos_f32) && !(do_sac && u->next_f32)) {
+        // the replay path: obs / pos / next_obs windows and the batch's action / reward / not_done rows
+        // in ONE bulk-staged launch (utils.py:151-166)
+        curla_gather_seg gs[3];
+        int ng = 0;
+        gs[ng++] = {u->obses, u->h1_obs, u->w1_obs, a->s2d_obs};
+        if (need_pos) gs[ng++] = {u->obses, u->h1_pos, u->w1_pos, a->s2d_pos};
+        if (do_sac) gs[ng++] = {u->next_obses, u->h1_next, u->w1_next, a->s2d_next};
+        const curla_gather_rows rows = {u->actions, u->rewards, u->not_dones, a->act_b, a->rew_b, a->nd_b, A};
+        r.chk(curla_gather_crop_s2d_multi(gs, ng, u->idxs, c.C, c.Hf, c.Wf, B, c.H, c.W, a->CP1, a->s2d_sstride,
+                                          do_sac ? &rows : nullptr, st));
+    } else if (do_sample) {
+        stage(u->obs_f32, u->obses, u->h1_obs, u->w1_obs, a->s2d_obs);
+        if (need_pos) stage(u->pos_f32, u->obses, u->h1_pos, u->w1_pos, a->s2d_pos);
+        if (do_sac) {
+            stage(u->next_f32, u->next_obses, u->h1_next, u->w1_next, a->s2d_next);
+            if (r.ok()) r.chk(curla_gather_rows_f32(u->actions, u->idxs, B, A, a->act_b, st));
+            if (r.ok()) r.chk(curla_gather_rows_f32(u->rewards, u->idxs, B, 1, a->rew_b, st));
+            if (r.ok()) r.chk(curla_gather_rows_f32(u->not_dones, u->idxs, B, 1, a->nd_b, st));
+        }
     }
 
     bool have_p5 = false;
@@ -881,11 +938,27 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         float* gC = a->G + a->g_critic;
         r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, gC, a->off_critic,
                     a->dX[0], a->dX[1] - a->dX[0]);
+        const int tc_ = ++a->t_critic;
+        // critic bucket = [conv w,b x4 | fc_w fc_b ln_w ln_b | Q1 | Q2]: everything from fc_w on (99 % of the
+        // bytes) is final after the fc weight gradient, i.e. BEFORE the conv backward (0.7 ms at the
+        // default batch) starts: its all-reduce and Adam overlap that
+        const long long split1 = a->enc_critic.fc_w - a->off_critic;
+        auto early1 = [&]() {
+            if (overlap) reduce_step(0, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, split1, a->n_critic, a->n_critic,
+                                     c.critic_lr, c.critic_beta, tc_);
+        };
         r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
-                  a->off_critic, !c.detach_encoder);
-        if (r.ok()) r.chk(all_reduce(a, gC, (size_t)a->n_critic, NCCL_F32, st));
-        if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, a->n_critic, a->n_critic,
-                                         c.critic_lr, c.critic_beta, 0.999, 1e-8, ++a->t_critic, nullptr, st));
+                  a->off_critic, !c.detach_encoder, early1);
+        if (overlap) {
+            reduce_step(1, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, 0, split1, a->n_critic,
+                        c.critic_lr, c.critic_beta, tc_);
+            cudaEventRecord(a->cev[2], cs);
+            cudaStreamWaitEvent(st, a->cev[2], 0);
+        } else {
+            if (r.ok()) r.chk(all_reduce(a, gC, (size_t)a->n_critic, NCCL_F32, st));
+            if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, a->n_critic, a->n_critic,
+                                             c.critic_lr, c.critic_beta, 0.999, 1e-8, tc_, nullptr, st));
+        }
         r.pack(a->pack_critic);
     }
     const int mm = merge_mode();
@@ -906,13 +979,26 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     const Run::Pass p_key = {s2d_pos, &a->enc_target, &a->s_target, a->actB};          // F7
     bool key_done = false, join7 = false;
     // tail of one pass on the side stream (fc_partial2 is the side stream's split-K buffer)
-    auto side_tail = [&](const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t) {
+    // all-gather of the CURL keys (the one real exchange step of the update): issued on the stream that
+    // produced them, as early as they exist -- before the actor bucket's all-reduce is queued on the
+    // communicator, which runs its collectives in issue order
+    bool keys_gathered = false;
+    auto gather_keys = [&](cudaStream_t s_) {
+        if (c.world == 1 || !r.ok()) return;
+        if (!a->comm) { r.chk(-1); set_last_error("update: world>1 but no communicator"); return; }
+        const int rc_ = g_nccl.all_gather(a->t_p7.z, a->z_pos_all, (size_t)B * 64, NCCL_F32, a->comm, s_);
+        if (rc_ != 0) { r.chk(-1); set_last_error("ncclAllGather failed (%d)", rc_); return; }
+        profile_mark("nccl_all_gather");
+        keys_gathered = true;
+    };
+    auto side_tail = [&](const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, bool keys) {
         Run r2{a, ss7};
         r2.rc = r.rc;
         if (forked7) { cudaEventRecord(a->ev[3], st); cudaStreamWaitEvent(ss7, a->ev[3], 0); }
         r2.tail(act4, fc_shadow, e, t, B, 0, nullptr, nullptr, a->fc_partial2);
-        if (forked7) { cudaEventRecord(a->ev[2], ss7); join7 = true; }
         r.chk(r2.rc);
+        if (keys) gather_keys(ss7);
+        if (forked7) { cudaEventRecord(a->ev[2], ss7); join7 = true; }
     };
     if (do_sac) {
         if (do_actor) {
@@ -921,7 +1007,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             if (mm && do_cpc) {
                 const Run::Pass ps[2] = {p_anchor, p_key};
                 r.conv_stack_multi(ps, 2);
-                side_tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7);   // keys: beside the actor step
+                side_tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, true);   // keys: beside the actor step
                 key_done = true;
             } else {
                 r.conv_stack_multi(&p_anchor, 1);
@@ -942,13 +1028,21 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             float* gA = a->G + a->g_actor;
             r.mlp_bwd_n(a->dt4, 0, a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, gA, a->off_actor, a->dXa, 0);
             r.enc_bwd(a->dXa, nullptr, a->t_p4, a->enc_actor, a->s_actor_fc, nullptr, a->actA, nullptr, gA, a->off_actor, false);
-            if (r.ok()) r.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, st));
-            if (r.ok()) r.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, st));
-            if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_actor, gA, a->Ad + a->a_m2, a->Ad + a->a_v2, a->n_actor, a->n_actor,
-                                             c.actor_lr, c.actor_beta, 0.999, 1e-8, ++a->t_actor, nullptr, st));
-            r.pack(a->pack_actor);
-            if (r.ok()) r.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
-                                                    1e-8, ++a->t_alpha, nullptr, st));
+            // Nothing later in THIS update reads the actor's own parameters or log_alpha (the CURL phase uses
+            // the critic / target encoders): with world > 1 the whole reduce -> Adam -> shadow pack chain
+            // runs on the communication stream beside the CURL phase and is joined at the end of the update
+            const cudaStream_t as = overlap ? cs : st;
+            Run ra{a, as};
+            ra.rc = r.rc;
+            if (overlap) { cudaEventRecord(a->cev[3], st); cudaStreamWaitEvent(cs, a->cev[3], 0); actor_pending = true; }
+            if (ra.ok()) ra.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, as));
+            if (ra.ok()) ra.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, as));
+            if (ra.ok()) ra.chk(curla_adam_f32(a->P + a->off_actor, gA, a->Ad + a->a_m2, a->Ad + a->a_v2, a->n_actor, a->n_actor,
+                                               c.actor_lr, c.actor_beta, 0.999, 1e-8, ++a->t_actor, nullptr, as));
+            ra.pack(a->pack_actor);
+            if (ra.ok()) ra.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
+                                                      1e-8, ++a->t_alpha, nullptr, as));
+            r.chk(ra.rc);
         }
         if (do_ema && !ema_first) ema();
     }
@@ -964,32 +1058,44 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             } else {
                 r.conv_stack_multi(&p_anchor, 1);
             }
-            side_tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5);
+            side_tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, false);
         }
         if (!key_done) {
             if (!(mm && !have_p5)) r.conv_stack_multi(&p_key, 1);
             r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
         }
         if (join7) cudaStreamWaitEvent(st, a->ev[2], 0);
-        const float* zpos = a->t_p7.z;
-        if (c.world > 1 && r.ok()) {
-            CURLA_CHECK(a->comm, "update: world>1 but no communicator");
-            const int rc = g_nccl.all_gather(a->t_p7.z, a->z_pos_all, (size_t)B * 64, NCCL_F32, a->comm, st);
-            CURLA_CHECK(rc == 0, "ncclAllGather failed (%d)", rc);
-            profile_mark("nccl_all_gather");
-            zpos = a->z_pos_all;
-        }
+        if (!keys_gathered) gather_keys(st);
+        const float* zpos = c.world > 1 ? a->z_pos_all : a->t_p7.z;
         float* gK = a->G + a->g_cpc;
         if (r.ok()) r.chk(curla_curl_fwd_bwd(a->t_p5.z, zpos, a->P + a->off_W, B, c.global_batch, feat, c.rank * B, gs, a->curl_ws,
                                              a->metrics + 6, a->dz_curl, gK, nullptr, st));
         // g_cpc mirrors [W | critic.encoder]: encoder grads start at n_W
+        // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once (double_from = n_W).
+        // Bucket = [W | conv w,b x4 | fc_w fc_b ln_w ln_b]: the fc/ln tail is final after the fc weight gradient
+        const int tk_ = ++a->t_cpc;
+        const long long split3 = a->n_W + (a->enc_critic.fc_w - a->off_critic);
+        auto early3 = [&]() {
+            if (overlap) reduce_step(4, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, split3, a->n_cpc, a->n_W,
+                                     c.encoder_lr, 0.9, tk_);
+        };
         r.enc_bwd(a->dz_curl, nullptr, a->t_p5, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs,
-                  gK + a->n_W, a->off_critic, true);
-        if (r.ok()) r.chk(all_reduce(a, gK, (size_t)a->n_cpc, NCCL_F32, st));
-        // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once
-        if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, a->n_cpc, a->n_W, c.encoder_lr, 0.9,
-                                         0.999, 1e-8, ++a->t_cpc, nullptr, st));
+                  gK + a->n_W, a->off_critic, true, early3);
+        if (overlap) {
+            reduce_step(5, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, 0, split3, a->n_W, c.encoder_lr, 0.9, tk_);
+            cudaEventRecord(a->cev[2], cs);
+            cudaStreamWaitEvent(st, a->cev[2], 0);
+            actor_pending = false;                 // cs is in order: the actor chain issued before is complete as well
+        } else {
+            if (r.ok()) r.chk(all_reduce(a, gK, (size_t)a->n_cpc, NCCL_F32, st));
+            if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, a->n_cpc, a->n_W, c.encoder_lr, 0.9,
+                                             0.999, 1e-8, tk_, nullptr, st));
+        }
         r.pack(a->pack_critic_enc);
+    }
+    if (actor_pending) {                           // join: everything of this update is complete when `st` is
+        cudaEventRecord(a->cev[2], cs);
+        cudaStreamWaitEvent(st, a->cev[2], 0);
     }
     a->last_launches = g_launches - launches0;
     return r.rc;

@@ -14,7 +14,11 @@
 //                      planes [CP/8][S][8] per sample.
 //                      uint8 values are exact in bf16.
 #include "common.cuh"
+#include "tc.cuh"
 #include "../../include/curla_b200.h"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace curla {
 
@@ -110,6 +114,105 @@ k_gather_s2d(const SrcT* __restrict__ frames, int C, int Hf, int Wf,
     }
 }
 
+// ------------------------------------------------------------------ s2d bf16 from uint8 frames, bulk-staged
+// The replay path of the update (uint8 frames, 16-byte aligned rows).  Same CTA = (sample, output
+// plane) decomposition and output as k_gather_s2d<uint8_t>, with three differences:
+//  * staging: ONE elected thread issues one cp.async.bulk (the TMA unit's linear copy) per stored
+//    channel -- H*Wf contiguous bytes each -- completing on an mbarrier; no thread spends issue slots
+//    on 16-byte cp.async and the CTA's other warps go straight to the barrier;
+//  * conversion: a thread produces FOUR consecutive output positions (64 bytes) from four unaligned
+//    8-byte runs, each read as three aligned 32-bit words + two funnel shifts, and turns bytes into
+//    bf16 with the 2^23 magic-number add (PRMT + FADD per byte, full-rate pipes) instead of one
+//    LDS.U8 + I2F (quarter-rate conversion pipe) per byte: the old kernel was issue-bound at 70 % SM
+//    throughput and 33 % of DRAM peak (profiles/r02n_gemm_wgrad_gather_ncu_full.txt);
+//  * up to three streams (obs / pos / next_obs: utils.py:151-158) and the gather of the batch's
+//    action / reward / not_done rows (utils.py:163-165) share ONE launch (blockIdx.z = stream).
+struct GatherSegs {
+    const uint8_t* frames[3];
+    const int64_t* h1[3];
+    const int64_t* w1[3];
+    bf16* out[3];
+    // optional row gather, done by the CTAs (plane 0, stream 0): out_x[b] = x[idxs[b]]
+    const float* actions; const float* rewards; const float* not_dones;
+    float* out_act; float* out_rew; float* out_nd;
+    int A;
+};
+template <typename T>
+__device__ __forceinline__ T pick3(T const (&a)[3], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
+
+__global__ void __launch_bounds__(256)
+k_gather_s2d_u8(const __grid_constant__ GatherSegs sg, const int64_t* __restrict__ idxs, int C, int Hf, int Wf,
+                int H, int W, int Hs, int Ws, long long out_sample_stride) {
+    extern __shared__ __align__(128) uint8_t s_raw[];      // [0,16) mbarrier | [2][ppitch] staged channels
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
+    const uint32_t bar = smem_u32(s_raw);
+    const int plane_bytes = H * Wf;                         // multiple of 16 (launch precondition)
+    const int ppitch = plane_bytes + 16;                    // slack: the last run's aligned words end past the plane
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    pdl_grid_sync();
+    const int64_t* h1 = pick3(sg.h1, s);
+    const int64_t* w1 = pick3(sg.w1, s);
+    const long long fi = idxs ? idxs[b] : b;
+    const int oy = h1 ? (int)h1[b] : 0;
+    const int ox = w1 ? (int)w1[b] : 0;
+    const int c0 = 2 * j;
+    const int nch = C - c0 < 2 ? C - c0 : 2;
+    if (tid == 0) {
+        const uint8_t* frames = pick3(sg.frames, s);
+        mbar_expect_tx(bar, (uint32_t)(nch * plane_bytes));
+        for (int lp = 0; lp < nch; ++lp)
+            bulk_g2s(smem_u32(s_raw + 16 + lp * ppitch), frames + ((fi * C + c0 + lp) * Hf + oy) * (long long)Wf,
+                     (uint32_t)plane_bytes, bar);
+    }
+    if (j == 0 && s == 0 && sg.actions && tid < sg.A + 2) {
+        if (tid < sg.A) sg.out_act[b * sg.A + tid] = sg.actions[fi * sg.A + tid];
+        else if (tid == sg.A) sg.out_rew[b] = sg.rewards[fi];
+        else sg.out_nd[b] = sg.not_dones[fi];
+    }
+    mbar_wait(bar, 0);
+    const uint8_t* pl = s_raw + 16;
+    const int QW = (Ws + 3) >> 2;                           // groups of four positions per output row
+    const int nq = Hs * QW;
+    bf16* oplane = pick3(sg.out, s) + b * out_sample_stride + (long long)j * Hs * Ws * 8;
+    for (int q = tid; q < nq; q += 256) {
+        const int yb = q / QW, xb0 = (q - yb * QW) * 4;
+        const int nv = W - 2 * xb0;                         // valid bytes of the 8-byte runs of this group
+        uint32_t w[4][4];                                   // [position][word h]: word h = channel c0 + (h >> 1), sub-row h & 1
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int lp = h >> 1, y = 2 * yb + (h & 1);
+            uint32_t lo = 0u, hi = 0u;
+            if (lp < nch && y < H && nv > 0) {
+                const int o = lp * ppitch + y * Wf + ox + 2 * xb0;
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(pl + (o & ~3));
+                const uint32_t w0 = wp[0], w1_ = wp[1], w2 = wp[2];
+                const int sh = (o & 3) * 8;
+                lo = __funnelshift_r(w0, w1_, sh);
+                hi = __funnelshift_r(w1_, w2, sh);
+                if (nv < 8) {                               // the crop's right edge: bytes at x >= W are zero
+                    if (nv <= 4) { hi = 0u; if (nv < 4) lo &= (1u << (8 * nv)) - 1u; }
+                    else hi &= (1u << (8 * (nv - 4))) - 1u;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t src = i < 2 ? lo : hi;
+                const int k = (i & 1) * 2;
+                // 0x4B0000bb = 2^23 + bb as a float; minus 2^23 = (float)bb exactly; exact in bf16 too
+                const float v0 = __uint_as_float(__byte_perm(src, 0x4B000000u, 0x7650 + k)) - 8388608.f;
+                const float v1 = __uint_as_float(__byte_perm(src, 0x4B000000u, 0x7651 + k)) - 8388608.f;
+                w[i][h] = pack_bf16x2(v0, v1);
+            }
+        }
+        bf16* op = oplane + ((long long)yb * Ws + xb0) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (xb0 + i < Ws) *reinterpret_cast<uint4*>(op + i * 8) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+    }
+}
+
 // ------------------------------------------------------------------ small row gather
 // out[b][k] = src[idx[b]][k]   (actions / rewards / not_dones: utils.py:163-165)
 __global__ void k_gather_rows_f32(const float* __restrict__ src, const int64_t* __restrict__ idxs,
@@ -172,12 +275,59 @@ static int launch_s2d(const SrcT* frames, int C, int Hf, int Wf, const int64_t* 
     return check_launch("gather_s2d");
 }
 
+// Up to three streams of the same geometry (and the batch's action / reward / not_done rows) in one
+// launch of the bulk-staged kernel; falls back to one k_gather_s2d<uint8_t> launch per stream (+ three
+// row gathers) when a frame pointer or the stored row length is not 16-byte aligned.
+extern "C" int curla_gather_crop_s2d_multi(const curla_gather_seg* segs, int nseg, const int64_t* idxs,
+                                           int C, int Hf, int Wf, int B, int H, int W, int CP,
+                                           long long out_sample_stride, const curla_gather_rows* rows,
+                                           cudaStream_t stream) {
+    CURLA_CHECK(nseg >= 1 && nseg <= 3, "gather_s2d_multi: 1..3 streams (got %d)", nseg);
+    CURLA_CHECK(B > 0 && H <= Hf && W <= Wf && CP % 8 == 0 && CP >= 4 * C, "gather_s2d: bad shape");
+    const int Hs = (H + 1) / 2, Ws = (W + 1) / 2;
+    CURLA_CHECK(out_sample_stride >= (long long)Hs * Ws * CP, "gather_s2d: sample stride too small");
+    if (rows) CURLA_CHECK(rows->action_dim >= 1 && rows->action_dim <= 62 && idxs, "gather_s2d_multi: bad row gather");
+    bool bulk = (Wf % 16 == 0) && B <= 65535;
+    for (int i = 0; i < nseg; ++i) bulk = bulk && segs[i].frames && segs[i].out && ((reinterpret_cast<uintptr_t>(segs[i].frames) & 15) == 0);
+    const size_t smem = 16 + 2 * ((size_t)H * Wf + 16);
+    if (smem > 220 * 1024) bulk = false;
+    { const char* e = getenv("CURLA_GATHER_BULK"); if (e && e[0] == '0') bulk = false; }
+    if (!bulk) {
+        for (int i = 0; i < nseg; ++i)
+            if (launch_s2d<uint8_t>((const uint8_t*)segs[i].frames, C, Hf, Wf, idxs, segs[i].h1, segs[i].w1, B, H, W, CP,
+                                    out_sample_stride, (bf16*)segs[i].out, stream)) return -1;
+        if (rows) {
+            if (curla_gather_rows_f32(rows->actions, idxs, B, rows->action_dim, rows->out_actions, stream)) return -1;
+            if (curla_gather_rows_f32(rows->rewards, idxs, B, 1, rows->out_rewards, stream)) return -1;
+            if (curla_gather_rows_f32(rows->not_dones, idxs, B, 1, rows->out_not_dones, stream)) return -1;
+        }
+        return 0;
+    }
+    GatherSegs sg;
+    memset(&sg, 0, sizeof(sg));
+    for (int i = 0; i < nseg; ++i) {
+        sg.frames[i] = (const uint8_t*)segs[i].frames; sg.h1[i] = segs[i].h1; sg.w1[i] = segs[i].w1; sg.out[i] = (bf16*)segs[i].out;
+    }
+    if (rows) {
+        sg.actions = rows->actions; sg.rewards = rows->rewards; sg.not_dones = rows->not_dones;
+        sg.out_act = rows->out_actions; sg.out_rew = rows->out_rewards; sg.out_nd = rows->out_not_dones; sg.A = rows->action_dim;
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_gather_s2d_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CURLA_CHECK(e == cudaSuccess, "gather_s2d: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    }
+    const int real_planes = (4 * C + 7) / 8;        // planes beyond these are all zero: left untouched
+    launch_k(k_gather_s2d_u8, dim3(real_planes, B, nseg), dim3(256), smem, stream, sg, idxs, C, Hf, Wf, H, W, Hs, Ws,
+             out_sample_stride);
+    return check_launch("gather_s2d");
+}
+
 extern "C" int curla_gather_crop_s2d(const uint8_t* frames, int C, int Hf, int Wf,
                                      const int64_t* idxs, const int64_t* h1, const int64_t* w1,
                                      int B, int H, int W, int CP, long long out_sample_stride,
                                      void* out, cudaStream_t stream) {
-    return launch_s2d<uint8_t>(frames, C, Hf, Wf, idxs, h1, w1, B, H, W, CP, out_sample_stride,
-                               (bf16*)out, stream);
+    const curla_gather_seg seg = {frames, h1, w1, out};
+    return curla_gather_crop_s2d_multi(&seg, 1, idxs, C, Hf, Wf, B, H, W, CP, out_sample_stride, nullptr, stream);
 }
 
 extern "C" int curla_f32_to_s2d(const float* obs, int C, int H, int W, int B, int CP,

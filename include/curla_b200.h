@@ -54,6 +54,25 @@ int curla_replay_add(const uint8_t* obs_pinned, const uint8_t* next_pinned, long
                      const float* vec_pinned, float* vec_dev, int na, long long row, uint8_t* obses,
                      uint8_t* next_obses, float* actions, float* rewards, float* not_dones,
                      curla_stream_t stream);
+/* up to three streams (obs / pos / next_obs of one sampled index block: utils.py:151-158) of the
+ * same geometry in ONE launch, frames staged with cp.async.bulk; `rows` (optional) also gathers the
+ * batch's action / reward / not_done rows (utils.py:163-165).  Bitwise identical to nseg
+ * curla_gather_crop_s2d calls + three curla_gather_rows_f32 calls.                              */
+typedef struct curla_gather_seg {
+    const void* frames;              /* uint8 [capacity][C][Hf][Wf] */
+    const int64_t* h1;               /* crop offsets of this stream (NULL = 0) */
+    const int64_t* w1;
+    void* out;                       /* bf16 s2d planes */
+} curla_gather_seg;
+typedef struct curla_gather_rows {
+    const float* actions; const float* rewards; const float* not_dones;
+    float* out_actions; float* out_rewards; float* out_not_dones;
+    int action_dim;
+} curla_gather_rows;
+int curla_gather_crop_s2d_multi(const curla_gather_seg* segs, int nseg, const int64_t* idxs, int C,
+                                int Hf, int Wf, int B, int H, int W, int CP,
+                                long long out_sample_stride, const curla_gather_rows* rows,
+                                curla_stream_t stream);
 int curla_gather_rows_f32(const float* src, const int64_t* idxs, int B, int K, float* out,
                           curla_stream_t stream);
 

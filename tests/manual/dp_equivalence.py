@@ -56,8 +56,11 @@ def run():
     sums = {k: float(t[k].double().abs().sum()) for k in ('critic.encoder.convs.0.weight', 'critic.encoder.fc.weight_canon',
                                                            'critic.Q1.trunk.2.weight', 'actor.trunk.4.weight', 'CURL.W',
                                                            'target.encoder.convs.3.weight')}
+    import zlib
+    crc = zlib.crc32(agent.engine.arenas[0].cpu().numpy().tobytes())          # every fp32 master parameter, bit for bit
     if rank == 0:
-        print(json.dumps({'world': world, 'rows': log.rows, 'sums': sums, 'log_alpha': float(t['log_alpha'])}))
+        print(json.dumps({'world': world, 'rows': log.rows, 'sums': sums, 'log_alpha': float(t['log_alpha']), 'param_crc': crc,
+                          'overlap': os.environ.get('CURLA_COMM_OVERLAP', '1')}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -80,8 +83,19 @@ def compare(a, b):
     print('DP EQUIVALENCE OK (world %d vs %d)' % (A['world'], B['world']))
 
 
+def same(a, b):
+    """Two runs that must agree BIT FOR BIT (same world size: collectives + Adam on the communication
+    stream beside the backward, CURLA_COMM_OVERLAP=1, vs in line on the main stream, =0)."""
+    A, B = [json.loads([l for l in open(p) if l.startswith('{')][-1]) for p in (a, b)]
+    assert A['world'] == B['world'] and A['rows'] == B['rows'] and A['param_crc'] == B['param_crc'], (A['param_crc'], B['param_crc'])
+    print('BITWISE IDENTICAL (world %d, overlap %s vs %s): %d logged values, parameter crc %08x'
+          % (A['world'], A['overlap'], B['overlap'], len(A['rows']), A['param_crc']))
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == '--compare':
+    if len(sys.argv) > 1 and sys.argv[1] == '--same':
+        same(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) > 1 and sys.argv[1] == '--compare':
         compare(sys.argv[2], sys.argv[3])
     else:
         run()
