@@ -496,6 +496,329 @@ k_conv_tc(const __grid_constant__ TcSegs sg, long long in_sstride,    // weights
     }
 }
 
+// ---------------------------------------------------------------- N = 96: the three horizontal taps in ONE MMA
+// What bounds k_conv_tc on layers 2..4 is the A-operand stream: every tcgen05.mma re-reads its 128 x 32 B
+// activation tile from shared memory whatever N is, so nine N = 32 taps x two K steps move 90 KB of operands
+// per 128 positions (40 clk per MMA, 16 of them tensor work: profiles/r01c_microbench.txt).  Here the weights of
+// the three horizontal taps sit side by side in N,
+//     D[p][dx*32 + n] = sum_dy sum_k A[p + dy*pitch][k] . W(dy,dx)[n][k]          (6 MMAs of N = 96, 42 KB)
+// and the horizontal shift moves from the operand address into the epilogue:
+//     out[p][n] = D[p][n] + D[p+1][32 + n] + D[p+2][64 + n]      (dgrad: p-1, p-2 and transposed weights)
+// Positions are TMEM lanes, so the shift is a warp shuffle of the accumulator registers; the two lanes at a
+// warp's edge take their neighbours' rows from a 384-byte per-warp exchange slot in shared memory (one named
+// barrier per tile among the 8 warps of an epilogue group), and tiles overlap by two rows (254 outputs per
+// 256-row tile) so that no tile needs another tile's accumulators.
+// Pipeline roles are those of k_conv_tc; 2 accumulator stages x 2 sub-tiles x 96 columns = 384 TMEM columns, so
+// (issuer warp w, stage w, epilogue group w) form two independent lanes that alternate tiles.
+constexpr int kT96Out = 254;
+constexpr int kAcc96 = 2;
+constexpr uint32_t kIdesc96 = (1u << 4) | (1u << 7) | (1u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kXch = 96;                                     // floats per warp slot
+constexpr int kSmemHdr96 = 768 + 2 * kEpiAll * kXch * 4;     // header + exchange slots [tile parity][warp][96]
+constexpr uint32_t kW96Bytes = 3 * 4 * 96 * 16;              // one weight set: [dy][k chunk][96 n][8 k]
+
+template <bool DGRAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale, const bf16* __restrict__ relu_src,
+            long long out_sstride, TcGeom g) {
+    constexpr int CH = 4, KS = 2, TM = kTcSub * 128;
+    constexpr uint32_t TMEM_COLS = 512;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 192;
+    const uint32_t s_tptr = s_base + 576;
+    const uint32_t s_w = s_base + kSmemHdr96;
+    const uint32_t PS = (uint32_t)g.plane_bytes;
+    const uint32_t slab_bytes = CH * PS;
+    const uint32_t s_slab0 = s_w + (uint32_t)sg.nw * kW96Bytes;
+    const int stages = g.stages;
+    const long long plane = (long long)g.S * 8;
+    const int tile_shift = DGRAD ? -2 : 0;                   // position of a tile's row 0: t * 254 + tile_shift
+
+    if (tid == 0) {
+        for (int i = 0; i < kRing; ++i) reinterpret_cast<volatile uint32_t*>(smem + 512)[i] = 0xFFFFFFFFu;
+        for (int i = 0; i < 32; ++i) reinterpret_cast<volatile int*>(smem + 640)[i] = 1;
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(s_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < kAcc96; ++i) {
+            mbar_init(s_tfull + 8 * i, 1);
+            mbar_init(s_tempty + 8 * i, kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 576);
+    pdl_grid_sync();
+    constexpr int kStageThreads = kTcThreads - 32;
+    if (warp != kEpiAll + kMmaWarps) {
+        // weights: B[n = dx*32 + (co | ci)][k] per dy, K-major, [dy][k chunk][96 n][8 k]
+        for (int ws = 0; ws < sg.nw; ++ws) {
+            const bf16* __restrict__ wts = ws ? sg.wts[1] : sg.wts[0];            // global: [tap = dy*3 + dx][co][ci]
+            if (!DGRAD) {
+                for (int i = tid; i < 9 * 32 * CH; i += kStageThreads) {
+                    const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
+                    const int dy = t / 3, dx = t - dy * 3;
+                    cp_async16(s_w + ws * kW96Bytes + (uint32_t)((((dy * CH + kc) * 96) + dx * 32 + n) * 16), wts + ((t * 32 + n) * 32 + kc * 8), 16);
+                }
+                if (tid < 32) reinterpret_cast<float*>(smem + 256 + ws * 128)[tid] = (ws ? sg.bias[1] : sg.bias[0])[tid];
+            } else {
+                for (int i = tid; i < 9 * 32 * 32; i += kStageThreads) {
+                    const int t = i / 1024, rem = i - t * 1024, co = rem >> 5, ci = rem & 31;
+                    const int dy = t / 3, dx = t - dy * 3;
+                    reinterpret_cast<bf16*>(smem + kSmemHdr96 + ws * kW96Bytes)[(((dy * CH + (co >> 3)) * 96) + dx * 32 + ci) * 8 + (co & 7)] = wts[i];
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+    }
+
+    if (warp < kEpiAll) {
+        // ================= epilogue
+        const int egroup = warp / kEpiWarps, ew = warp % kEpiWarps;
+        const int sub = ew >> 2, quarter = ew & 3;
+        const int row_in_tile = sub * 128 + quarter * 32 + lane;
+        const bool row_out = DGRAD ? (row_in_tile >= 2) : (row_in_tile < kT96Out);      // rows this tile stores
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 96);
+        float* const xch = reinterpret_cast<float*>(smem + 768);
+        uint32_t acc_phase = 0;
+        const uint32_t acc = (uint32_t)egroup;
+        auto load_mask = [&](int tile_, uint4 (&dst)[4]) {          // dgrad launches have one segment
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+            const int b_ = tc_div(tile_, g.inv_tps);
+            const int p_ = (tile_ - b_ * g.tiles_per_sample) * kT96Out + tile_shift + row_in_tile;
+            if (p_ >= 0 && p_ < g.S && row_out) {
+                const int y_ = tc_div(p_, g.inv_pitch), x_ = p_ - y_ * g.pitch;
+                if (y_ < g.Hv && x_ < g.Wv) {
+                    const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(relu_src + o_ + c * plane);
+                }
+            }
+        };
+        int par = 0;
+        for (int j = egroup;; j += kEpiGroups, par ^= 1) {
+            uint32_t ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1)));
+            if (!ring_ready(ent, j)) {
+                const long long t0 = clock64();
+                while (!ring_ready(ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))), j))
+                    if (clock64() - t0 > (1ll << 31)) __trap();
+            }
+            const int tile = ring_tile(ent);
+            if (tile < 0) break;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            const int p = tl.t * kT96Out + tile_shift + row_in_tile;
+            const bool inside = p >= 0 && p < g.S && row_out;
+            int y = 0, x = 0;
+            if (inside) { y = tc_div(p, g.inv_pitch); x = p - y * g.pitch; }
+            const bool valid = inside && (y < g.Hv) && (x < g.Wv);
+            bf16* __restrict__ out = tc_pick(sg.out, tl.seg);
+            const long long o = (long long)tl.b * out_sstride + (long long)p * 8;   // + c*plane
+            const float* bias = reinterpret_cast<const float*>(smem + 256 + (DGRAD ? 0 : tc_pick(sg.wsel, tl.seg)) * 128);
+            // dgrad: the ReLU mask (X at the same position) is requested before the wait for the accumulator:
+            // its latency overlaps this tile's MMAs (the tile id is published a ring of slabs ahead)
+            uint4 xm[4];
+            if (DGRAD) load_mask(tile, xm);
+            float* const xw = xch + (size_t)(par * kEpiAll + warp) * kXch;
+            mbar_wait(s_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = taddr0 + acc * (kTcSub * 96);
+            float av[32];
+            uint32_t r[32];
+            // ---- D1 (dx = 1): row p +- 1
+            tmem_ld32(taddr + 32, r);
+            if (lane == (DGRAD ? 31 : 0)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float v = DGRAD ? __shfl_up_sync(0xffffffffu, __uint_as_float(r[i]), 1) : __shfl_down_sync(0xffffffffu, __uint_as_float(r[i]), 1);
+                av[i] = (lane == (DGRAD ? 0 : 31)) ? 0.f : v;
+            }
+            // ---- D2 (dx = 2): row p +- 2
+            tmem_ld32(taddr + 64, r);
+            if (lane == (DGRAD ? 31 : 0)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + 32 + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            }
+            if (lane == (DGRAD ? 30 : 1)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + 64 + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float v = DGRAD ? __shfl_up_sync(0xffffffffu, __uint_as_float(r[i]), 2) : __shfl_down_sync(0xffffffffu, __uint_as_float(r[i]), 2);
+                av[i] += (DGRAD ? lane < 2 : lane >= 30) ? 0.f : v;
+            }
+            // ---- D0
+            tmem_ld32(taddr, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) av[i] += __uint_as_float(r[i]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tempty + 8 * acc);      // accumulator stage drained by this warp
+            // ---- the warp's edge rows: neighbours' accumulators through the exchange slots
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + egroup), "n"(kEpiWarps * 32) : "memory");
+            if (!DGRAD) {
+                if (ew + 1 < kEpiWarps && lane >= 30) {
+                    const float* xo = xch + (size_t)(par * kEpiAll + warp + 1) * kXch;
+                    if (lane == 31) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) av[i] += xo[i] + xo[64 + i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) av[i] += xo[32 + i];
+                    }
+                }
+            } else {
+                if (ew > 0 && lane < 2) {
+                    const float* xo = xch + (size_t)(par * kEpiAll + warp - 1) * kXch;
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) av[i] += xo[i] + xo[64 + i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) av[i] += xo[32 + i];
+                    }
+                }
+            }
+            if (inside) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v0 = av[c * 8 + q * 2], v1 = av[c * 8 + q * 2 + 1];
+                        if (!DGRAD) {
+                            v0 = valid ? fmaxf(fmaf(v0, scale, bias[c * 8 + q * 2]), 0.f) : 0.f;
+                            v1 = valid ? fmaxf(fmaf(v1, scale, bias[c * 8 + q * 2 + 1]), 0.f) : 0.f;
+                        } else {
+                            const uint32_t m = q == 0 ? xm[c].x : (q == 1 ? xm[c].y : (q == 2 ? xm[c].z : xm[c].w));
+                            const float2 xv = unpack_bf16x2(m);
+                            v0 = xv.x > 0.f ? v0 : 0.f;
+                            v1 = xv.y > 0.f ? v1 : 0.f;
+                        }
+                        w[q] = pack_bf16x2(v0, v1);
+                    }
+                    *reinterpret_cast<uint4*>(out + o + c * plane) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            acc_phase ^= 1;
+        }
+    } else if (warp < kEpiAll + kMmaWarps) {
+        // ================= MMA issuers: warp mw takes the CTA's local tiles mw, mw + 2, ... into accumulator stage mw
+        const int mw = warp - kEpiAll;
+        uint32_t stage = (uint32_t)mw, phase = 0, acc_phase = 0;
+        const uint32_t acc = (uint32_t)mw;
+        const uint64_t a_hi = make_desc(0, PS, 128), b_hi = make_desc(0, 96 * 16, 128);
+        uint32_t a_off[3 * KS];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                a_off[dy * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)((DGRAD ? 2 - dy : dy) * g.pitch) * 16u) >> 4;
+        const int valid_pos = g.Hv * g.pitch;
+        for (int j = mw;; j += kMmaWarps) {
+            mbar_wait(s_full + 8 * stage, phase);
+            const int tile = ring_tile((uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))));
+            if (tile < 0) break;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            // the second sub-tile holds no valid position when it starts at or beyond the last valid row
+            const int nsub = (tl.t * kT96Out + tile_shift + 128 >= valid_pos) ? 1 : kTcSub;
+            const uint32_t w16 = (s_w + (uint32_t)tc_pick(sg.wsel, tl.seg) * kW96Bytes) >> 4;
+            const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
+            mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int s2 = 0; s2 < kTcSub; ++s2) {
+                    if (s2 >= nsub) break;
+                    const uint32_t d = tmem_base + acc * (kTcSub * 96) + (uint32_t)(s2 * 96);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint64_t ad = a_hi | (uint64_t)((slab16 + (uint32_t)(s2 * 128) + a_off[dy * KS + ks]) & 0x3FFFu);
+                            const uint64_t bd = b_hi | (uint64_t)((w16 + (uint32_t)((dy * CH + 2 * ks) * 96)) & 0x3FFFu);
+                            umma_bf16_rt(d, ad, bd, kIdesc96, (dy | ks) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(s_empty + 8 * stage);
+                umma_commit(s_tfull + 8 * acc);
+            }
+            __syncwarp();
+            stage += (uint32_t)kMmaWarps;
+            if (stage >= (uint32_t)stages) { stage -= (uint32_t)stages; phase ^= 1; }
+            acc_phase ^= 1;
+        }
+    } else {
+        const int one = ld_volatile_s32(smem + 640 + 4 * lane);
+        if (lane == 0) {
+            // ================= producer: identical to k_conv_tc's, tiles 254 positions apart
+            uint32_t stage = 0, phase = 0;
+            const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
+            int* const ctr = g_tc_ctr + 2 * g.ctr_slot;
+            const int G = (int)gridDim.x;
+            int q[4];
+            q[0] = (int)blockIdx.x - 2 * G; q[1] = q[0] + G;
+            q[2] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[1] + G;
+            q[3] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[2] + G;
+            int sentinels = 0, j = 0;
+            while (sentinels < 2) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (sentinels >= 2) break;
+                    const int tile = q[u] + 2 * G;
+                    const bool real = tile < g.total_tiles;
+                    mbar_wait(s_empty + 8 * stage, phase ^ 1);
+                    *reinterpret_cast<volatile uint32_t*>(smem + 512 + 4 * (j & (kRing - 1))) = ring_entry(j, real ? tile : -1);
+                    const uint32_t bar = s_full + 8 * stage;
+                    if (!real) {
+                        mbar_arrive(bar);
+                    } else {
+                        const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+                        const int p0 = tl.t * kT96Out + tile_shift;
+                        const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
+                        const uint32_t dst = s_slab0 + stage * slab_bytes;
+                        mbar_expect_tx(bar, bytes * CH);
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
+                    }
+                    ++j;
+                    if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+                    if (!real) ++sentinels;
+                    else q[u] = g.dynamic ? atom_add_nonuniform(ctr, one) : tile + 2 * G;
+                }
+            }
+            if (g.dynamic) {
+                __threadfence();
+                if (atomicAdd(ctr + 1, 1) == G - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 static TcGeom make_tc_geom(int B, int pitch, int S, int Hv, int Wv, int span, int min_off) {
     TcGeom g;
     g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv;
@@ -574,6 +897,50 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     return 0;
 }
 
+// N = 96 variant: layers 2..4 forward and dgrad.  CURLA_CONV_N96=0 keeps the N = 32 kernel (A/B switch).
+static bool use_n96(int pitch, int Wv, bool dgrad) {
+    const char* e = getenv("CURLA_CONV_N96");
+    if (e && e[0] == '0') return false;
+    // forward: outputs whose horizontal taps would wrap into the next image row must be invalid columns
+    return dgrad || Wv <= pitch - 2;
+}
+
+template <bool DGRAD>
+static int launch_tc96(const TcSegs& sg, long long in_sstride, float scale, const void* relu_src, long long out_sstride,
+                       TcGeom g, cudaStream_t stream) {
+    const size_t fixed = kSmemHdr96 + (size_t)sg.nw * kW96Bytes;
+    g.debug = 0;
+    g.plane_bytes = g.plane_rows * 16;
+    const size_t slab = (size_t)4 * g.plane_bytes;
+    size_t budget = 200 * 1024;
+    { const char* e = getenv("CURLA_TC_SMEM_KB"); if (e && atoi(e) >= 64 && atoi(e) <= 225) budget = (size_t)atoi(e) * 1024; }
+    int stages = (int)((budget - fixed) / slab);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) { set_last_error("conv_tc96: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
+    stages &= ~1;                                   // even ring depth: see launch_tc
+    g.stages = stages;
+    const size_t smem = fixed + stages * slab;
+    auto kern = k_conv_tc96<DGRAD>;
+    if (tc_set_smem(kern, smem)) return -1;
+    const int cap = sm_count();
+    const int grid = g.total_tiles < cap ? g.total_tiles : cap;
+    {
+        const char* e = getenv("CURLA_TC_STATIC");
+        g.dynamic = (g.total_tiles > 2 * grid && !(e && e[0] == '1')) ? 1 : 0;
+        g.ctr_slot = g.dynamic ? next_ctr_slot(stream) : 0;
+    }
+    launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, sg, in_sstride, scale, (const bf16*)relu_src, out_sstride, g);
+    return 0;
+}
+
+static TcGeom make_tc96_geom(int pitch, int S, int Hv, int Wv, bool dgrad) {
+    TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch, dgrad ? -2 * pitch : 0);
+    g.tiles_per_sample = cdiv((long long)Hv * pitch, kT96Out);
+    g.total_tiles = g.tiles_per_sample;
+    g.inv_tps = 1.0f / (float)g.tiles_per_sample;
+    return g;
+}
+
 // fills the segment table; total tiles -> g.total_tiles
 static int make_segs(const curla_conv_seg* segs, int nseg, TcGeom& g, TcSegs& sg) {
     CURLA_CHECK(nseg >= 1 && nseg <= 3, "conv: 1..3 segments per launch (got %d)", nseg);
@@ -633,6 +1000,10 @@ extern "C" int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long l
         }
         if (make_segs(segs, nseg, g, sg)) return -1;
         if (launch_tc<48, 4, false>(sg, in_sstride, scale, nullptr, out_sstride, g, taps, stream)) return -1;
+    } else if (use_n96(pitch, Wv, false)) {
+        TcGeom g = make_tc96_geom(pitch, S, Hv, Wv, false);
+        if (make_segs(segs, nseg, g, sg)) return -1;
+        if (launch_tc96<false>(sg, in_sstride, scale, nullptr, out_sstride, g, stream)) return -1;
     } else {
         for (int t = 0; t < 9; ++t) taps.off[t] = (t / 3) * pitch + (t % 3);
         TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch + 2, 0);
@@ -656,9 +1027,15 @@ extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void
                                 int S, int Hv, int Wv, cudaStream_t stream) {
     TcTaps taps;
     TcSegs sg;
+    const curla_conv_seg seg = {dy, wts, nullptr, dx, B};
+    if (use_n96(pitch, Wv, true)) {
+        TcGeom g = make_tc96_geom(pitch, S, Hv, Wv, true);
+        if (make_segs(&seg, 1, g, sg)) return -1;
+        if (launch_tc96<true>(sg, dy_sstride, 1.f, x, dx_sstride, g, stream)) return -1;
+        return check_launch("conv_dgrad");
+    }
     for (int t = 0; t < 9; ++t) taps.off[t] = -((t / 3) * pitch + (t % 3));
     TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch + 2, -(2 * pitch + 2));
-    const curla_conv_seg seg = {dy, wts, nullptr, dx, B};
     if (make_segs(&seg, 1, g, sg)) return -1;
     if (launch_tc<32, 9, true>(sg, dy_sstride, 1.f, x, dx_sstride, g, taps, stream)) return -1;
     return check_launch("conv_dgrad");

@@ -5,6 +5,7 @@ operands and fp32 accumulation: compared against fp32 torch references evaluated
 SAME bf16-rounded operands (tolerance 2e-3 relative L2: accumulation-order noise only),
 and against the un-rounded fp32 reference at 2e-2 (bf16 operand rounding)."""
 import ctypes as C
+import ctypes as C_
 
 import numpy as np
 import pytest
@@ -56,6 +57,51 @@ def test_gather_crop_bit_exact(B, crop):
     assert torch.equal(view2, view)
 
 
+@pytest.mark.parametrize('bulk', ['1', '0'])
+@pytest.mark.parametrize('hw,out_hw,C', [((90, 160), (76, 135), 9), ((90, 160), (90, 160), 9), ((48, 64), (41, 33), 3),
+                                         ((90, 160), (75, 134), 12)])
+def test_gather_multi_stream_bit_exact(hw, out_hw, C, bulk, monkeypatch):
+    """obs / pos / next_obs windows + the batch's action / reward / not_done rows in ONE launch (frames staged
+    with cp.async.bulk, magic-number uint8 -> bf16) == the oracle's gather + crop, bit for bit; odd sizes
+    (odd H and W, a lone last channel, right-edge groups) included.  bulk = '0': the per-stream fallback."""
+    monkeypatch.setenv('CURLA_GATHER_BULK', bulk)
+    rs = np.random.RandomState(3)
+    cap, B = 13, 7
+    Hf, Wf = hw
+    oh, ow = out_hw
+    f_obs = rs.randint(0, 256, size=(cap, C, Hf, Wf), dtype=np.uint8)
+    f_next = rs.randint(0, 256, size=(cap, C, Hf, Wf), dtype=np.uint8)
+    acts = rs.uniform(-1, 1, size=(cap, 2)).astype(np.float32)
+    rews = rs.standard_normal((cap, 1)).astype(np.float32)
+    nds = (rs.uniform(size=(cap, 1)) > 0.3).astype(np.float32)
+    idxs = rs.randint(0, cap, size=B)
+    offs = [(rs.randint(0, Hf - oh + 1, size=B), rs.randint(0, Wf - ow + 1, size=B)) for _ in range(3)]
+    d_obs, d_next, d_idx = dv(f_obs), dv(f_next), dv(idxs)
+    d_offs = [(dv(h), dv(w)) for h, w in offs]
+    g = Geom(oh, ow, B, C)
+    bufs = [g.alloc(g.CP1) for _ in range(3)]
+    segs = (_lib.GatherSeg * 3)()
+    for k, src in enumerate((d_obs, d_obs, d_next)):
+        segs[k].frames = src.data_ptr(); segs[k].h1 = d_offs[k][0].data_ptr(); segs[k].w1 = d_offs[k][1].data_ptr()
+        segs[k].out = bufs[k][1].data_ptr()
+    rows = _lib.GatherRows()
+    d_a, d_r, d_n = dv(acts), dv(rews), dv(nds)
+    o_a = torch.zeros((B, 2), device=DEV); o_r = torch.zeros(B, device=DEV); o_n = torch.zeros(B, device=DEV)
+    rows.actions, rows.rewards, rows.not_dones = d_a.data_ptr(), d_r.data_ptr(), d_n.data_ptr()
+    rows.out_actions, rows.out_rewards, rows.out_not_dones, rows.action_dim = o_a.data_ptr(), o_r.data_ptr(), o_n.data_ptr(), 2
+    _lib.call('curla_gather_crop_s2d_multi', C_.byref(segs), 3, _lib.ptr(d_idx), C, Hf, Wf, B, oh, ow, g.CP1, g.S * g.CP1,
+              C_.byref(rows), stream())
+    torch.cuda.synchronize()
+    for k, frames in enumerate((f_obs, f_obs, f_next)):
+        ref = O.gather_crop(frames, idxs, offs[k][0], offs[k][1], (oh, ow))
+        want = g.s2d_ref(torch.from_numpy(ref).to(DEV))
+        assert torch.equal(g.nhwc(bufs[k][1]).float(), want), k
+        full = bufs[k][0]
+        assert float(full[:g.PAD].abs().sum()) == 0 and float(full[g.PAD + B * g.S:].abs().sum()) == 0
+    assert np.array_equal(o_a.cpu().numpy(), acts[idxs]) and np.array_equal(o_r.cpu().numpy(), rews[idxs, 0])
+    assert np.array_equal(o_n.cpu().numpy(), nds[idxs, 0])
+
+
 def test_gather_rows():
     rs = np.random.RandomState(1)
     src = rs.standard_normal((17, 2)).astype(np.float32)
@@ -98,8 +144,12 @@ def _run_conv_stack(g, x, ws, bs):
     return s2d, acts, keep
 
 
+@pytest.mark.parametrize('n96', ['1', '0'])
 @pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (64, 64, 5)])
-def test_conv_forward(H, W, B):
+def test_conv_forward(H, W, B, n96, monkeypatch):
+    """n96 = '1': layers 2..4 run the N = 96 kernel (three horizontal taps per MMA, shuffle epilogue);
+    '0': the N = 32 kernel (one tap per MMA).  Same tolerances for both."""
+    monkeypatch.setenv('CURLA_CONV_N96', n96)
     g, x, ws, bs = _conv_case(H, W, B)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     # reference on bf16-rounded operands, layer by layer (our activations are stored bf16)
@@ -169,7 +219,8 @@ def test_conv_forward_multi_segment(H, W):
                   1.0 / 255.0 if l == 0 else 1.0, g0.S * 32, g0.pitch, g0.S, g0.Ho[l], g0.Wo[l], 36 if l == 0 else 0,
                   stream())                                        # 36 real s2d channels: the all-zero plane is not read
         torch.cuda.synchronize()
-        n = min(g0.S, -(-g0.Ho[l] * g0.pitch // 256) * 256)        # positions a launch writes per sample and plane
+        tile_out = 254 if (l > 0 and g0.Wo[l] <= g0.pitch - 2) else 256   # N = 96 kernel: tiles overlap by two rows
+        n = min(g0.S, -(-g0.Ho[l] * g0.pitch // tile_out) * tile_out)   # positions a launch writes per sample and plane
         for k in range(3):
             a = outs[k].view(torch.int16).view(Bs[k], 4, g0.S, 8)
             b = singles[k][l].view(torch.int16).view(Bs[k], 4, g0.S, 8)
@@ -186,8 +237,10 @@ def test_conv_forward_multi_segment(H, W):
                   g0.Wo[0], 1, stream())
 
 
-@pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2)])
-def test_conv_backward(H, W, B):
+@pytest.mark.parametrize('n96', ['1', '0'])
+@pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (76, 135, 40)])
+def test_conv_backward(H, W, B, n96, monkeypatch):
+    monkeypatch.setenv('CURLA_CONV_N96', n96)
     g, x, ws, bs = _conv_case(H, W, B, seed=1)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(2)
