@@ -510,8 +510,11 @@ def main():
         'conv_wgrad': dict(kernel='k_conv_wgrad (conv wgrad, 4 layers)', launches=4,
                            bytes=s2d_bytes + act(0) + sum(act(l - 1) + act(l) for l in (1, 2, 3)),
                            flops=sum(conv_flops(l) for l in range(4))),
-        'gather_s2d': dict(kernel='k_gather_s2d (replay gather + crop + u8->bf16 s2d)', launches=1,
-                           bytes=Bb * 9 * H_ * W_ + s2d_bytes, flops=0.0),
+        # ONE launch gathers every stream of the update (obs, next_obs, and for the random crop an independent pos
+        # window: utils.py:151-158): algorithmic bytes = streams x (uint8 window read + bf16 s2d planes written)
+        'gather_s2d': dict(kernel='k_gather_s2d_u8 (replay gather + crop + u8->bf16 s2d, cp.async.bulk staged, all streams in one launch)',
+                           launches=1, bytes=(3 if (wl['aug'] == 'random_crop' and not wl['pixel_sac']) else 2) * (Bb * 9 * H_ * W_ + s2d_bytes),
+                           flops=0.0),
         'gemm_fc_fwd': dict(kernel='k_gemm_tc (tcgen05 + TMA, encoder fc forward, split-K)', launches=1,
                             bytes=Bb * kfc * 2 + 64 * kfc * 2, flops=2.0 * Bb * 64 * kfc),
         'gemm_fc_dgrad': dict(kernel='k_gemm_tc_nloop (tcgen05 + TMA, encoder fc dgrad + ReLU mask)', launches=1,

@@ -96,6 +96,8 @@ SIGNATURES = {
                               c_vp, c_vp, c_vp, c_vp]),
     'curla_policy_fwd_rows': (_i, [c_vp, c_vp, C.c_ulonglong, C.c_ulonglong, _i, _i, _i, _f, _f, _i, _i, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp]),
+    'curla_policy_fwd_rows_dyn': (_i, [c_vp, c_vp, C.c_ulonglong, C.c_ulonglong, c_vp, _i, _i, _i, _f, _f, _i, _i, c_vp, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp]),
     'curla_policy_bwd': (_i, [c_vp, c_vp, _i, c_vp, c_vp, c_vp, c_vp, c_vp, _i, _i, _f, _f, c_vp, c_vp]),
     'curla_critic_loss': (_i, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, _f, c_vp, c_vp, _i, _f, c_vp, c_vp, c_vp,
                                c_vp, c_vp]),

@@ -14,6 +14,7 @@
 #include "../../include/curla_b200.h"
 
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges are no-ops unless a profiler is attached
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -166,6 +167,12 @@ struct curla_agent {
 };
 
 namespace {
+
+// NVTX range per phase of the update (nsys / ncu --nvtx show "curla/critic" ... around its launches)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------- layout helpers
 struct Builder {
@@ -851,6 +858,8 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         if (f32) r.chk(curla_f32_to_s2d(f32, c.C, c.H, c.W, B, a->CP1, a->s2d_sstride, dst, st));
         else r.chk(curla_gather_crop_s2d(frames, c.C, c.Hf, c.Wf, u->idxs, h1, w1, B, c.H, c.W, a->CP1, a->s2d_sstride, dst, st));
     };
+    NvtxRange nv_update("curla/update");
+    nvtxRangePushA("curla/sample");
     const bool do_sample = (ph & CURLA_PHASE_SAMPLE) != 0;
     const bool want_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
     const bf16* s2d_pos = u->pos_is_obs ? a->s2d_obs : a->s2d_pos;
@@ -877,8 +886,10 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         }
     }
 
+    nvtxRangePop();
     bool have_p5 = false;
     if (do_critic) {
+        NvtxRange nv("curla/critic");
         // ---------------- update_critic (curl_sac.py:349-371)
         // The tail of each pass (fc split-K GEMM, LayerNorm, MLP heads: latency-bound kernels that
         // fill a fraction of the GPU) runs on the side stream while the main stream already runs
@@ -972,7 +983,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     // and writes the target only, neither of which the actor step touches, so running it first
     // is the same computation -- and lets the post-EMA key pass F7 share conv launches with F4.
     const bool ema_first = mm != 0;
-    if (do_sac && do_ema && ema_first) ema();
+    if (do_sac && do_ema && ema_first) { NvtxRange nv("curla/ema"); ema(); }
     const cudaStream_t ss7 = do_cpc ? side_stream(a, st) : st;
     const bool forked7 = ss7 != st;
     const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA};    // F4 == F5 == F6 conv part
@@ -1002,6 +1013,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     };
     if (do_sac) {
         if (do_actor) {
+            NvtxRange nv("curla/actor_alpha");
             // ---------------- update_actor_and_alpha (curl_sac.py:373-404)
             // F4: conv_theta'(obs) shared by actor(obs), critic(obs, pi) and the CURL anchor
             if (mm && do_cpc) {
@@ -1048,6 +1060,7 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     }
 
     if (do_cpc) {
+        NvtxRange nv("curla/cpc");
         // ---------------- update_cpc (curl_sac.py:406-423)
         if (!have_p5) {
             // F6: anchor through the current critic encoder (its tail on the side stream);

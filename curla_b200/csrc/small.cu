@@ -288,10 +288,12 @@ __global__ void k_policy_fwd(const float* __restrict__ t, const float* __restric
                              float ls_min, float ls_max, int compute_pi, int compute_log_pi,
                              float* __restrict__ mu_out, float* __restrict__ pi_out,
                              float* __restrict__ log_pi_out, float* __restrict__ ls_out,
-                             float* __restrict__ noise_out, int row0) {
+                             float* __restrict__ noise_out, int row0,
+                             const unsigned long long* __restrict__ offset_dev) {
     pdl_grid_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (offset_dev) offset += *offset_dev;          // replayed CUDA graph: the per-update counter lives in device memory
     float n[4] = {0.f, 0.f, 0.f, 0.f};
     if (compute_pi) {
         if (noise_in) {
@@ -538,10 +540,21 @@ extern "C" int curla_policy_fwd_rows(const float* t, const float* noise_in, unsi
                                      float ls_max, int compute_pi, int compute_log_pi, float* mu,
                                      float* pi, float* log_pi, float* ls, float* noise_out,
                                      cudaStream_t stream) {
+    return curla_policy_fwd_rows_dyn(t, noise_in, seed, offset, nullptr, row0, B, A, ls_min, ls_max, compute_pi, compute_log_pi,
+                                     mu, pi, log_pi, ls, noise_out, stream);
+}
+
+// Same with the Philox offset = offset + *offset_dev (offset_dev: device pointer or NULL): lets a captured
+// CUDA graph of the update draw fresh policy noise on every replay.
+extern "C" int curla_policy_fwd_rows_dyn(const float* t, const float* noise_in, unsigned long long seed,
+                                         unsigned long long offset, const unsigned long long* offset_dev, int row0,
+                                         int B, int A, float ls_min, float ls_max, int compute_pi,
+                                         int compute_log_pi, float* mu, float* pi, float* log_pi, float* ls,
+                                         float* noise_out, cudaStream_t stream) {
     CURLA_CHECK(A <= 4, "policy_fwd: action dim > 4 unsupported");
     launch_k(k_policy_fwd, dim3(cdiv(B, 128)), dim3(128), 0, stream, t, noise_in, seed, offset, B, A, ls_min, ls_max,
                                                    compute_pi, compute_log_pi, mu, pi, log_pi, ls,
-                                                   noise_out, row0);
+                                                   noise_out, row0, offset_dev);
     return check_launch("policy_fwd");
 }
 

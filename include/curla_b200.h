@@ -203,6 +203,13 @@ int curla_policy_fwd_rows(const float* t, const float* noise_in, unsigned long l
                           unsigned long long offset, int row0, int B, int A, float ls_min,
                           float ls_max, int compute_pi, int compute_log_pi, float* mu, float* pi,
                           float* log_pi, float* ls, float* noise_out, curla_stream_t stream);
+/* Philox offset = offset + *offset_dev (device pointer, may be NULL): the update's captured CUDA graph
+ * keeps its per-update counter in device memory */
+int curla_policy_fwd_rows_dyn(const float* t, const float* noise_in, unsigned long long seed,
+                              unsigned long long offset, const unsigned long long* offset_dev,
+                              int row0, int B, int A, float ls_min, float ls_max, int compute_pi,
+                              int compute_log_pi, float* mu, float* pi, float* log_pi, float* ls,
+                              float* noise_out, curla_stream_t stream);
 int curla_policy_bwd(const float* dx1, const float* dx2, int feat, const float* glogpi,
                      const float* t, const float* noise, const float* pi, const float* ls, int B,
                      int A, float ls_min, float ls_max, float* dt, curla_stream_t stream);
