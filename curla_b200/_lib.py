@@ -107,6 +107,7 @@ SIGNATURES = {
     'curla_curl_workspace_floats': (c_ll, [_i, _i]),
     'curla_curl_fwd_bwd': (_i, [c_vp, c_vp, c_vp, _i, _i, _i, _i, _f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'curla_adam_f32': (_i, [c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, _d, _d, _d, _d, _i, c_vp, c_vp]),
+    'curla_set_dev_state': (_i, [c_vp, _i, _i, _i, _i, C.c_ulonglong, c_vp]),
     'curla_adam_f64_scalar': (_i, [c_vp, c_vp, c_vp, _d, _d, _d, _d, _i, c_vp, c_vp]),
     'curla_ema_f32': (_i, [c_vp, c_vp, c_ll, c_ll, _d, _d, c_vp]),
     'curla_pack_shadows': (_i, [c_vp, c_vp, c_vp, _i, c_vp]),

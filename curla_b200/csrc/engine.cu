@@ -162,6 +162,12 @@ struct curla_agent {
     // optimizer step counters (host)
     int t_critic, t_actor, t_alpha, t_cpc;
     long long last_launches;
+    // whole-update CUDA graphs: one per update variant (step parity, only_cpc, argument pointers); the per-update
+    // scalars a replay needs (Adam step counters, Philox offset) live in dev_state (see curla_set_dev_state)
+    int* dev_state;
+    struct GraphEntry { cudaGraphExec_t exec; long long launches; int seen; };
+    std::map<std::string, GraphEntry> graphs;
+    int graph_mode;                          // -1 = not decided yet, 0 = off (CURLA_GRAPH=0), 1 = on
     // NCCL (dlopen'ed)
     void* nccl_lib; void* comm;
 };
@@ -425,6 +431,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->log_alpha = b.w<double>("log_alpha", DT_F64, {1});
     a->g_log_alpha = b.w<double>("grad.log_alpha", DT_F64, {1});
     a->alpha_state = b.w<double>("adam.log_alpha", DT_F64, {2});
+    a->dev_state = b.w<int>("dev_state", DT_I32, {8});
     a->arena_bytes[CURLA_ARENA_WORK] = (b.cur[4] + 255) / 256 * 256;
     {   // the batched Q1 || Q2 launches rely on one constant stride per arena between the two heads
         bool okp = true;
@@ -440,6 +447,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->bound = false;
     a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
     a->last_launches = 0;
+    a->graph_mode = -1;
     a->nccl_lib = nullptr; a->comm = nullptr;
     a->side = nullptr; a->side_state = 0;
     a->comm_st = nullptr; a->comm_state = 0;
@@ -449,6 +457,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
 static void destroy_comm(curla_agent* a);
 extern "C" void curla_agent_destroy(curla_agent* a) {
     if (!a) return;
+    for (auto& kv : a->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (a->side_state == 1) {
         for (auto& e : a->ev) cudaEventDestroy(e);
         cudaStreamDestroy(a->side);
@@ -495,7 +504,7 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
     rb(a->target_q); rb(a->dq[0]); rb(a->dq[1]); rb(a->dt4); rb(a->dH2); rb(a->dH1);
     rb(a->dX[0]); rb(a->dX[1]); rb(a->dXa); rb(a->dz_curl); rb(a->dfc_f32); rb(a->dfc_bf16);
     rb(a->z_pos_all); rb(a->act_b); rb(a->rew_b); rb(a->nd_b); rb(a->metrics); rb(a->glogpi);
-    rb(a->log_alpha); rb(a->g_log_alpha); rb(a->alpha_state);
+    rb(a->log_alpha); rb(a->g_log_alpha); rb(a->alpha_state); rb(a->dev_state);
     a->bound = true;
     return 0;
 }
@@ -823,9 +832,16 @@ static cudaStream_t comm_stream(curla_agent* a, cudaStream_t st) {
 }
 
 // ================================================================== the update
-extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
-    CURLA_CHECK(a->bound, "agent not bound");
+// The launch sequence of one update.  dev != nullptr (graph capture): the Adam step counters and the Philox offset
+// are read from a->dev_state by the kernels instead of being baked into their parameters.
+static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t st, const int* dev) {
     const auto& c = a->cfg;
+    const int* const td_critic = dev ? dev + 0 : nullptr;
+    const int* const td_actor = dev ? dev + 1 : nullptr;
+    const int* const td_alpha = dev ? dev + 2 : nullptr;
+    const int* const td_cpc = dev ? dev + 3 : nullptr;
+    const unsigned long long* const off_dev = dev ? reinterpret_cast<const unsigned long long*>(dev + 4) : nullptr;
+    const unsigned long long off_next = dev ? 0ull : u->offset * 2, off_cur = dev ? 1ull : u->offset * 2 + 1;
     const int B = c.batch, A = c.action_dim, feat = c.feature_dim;
     const float gs = 1.0f / (float)c.global_batch;
     const long long launches0 = g_launches;
@@ -836,14 +852,14 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     bool actor_pending = false;
     // [split, n) of a bucket on the communication stream: all-reduce, then Adam on the reduced slice
     auto reduce_step = [&](int ev_fork, float* pbase, float* gbase, float* m, float* v, long long from, long long to,
-                           long long double_from, double lr, double beta, int t) {
+                           long long double_from, double lr, double beta, int t, const int* t_dev) {
         if (!r.ok()) return;
         cudaEventRecord(a->cev[ev_fork], st);
         cudaStreamWaitEvent(cs, a->cev[ev_fork], 0);
         r.chk(all_reduce(a, gbase + from, (size_t)(to - from), NCCL_F32, cs));
         const long long df = double_from > from ? double_from - from : 0;
         if (r.ok()) r.chk(curla_adam_f32(pbase + from, gbase + from, m + from, v + from, to - from, df, lr, beta, 0.999, 1e-8, t,
-                                         nullptr, cs));
+                                         t_dev, cs));
     };
     const int ph = u->phases ? u->phases : CURLA_PHASE_ALL;
     const bool do_sac = !u->only_cpc;
@@ -907,8 +923,9 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         auto tail1 = [&]() {
             r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
             r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
-            if (r2.ok()) r2.chk(curla_policy_fwd_rows(a->t_out1, u->noise_next, u->seed, u->offset * 2, c.rank * B, B, A, (float)c.log_std_min,
-                                                 (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next, a->logpi_next, a->ls1, nullptr, ss));
+            if (r2.ok()) r2.chk(curla_policy_fwd_rows_dyn(a->t_out1, u->noise_next, u->seed, off_next, off_dev, c.rank * B, B, A,
+                                                     (float)c.log_std_min, (float)c.log_std_max, 1, 1, a->mu_scratch, a->a_next,
+                                                     a->logpi_next, a->ls1, nullptr, ss));
         };
         auto tail2 = [&]() {
             r2.tail(act2[3], a->s_target.fc, a->enc_target, a->t_p2, B, 0, a->a_next, a->m_p2q[0].X, a->fc_partial2);
@@ -956,19 +973,19 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         const long long split1 = a->enc_critic.fc_w - a->off_critic;
         auto early1 = [&]() {
             if (overlap) reduce_step(0, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, split1, a->n_critic, a->n_critic,
-                                     c.critic_lr, c.critic_beta, tc_);
+                                     c.critic_lr, c.critic_beta, tc_, td_critic);
         };
         r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
                   a->off_critic, !c.detach_encoder, early1);
         if (overlap) {
             reduce_step(1, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, 0, split1, a->n_critic,
-                        c.critic_lr, c.critic_beta, tc_);
+                        c.critic_lr, c.critic_beta, tc_, td_critic);
             cudaEventRecord(a->cev[2], cs);
             cudaStreamWaitEvent(st, a->cev[2], 0);
         } else {
             if (r.ok()) r.chk(all_reduce(a, gC, (size_t)a->n_critic, NCCL_F32, st));
             if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, a->n_critic, a->n_critic,
-                                             c.critic_lr, c.critic_beta, 0.999, 1e-8, tc_, nullptr, st));
+                                             c.critic_lr, c.critic_beta, 0.999, 1e-8, tc_, td_critic, st));
         }
         r.pack(a->pack_critic);
     }
@@ -1026,8 +1043,9 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             }
             r.tail(a->actA[3], a->s_actor_fc, a->enc_actor, a->t_p4, B, 0, nullptr, a->m_p4.X);
             r.mlp_fwd_n(a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, B);
-            if (r.ok()) r.chk(curla_policy_fwd_rows(a->t_out4, u->noise_cur, u->seed, u->offset * 2 + 1, c.rank * B, B, A, (float)c.log_std_min,
-                                               (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4, a->ls4, a->noise4, st));
+            if (r.ok()) r.chk(curla_policy_fwd_rows_dyn(a->t_out4, u->noise_cur, u->seed, off_cur, off_dev, c.rank * B, B, A,
+                                                   (float)c.log_std_min, (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4,
+                                                   a->ls4, a->noise4, st));
             r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
             have_p5 = true;
             r.mlp_fwd_n(a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, B);
@@ -1050,10 +1068,10 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             if (ra.ok()) ra.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, as));
             if (ra.ok()) ra.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, as));
             if (ra.ok()) ra.chk(curla_adam_f32(a->P + a->off_actor, gA, a->Ad + a->a_m2, a->Ad + a->a_v2, a->n_actor, a->n_actor,
-                                               c.actor_lr, c.actor_beta, 0.999, 1e-8, ++a->t_actor, nullptr, as));
+                                               c.actor_lr, c.actor_beta, 0.999, 1e-8, ++a->t_actor, td_actor, as));
             ra.pack(a->pack_actor);
             if (ra.ok()) ra.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
-                                                      1e-8, ++a->t_alpha, nullptr, as));
+                                                      1e-8, ++a->t_alpha, td_alpha, as));
             r.chk(ra.rc);
         }
         if (do_ema && !ema_first) ema();
@@ -1090,19 +1108,19 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
         const long long split3 = a->n_W + (a->enc_critic.fc_w - a->off_critic);
         auto early3 = [&]() {
             if (overlap) reduce_step(4, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, split3, a->n_cpc, a->n_W,
-                                     c.encoder_lr, 0.9, tk_);
+                                     c.encoder_lr, 0.9, tk_, td_cpc);
         };
         r.enc_bwd(a->dz_curl, nullptr, a->t_p5, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs,
                   gK + a->n_W, a->off_critic, true, early3);
         if (overlap) {
-            reduce_step(5, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, 0, split3, a->n_W, c.encoder_lr, 0.9, tk_);
+            reduce_step(5, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, 0, split3, a->n_W, c.encoder_lr, 0.9, tk_, td_cpc);
             cudaEventRecord(a->cev[2], cs);
             cudaStreamWaitEvent(st, a->cev[2], 0);
             actor_pending = false;                 // cs is in order: the actor chain issued before is complete as well
         } else {
             if (r.ok()) r.chk(all_reduce(a, gK, (size_t)a->n_cpc, NCCL_F32, st));
             if (r.ok()) r.chk(curla_adam_f32(a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, a->n_cpc, a->n_W, c.encoder_lr, 0.9,
-                                             0.999, 1e-8, tk_, nullptr, st));
+                                             0.999, 1e-8, tk_, td_cpc, st));
         }
         r.pack(a->pack_critic_enc);
     }
@@ -1112,6 +1130,70 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
     }
     a->last_launches = g_launches - launches0;
     return r.rc;
+}
+
+// Whole-update CUDA graph.  An update variant is everything that shapes the launch sequence: which phases the step
+// runs (actor / EMA / CPC frequencies, only_cpc), every argument pointer (the replay arrays, the index staging slot)
+// and the noise seed.  A variant runs eagerly the first time it is seen (kernel attributes, streams, NCCL
+// connections are set up outside any capture), is captured on its second appearance and replayed from then on:
+// one cudaGraphLaunch (+ the one-thread curla_set_dev_state launch that carries this update's Adam step counters
+// and Philox offset) instead of ~90 kernel launches and a dozen event operations issued by the host.
+// CURLA_GRAPH=0 keeps every update eager.  Not captured: teacher-forced calls (phases mask, injected noise),
+// pre-augmented float inputs (their buffers change per call), profiled runs, callers that are capturing themselves.
+static bool graph_on(curla_agent* a) {
+    if (a->graph_mode < 0) { const char* e = getenv("CURLA_GRAPH"); a->graph_mode = (e && e[0] == '0') ? 0 : 1; }
+    return a->graph_mode == 1;
+}
+
+extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cudaStream_t st) {
+    CURLA_CHECK(a->bound, "agent not bound");
+    const auto& c = a->cfg;
+    bool eligible = graph_on(a) && !g_prof.on && (u->phases == 0 || u->phases == CURLA_PHASE_ALL) && !u->noise_next &&
+                    !u->noise_cur && !u->obs_f32 && !u->next_f32 && !u->pos_f32;
+    if (eligible) {
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cst) != cudaSuccess || cst != cudaStreamCaptureStatusNone) eligible = false;
+    }
+    if (!eligible) return update_body(a, u, st, nullptr);
+
+    const bool do_sac = !u->only_cpc;
+    const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0);
+    const bool do_ema = do_sac && (u->step % c.critic_target_update_freq == 0);
+    const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0);
+    curla_update_args k = *u;
+    k.step = (do_actor ? 1 : 0) | (do_ema ? 2 : 0) | (do_cpc ? 4 : 0);
+    k.offset = 0;
+    k.phases = 0;
+    const std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
+    auto& ent = a->graphs[key];                      // value-initialised on first sight: {nullptr, 0, 0}
+    if (ent.seen++ == 0) return update_body(a, u, st, nullptr);
+    const int t0[4] = {a->t_critic, a->t_actor, a->t_alpha, a->t_cpc};
+    if (!ent.exec) {
+        if (a->graphs.size() > 64) {                 // a caller cycling through pointers: stop collecting graphs
+            a->graph_mode = 0;
+            return update_body(a, u, st, nullptr);
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+        CURLA_CHECK(e == cudaSuccess, "update: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        const int rc = update_body(a, u, st, a->dev_state);
+        e = cudaStreamEndCapture(st, &graph);
+        a->t_critic = t0[0]; a->t_actor = t0[1]; a->t_alpha = t0[2]; a->t_cpc = t0[3];     // nothing has run yet
+        if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        CURLA_CHECK(e == cudaSuccess && graph, "update: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&ent.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { ent.exec = nullptr; set_last_error("update: cudaGraphInstantiate: %s", cudaGetErrorString(e)); return -1; }
+        ent.launches = a->last_launches;
+    }
+    // this update's scalars, then the replay
+    const int t1[4] = {t0[0] + (do_sac ? 1 : 0), t0[1] + (do_actor ? 1 : 0), t0[2] + (do_actor ? 1 : 0), t0[3] + (do_cpc ? 1 : 0)};
+    if (curla_set_dev_state(a->dev_state, t1[0], t1[1], t1[2], t1[3], u->offset * 2, st)) return -1;
+    const cudaError_t e = cudaGraphLaunch(ent.exec, st);
+    CURLA_CHECK(e == cudaSuccess, "update: cudaGraphLaunch: %s", cudaGetErrorString(e));
+    a->t_critic = t1[0]; a->t_actor = t1[1]; a->t_alpha = t1[2]; a->t_cpc = t1[3];
+    a->last_launches = ent.launches + 1;
+    return 0;
 }
 
 // ================================================================== inference entry points

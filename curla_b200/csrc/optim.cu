@@ -212,6 +212,21 @@ extern "C" int curla_adam_f64_scalar(double* p, const double* g, double* state, 
     return check_launch("adam_f64_scalar");
 }
 
+// Per-update scalars of a replayed CUDA graph: the four Adam step counters and the Philox offset of the policy
+// noise live in 24 bytes of device memory.  They arrive as kernel PARAMETERS of this one-thread launch (copied at
+// launch time), so the host may run any number of updates ahead of the device without a staging buffer to protect.
+__global__ void k_set_state(int* __restrict__ state, int t0, int t1, int t2, int t3, unsigned long long off2) {
+    pdl_grid_sync();
+    if (threadIdx.x || blockIdx.x) return;
+    state[0] = t0; state[1] = t1; state[2] = t2; state[3] = t3;
+    *reinterpret_cast<unsigned long long*>(state + 4) = off2;
+}
+extern "C" int curla_set_dev_state(int* state, int t_critic, int t_actor, int t_alpha, int t_cpc,
+                                   unsigned long long philox_offset, cudaStream_t stream) {
+    launch_k(k_set_state, dim3(1), dim3(32), 0, stream, state, t_critic, t_actor, t_alpha, t_cpc, philox_offset);
+    return check_launch("set_dev_state");
+}
+
 extern "C" int curla_ema_f32(float* target, const float* p, long long n, long long split,
                              double tau_a, double tau_b, cudaStream_t stream) {
     if (n <= 0) return 0;

@@ -238,6 +238,10 @@ int curla_adam_f32(float* p, const float* g, float* m, float* v, long long n,
 int curla_adam_f64_scalar(double* p, const double* g, double* state, double lr, double beta1,
                           double beta2, double eps, int t_host, const int* t_dev,
                           curla_stream_t stream);
+/* device-resident per-update scalars of a replayed update graph: state = int[4] Adam step counters
+ * {critic, actor, log_alpha, encoder+cpc} followed (byte 16) by the uint64 Philox offset of the policy noise */
+int curla_set_dev_state(int* state, int t_critic, int t_actor, int t_alpha, int t_cpc,
+                        unsigned long long philox_offset, curla_stream_t stream);
 int curla_ema_f32(float* target, const float* p, long long n, long long split, double tau_a,
                   double tau_b, curla_stream_t stream);
 int curla_pack_shadows(const float* src_arena, void* dst_arena, const long long* segs, int n,

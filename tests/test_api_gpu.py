@@ -450,3 +450,47 @@ def test_replay_sample_proprio_and_getitem():
     o1, a1, r1, n1, d1 = rb[123]
     i = np.random.RandomState(4).randint(0, cap, size=1)[0]
     assert np.array_equal(o1, arrays[0][i]) and np.array_equal(n1, arrays[1][i]) and np.array_equal(a1, arrays[2][i])
+
+
+# ------------------------------------------------------------------ whole-update CUDA graph
+@pytest.mark.parametrize('name', ['crop90x160', 'pixelsac90x160'])
+def test_graph_replayed_updates_equal_eager_updates(name, monkeypatch):
+    """curla_agent_update replays one captured CUDA graph per update variant (engine.cu); the Adam step
+    counters and the Philox offset of the policy noise then live in device memory.  Ten updates (both step
+    parities, one only_cpc stretch) replayed must leave parameters, Adam moments and optimizer step
+    counters bit-identical to the same ten updates launched eagerly (CURLA_GRAPH=0)."""
+    import ctypes as C
+    cfg = dict(S.SCENARIOS[name])
+    run = S.OracleRun(cfg)
+    agents = []
+    for flag in ('0', '1'):
+        monkeypatch.setenv('CURLA_GRAPH', flag)
+        agent, rb = T.build_cuda_agent(cfg, run)
+        agent._noise_seed = 1234
+        agents.append((agent, rb))
+    L = T.NullLogger()
+    st = np.random.get_state()
+    launches = {}
+    for u in range(10):
+        only = (not cfg.get('pixel_sac', False)) and u in (6, 7)
+        for flag, (agent, rb) in zip(('0', '1'), agents):
+            monkeypatch.setenv('CURLA_GRAPH', flag)       # read once per engine, at its first update
+            np.random.set_state(st)
+            agent.update(rb, L, u, only_cpc=only)
+            after = np.random.get_state()
+            launches.setdefault(flag, []).append(agent.engine.last_launches())
+        st = after
+    torch.cuda.synchronize()
+    (a0, _), (a1, _) = agents
+    assert len(a1.engine.t) == len(a0.engine.t)
+    # replays count the captured kernel nodes + the one-thread state launch
+    assert launches['1'][-1] == launches['0'][-1] + 1, (launches['0'][-1], launches['1'][-1])
+    s0, s1 = (np.zeros(4, dtype=np.int32) for _ in range(2))
+    a0.engine.lib.curla_agent_get_opt_steps(a0.engine.h, s0.ctypes.data_as(C.POINTER(C.c_int)))
+    a1.engine.lib.curla_agent_get_opt_steps(a1.engine.h, s1.ctypes.data_as(C.POINTER(C.c_int)))
+    assert list(s0) == list(s1)
+    for arena in (0, 3):                                  # fp32 parameters, Adam moments
+        p0, p1 = a0.engine.arenas[arena].view(torch.float32), a1.engine.arenas[arena].view(torch.float32)
+        assert torch.equal(p0, p1), (arena, float((p0 - p1).abs().max()))
+    assert torch.equal(a0.engine.t['log_alpha'], a1.engine.t['log_alpha'])
+    assert torch.equal(a0.engine.t['metrics'], a1.engine.t['metrics'])
