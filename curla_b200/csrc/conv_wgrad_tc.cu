@@ -32,7 +32,12 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
 
 namespace curla {
 
@@ -43,7 +48,24 @@ struct WgGeom {
     int kwin;              // 16-position K windows per image row = ceil((Wv + NDX - 1) / 16)
     int dyr;               // rows of a staged dy plane (>= pitch + NDX - 1, >= kwin*16), zero outside the copy
     int nst;               // pipeline stages (2..4): more, shorter stages keep more of the fill latency covered
+    int tmap;              // 1: operands staged by tensor-map TMA boxes (one per image row / per dy copy, all channel
+                           //    planes at once); 0: one linear cp.async.bulk per plane per image row
+    int pss;               // shared-memory stride of one plane of one image row (bytes): pitch*16, rounded up to 128 with tmap
 };
+
+// Tensor-map staging.  The producer of the first version issued one 1088-byte linear bulk copy per channel plane
+// per image row: 88 copies per 5-row stage, and the fill of a stage -- not the MMAs (1400 clk) nor the bytes (L2
+// delivered half its cap) -- set the kernel's pace at ~3800 clk per stage (the TMA unit spends a fixed cost per
+// request).  A 4-D tensor map over the activation buffer, (x in 8-byte units, plane, y, sample), lets ONE request
+// bring all planes of an image row (A: 4-6 planes, ~4.5 KB) or one shifted copy of a dy row (4 planes, 5 KB): 22
+// requests per stage.  The shift and the zero rows around a dy copy come from the box itself: it starts at
+// x = -dx and is dyr positions long, and the TMA unit zero-fills what lies outside [0, pitch).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 
 constexpr int kWgThreads = 6 * 32;      // 4 epilogue warps + MMA + producer
 // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), M=128, N = n
@@ -54,7 +76,8 @@ constexpr uint32_t idesc_mn(uint32_t n) {
 // CP: input channels (32, or 48 for the space-to-depth conv1 input); GR x NDX taps (3x3 or 2x2)
 template <int CP, int GR, int NDX>
 __global__ void __launch_bounds__(kWgThreads, 1)
-k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ dy,
+k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy,
+                const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ dy,
                 long long dy_sstride, float* __restrict__ partial, WgGeom g) {
     constexpr int CH = CP / 8, CPL = CH + 1;          // planes per slot incl. the ones-plane
     static_assert(GR * CPL <= 16, "M = 128 holds 16 chunks");
@@ -66,7 +89,8 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     // header: full[4] @0, empty[4] @32, done @64, tmem ptr @72
     const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72;
     const int nst = g.nst;
-    const uint32_t PS = (uint32_t)g.pitch * 16u;                       // one plane of one image row
+    const uint32_t PS = (uint32_t)g.pss;                               // one plane of one image row (shared memory)
+    const uint32_t PG = (uint32_t)g.pitch * 16u;                       // ... in global memory
     const uint32_t slot_bytes = CPL * PS;
     const int slots = g.R + GR - 1;
     const uint32_t a_bytes = (uint32_t)slots * slot_bytes;
@@ -96,9 +120,10 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
     // constant parts of both stages: ones-planes (bf16 1.0); the tail of every dy plane stays zero
     for (int st = 0; st < nst; ++st) {
         uint8_t* sb = smem + 128 + (size_t)st * stage_bytes;
-        const int ones16 = slots * g.pitch;                              // 16-byte rows of ones
+        const int prow = (int)(PS / 16);
+        const int ones16 = slots * prow;                                 // 16-byte rows of ones
         for (int i = tid; i < ones16; i += kWgThreads) {
-            const int r = i / g.pitch, row = i - r * g.pitch;
+            const int r = i / prow, row = i - r * prow;
             *reinterpret_cast<uint4*>(sb + (size_t)r * slot_bytes + (size_t)CH * PS + (size_t)row * 16) =
                 make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
         }
@@ -123,13 +148,22 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
             if (elect_one()) {
                 const uint32_t bar = s_full + 8 * stage;
                 const int arows = rv + GR - 1;
-                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * NDX) * PS);
+                if (g.tmap) {
+                    mbar_expect_tx(bar, (uint32_t)arows * CH * PS + (uint32_t)(rv * NDX) * 4u * DYB);
+                    for (int r = 0; r < arows; ++r)
+                        tma_load_4d(sa + (uint32_t)r * slot_bytes, &tmIn, 0, 0, y0 + r, b, bar);
+                    for (int r = 0; r < rv; ++r)
+#pragma unroll
+                        for (int dx = 0; dx < NDX; ++dx)
+                            tma_load_4d(sd + (uint32_t)((r * NDX + dx) * 4) * DYB, &tmDy, -2 * dx, 0, y0 + r, b, bar);
+                } else {
+                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * NDX) * PG);
                 const bf16* src_a = in + (long long)b * in_sstride + (long long)y0 * g.pitch * 8;
                 for (int r = 0; r < arows; ++r)
 #pragma unroll
                     for (int c = 0; c < CH; ++c)
                         bulk_g2s(sa + (uint32_t)r * slot_bytes + (uint32_t)c * PS,
-                                 src_a + c * plane + (long long)r * g.pitch * 8, PS, bar);
+                                 src_a + c * plane + (long long)r * g.pitch * 8, PG, bar);
                 const bf16* src_d = dy + (long long)b * dy_sstride + (long long)y0 * g.pitch * 8;
                 for (int r = 0; r < rv; ++r)
 #pragma unroll
@@ -137,7 +171,8 @@ k_conv_wgrad_tc(const bf16* __restrict__ in, long long in_sstride, const bf16* _
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             bulk_g2s(sd + (uint32_t)((r * NDX + dx) * 4 + c) * DYB + (uint32_t)dx * 16u,
-                                     src_d + c * plane + (long long)r * g.pitch * 8, PS, bar);
+                                     src_d + c * plane + (long long)r * g.pitch * 8, PG, bar);
+                }
             }
             __syncwarp();
             if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
@@ -271,6 +306,49 @@ k_conv_wgrad_reduce_multi(WgReduceJobs jobs) {
     }
 }
 
+// ---- tensor maps (host): (x in 8-byte units, image row, channel plane, sample) over a channel-plane buffer
+typedef CUresult (*WgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WgEncodeFn wg_encode_fn() {
+    static WgEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (WgEncodeFn)f;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// false: no map (the caller falls back to linear bulk copies)
+static bool wg_map(CUtensorMap* out, const void* ptr, int pitch, int rows, int planes, int B, long long plane_elems,
+                   long long sstride_elems, int box_x8) {
+    struct Key { const void* p; long long a, b; int c[5]; };
+    static thread_local std::vector<std::pair<Key, CUtensorMap>> cache;
+    Key k;
+    memset(&k, 0, sizeof(k));
+    k.p = ptr; k.a = plane_elems; k.b = sstride_elems; k.c[0] = pitch; k.c[1] = rows; k.c[2] = planes; k.c[3] = B; k.c[4] = box_x8;
+    for (auto& e : cache) if (!memcmp(&e.first, &k, sizeof(k))) { *out = e.second; return true; }
+    WgEncodeFn enc = wg_encode_fn();
+    if (!enc || box_x8 > 256 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
+    const cuuint64_t gd[4] = {(cuuint64_t)2 * pitch, (cuuint64_t)rows, (cuuint64_t)planes, (cuuint64_t)B};
+    const cuuint64_t gs[3] = {(cuuint64_t)pitch * 16, (cuuint64_t)plane_elems * 2, (cuuint64_t)sstride_elems * 2};
+    const cuuint32_t bx[4] = {(cuuint32_t)box_x8, 1, (cuuint32_t)planes, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUtensorMap tm;
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (cache.size() >= 64) cache.clear();            // maps are handed out by value: nothing dangles
+    cache.emplace_back(k, tm);
+    *out = tm;
+    return true;
+}
+
 template <int CP, int GR, int NDX>
 static int launch_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
                         float* workspace, int B, int pitch, int S, int Hv, int Wv, int* grid_out,
@@ -281,7 +359,21 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     g.kwin = cdiv(Wv + NDX - 1, 16);
     g.dyr = g.kwin * 16 > pitch + NDX - 1 ? g.kwin * 16 : pitch + NDX - 1;
     g.dyr = (g.dyr + 7) / 8 * 8;
-    const size_t PS = (size_t)pitch * 16, DYB = (size_t)g.dyr * 16;
+    // operand staging: tensor-map boxes (CURLA_WG_TMAP=0: one linear bulk copy per plane per image row)
+    CUtensorMap tmIn, tmDy;
+    memset(&tmIn, 0, sizeof(tmIn));
+    memset(&tmDy, 0, sizeof(tmDy));
+    g.tmap = 1;
+    { const char* e = getenv("CURLA_WG_TMAP"); if (e && e[0] == '0') g.tmap = 0; }
+    g.pss = pitch * 16;
+    if (g.tmap) {
+        const int pss = (pitch * 16 + 127) / 128 * 128;
+        const bool ok = S % pitch == 0 &&
+                        wg_map(&tmIn, in, pitch, S / pitch, CP / 8, B, (long long)S * 8, in_sstride, pss / 8) &&
+                        wg_map(&tmDy, dy, pitch, S / pitch, 4, B, (long long)S * 8, dy_sstride, g.dyr * 2);
+        if (ok) g.pss = pss; else g.tmap = 0;
+    }
+    const size_t PS = (size_t)g.pss, DYB = (size_t)g.dyr * 16;
     const size_t budget = 225 * 1024 - 256;
     // CURLA_WG_STAGES (timing experiments): ring depth 2..4; R = the most dy rows per stage that fit
     int nst = 2;
@@ -295,6 +387,7 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     }
     if (R < 1) { set_last_error("conv_wgrad: pitch %d does not fit shared memory", pitch); return -1; }
     if (R > Hv) R = Hv;
+    { const char* e = getenv("CURLA_WG_ROWS"); if (e && atoi(e) >= 1 && atoi(e) <= R) R = atoi(e); }     // timing experiments
     g.R = R;
     g.nst = nst;
     g.runs_per_sample = cdiv(Hv, R);
@@ -306,7 +399,8 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }
     const int cap = sm_count();
     const int grid = g.total_runs < cap ? g.total_runs : cap;
-    launch_k(kern, dim3(grid), dim3(kWgThreads), smem, stream, (const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride, workspace, g);
+    launch_k(kern, dim3(grid), dim3(kWgThreads), smem, stream, tmIn, tmDy, (const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride,
+             workspace, g);
     *grid_out = grid;
     return 0;
 }

@@ -286,6 +286,36 @@ def test_conv_backward(H, W, B, n96, monkeypatch):
             dy_ref = bf16r(ours)
 
 
+@pytest.mark.parametrize('H,W,B', [(76, 135, 5), (90, 160, 3)])
+def test_conv_wgrad_tensor_map_staging_equals_linear_staging(H, W, B, monkeypatch):
+    """conv_wgrad_tc.cu stages its operands with tensor-map TMA boxes (all channel planes of an image row per request,
+    the shifted dy copies zero-filled by the TMA unit); CURLA_WG_TMAP=0 keeps one linear bulk copy per plane per
+    row.  Same MMAs in the same order: the weight / bias gradients must be bit-identical, conv-1 (2x2 taps on
+    the space-to-depth input, 6 planes) and a 3x3 layer."""
+    g, x, ws, bs = _conv_case(H, W, B, seed=4)
+    s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
+    torch.manual_seed(5)
+    ws_buf = torch.zeros(int(max(_lib.load().curla_conv_wgrad_workspace_floats(0),
+                                 _lib.load().curla_conv_wgrad_workspace_floats(1))), device=DEV)
+    for l in (0, 2):
+        dy = torch.randn(B, 32, g.Ho[l], g.Wo[l], device=DEV)
+        dfull, dview = g.to_pitch(bf16r(dy), l)
+        inp = acts[l - 1] if l > 0 else s2d
+        got = {}
+        for mode in ('0', '1'):
+            monkeypatch.setenv('CURLA_WG_TMAP', mode)
+            dW = torch.zeros(ws[l].shape, device=DEV)
+            db = torch.zeros(32, device=DEV)
+            _lib.call('curla_conv_wgrad', _lib.ptr(inp), g.S * (32 if l > 0 else g.CP1), _lib.ptr(dview), g.S * 32,
+                      _lib.ptr(ws_buf), _lib.ptr(dW), _lib.ptr(db), 1.0, B, g.pitch, g.S,
+                      g.Ho[l], g.Wo[l], ws[l].shape[1], 1 if l == 0 else 0, stream())
+            torch.cuda.synchronize()
+            got[mode] = (dW, db)
+        assert torch.equal(got['0'][0], got['1'][0]), (l, float((got['0'][0] - got['1'][0]).abs().max()))
+        assert torch.equal(got['0'][1], got['1'][1]), l
+        assert float(got['1'][0].abs().sum()) > 0
+
+
 # ------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize('layout', [3, 1, 2, 0])
 @pytest.mark.parametrize('M,N,K', [(70, 72, 96), (5, 64, 64), (130, 200, 40), (64, 64, 2048), (128, 64, 64), (300, 136, 200),
