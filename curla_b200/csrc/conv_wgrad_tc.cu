@@ -56,7 +56,7 @@ struct WgGeom {
 // Tensor-map staging.  The producer of the first version issued one 1088-byte linear bulk copy per channel plane
 // per image row: 88 copies per 5-row stage, and the fill of a stage -- not the MMAs (1400 clk) nor the bytes (L2
 // delivered half its cap) -- set the kernel's pace at ~3800 clk per stage (the TMA unit spends a fixed cost per
-// request).  A 4-D tensor map over the activation buffer, (x in 8-byte units, plane, y, sample), lets ONE request
+// request).  A 4-D tensor map over the activation buffer, (x in 8-byte units, y, plane, sample), lets ONE request
 // bring all planes of an image row (A: 4-6 planes, ~4.5 KB) or one shifted copy of a dy row (4 planes, 5 KB): 22
 // requests per stage.  The shift and the zero rows around a dy copy come from the box itself: it starts at
 // x = -dx and is dyr positions long, and the TMA unit zero-fills what lies outside [0, pitch).
@@ -151,11 +151,11 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
                 if (g.tmap) {
                     mbar_expect_tx(bar, (uint32_t)arows * CH * PS + (uint32_t)(rv * NDX) * 4u * DYB);
                     for (int r = 0; r < arows; ++r)
-                        tma_load_4d(sa + (uint32_t)r * slot_bytes, &tmIn, 0, 0, y0 + r, b, bar);
+                        tma_load_4d(sa + (uint32_t)r * slot_bytes, &tmIn, 0, y0 + r, 0, b, bar);
                     for (int r = 0; r < rv; ++r)
 #pragma unroll
                         for (int dx = 0; dx < NDX; ++dx)
-                            tma_load_4d(sd + (uint32_t)((r * NDX + dx) * 4) * DYB, &tmDy, -2 * dx, 0, y0 + r, b, bar);
+                            tma_load_4d(sd + (uint32_t)((r * NDX + dx) * 4) * DYB, &tmDy, -2 * dx, y0 + r, 0, b, bar);
                 } else {
                 mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * NDX) * PG);
                 const bf16* src_a = in + (long long)b * in_sstride + (long long)y0 * g.pitch * 8;

@@ -165,6 +165,8 @@ struct curla_agent {
     // whole-update CUDA graphs: one per update variant (step parity, only_cpc, argument pointers); the per-update
     // scalars a replay needs (Adam step counters, Philox offset) live in dev_state (see curla_set_dev_state)
     int* dev_state;
+    cudaStream_t cap_st;                     // private capture stream (the caller's may be the legacy default stream,
+                                             // which cannot be captured); replays are launched into the caller's stream
     struct GraphEntry { cudaGraphExec_t exec; long long launches; int seen; };
     std::map<std::string, GraphEntry> graphs;
     int graph_mode;                          // -1 = not decided yet, 0 = off (CURLA_GRAPH=0), 1 = on
@@ -448,6 +450,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
     a->last_launches = 0;
     a->graph_mode = -1;
+    a->cap_st = nullptr;
     a->nccl_lib = nullptr; a->comm = nullptr;
     a->side = nullptr; a->side_state = 0;
     a->comm_st = nullptr; a->comm_state = 0;
@@ -458,6 +461,7 @@ static void destroy_comm(curla_agent* a);
 extern "C" void curla_agent_destroy(curla_agent* a) {
     if (!a) return;
     for (auto& kv : a->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (a->cap_st) cudaStreamDestroy(a->cap_st);
     if (a->side_state == 1) {
         for (auto& e : a->ev) cudaEventDestroy(e);
         cudaStreamDestroy(a->side);
@@ -1174,10 +1178,14 @@ extern "C" int curla_agent_update(curla_agent* a, const curla_update_args* u, cu
             return update_body(a, u, st, nullptr);
         }
         cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+        if (!a->cap_st && cudaStreamCreateWithFlags(&a->cap_st, cudaStreamNonBlocking) != cudaSuccess) {
+            a->cap_st = nullptr; a->graph_mode = 0; cudaGetLastError();
+            return update_body(a, u, st, nullptr);
+        }
+        cudaError_t e = cudaStreamBeginCapture(a->cap_st, cudaStreamCaptureModeRelaxed);
         CURLA_CHECK(e == cudaSuccess, "update: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
-        const int rc = update_body(a, u, st, a->dev_state);
-        e = cudaStreamEndCapture(st, &graph);
+        const int rc = update_body(a, u, a->cap_st, a->dev_state);
+        e = cudaStreamEndCapture(a->cap_st, &graph);
         a->t_critic = t0[0]; a->t_actor = t0[1]; a->t_alpha = t0[2]; a->t_cpc = t0[3];     // nothing has run yet
         if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
         CURLA_CHECK(e == cudaSuccess && graph, "update: cudaStreamEndCapture: %s", cudaGetErrorString(e));
