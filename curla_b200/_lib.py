@@ -18,6 +18,11 @@ class ConvSeg(C.Structure):
     _fields_ = [('inp', c_vp), ('wts', c_vp), ('bias', c_vp), ('out', c_vp), ('B', C.c_int)]
 
 
+class ConvStackSeg(C.Structure):
+    """curla_conv_stack_seg: one pass of the fused conv-2..4 launch."""
+    _fields_ = [('inp', c_vp), ('w96', c_vp), ('bias', c_vp * 3), ('out', c_vp * 3), ('B', C.c_int)]
+
+
 class GatherSeg(C.Structure):
     """curla_gather_seg: one stream of a multi-stream gather launch."""
     _fields_ = [('frames', c_vp), ('h1', c_vp), ('w1', c_vp), ('out', c_vp)]
@@ -66,6 +71,9 @@ SIGNATURES = {
     'curla_conv_pad_rows': (_i, [_i]),
     'curla_conv_fwd': (_i, [c_vp, c_ll, c_vp, c_vp, _f, c_vp, c_ll, _i, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_dgrad': (_i, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, _i, _i, _i, _i, _i, c_vp]),
+    'curla_conv_stack_fits': (_i, [_i, _i, c_vp, c_vp]),
+    'curla_conv_stack_fwd': (_i, [c_vp, _i, c_ll, _i, _i, c_vp, c_vp, c_vp]),
+    'curla_agent_set_keep_acts': (_i, [c_vp, _i]),
     'curla_conv_fwd_multi': (_i, [c_vp, _i, c_ll, _f, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_debug_read': (_i, [c_vp, _i]),
     'curla_gemm_tc_debug_read': (_i, [c_vp]),

@@ -610,6 +610,8 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             }
         };
         int par = 0;
+        const bool edbg = (g.debug & 64) != 0;             // CURLA_TC_DEBUG=64: cycle counters of epilogue warp 0 and issuer 0
+        long long e_wait = 0, e_tm = 0, e_bar = 0, e_rest = 0;
         for (int j = egroup;; j += kEpiGroups, par ^= 1) {
             uint32_t ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1)));
             if (!ring_ready(ent, j)) {
@@ -633,7 +635,9 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             uint4 xm[4];
             if (DGRAD) load_mask(tile, xm);
             float* const xw = xch + (size_t)(par * kEpiAll + warp) * kXch;
+            const long long e0 = edbg ? clock64() : 0;
             mbar_wait(s_tfull + 8 * acc, acc_phase);
+            const long long e1 = edbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t taddr = taddr0 + acc * (kTcSub * 96);
             float av[32];
@@ -671,8 +675,10 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_tempty + 8 * acc);      // accumulator stage drained by this warp
+            const long long e2 = edbg ? clock64() : 0;
             // ---- the warp's edge rows: neighbours' accumulators through the exchange slots
             asm volatile("bar.sync %0, %1;" ::"r"(2 + egroup), "n"(kEpiWarps * 32) : "memory");
+            const long long e3 = edbg ? clock64() : 0;
             if (!DGRAD) {
                 if (ew + 1 < kEpiWarps && lane >= 30) {
                     const float* xo = xch + (size_t)(par * kEpiAll + warp + 1) * kXch;
@@ -718,6 +724,11 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
                 }
             }
             acc_phase ^= 1;
+            if (edbg) { const long long e4 = clock64(); e_wait += e1 - e0; e_tm += e2 - e1; e_bar += e3 - e2; e_rest += e4 - e3; }
+        }
+        if (edbg && tid == 0) {
+            long long* d = g_tc_dbg[blockIdx.x];
+            d[6] = e_wait; d[7] = e_tm + e_bar + e_rest; d[15] = e_tm; d[16] = e_bar; d[17] = e_rest;
         }
     } else if (warp < kEpiAll + kMmaWarps) {
         // ================= MMA issuers: warp mw takes the CTA's local tiles mw, mw + 2, ... into accumulator stage mw
@@ -732,8 +743,13 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             for (int ks = 0; ks < KS; ++ks)
                 a_off[dy * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)((DGRAD ? 2 - dy : dy) * g.pitch) * 16u) >> 4;
         const int valid_pos = g.Hv * g.pitch;
+        const bool dbg = (g.debug & 64) != 0;
+        long long c_te = 0, c_fu = 0, c_is = 0, c_n = 0;
+        const long long c_start = clock64();
         for (int j = mw;; j += kMmaWarps) {
+            const long long c1 = dbg ? clock64() : 0;
             mbar_wait(s_full + 8 * stage, phase);
+            const long long c2 = dbg ? clock64() : 0;
             const int tile = ring_tile((uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))));
             if (tile < 0) break;
             const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
@@ -742,6 +758,7 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             const uint32_t w16 = (s_w + (uint32_t)tc_pick(sg.wsel, tl.seg) * kW96Bytes) >> 4;
             const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
             mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            const long long c3 = dbg ? clock64() : 0;
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -762,9 +779,14 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
                 umma_commit(s_tfull + 8 * acc);
             }
             __syncwarp();
+            if (dbg) { c_fu += c2 - c1; c_te += c3 - c2; c_is += clock64() - c3; ++c_n; }
             stage += (uint32_t)kMmaWarps;
             if (stage >= (uint32_t)stages) { stage -= (uint32_t)stages; phase ^= 1; }
             acc_phase ^= 1;
+        }
+        if (dbg && lane == 0 && mw == 0) {
+            long long* d = g_tc_dbg[blockIdx.x];
+            d[0] = c_te; d[1] = c_fu; d[2] = c_is; d[4] = clock64() - c_start; d[5] = c_n;
         }
     } else {
         const int one = ld_volatile_s32(smem + 640 + 4 * lane);
@@ -808,6 +830,314 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
             if (g.dynamic) {
                 __threadfence();
                 if (atomicAdd(ctr + 1, 1) == G - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- layers 2..4 fused: one sample resident in shared memory
+// k_conv_tc96 still writes every layer's activations to HBM and the next layer's launch reads them back: per
+// encoder pass 428 MB of the 616 MB the conv stack moves.  Here a CTA keeps ONE sample's activation map in
+// shared memory (crop geometry: 2552 positions x 64 B = 163 KB) and runs conv-2, conv-3 and conv-4 over it IN
+// PLACE: a 3x3 valid conv only looks "forward" in the flattened position index (out[p] reads in[p .. p + 2*pitch
+// + 2]), tiles are processed in increasing position order, so tile t's output can overwrite positions
+// [254 t, 254 t + 254) as soon as the MMAs of tiles t-1 and t have read them.  HBM traffic per pass: act0 in, act3
+// out (+ act1 / act2 out for the passes whose backward needs them).  The weights of all three layers of one
+// weight set stay resident next to the sample (55 KB, pre-packed by curla_pack_shadows in the N = 96 operand
+// layout, one bulk copy).
+//
+// Pipeline (warp roles as in k_conv_tc96).  The buffer is a ring of T slots of 254 positions:
+//   full[t]   producer -> issuers   slot t holds the sample's conv-1 output (4 bulk copies, one per channel plane)
+//   wr[t]     epilogue -> issuers   slot t holds this layer's output (8 warp arrivals, after fence.proxy.async)
+//   empty[t]  issuers  -> producer  conv-4's MMAs of tile t are complete: slot t may receive the NEXT sample --
+//                                   so the next sample streams in behind the last layer, slot by slot
+//   tfull / tempty[2]               accumulator stages, (issuer warp w, stage w, epilogue group w) as in k_conv_tc96
+// Tile (layer l, slot t) reads slots t and t+1: its issuer waits for full / wr of both.  Nothing relies on the
+// order in which the two issuer warps' MMAs execute: before an epilogue group overwrites slot t it waits until
+// the OTHER group has drained the accumulators of the previous tile (a monotonic counter in shared memory), whose
+// MMAs are the only other readers of slot t; the producer takes empty[0], empty[1], ... in order.
+struct StackSegs {
+    const bf16* in[3];           // conv-1 output of each pass
+    bf16* out[3][3];             // [pass][layer]: conv-2 / conv-3 output (NULL: not kept), conv-4 output
+    const bf16* w96[2];          // packed weights of the (at most) two weight sets: [3 layers][3 dy][4 k chunks][96 n][8 k]
+    const float* bias[2][3];
+    int item_end[3];             // items (samples) [item_end[s-1], item_end[s]) belong to pass s
+    int wsel[3];
+};
+struct StackGeom {
+    int pitch, S, rows, T;       // buffer rows (positions), slots
+    int Hv[3], Wv[3];
+    int total_items;
+    float inv_pitch;
+};
+constexpr int kStackHdr = 768;           // barriers @0 (full[16] @0, empty[16] @128, wr[16] @256, tfull[2] @384, tempty[2] @400, wfull @416),
+                                         // tmem ptr @424, drained[2] @432
+constexpr int kStackXch = 2 * kEpiAll * kXch * 4;
+constexpr uint32_t kStackWBytes = 3 * kW96Bytes;
+constexpr int kStackMaxT = 16;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_stack96(const __grid_constant__ StackSegs sg, long long sstride, StackGeom g) {
+    constexpr int KS = 2;
+    constexpr uint32_t TMEM_COLS = 512;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_full = s_base, s_empty = s_base + 128, s_wr = s_base + 256, s_tfull = s_base + 384, s_tempty = s_base + 400;
+    const uint32_t s_wfull = s_base + 416, s_tptr = s_base + 424;
+    volatile int* const drained = reinterpret_cast<volatile int*>(smem + 432);
+    const uint32_t s_w = s_base + kStackHdr + kStackXch;
+    const uint32_t s_buf = s_w + kStackWBytes;
+    const uint32_t PS = (uint32_t)g.rows * 16u;
+    const long long plane = (long long)g.S * 8;
+    const int T = g.T;
+    // this CTA's contiguous range of samples
+    const int i0 = (int)(((long long)blockIdx.x * g.total_items) / gridDim.x);
+    const int i1 = (int)(((long long)(blockIdx.x + 1) * g.total_items) / gridDim.x);
+
+    if (tid == 0) {
+        for (int i = 0; i < kStackMaxT; ++i) {
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(s_empty + 8 * i, 1);
+            mbar_init(s_wr + 8 * i, kEpiWarps);
+        }
+        for (int i = 0; i < kAcc96; ++i) {
+            mbar_init(s_tfull + 8 * i, 1);
+            mbar_init(s_tempty + 8 * i, kEpiWarps);
+        }
+        mbar_init(s_wfull, 1);
+        drained[0] = 0; drained[1] = 0;
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 424);
+    pdl_grid_sync();
+
+    auto seg_of = [&](int item) { return item >= sg.item_end[1] ? 2 : (item >= sg.item_end[0] ? 1 : 0); };
+    auto seg_start = [&](int s) { return s == 0 ? 0 : (s == 1 ? sg.item_end[0] : sg.item_end[1]); };
+
+    if (warp < kEpiAll) {
+        // ================= epilogue: group eg drains the tiles with t & 1 == eg
+        const int eg = warp / kEpiWarps, ew = warp % kEpiWarps;
+        const int sub = ew >> 2, quarter = ew & 3;
+        const int row_in_tile = sub * 128 + quarter * 32 + lane;
+        const bool row_out = row_in_tile < kT96Out;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 96) + (uint32_t)eg * (kTcSub * 96);
+        float* const xch = reinterpret_cast<float*>(smem + kStackHdr);
+        uint32_t acc_phase = 0;
+        int par = 0;
+        int j = eg;                                    // running tile index of this CTA: ((k*3 + l) * T + t); T is even
+        for (int item = i0; item < i1; ++item) {
+            const int seg = seg_of(item), b = item - seg_start(seg);
+            const int ws = tc_pick(sg.wsel, seg);
+            for (int l = 0; l < 3; ++l) {
+                bf16* __restrict__ outg = seg == 0 ? sg.out[0][l] : (seg == 1 ? sg.out[1][l] : sg.out[2][l]);
+                const float* __restrict__ bias = ws ? sg.bias[1][l] : sg.bias[0][l];
+                const int Hv = g.Hv[l], Wv = g.Wv[l];
+                for (int t = eg; t < T; t += kEpiGroups, j += kEpiGroups, par ^= 1) {
+                    const int p = t * kT96Out + row_in_tile;
+                    const bool inside = p < g.rows && row_out;
+                    int y = 0, x = 0;
+                    if (inside) { y = tc_div(p, g.inv_pitch); x = p - y * g.pitch; }
+                    const bool valid = inside && (y < Hv) && (x < Wv);
+                    float* const xw = xch + (size_t)(par * kEpiAll + warp) * kXch;
+                    mbar_wait(s_tfull + 8 * eg, acc_phase);
+                    tc_fence_after();
+                    float av[32];
+                    uint32_t r[32];
+                    // ---- D1 (dx = 1): row p + 1
+                    tmem_ld32(taddr + 32, r);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i]), 1);
+                        av[i] = (lane == 31) ? 0.f : v;
+                    }
+                    // ---- D2 (dx = 2): row p + 2
+                    tmem_ld32(taddr + 64, r);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + 32 + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+                    }
+                    if (lane == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + 64 + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i]), 2);
+                        av[i] += (lane >= 30) ? 0.f : v;
+                    }
+                    // ---- D0
+                    tmem_ld32(taddr, r);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) av[i] += __uint_as_float(r[i]);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_tempty + 8 * eg);
+                    asm volatile("bar.sync %0, %1;" ::"r"(2 + eg), "n"(kEpiWarps * 32) : "memory");
+                    // every warp of the group has its accumulators in registers: this tile's MMAs are complete
+                    if (ew == 0 && lane == 0) drained[eg] = (j >> 1) + 1;
+                    if (ew + 1 < kEpiWarps && lane >= 30) {
+                        const float* xo = xch + (size_t)(par * kEpiAll + warp + 1) * kXch;
+                        if (lane == 31) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) av[i] += xo[i] + xo[64 + i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) av[i] += xo[32 + i];
+                        }
+                    }
+                    uint4 ov[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 bq = __ldg(reinterpret_cast<const float2*>(bias) + c * 4 + q);
+                            const float v0 = valid ? fmaxf(av[c * 8 + q * 2] + bq.x, 0.f) : 0.f;
+                            const float v1 = valid ? fmaxf(av[c * 8 + q * 2 + 1] + bq.y, 0.f) : 0.f;
+                            w[q] = pack_bf16x2(v0, v1);
+                        }
+                        ov[c] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    if (inside && outg && p < g.S) {
+                        bf16* o = outg + (long long)b * sstride + (long long)p * 8;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(o + c * plane) = ov[c];
+                    }
+                    if (l < 2) {
+                        // in place: slot t is also read by the previous tile's MMAs (the other group's tile)
+                        const int need = (j + 1) >> 1;
+                        if (drained[eg ^ 1] < need) {
+                            const long long t0 = clock64();
+                            while (drained[eg ^ 1] < need)
+                                if (clock64() - t0 > (1ll << 31)) __trap();
+                        }
+                        if (inside) {
+                            const uint32_t so = s_buf + (uint32_t)p * 16u;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(so + (uint32_t)c * PS), "r"(ov[c].x), "r"(ov[c].y),
+                                             "r"(ov[c].z), "r"(ov[c].w) : "memory");
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_wr + 8 * t);
+                    }
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp < kEpiAll + kMmaWarps) {
+        // ================= MMA issuers: warp mw issues the tiles with t & 1 == mw into accumulator stage mw
+        const int mw = warp - kEpiAll;
+        uint32_t acc_phase = 0, wphase = 0;
+        const uint64_t a_hi = make_desc(0, PS, 128), b_hi = make_desc(0, 96 * 16, 128);
+        uint32_t a_off[3 * KS];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+                a_off[dy * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)(dy * g.pitch) * 16u) >> 4;
+        int cur_w = -1;
+        for (int item = i0, k = 0; item < i1; ++item, ++k) {
+            const int ws = tc_pick(sg.wsel, seg_of(item));
+            if (ws != cur_w) {
+                mbar_wait(s_wfull, wphase);
+                wphase ^= 1;
+                cur_w = ws;
+            }
+            for (int l = 0; l < 3; ++l) {
+                const int valid_pos = g.Hv[l] * g.pitch;
+                const uint32_t w16 = (s_w + (uint32_t)l * kW96Bytes) >> 4;
+                for (int t = mw; t < T; t += kMmaWarps) {
+                    const int t1 = t + 1 < T ? t + 1 : t;
+                    if (l == 0) {
+                        mbar_wait(s_full + 8 * t, (uint32_t)(k & 1));
+                        mbar_wait(s_full + 8 * t1, (uint32_t)(k & 1));
+                    } else {
+                        mbar_wait(s_wr + 8 * t, (uint32_t)(l - 1));
+                        mbar_wait(s_wr + 8 * t1, (uint32_t)(l - 1));
+                    }
+                    const int p0 = t * kT96Out;
+                    const int nsub = p0 >= valid_pos ? 0 : (p0 + 128 >= valid_pos ? 1 : kTcSub);
+                    const uint32_t slab16 = (s_buf + (uint32_t)p0 * 16u) >> 4;
+                    mbar_wait(s_tempty + 8 * mw, acc_phase ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s2 = 0; s2 < kTcSub; ++s2) {
+                            if (s2 >= nsub) break;
+                            const uint32_t d = tmem_base + (uint32_t)mw * (kTcSub * 96) + (uint32_t)(s2 * 96);
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                                for (int ks = 0; ks < KS; ++ks) {
+                                    const uint64_t ad = a_hi | (uint64_t)((slab16 + (uint32_t)(s2 * 128) + a_off[dy * KS + ks]) & 0x3FFFu);
+                                    const uint64_t bd = b_hi | (uint64_t)((w16 + (uint32_t)((dy * 4 + 2 * ks) * 96)) & 0x3FFFu);
+                                    umma_bf16_rt(d, ad, bd, kIdesc96, (dy | ks) ? 1u : 0u);
+                                }
+                            }
+                        }
+                        if (l == 2) umma_commit(s_empty + 8 * t);      // the sample's last reader of slot t (with tile t-1, committed before)
+                        umma_commit(s_tfull + 8 * mw);
+                    }
+                    __syncwarp();
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        if (lane == 0) {
+            // ================= producer: weights (one bulk copy per weight-set change) and the sample, slot by slot
+            int cur_w = -1;
+            for (int item = i0, k = 0; item < i1; ++item, ++k) {
+                const int seg = seg_of(item), b = item - seg_start(seg);
+                const int ws = tc_pick(sg.wsel, seg);
+                if (ws != cur_w) {
+                    // every MMA that reads the old weights is complete once the last slot of the previous sample is released
+                    // (each issuer's commits complete in its own order: its last tile's commit covers all of its MMAs)
+                    if (k > 0) {
+                        mbar_wait(s_empty + 8 * (T - 2), (uint32_t)((k - 1) & 1));
+                        mbar_wait(s_empty + 8 * (T - 1), (uint32_t)((k - 1) & 1));
+                    }
+                    mbar_expect_tx(s_wfull, kStackWBytes);
+                    bulk_g2s(s_w, ws ? sg.w96[1] : sg.w96[0], kStackWBytes, s_wfull);
+                    cur_w = ws;
+                }
+                const bf16* src = tc_pick(sg.in, seg) + (long long)b * sstride;
+                for (int t = 0; t < T; ++t) {
+                    if (k > 0) mbar_wait(s_empty + 8 * t, (uint32_t)((k - 1) & 1));
+                    const int p0 = t * kT96Out;
+                    const int pend = (t + 1 < T && (t + 1) * kT96Out < g.rows) ? (t + 1) * kT96Out : g.rows;
+                    const int np = pend - p0;
+                    const uint32_t bar = s_full + 8 * t;
+                    if (np <= 0) {                             // T is rounded up to even: a last slot past the buffer stays empty
+                        mbar_arrive(bar);
+                        continue;
+                    }
+                    mbar_expect_tx(bar, (uint32_t)np * 64u);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        bulk_g2s(s_buf + (uint32_t)c * PS + (uint32_t)p0 * 16u, src + c * plane + (long long)p0 * 8, (uint32_t)np * 16u, bar);
+                }
             }
         }
     }
@@ -897,10 +1227,13 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     return 0;
 }
 
-// N = 96 variant: layers 2..4 forward and dgrad.  CURLA_CONV_N96=0 keeps the N = 32 kernel (A/B switch).
+// N = 96 variant: layers 2..4 forward and dgrad, CURLA_CONV_N96=1.  Off by default: measured on the B200 at the
+// benchmarked batch it is SLOWER than the N = 32 kernel (conv forward 1.00 vs 0.71 ms per update, dgrad 0.42 vs
+// 0.29: gpurun r03c) -- the MMAs of a tile shrink from 1440 to 672 clk, but every tile now pays three serialised
+// TMEM loads, 64 shuffles and a named barrier among eight epilogue warps on only two accumulator stages.
 static bool use_n96(int pitch, int Wv, bool dgrad) {
     const char* e = getenv("CURLA_CONV_N96");
-    if (e && e[0] == '0') return false;
+    if (!(e && e[0] == '1')) return false;
     // forward: outputs whose horizontal taps would wrap into the next image row must be invalid columns
     return dgrad || Wv <= pitch - 2;
 }
@@ -909,7 +1242,7 @@ template <bool DGRAD>
 static int launch_tc96(const TcSegs& sg, long long in_sstride, float scale, const void* relu_src, long long out_sstride,
                        TcGeom g, cudaStream_t stream) {
     const size_t fixed = kSmemHdr96 + (size_t)sg.nw * kW96Bytes;
-    g.debug = 0;
+    { const char* e = getenv("CURLA_TC_DEBUG"); g.debug = e ? atoi(e) : 0; }
     g.plane_bytes = g.plane_rows * 16;
     const size_t slab = (size_t)4 * g.plane_bytes;
     size_t budget = 200 * 1024;
@@ -968,6 +1301,30 @@ static int make_segs(const curla_conv_seg* segs, int nseg, TcGeom& g, TcSegs& sg
     return 0;
 }
 
+
+// Geometry of the fused launch; false when a sample (plus weights) does not fit one SM's shared memory or the
+// N = 96 formulation does not apply (90 x 160 inputs: 225 KB per sample -- those run layer by layer).
+static bool make_stack_geom(int pitch, int S, const int* Hv, const int* Wv, StackGeom& g, size_t& smem) {
+    for (int l = 0; l < 3; ++l)
+        if (Wv[l] > pitch - 2 || Hv[l] < 1 || Wv[l] < 1) return false;
+    if (Hv[1] > Hv[0] || Hv[2] > Hv[1]) return false;
+    const int valid0 = Hv[0] * pitch;
+    int T = cdiv(valid0, kT96Out);
+    T = (T + 1) & ~1;                                  // even: (issuer w, accumulator w, epilogue group w) keep their tile parity across layers
+    if (T < 2 || T > kStackMaxT) return false;
+    // rows the MMAs of the first fused layer read: its last non-empty sub-tile + 127 rows + two image rows below
+    const int tl = (valid0 - 1) / kT96Out;
+    const int last_sub = tl * kT96Out + ((tl * kT96Out + 128 < valid0) ? 128 : 0);
+    int rows = last_sub + 128 + 2 * pitch;
+    rows = (rows + 7) / 8 * 8;
+    if (rows > S + 256) return false;                  // reads past a plane's S positions stay inside the buffers' padding (curla_conv_pad_rows)
+    g.pitch = pitch; g.S = S; g.rows = rows; g.T = T;
+    for (int l = 0; l < 3; ++l) { g.Hv[l] = Hv[l]; g.Wv[l] = Wv[l]; }
+    g.inv_pitch = 1.0f / (float)pitch;
+    g.total_items = 0;
+    smem = (size_t)kStackHdr + kStackXch + kStackWBytes + (size_t)rows * 64;
+    return smem <= 232448;
+}
 }  // namespace curla
 
 using namespace curla;
@@ -1039,4 +1396,48 @@ extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void
     if (make_segs(&seg, 1, g, sg)) return -1;
     if (launch_tc<32, 9, true>(sg, dy_sstride, 1.f, x, dx_sstride, g, taps, stream)) return -1;
     return check_launch("conv_dgrad");
+}
+
+// ---- conv-2..4 fused (k_conv_stack96).  Hv / Wv: valid output dims of the three layers.
+extern "C" int curla_conv_stack_fits(int pitch, int S, const int* Hv, const int* Wv) {
+    const char* e = getenv("CURLA_CONV_FUSED");
+    if (!(e && e[0] == '1')) return 0;                 // opt-in (experiment): built on the N = 96 epilogue, see use_n96
+    StackGeom g;
+    size_t smem = 0;
+    return make_stack_geom(pitch, S, Hv, Wv, g, smem) ? 1 : 0;
+}
+
+extern "C" int curla_conv_stack_fwd(const curla_conv_stack_seg* segs, int nseg, long long sstride, int pitch, int S,
+                                    const int* Hv, const int* Wv, cudaStream_t stream) {
+    CURLA_CHECK(nseg >= 1 && nseg <= 3, "conv_stack: 1..3 passes per launch (got %d)", nseg);
+    StackGeom g;
+    size_t smem = 0;
+    CURLA_CHECK(make_stack_geom(pitch, S, Hv, Wv, g, smem), "conv_stack: geometry (pitch %d, %d x %d) does not fit shared memory", pitch, Hv[0], Wv[0]);
+    StackSegs sg;
+    memset(&sg, 0, sizeof(sg));
+    int items = 0, nw = 0;
+    for (int s = 0; s < nseg; ++s) {
+        CURLA_CHECK(segs[s].B >= 1 && segs[s].in && segs[s].w96 && segs[s].out[2], "conv_stack: bad pass %d", s);
+        CURLA_CHECK((reinterpret_cast<uintptr_t>(segs[s].w96) & 15) == 0, "conv_stack: packed weights must be 16-byte aligned");
+        sg.in[s] = (const bf16*)segs[s].in;
+        for (int l = 0; l < 3; ++l) sg.out[s][l] = (bf16*)segs[s].out[l];
+        int w = -1;
+        for (int k = 0; k < nw; ++k) if (sg.w96[k] == (const bf16*)segs[s].w96) w = k;
+        if (w < 0) {
+            CURLA_CHECK(nw < 2, "conv_stack: at most two distinct weight sets per launch");
+            w = nw++;
+            sg.w96[w] = (const bf16*)segs[s].w96;
+            for (int l = 0; l < 3; ++l) sg.bias[w][l] = segs[s].bias[l];
+        }
+        sg.wsel[s] = w;
+        items += segs[s].B;
+        sg.item_end[s] = items;
+    }
+    for (int s = nseg; s < 3; ++s) sg.item_end[s] = items;
+    g.total_items = items;
+    if (tc_set_smem(k_conv_stack96, smem)) return -1;
+    const int cap = sm_count();
+    const int grid = items < cap ? items : cap;
+    launch_k(k_conv_stack96, dim3(grid), dim3(kTcThreads), smem, stream, sg, sstride, g);
+    return check_launch("conv_stack");
 }

@@ -51,6 +51,8 @@ struct WgGeom {
     int tmap;              // 1: operands staged by tensor-map TMA boxes (one per image row / per dy copy, all channel
                            //    planes at once); 0: one linear cp.async.bulk per plane per image row
     int pss;               // shared-memory stride of one plane of one image row (bytes): pitch*16, rounded up to 128 with tmap
+    int dy1;               // 1: dy comes from L2 ONCE; the shifted copies of the N = 32*NDX trick are made inside shared memory
+                           //    by the four otherwise idle epilogue warps (L2 -> SM traffic of a 3x3 layer: 96 -> 52 KB per run)
 };
 
 // Tensor-map staging.  The producer of the first version issued one 1088-byte linear bulk copy per channel plane
@@ -86,8 +88,8 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    // header: full[4] @0, empty[4] @32, done @64, tmem ptr @72
-    const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72;
+    // header: full[4] @0, empty[4] @32, done @64, tmem ptr @72, ready[4] @96
+    const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72, s_ready = s_base + 96;
     const int nst = g.nst;
     const uint32_t PS = (uint32_t)g.pss;                               // one plane of one image row (shared memory)
     const uint32_t PG = (uint32_t)g.pitch * 16u;                       // ... in global memory
@@ -101,7 +103,7 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     const long long plane = (long long)g.S * 8;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); mbar_init(s_ready + 8 * i, 4); }
         mbar_init(s_done, 1);
         fence_mbar_init();
     }
@@ -148,16 +150,17 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
             if (elect_one()) {
                 const uint32_t bar = s_full + 8 * stage;
                 const int arows = rv + GR - 1;
+                const int ndx = g.dy1 ? 1 : NDX;             // copies of dy that come from global memory
                 if (g.tmap) {
-                    mbar_expect_tx(bar, (uint32_t)arows * CH * PS + (uint32_t)(rv * NDX) * 4u * DYB);
+                    mbar_expect_tx(bar, (uint32_t)arows * CH * PS + (uint32_t)(rv * ndx) * 4u * DYB);
                     for (int r = 0; r < arows; ++r)
                         tma_load_4d(sa + (uint32_t)r * slot_bytes, &tmIn, 0, y0 + r, 0, b, bar);
                     for (int r = 0; r < rv; ++r)
 #pragma unroll
                         for (int dx = 0; dx < NDX; ++dx)
-                            tma_load_4d(sd + (uint32_t)((r * NDX + dx) * 4) * DYB, &tmDy, -2 * dx, y0 + r, 0, b, bar);
+                            if (dx < ndx) tma_load_4d(sd + (uint32_t)((r * NDX + dx) * 4) * DYB, &tmDy, -2 * dx, y0 + r, 0, b, bar);
                 } else {
-                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * NDX) * PG);
+                mbar_expect_tx(bar, (uint32_t)(arows * CH + rv * 4 * ndx) * PG);
                 const bf16* src_a = in + (long long)b * in_sstride + (long long)y0 * g.pitch * 8;
                 for (int r = 0; r < arows; ++r)
 #pragma unroll
@@ -170,8 +173,9 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
                     for (int dx = 0; dx < NDX; ++dx)
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            bulk_g2s(sd + (uint32_t)((r * NDX + dx) * 4 + c) * DYB + (uint32_t)dx * 16u,
-                                     src_d + c * plane + (long long)r * g.pitch * 8, PG, bar);
+                            if (dx < ndx)
+                                bulk_g2s(sd + (uint32_t)((r * NDX + dx) * 4 + c) * DYB + (uint32_t)dx * 16u,
+                                         src_d + c * plane + (long long)r * g.pitch * 8, PG, bar);
                 }
             }
             __syncwarp();
@@ -185,7 +189,7 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
             const int b = run / g.runs_per_sample;
             const int y0 = (run - b * g.runs_per_sample) * g.R;
             const int rv = (g.Hv - y0) < g.R ? (g.Hv - y0) : g.R;
-            mbar_wait(s_full + 8 * stage, phase);
+            mbar_wait((g.dy1 ? s_ready : s_full) + 8 * stage, phase);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t sa16 = (s_stage0 + stage * stage_bytes) >> 4, sd16 = sa16 + (a_bytes >> 4);
@@ -206,6 +210,32 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
         if (elect_one()) umma_commit(s_done);
         __syncwarp();
     } else {
+        // ================= while the runs stream through: the shifted dy copies, made inside shared memory
+        if (g.dy1) {
+            uint32_t stage = 0, phase = 0;
+            for (int run = blockIdx.x; run < g.total_runs; run += gridDim.x) {
+                const int b = run / g.runs_per_sample;
+                const int y0 = (run - b * g.runs_per_sample) * g.R;
+                const int rv = (g.Hv - y0) < g.R ? (g.Hv - y0) : g.R;
+                const uint32_t sd = s_stage0 + stage * stage_bytes + a_bytes;
+                mbar_wait(s_full + 8 * stage, phase);
+                const int per = 4 * g.pitch;                                  // 16-byte rows of one dy image row (4 planes)
+                for (int i = tid; i < rv * per; i += 4 * 32) {
+                    const int r = i / per, rem = i - r * per, c = rem / g.pitch, k = rem - c * g.pitch;
+                    const uint32_t src = sd + (uint32_t)((r * NDX) * 4 + c) * DYB + (uint32_t)k * 16u;
+                    uint32_t v0, v1, v2, v3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src) : "memory");
+#pragma unroll
+                    for (int dx = 1; dx < NDX; ++dx)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(src + (uint32_t)(dx * 4) * DYB + (uint32_t)dx * 16u),
+                                     "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+                }
+                fence_proxy_async();            // generic-proxy writes -> visible to the tensor core's operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_ready + 8 * stage);
+                if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
+            }
+        }
         // ================= epilogue (once): TMEM -> this CTA's fp32 partial [tap][ci][co] + bias[co]
         float* ws = partial + (long long)blockIdx.x * (NTAPS * CP * 32 + 32);
         const int m = warp * 32 + lane;                     // D row = chunk*8 + e
@@ -363,8 +393,12 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     CUtensorMap tmIn, tmDy;
     memset(&tmIn, 0, sizeof(tmIn));
     memset(&tmDy, 0, sizeof(tmDy));
-    g.tmap = 1;
-    { const char* e = getenv("CURLA_WG_TMAP"); if (e && e[0] == '0') g.tmap = 0; }
+    // CURLA_WG_TMAP=1 (experiment, off by default: measured no faster, 0.380 vs 0.382 ms per update -- the number of
+    // requests per stage was not what paces the fill)
+    g.tmap = 0;
+    { const char* e = getenv("CURLA_WG_TMAP"); if (e && e[0] == '1') g.tmap = 1; }
+    g.dy1 = 0;
+    { const char* e = getenv("CURLA_WG_DY1"); if (e && e[0] == '1') g.dy1 = 1; }
     g.pss = pitch * 16;
     if (g.tmap) {
         const int pss = (pitch * 16 + 127) / 128 * 128;

@@ -110,7 +110,7 @@ struct TensorInfo {
 
 struct EncP { long long conv_w[4], conv_b[4], fc_w, fc_b, ln_w, ln_b; };      // float offsets
 struct MlpP { long long w0, b0, w1, b1, w2, b2; int in_real, out; };
-struct EncS { long long conv[4], fc; };                                        // bf16 offsets
+struct EncS { long long conv[4], fc, conv96; };                                // bf16 offsets (conv96: conv-2..4 packed for the fused kernel)
 struct MlpS { long long w0, w1; };
 struct MlpBuf { bf16 *X, *H1, *H2; float* out; };
 struct TailBuf { float *fc_out, *z; };
@@ -164,6 +164,7 @@ struct curla_agent {
     long long last_launches;
     // whole-update CUDA graphs: one per update variant (step parity, only_cpc, argument pointers); the per-update
     // scalars a replay needs (Adam step counters, Philox offset) live in dev_state (see curla_set_dev_state)
+    int keep_acts;                           // 1: every encoder pass stores conv-2 / conv-3 activations (logging taps read them)
     int* dev_state;
     cudaStream_t cap_st;                     // private capture stream (the caller's may be the legacy default stream,
                                              // which cannot be captured); replays are launched into the caller's stream
@@ -251,6 +252,10 @@ void shadow_encoder(Builder& b, const std::string& pre, const EncP& e, EncS& s, 
             s.conv[i] = b.s(pre + "convs." + std::to_string(i), {9, c.num_filters, c.num_filters});
             for (int k = 0; k < npacks; ++k) seg(*packs[k], e.conv_w[i], s.conv[i], 1, c.num_filters, c.num_filters, c.num_filters, c.num_filters);
         }
+        // conv-2..4 once more in the N = 96 operand image of the fused kernel (curla_conv_stack_fwd): one 55 KB bulk copy
+        s.conv96 = b.s(pre + "convs96", {3, 12, 96, 8});
+        for (int i = 1; i < 4; ++i)
+            for (int k = 0; k < npacks; ++k) seg(*packs[k], e.conv_w[i], s.conv96 + (long long)(i - 1) * 9216, 3, 32, 32, 32, 32);
     }
     s.fc = b.s(pre + "fc", {64, a->Kfc});
     for (int k = 0; k < npacks; ++k) seg(*packs[k], e.fc_w, s.fc, 0, c.feature_dim, a->Kfc, 64, a->Kfc);
@@ -450,6 +455,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->t_critic = a->t_actor = a->t_alpha = a->t_cpc = 0;
     a->last_launches = 0;
     a->graph_mode = -1;
+    a->keep_acts = 0;
     a->cap_st = nullptr;
     a->nccl_lib = nullptr; a->comm = nullptr;
     a->side = nullptr; a->side_state = 0;
@@ -543,7 +549,8 @@ struct Run {
     // weights and output buffers) run as ONE launch per layer (curla_conv_fwd_multi): 4 launches
     // instead of 4 per pass, and no pipeline fill/drain between passes.  CURLA_MERGE=0 launches
     // each pass separately (same results bit for bit).
-    struct Pass { const bf16* s2d; const EncP* e; const EncS* s; bf16* const* acts; };
+    // keep: the pass's backward (or a logging tap) reads its conv-2 / conv-3 activations; the others only need conv-4's
+    struct Pass { const bf16* s2d; const EncP* e; const EncS* s; bf16* const* acts; bool keep; };
     void conv_stack_multi(const Pass* ps, int np, int B = 0) {
         if (!ok() || np <= 0) return;
         if (!merge_mode() && np > 1) {
@@ -551,7 +558,10 @@ struct Run {
             return;
         }
         if (B <= 0) B = a->cfg.batch;
-        for (int i = 0; i < 4 && ok(); ++i) {
+        // conv-2..4 as ONE launch that keeps each sample in shared memory (the 76 x 135 crop fits, 90 x 160 does not)
+        const int Hv3[3] = {a->Ho[1], a->Ho[2], a->Ho[3]}, Wv3[3] = {a->Wo[1], a->Wo[2], a->Wo[3]};
+        const bool fused = curla_conv_stack_fits(a->pitch, a->S, Hv3, Wv3) != 0;
+        for (int i = 0; i < (fused ? 1 : 4) && ok(); ++i) {
             curla_conv_seg sg[3];
             for (int k = 0; k < np; ++k) {
                 sg[k].in = i == 0 ? ps[k].s2d : ps[k].acts[i - 1];
@@ -563,9 +573,23 @@ struct Run {
             chk(curla_conv_fwd_multi(sg, np, i == 0 ? a->s2d_sstride : a->act_sstride, i == 0 ? 1.0f / 255.0f : 1.0f,
                                      a->act_sstride, a->pitch, a->S, a->Ho[i], a->Wo[i], i == 0 ? 4 * a->cfg.C : 0, st));
         }
+        if (fused && ok()) {
+            curla_conv_stack_seg sg[3];
+            for (int k = 0; k < np; ++k) {
+                const bool keep = ps[k].keep || a->keep_acts;
+                sg[k].in = ps[k].acts[0];
+                sg[k].w96 = Sh(ps[k].s->conv96);
+                for (int l = 0; l < 3; ++l) sg[k].bias[l] = P(ps[k].e->conv_b[l + 1]);
+                sg[k].out[0] = keep ? ps[k].acts[1] : nullptr;
+                sg[k].out[1] = keep ? ps[k].acts[2] : nullptr;
+                sg[k].out[2] = ps[k].acts[3];
+                sg[k].B = B;
+            }
+            chk(curla_conv_stack_fwd(sg, np, a->act_sstride, a->pitch, a->S, Hv3, Wv3, st));
+        }
     }
     void conv_stack(const bf16* s2d, const EncP& e, const EncS& s, bf16* const acts[4], int B = 0) {
-        const Pass p = {s2d, &e, &s, acts};
+        const Pass p = {s2d, &e, &s, acts, false};
         conv_stack_multi(&p, 1, B);
     }
     // fc (split-K) + bias + LayerNorm
@@ -766,6 +790,18 @@ extern "C" int curla_agent_refresh_shadows(curla_agent* a, cudaStream_t stream) 
 
 extern "C" int curla_agent_last_launches(const curla_agent* a) { return (int)a->last_launches; }
 
+// 1: every encoder pass of the update stores its conv-2 / conv-3 activations (--log_param_hist_imgs reads the
+// target encoder's, encoder.py:118-130); 0 (default): only the passes a backward follows.  Captured update graphs
+// are dropped: the launch arguments change.
+extern "C" int curla_agent_set_keep_acts(curla_agent* a, int on) {
+    if ((on != 0) != (a->keep_acts != 0)) {
+        for (auto& kv : a->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        a->graphs.clear();
+    }
+    a->keep_acts = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int curla_agent_set_opt_steps(curla_agent* a, int t_critic, int t_actor, int t_alpha, int t_cpc) {
     a->t_critic = t_critic; a->t_actor = t_actor; a->t_alpha = t_alpha; a->t_cpc = t_cpc;
     return 0;
@@ -921,9 +957,9 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         const int mm = merge_mode();
         // F1: actor(next_obs) -> a', log_pi';  F2: critic_target(next_obs, a');  F3: critic(obs, action)
         bf16* const* act2 = (forked || mm) ? a->actC : a->actB;      // F1's tail may still be reading actB[3]
-        const Run::Pass p1 = {a->s2d_next, &a->enc_critic, &a->s_critic, a->actB};
-        const Run::Pass p2 = {a->s2d_next, &a->enc_target, &a->s_target, act2};
-        const Run::Pass p3 = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA};
+        const Run::Pass p1 = {a->s2d_next, &a->enc_critic, &a->s_critic, a->actB, false};
+        const Run::Pass p2 = {a->s2d_next, &a->enc_target, &a->s_target, act2, false};
+        const Run::Pass p3 = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA, true};
         auto tail1 = [&]() {
             r2.tail(a->actB[3], a->s_actor_fc, a->enc_actor, a->t_p1, B, 0, nullptr, a->m_p1.X, a->fc_partial2);
             r2.mlp_fwd_n(a->m_p1.X, &a->trunk_actor, &a->s_trunk, &a->m_p1, 1, B);
@@ -1007,8 +1043,8 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
     if (do_sac && do_ema && ema_first) { NvtxRange nv("curla/ema"); ema(); }
     const cudaStream_t ss7 = do_cpc ? side_stream(a, st) : st;
     const bool forked7 = ss7 != st;
-    const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA};    // F4 == F5 == F6 conv part
-    const Run::Pass p_key = {s2d_pos, &a->enc_target, &a->s_target, a->actB};          // F7
+    const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA, true};    // F4 == F5 == F6 conv part
+    const Run::Pass p_key = {s2d_pos, &a->enc_target, &a->s_target, a->actB, false};          // F7
     bool key_done = false, join7 = false;
     // tail of one pass on the side stream (fc_partial2 is the side stream's split-K buffer)
     // all-gather of the CURL keys (the one real exchange step of the update): issued on the stream that

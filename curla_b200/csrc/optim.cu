@@ -108,7 +108,7 @@ k_ema(float* __restrict__ tgt, const float* __restrict__ p, long long n, long lo
 }
 
 // ---------------------------------------------------------------- shadow packers
-enum { PACK_ROWS = 0, PACK_CONV = 1, PACK_CONV1_S2D = 2 };
+enum { PACK_ROWS = 0, PACK_CONV = 1, PACK_CONV1_S2D = 2, PACK_CONV96 = 3 };
 struct PackSeg {
     long long src_off;   // floats into the fp32 arena
     long long dst_off;   // bf16 elements into the shadow arena
@@ -168,6 +168,14 @@ k_pack(const float* __restrict__ src_arena, bf16* __restrict__ dst_arena, PackTa
             const int co = (int)((i / s.cols_pad) % s.rows);
             const int t = (int)(i / ((long long)s.cols_pad * s.rows));
             dst[i] = __float2bfloat16(ci < s.cols ? src[((long long)co * s.cols + ci) * 9 + t] : 0.f);
+        }
+    } else if (s.kind == PACK_CONV96) {
+        // OIHW [32][32][3][3] -> the N = 96 operand image of conv_tc.cu: [dy][k chunk][n = dx*32 + co][8 k]
+        const long long n = 9LL * 32 * 32;
+        for (; i < n; i += stride) {
+            const int k8 = (int)(i & 7), r = (int)(i >> 3);
+            const int col = r % 96, dk = r / 96, kc = dk & 3, dy = dk >> 2, dx = col >> 5, co = col & 31;
+            dst[i] = __float2bfloat16(src[((long long)co * 32 + kc * 8 + k8) * 9 + dy * 3 + dx]);
         }
     } else {
         // stride-2 3x3 conv1 as a 2x2 conv on the space-to-depth input:
@@ -248,7 +256,7 @@ extern "C" int curla_pack_shadows(const float* src_arena, void* dst_arena, const
             s.src_off = r[0]; s.dst_off = r[1]; s.kind = (int)r[2]; s.rows = (int)r[3];
             s.cols = (int)r[4]; s.rows_pad = (int)r[5]; s.cols_pad = (int)r[6];
             long long cnt = s.kind == PACK_ROWS ? (long long)s.rows_pad * s.cols_pad
-                          : (s.kind == PACK_CONV ? 9LL : 4LL) * s.rows * s.cols_pad;
+                          : (s.kind == PACK_CONV || s.kind == PACK_CONV96 ? 9LL : 4LL) * s.rows * s.cols_pad;
             // the vectorised row path moves 8 elements per thread; a CTA gets ~2 items per thread
             const long long items = (s.kind == PACK_ROWS && (s.cols_pad & 7) == 0 && (s.dst_off & 7) == 0) ? cnt / 8 : cnt;
             long long b = (items + 511) / 512;

@@ -119,6 +119,23 @@ typedef struct curla_conv_seg {
 int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long long in_sstride, float scale,
                          long long out_sstride, int pitch, int S, int Hv, int Wv,
                          int first_layer, curla_stream_t stream);
+/* conv-2 .. conv-4 (encoder.py:83-87, the three 32 -> 32 channel 3x3 layers + ReLU) in ONE launch: a CTA keeps
+ * one sample's activation map in shared memory and runs the three layers over it in place, so the intermediate
+ * activations only reach HBM where the caller asks for them (out[0], out[1] non-NULL: passes whose backward reads
+ * them).  in = conv-1 output, out[2] = conv-4 output, all [B][4 planes][S][8] bf16 with sample stride `sstride`
+ * elements; w96 = the three layers' weights packed by curla_pack_shadows kind 3 ([layer][dy][k chunk][96][8]).
+ * Up to three passes (two distinct weight sets) per launch.  curla_conv_stack_fits: 1 when the geometry fits
+ * one SM's shared memory (the 76 x 135 crop does, 90 x 160 does not) and CURLA_CONV_FUSED=1 (opt-in experiment). */
+typedef struct curla_conv_stack_seg {
+    const void* in;
+    const void* w96;
+    const float* bias[3];
+    void* out[3];
+    int B;
+} curla_conv_stack_seg;
+int curla_conv_stack_fits(int pitch, int S, const int* Hv, const int* Wv);
+int curla_conv_stack_fwd(const curla_conv_stack_seg* segs, int nseg, long long sstride, int pitch, int S,
+                         const int* Hv, const int* Wv, curla_stream_t stream);
 /* timing experiments (CURLA_TC_DEBUG=64): per-CTA cycle counters of the conv pipeline roles */
 int curla_conv_debug_read(long long* out, int n);
 long long curla_conv_wgrad_workspace_floats(int first_layer);
@@ -315,6 +332,9 @@ enum { CURLA_PHASE_SAMPLE = 1, CURLA_PHASE_CRITIC = 2, CURLA_PHASE_ACTOR = 4, CU
 /* One whole update.  metrics: device float[16]
  * {batch_reward, critic_loss, actor_loss, entropy, alpha_loss, alpha, curl_loss, target_entropy} */
 int curla_agent_update(curla_agent* a, const curla_update_args* args, curla_stream_t stream);
+/* 1: every encoder pass stores its conv-2 / conv-3 activations (the --log_param_hist_imgs taps read them,
+ * encoder.py:118-130); 0 (default): only the passes a backward follows (the fused conv kernel keeps the rest on chip) */
+int curla_agent_set_keep_acts(curla_agent* a, int on);
 /* number of kernel launches issued by the last curla_agent_update */
 int curla_agent_last_launches(const curla_agent* a);
 /* per-optimizer Adam step counters {critic, actor, log_alpha, encoder+cpc} (the reference

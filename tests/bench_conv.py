@@ -62,6 +62,10 @@ if int(os.environ.get('CURLA_TC_DEBUG', '0')) & 64:
              'epi w0 wait tfull', 'epi w0 busy']
     for i, nme in enumerate(names):
         print('   %-22s mean %9.0f  min %9d  max %9d clk' % (nme, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
+    if os.environ.get('CURLA_CONV_N96') == '1' and layer > 0:
+        for i, nme in ((15, 'epi w0 TMEM phase'), (16, 'epi w0 bar.sync'), (17, 'epi w0 exchange+store')):
+            print('   %-22s mean %9.0f  min %9d  max %9d clk' % (nme, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
+        sys.exit(0)
     t0 = a[:, 8].min()
     for i, nme in ((8, 'CTA entry'), (9, 'MMA loop start'), (10, 'MMA loop end'), (11, 'CTA exit')):
         v = (a[:, i] - t0) / 1e3

@@ -42,6 +42,9 @@ def test_header_is_plain_c_and_structs_match_ctypes(tmp_path):
         '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(curla_conv_seg), offsetof(curla_conv_seg, in), offsetof(curla_conv_seg, wts),\n'
         '         offsetof(curla_conv_seg, bias), offsetof(curla_conv_seg, out), offsetof(curla_conv_seg, B));\n'
         '  printf("%zu %zu\\n", sizeof(curla_agent_config), sizeof(curla_update_args));\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(curla_conv_stack_seg), offsetof(curla_conv_stack_seg, in),\n'
+        '         offsetof(curla_conv_stack_seg, w96), offsetof(curla_conv_stack_seg, bias), offsetof(curla_conv_stack_seg, out),\n'
+        '         offsetof(curla_conv_stack_seg, B));\n'
         '  return 0;\n}\n')
     exe = tmp_path / 'probe'
     subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
@@ -50,9 +53,11 @@ def test_header_is_plain_c_and_structs_match_ctypes(tmp_path):
     cs = _lib.ConvSeg
     assert vals[:6] == [C.sizeof(cs), cs.inp.offset, cs.wts.offset, cs.bias.offset, cs.out.offset, cs.B.offset]
     assert vals[6] == C.sizeof(_lib.AgentConfig) and vals[7] == C.sizeof(_lib.UpdateArgs)
+    ss = _lib.ConvStackSeg
+    assert vals[8:14] == [C.sizeof(ss), ss.inp.offset, ss.w96.offset, ss.bias.offset, ss.out.offset, ss.B.offset]
 
 
-def test_host_only_helpers(lib):
+def test_host_only_helpers(lib, monkeypatch):
     """Pure host functions of the C ABI (no GPU): split-K ranges are multiples of 64 -- the K step of the
     tcgen05 GEMM -- so the number of partial slices the engine allocates does not depend on which GEMM
     kernel runs; the conv padding covers a slab's halo."""
@@ -65,6 +70,13 @@ def test_host_only_helpers(lib):
     assert lib.curla_gemm_effective_splits(67456, 74) == 71      # the encoder fc forward at train.py defaults
     for pitch in (32, 42, 68, 80):
         assert lib.curla_conv_pad_rows(pitch) >= 256 + 2 * pitch + 2
+    # conv-2..4 fused in shared memory: the default 76 x 135 crop fits one SM (2552 positions x 64 B + weights),
+    # the 90 x 160 identity / pixel-SAC input does not and runs layer by layer
+    I3 = C.c_int * 3
+    monkeypatch.setenv('CURLA_CONV_FUSED', '1')
+    assert lib.curla_conv_stack_fits(68, 38 * 68, I3(35, 33, 31), I3(65, 63, 61)) == 1
+    assert lib.curla_conv_stack_fits(80, 45 * 80, I3(42, 40, 38), I3(77, 75, 73)) == 0
+    assert lib.curla_conv_stack_fits(42, 42 * 42, I3(39, 37, 35), I3(39, 37, 35)) == 1          # 84 x 84
 
 
 def test_engine_layout_host_side(lib):

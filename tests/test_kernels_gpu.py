@@ -144,6 +144,78 @@ def _run_conv_stack(g, x, ws, bs):
     return s2d, acts, keep
 
 
+@pytest.mark.parametrize('H,W,Bs', [(76, 135, (3, 2, 4)), (76, 135, (330,)), (64, 64, (5, 3)), (84, 84, (7,))])
+def test_conv_stack_fused_equals_layer_by_layer(H, W, Bs, monkeypatch):
+    """curla_conv_stack_fwd (conv-2..4 in ONE launch, each sample resident in shared memory, layers in place, weights
+    packed by curla_pack_shadows kind 3) against the three launches of the N = 96 kernel it shares its arithmetic with:
+    bit-identical outputs; passes that do not keep conv-2 / conv-3 leave those buffers untouched; up to three passes
+    with two weight sets per launch; more samples than CTAs (the buffer is refilled slot by slot behind conv-4)."""
+    monkeypatch.setenv('CURLA_CONV_N96', '1')
+    torch.manual_seed(11)
+    npass = len(Bs)
+    g0 = Geom(H, W, max(Bs))
+    Hv = (C.c_int * 3)(*g0.Ho[1:4])
+    Wv = (C.c_int * 3)(*g0.Wo[1:4])
+    monkeypatch.setenv('CURLA_CONV_FUSED', '1')
+    assert _lib.load().curla_conv_stack_fits(g0.pitch, g0.S, Hv, Wv) == 1
+    wsets = [[torch.randn(32, 32, 3, 3) * (2.0 / 288) ** 0.5 for _ in range(3)] for _ in range(2)]
+    bsets = [[(torch.randn(32) * 0.05).to(DEV) for _ in range(3)] for _ in range(2)]
+    # packed N = 96 images of both weight sets through the product's packer
+    w96 = []
+    for k in range(2):
+        src = torch.cat([w.reshape(-1) for w in wsets[k]]).to(DEV)
+        dst = torch.zeros(3 * 9216, dtype=torch.bfloat16, device=DEV)
+        segs = torch.tensor([[l * 9216, l * 9216, 3, 32, 32, 32, 32] for l in range(3)], dtype=torch.int64)
+        _lib.call('curla_pack_shadows', _lib.ptr(src), _lib.ptr(dst), C.c_void_p(segs.data_ptr()), 3, stream())
+        w96.append(dst)
+    keep_alive, ins, refs = [], [], []
+    for k, B in enumerate(Bs):
+        g = Geom(H, W, B)
+        full, a0 = g.to_pitch(torch.rand(B, 32, g.Ho[0], g.Wo[0], device=DEV), 0)
+        keep_alive.append(full)
+        ins.append((g, a0))
+        # reference: three launches of the per-layer kernel
+        cur, outs = a0, []
+        for l in range(3):
+            wsh = pack_conv_w(wsets[k % 2][l], False)
+            fo, o = g.alloc(32)
+            _lib.call('curla_conv_fwd', _lib.ptr(cur), g.S * 32, _lib.ptr(wsh), _lib.ptr(bsets[k % 2][l]), 1.0, _lib.ptr(o),
+                      g.S * 32, B, g.pitch, g.S, g.Ho[l + 1], g.Wo[l + 1], 0, stream())
+            keep_alive += [fo, wsh]
+            outs.append(o)
+            cur = o
+        refs.append(outs)
+    segs = (_lib.ConvStackSeg * 3)()
+    fused = []
+    for k, B in enumerate(Bs):
+        g, a0 = ins[k]
+        keep = (k % 2 == 0)                                        # passes 0 and 2 keep conv-2 / conv-3
+        outs = []
+        for l in range(3):
+            fo, o = g.alloc(32)
+            o.fill_(7.0)
+            keep_alive.append(fo)
+            outs.append(o)
+        fused.append((keep, outs))
+        segs[k].inp = a0.data_ptr(); segs[k].w96 = w96[k % 2].data_ptr(); segs[k].B = B
+        for l in range(3):
+            segs[k].bias[l] = bsets[k % 2][l].data_ptr()
+            segs[k].out[l] = outs[l].data_ptr() if (keep or l == 2) else None
+    _lib.call('curla_conv_stack_fwd', C.byref(segs), npass, g0.S * 32, g0.pitch, g0.S, Hv, Wv, stream())
+    torch.cuda.synchronize()
+    for k, B in enumerate(Bs):
+        g, _ = ins[k]
+        keep, outs = fused[k]
+        for l in range(3):
+            n = g.Ho[l + 1] * g.pitch
+            a = outs[l].view(torch.int16).view(B, 4, g.S, 8)
+            b = refs[k][l].view(torch.int16).view(B, 4, g.S, 8)
+            if keep or l == 2:
+                assert torch.equal(a[:, :, :n], b[:, :, :n]), (k, l, int((a[:, :, :n] != b[:, :, :n]).sum()))
+            else:
+                assert bool((outs[l] == 7.0).all()), (k, l)
+
+
 @pytest.mark.parametrize('n96', ['1', '0'])
 @pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (64, 64, 5)])
 def test_conv_forward(H, W, B, n96, monkeypatch):
@@ -287,11 +359,11 @@ def test_conv_backward(H, W, B, n96, monkeypatch):
 
 
 @pytest.mark.parametrize('H,W,B', [(76, 135, 5), (90, 160, 3)])
-def test_conv_wgrad_tensor_map_staging_equals_linear_staging(H, W, B, monkeypatch):
-    """conv_wgrad_tc.cu stages its operands with tensor-map TMA boxes (all channel planes of an image row per request,
-    the shifted dy copies zero-filled by the TMA unit); CURLA_WG_TMAP=0 keeps one linear bulk copy per plane per
-    row.  Same MMAs in the same order: the weight / bias gradients must be bit-identical, conv-1 (2x2 taps on
-    the space-to-depth input, 6 planes) and a 3x3 layer."""
+def test_conv_wgrad_staging_modes_agree(H, W, B, monkeypatch):
+    """conv_wgrad_tc.cu can stage its operands with tensor-map TMA boxes (CURLA_WG_TMAP=1: all channel planes of an
+    image row per request, the shifted dy copies zero-filled by the TMA unit) instead of one linear bulk copy per plane
+    per row, and can fetch dy from L2 once, making the shifted copies inside shared memory (CURLA_WG_DY1=1).  Same products, fp32 accumulation: the weight / bias gradients agree to 1e-5, conv-1 (2x2 taps on the
+    space-to-depth input, 6 planes) and a 3x3 layer."""
     g, x, ws, bs = _conv_case(H, W, B, seed=4)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(5)
@@ -302,8 +374,9 @@ def test_conv_wgrad_tensor_map_staging_equals_linear_staging(H, W, B, monkeypatc
         dfull, dview = g.to_pitch(bf16r(dy), l)
         inp = acts[l - 1] if l > 0 else s2d
         got = {}
-        for mode in ('0', '1'):
-            monkeypatch.setenv('CURLA_WG_TMAP', mode)
+        for mode in ('00', '10', '01', '11'):          # (tensor-map staging, dy staged once + replicated in shared memory)
+            monkeypatch.setenv('CURLA_WG_TMAP', mode[0])
+            monkeypatch.setenv('CURLA_WG_DY1', mode[1])
             dW = torch.zeros(ws[l].shape, device=DEV)
             db = torch.zeros(32, device=DEV)
             _lib.call('curla_conv_wgrad', _lib.ptr(inp), g.S * (32 if l > 0 else g.CP1), _lib.ptr(dview), g.S * 32,
@@ -311,9 +384,12 @@ def test_conv_wgrad_tensor_map_staging_equals_linear_staging(H, W, B, monkeypatc
                       g.Ho[l], g.Wo[l], ws[l].shape[1], 1 if l == 0 else 0, stream())
             torch.cuda.synchronize()
             got[mode] = (dW, db)
-        assert torch.equal(got['0'][0], got['1'][0]), (l, float((got['0'][0] - got['1'][0]).abs().max()))
-        assert torch.equal(got['0'][1], got['1'][1]), l
-        assert float(got['1'][0].abs().sum()) > 0
+        # (the modes may split the batch into different runs per CTA: same products, another fp32 summation order)
+        for mode in ('10', '01', '11'):
+            assert rel_l2(got[mode][0], got['00'][0]) < 1e-5, (l, mode, rel_l2(got[mode][0], got['00'][0]))
+            assert rel_l2(got[mode][1], got['00'][1]) < 1e-5, (l, mode)
+        assert torch.equal(got['01'][0], got['00'][0]) and torch.equal(got['01'][1], got['00'][1])      # same runs, same MMAs
+        assert float(got['11'][0].abs().sum()) > 0
 
 
 # ------------------------------------------------------------------ GEMM

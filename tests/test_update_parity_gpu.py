@@ -489,7 +489,7 @@ DRIFT = dict(aug='random_crop', frame_hw=(90, 160), B=64, capacity=256, hidden=2
 # within 4 % (critic), 0.15 (actor loss), 0.2 (entropy), 0.01 (alpha loss), 5 % (CURL loss).  The bands
 # are about three times that natural divergence.
 DRIFT_BAND = {'train/batch_reward': (1e-6, 1.0), 'train_critic/loss': (0.15, 0.05), 'train_actor/loss': (0.30, 1.0),
-              'train_actor/entropy': (0.20, 3.0), 'train_alpha/loss': (0.10, 0.3), 'train_alpha/value': (1e-3, 0.1),
+              'train_actor/entropy': (0.20, 3.0), 'train_alpha/loss': (0.15, 0.3), 'train_alpha/value': (1e-3, 0.1),
               'train/curl_loss': (0.10, 0.05)}
 
 
