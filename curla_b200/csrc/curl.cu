@@ -211,8 +211,11 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
 // The B x Bg bilinear contraction and its two gradient contractions on the tensor cores
 // (mma.sync m16n8k16, bf16 operands, fp32 accumulate).  The reference computes them in fp32
 // (curl_sac.py:211-222) and logits of magnitude ~30 sit in an exp(), so every fp32 operand x is split
-// into hi = bf16(x), lo = bf16(x - hi) and a product is  a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (three
-// MMAs; the dropped lo.lo term is 2^-18 relative): fp32-level results (tests: 1e-4 against torch fp32).
+// into THREE bf16 pieces  hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)  (24 mantissa bits: the fp32 value
+// exactly, up to the last rounding) and a product is  hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi  (six MMAs; the
+// dropped mid.lo / lo.mid / lo.lo terms are 2^-24 relative): fp32-equivalent results.  A two-piece split (three MMAs,
+// 2^-17) was measurably not enough once the CURL head collapses (loss -> ln B): the gradient of the early conv
+// layers is then a small difference of large batch sums and amplified that error to tens of percent.
 //
 // Work unit = one warp: 16 local rows x 64 key columns.  A CTA is 8 warps = the same 16 rows x 512
 // columns; grid (B/16 row blocks, Bg/512 column blocks), so a global batch of 4096 keys spreads over
@@ -232,43 +235,101 @@ __device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint3
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = pack_bf16x2(x - hf.x, y - hf.y);
 }
+__device__ __forceinline__ void split3_bf16(float x, float y, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const float2 hf = __bfloat1622float2(h);
+    const float rx = x - hf.x, ry = y - hf.y;                 // exact
+    const __nv_bfloat162 m = __floats2bfloat162_rn(rx, ry);
+    const float2 mf = __bfloat1622float2(m);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    mid = *reinterpret_cast<const uint32_t*>(&m);
+    lo = pack_bf16x2(rx - mf.x, ry - mf.y);
+}
+__device__ __forceinline__ void split3_store(float x, bf16* hi, bf16* mid, bf16* lo, long long o) {
+    const bf16 h = __float2bfloat16_rn(x);
+    const float r = x - __bfloat162float(h);
+    const bf16 m = __float2bfloat16_rn(r);
+    hi[o] = h; mid[o] = m; lo[o] = __float2bfloat16_rn(r - __bfloat162float(m));
+}
+// acc += a . b for 3-piece operands (a: A fragments [piece][4], b: B fragment pairs [piece][2])
+__device__ __forceinline__ void mma6(float* acc, const uint32_t (&ah)[4], const uint32_t (&am)[4], const uint32_t (&al)[4],
+                                     uint32_t bh0, uint32_t bh1, uint32_t bm0, uint32_t bm1, uint32_t bl0, uint32_t bl1) {
+    mma_bf16(acc, al[0], al[1], al[2], al[3], bh0, bh1);      // smallest terms first
+    mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+    mma_bf16(acc, am[0], am[1], am[2], am[3], bm0, bm1);
+    mma_bf16(acc, am[0], am[1], am[2], am[3], bh0, bh1);
+    mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bm0, bm1);
+    mma_bf16(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+}
 __device__ __forceinline__ uint32_t ldg_u32(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+
+// Centred operands.  Softmax and its gradient only see DIFFERENCES between keys: logits_ij = z_i . U_j may be
+// shifted by any per-row constant, and  dz_i = sum_j dl_ij U_j,  V_i = sum_j dl_ij z_j  with  sum_j dl_ij = 0  (up to
+// fp32 rounding, as in the reference's own softmax) are unchanged when a constant vector is subtracted from every
+// U_j / z_j.  The split products carry ~2^-17 of their OPERANDS' magnitude, so the contractions run on
+// U_j - mean(U), z_j - mean(z): when the keys are nearly equal -- a collapsing CURL head, logits ~ uniform, the
+// gradient a small difference of large terms -- the error stays relative to the differences, not to the common
+// part (measured on the 8-update parity scenario: conv-1 gradient error 81 % uncentred).
+constexpr int kMeanParts = 8;
+__global__ void __launch_bounds__(256)
+k_curl_means(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, float* __restrict__ part) {
+    pdl_grid_sync();
+    __shared__ float red[2][128];
+    const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const float* src = col < 64 ? U + col : z_pos + (col - 64);
+    const int per = (Bg + kMeanParts - 1) / kMeanParts;
+    const int j0 = blockIdx.x * per, j1 = min(Bg, j0 + per);
+    float acc = 0.f;
+    for (int j = j0 + half; j < j1; j += 2) acc += src[(long long)j * 64];
+    red[half][col] = acc;
+    __syncthreads();
+    if (half == 0) part[blockIdx.x * 128 + col] = red[0][col] + red[1][col];
+}
 
 // U, z_pos: fp32 [Bg][64].  Uk_*: bf16 [BgP][64]; UT_*, ZT_*: bf16 [64][BgP]; rows j >= Bg are zero.
 __global__ void __launch_bounds__(256)
-k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, int BgP,
-            bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_lo, bf16* __restrict__ UT_hi, bf16* __restrict__ UT_lo,
-            bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_lo) {
+k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, const float* __restrict__ mean_part,
+            float* __restrict__ means, int Bg, int BgP,
+            bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_mid, bf16* __restrict__ Uk_lo,
+            bf16* __restrict__ UT_hi, bf16* __restrict__ UT_mid, bf16* __restrict__ UT_lo,
+            bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_mid, bf16* __restrict__ ZT_lo) {
     pdl_grid_sync();
     __shared__ float su[32][65], sz[32][65];
+    __shared__ float mu[128];
+    if (threadIdx.x < 128) {
+        float m = 0.f;
+#pragma unroll
+        for (int q = 0; q < kMeanParts; ++q) m += mean_part[q * 128 + threadIdx.x];       // fixed order: deterministic
+        m /= (float)Bg;
+        mu[threadIdx.x] = m;
+        if (blockIdx.x == 0) means[threadIdx.x] = m;
+    }
+    __syncthreads();
     const int j0 = blockIdx.x * 32;
     for (int t = threadIdx.x; t < 2048; t += 256) {
         const int jj = t >> 6, k = t & 63, j = j0 + jj;
-        const float u = j < Bg ? U[(long long)j * 64 + k] : 0.f;
-        const float z = j < Bg ? z_pos[(long long)j * 64 + k] : 0.f;
+        const float u = j < Bg ? U[(long long)j * 64 + k] - mu[k] : 0.f;
+        const float z = j < Bg ? z_pos[(long long)j * 64 + k] - mu[64 + k] : 0.f;
         su[jj][k] = u; sz[jj][k] = z;
-        const bf16 h = __float2bfloat16_rn(u);
-        Uk_hi[(long long)j * 64 + k] = h;
-        Uk_lo[(long long)j * 64 + k] = __float2bfloat16_rn(u - __bfloat162float(h));
+        split3_store(u, Uk_hi, Uk_mid, Uk_lo, (long long)j * 64 + k);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < 2048; t += 256) {
         const int a = t >> 5, jj = t & 31;
         const long long o = (long long)a * BgP + j0 + jj;
-        const float u = su[jj][a], z = sz[jj][a];
-        const bf16 uh = __float2bfloat16_rn(u), zh = __float2bfloat16_rn(z);
-        UT_hi[o] = uh; UT_lo[o] = __float2bfloat16_rn(u - __bfloat162float(uh));
-        ZT_hi[o] = zh; ZT_lo[o] = __float2bfloat16_rn(z - __bfloat162float(zh));
+        split3_store(su[jj][a], UT_hi, UT_mid, UT_lo, o);
+        split3_store(sz[jj][a], ZT_hi, ZT_mid, ZT_lo, o);
     }
 }
 
 struct CurlTc {
     const float* z_a;                          // [B][64] fp32
-    const bf16 *Uk_hi, *Uk_lo, *UT_hi, *UT_lo, *ZT_hi, *ZT_lo;
+    const bf16 *Uk_hi, *Uk_mid, *Uk_lo, *UT_hi, *UT_mid, *UT_lo, *ZT_hi, *ZT_mid, *ZT_lo;
     float* pstat;                              // [NT][Bp][2]  (max, sum exp) per 64-column tile
     float* lab_logit;                          // [Bp]
     float* pdz; float* pV;                     // [NCB][Bp][64] column-block partials (NCB > 1), else dz_a / V directly
     float* logits_copy;                        // optional [B][Bg]
+    const float* means;                        // [128]: mean(U) | mean(z_pos): the operands are centred (see k_curl_means)
     int B, Bg, BgP, Bp, NT, label0;
     float grad_scale;
 };
@@ -287,7 +348,7 @@ k_curl_tc(const CurlTc p) {
     float lg[8][4];
     if (active) {
         // ---- A = z_a rows (hi / lo), all of K = 64 in registers
-        uint32_t a_hi[4][4], a_lo[4][4];
+        uint32_t a_hi[4][4], a_mid[4][4], a_lo[4][4];
 #pragma unroll
         for (int kt = 0; kt < 4; ++kt) {
 #pragma unroll
@@ -295,7 +356,7 @@ k_curl_tc(const CurlTc p) {
                 const int row = (h & 1) ? rowB : rowA, k = kt * 16 + 2 * t + (h >> 1) * 8;
                 float2 v = make_float2(0.f, 0.f);
                 if (row < p.B) v = *reinterpret_cast<const float2*>(p.z_a + (long long)row * 64 + k);
-                split_bf16(v.x, v.y, a_hi[kt][h], a_lo[kt][h]);
+                split3_bf16(v.x, v.y, a_hi[kt][h], a_mid[kt][h], a_lo[kt][h]);
             }
         }
         // ---- logits[16][64] = z_a . U^T : 8 column tiles of 8
@@ -306,16 +367,23 @@ k_curl_tc(const CurlTc p) {
 #pragma unroll
             for (int kt = 0; kt < 4; ++kt) {
                 const uint32_t bh0 = ldg_u32(p.Uk_hi + rowoff + kt * 16), bh1 = ldg_u32(p.Uk_hi + rowoff + kt * 16 + 8);
+                const uint32_t bm0 = ldg_u32(p.Uk_mid + rowoff + kt * 16), bm1 = ldg_u32(p.Uk_mid + rowoff + kt * 16 + 8);
                 const uint32_t bl0 = ldg_u32(p.Uk_lo + rowoff + kt * 16), bl1 = ldg_u32(p.Uk_lo + rowoff + kt * 16 + 8);
-                mma_bf16(lg[nt], a_hi[kt][0], a_hi[kt][1], a_hi[kt][2], a_hi[kt][3], bh0, bh1);
-                mma_bf16(lg[nt], a_lo[kt][0], a_lo[kt][1], a_lo[kt][2], a_lo[kt][3], bh0, bh1);
-                mma_bf16(lg[nt], a_hi[kt][0], a_hi[kt][1], a_hi[kt][2], a_hi[kt][3], bl0, bl1);
+                mma6(lg[nt], a_hi[kt], a_mid[kt], a_lo[kt], bh0, bh1, bm0, bm1, bl0, bl1);
             }
         }
     }
     const int labA = p.label0 + rowA, labB = p.label0 + rowB;
     if (PASS == 0) {
         if (!active) return;
+        float cA = 0.f, cB = 0.f;                  // the raw logits (tests) = centred logits + z_i . mean(U)
+        if (p.logits_copy) {
+            for (int k = 0; k < 64; ++k) {
+                const float m = __ldg(p.means + k);
+                if (rowA < p.B) cA = fmaf(p.z_a[(long long)rowA * 64 + k], m, cA);
+                if (rowB < p.B) cB = fmaf(p.z_a[(long long)rowB * 64 + k], m, cB);
+            }
+        }
         float mA = -INFINITY, mB = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
@@ -327,8 +395,8 @@ k_curl_tc(const CurlTc p) {
                     if (j == labA && rowA < p.B) p.lab_logit[rowA] = lg[nt][e];
                     if (j == labB && rowB < p.B) p.lab_logit[rowB] = lg[nt][2 + e];
                     if (p.logits_copy) {
-                        if (rowA < p.B) p.logits_copy[(long long)rowA * p.Bg + j] = lg[nt][e];
-                        if (rowB < p.B) p.logits_copy[(long long)rowB * p.Bg + j] = lg[nt][2 + e];
+                        if (rowA < p.B) p.logits_copy[(long long)rowA * p.Bg + j] = lg[nt][e] + cA;
+                        if (rowB < p.B) p.logits_copy[(long long)rowB * p.Bg + j] = lg[nt][2 + e] + cB;
                     }
                 }
             }
@@ -383,24 +451,26 @@ k_curl_tc(const CurlTc p) {
             // ---- dz_a[16][64] += dl . U ; V[16][64] += dl . z_pos   (k = j: 4 steps of 16 columns)
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                uint32_t dh[4], dlo[4];
-                split_bf16(lg[2 * m][0], lg[2 * m][1], dh[0], dlo[0]);
-                split_bf16(lg[2 * m][2], lg[2 * m][3], dh[1], dlo[1]);
-                split_bf16(lg[2 * m + 1][0], lg[2 * m + 1][1], dh[2], dlo[2]);
-                split_bf16(lg[2 * m + 1][2], lg[2 * m + 1][3], dh[3], dlo[3]);
+                uint32_t dh[4], dm[4], dlo[4];
+                split3_bf16(lg[2 * m][0], lg[2 * m][1], dh[0], dm[0], dlo[0]);
+                split3_bf16(lg[2 * m][2], lg[2 * m][3], dh[1], dm[1], dlo[1]);
+                split3_bf16(lg[2 * m + 1][0], lg[2 * m + 1][1], dh[2], dm[2], dlo[2]);
+                split3_bf16(lg[2 * m + 1][2], lg[2 * m + 1][3], dh[3], dm[3], dlo[3]);
 #pragma unroll
                 for (int na = 0; na < 8; ++na) {
                     const long long off = (long long)(na * 8 + g) * p.BgP + jw + m * 16 + 2 * t;
-                    const uint32_t uh0 = ldg_u32(p.UT_hi + off), uh1 = ldg_u32(p.UT_hi + off + 8);
-                    const uint32_t ul0 = ldg_u32(p.UT_lo + off), ul1 = ldg_u32(p.UT_lo + off + 8);
-                    mma_bf16(dz[na], dh[0], dh[1], dh[2], dh[3], uh0, uh1);
-                    mma_bf16(dz[na], dlo[0], dlo[1], dlo[2], dlo[3], uh0, uh1);
-                    mma_bf16(dz[na], dh[0], dh[1], dh[2], dh[3], ul0, ul1);
-                    const uint32_t zh0 = ldg_u32(p.ZT_hi + off), zh1 = ldg_u32(p.ZT_hi + off + 8);
-                    const uint32_t zl0 = ldg_u32(p.ZT_lo + off), zl1 = ldg_u32(p.ZT_lo + off + 8);
-                    mma_bf16(vv[na], dh[0], dh[1], dh[2], dh[3], zh0, zh1);
-                    mma_bf16(vv[na], dlo[0], dlo[1], dlo[2], dlo[3], zh0, zh1);
-                    mma_bf16(vv[na], dh[0], dh[1], dh[2], dh[3], zl0, zl1);
+                    {
+                        const uint32_t uh0 = ldg_u32(p.UT_hi + off), uh1 = ldg_u32(p.UT_hi + off + 8);
+                        const uint32_t um0 = ldg_u32(p.UT_mid + off), um1 = ldg_u32(p.UT_mid + off + 8);
+                        const uint32_t ul0 = ldg_u32(p.UT_lo + off), ul1 = ldg_u32(p.UT_lo + off + 8);
+                        mma6(dz[na], dh, dm, dlo, uh0, uh1, um0, um1, ul0, ul1);
+                    }
+                    {
+                        const uint32_t zh0 = ldg_u32(p.ZT_hi + off), zh1 = ldg_u32(p.ZT_hi + off + 8);
+                        const uint32_t zm0 = ldg_u32(p.ZT_mid + off), zm1 = ldg_u32(p.ZT_mid + off + 8);
+                        const uint32_t zl0 = ldg_u32(p.ZT_lo + off), zl1 = ldg_u32(p.ZT_lo + off + 8);
+                        mma6(vv[na], dh, dm, dlo, zh0, zh1, zm0, zm1, zl0, zl1);
+                    }
                 }
             }
         }
@@ -479,18 +549,19 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 using namespace curla;
 
 namespace {
-struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, total; };
+struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, off_means, total; };
 CurlPlan curl_plan(int B, int Bg) {
     CurlPlan c;
     c.BgP = (Bg + 63) / 64 * 64; c.Bp = (B + 15) / 16 * 16;
     c.NT = c.BgP / 64; c.NCB = (c.NT + 7) / 8;
     long long o = 2LL * Bg * 64 + (long long)B * 64 + B;       // U, Ut, V, row_loss (the CUDA-core path's layout)
     o = (o + 3) / 4 * 4;
-    c.off_bf16 = o; o += 6 * c.BgP * 64 / 2;                   // six bf16 [BgP x 64] arrays
+    c.off_bf16 = o; o += 9 * c.BgP * 64 / 2 + 2;               // nine bf16 [BgP x 64] arrays
     c.off_pstat = o; o += c.NT * c.Bp * 2;
     c.off_lab = o; o += c.Bp;
     c.off_pdz = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
     c.off_pV = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
+    c.off_means = o; o += 128 + kMeanParts * 128;               // mean(U) | mean(z_pos), and their per-slice partial sums
     c.total = o;
     return c;
 }
@@ -521,14 +592,19 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
             const long long n = cp.BgP * 64;
             CurlTc t;
             t.z_a = z_a;
-            t.Uk_hi = hb; t.Uk_lo = hb + n; t.UT_hi = hb + 2 * n; t.UT_lo = hb + 3 * n; t.ZT_hi = hb + 4 * n; t.ZT_lo = hb + 5 * n;
+            t.Uk_hi = hb; t.Uk_mid = hb + n; t.Uk_lo = hb + 2 * n; t.UT_hi = hb + 3 * n; t.UT_mid = hb + 4 * n; t.UT_lo = hb + 5 * n;
+            t.ZT_hi = hb + 6 * n; t.ZT_mid = hb + 7 * n; t.ZT_lo = hb + 8 * n;
             t.pstat = workspace + cp.off_pstat; t.lab_logit = workspace + cp.off_lab;
             t.pdz = cp.NCB > 1 ? workspace + cp.off_pdz : dz_a;
             t.pV = cp.NCB > 1 ? workspace + cp.off_pV : V;
             t.logits_copy = logits_copy;
             t.B = B; t.Bg = Bg; t.BgP = (int)cp.BgP; t.Bp = (int)cp.Bp; t.NT = (int)cp.NT; t.label0 = label0; t.grad_scale = grad_scale;
-            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, Bg, (int)cp.BgP,
-                     hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n);
+            float* means = workspace + cp.off_means;
+            t.means = means;
+            launch_k(k_curl_means, dim3(kMeanParts), dim3(256), 0, stream, (const float*)U, z_pos, Bg, means + 128);
+            if (check_launch("curl_prep")) return -1;
+            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, (const float*)(means + 128),
+                     means, Bg, (int)cp.BgP, hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n, hb + 6 * n, hb + 7 * n, hb + 8 * n);
             if (check_launch("curl_prep")) return -1;
             const dim3 grid((unsigned)(cp.Bp / 16), (unsigned)cp.NCB);
             launch_k(k_curl_tc<0>, grid, dim3(256), 0, stream, t);
