@@ -841,6 +841,310 @@ k_conv_tc96(const __grid_constant__ TcSegs sg, long long in_sstride, float scale
     }
 }
 
+// ---------------------------------------------------------------- N = 64 + 32: two horizontal taps side by side, the third by K accumulation
+// What bounds k_conv_tc<32,9> is the A-operand stream (40 clk per N = 32 MMA, 16 of them tensor work); the N = 96
+// kernel below cut the stream by 2.1x but its epilogue -- three TMEM loads, 64 shuffles, two exchanged edge rows per
+// warp and a group barrier per tile, ~650 instructions per warp per tile on two accumulator stages -- is
+// issue-bound at ~2900 clk per tile (measured: gpurun r03d, profiles/r03_conv_n96_roles.txt) against 1600 for the
+// N = 32 kernel.  The middle ground: per (dy, K step)
+//     MMA 1 (N = 64): D[p][0:32]  += A[p + dy*pitch]     . W(dy,0)      D[p][32:64] += A[p + dy*pitch] . W(dy,1)
+//     MMA 2 (N = 32): D[p][0:32]  += A[p + dy*pitch + 2] . W(dy,2)
+// 12 MMAs of 48 + 40 clk per 128 positions = 528 clk (720 for nine N = 32 taps), and ONE shifted add in the epilogue,
+//     out[p] = D[p][0:32] + D[p + 1][32:64]            (dgrad: transposed weights, A shifts 2 / 2 / 0 rows, D[p - 1])
+// i.e. two TMEM loads, 32 shuffles and one exchanged edge row per warp; 64 accumulator columns per sub-tile leave
+// room for the four accumulator stages of k_conv_tc (512 TMEM columns), so MMAs and epilogue stay decoupled.
+// Tiles overlap by one row (255 outputs per 256-row tile).  Pipeline roles, tile scheduler and slab ring are
+// k_conv_tc's.
+constexpr int kT64Out = 255;
+constexpr uint32_t kIdesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kXch64 = 32;                                    // floats per warp slot: one accumulator row of D[.][32:64]
+constexpr int kSmemHdr64 = 768 + 2 * kEpiAll * kXch64 * 4;    // header + exchange slots [tile parity of the group][warp][32]
+constexpr uint32_t kW64Dy = 6144;                             // per dy: B1 [4 k chunks][64 n][8 k] (4096 B) | B2 [4][32][8] (2048 B)
+constexpr uint32_t kW64Bytes = 3 * kW64Dy;
+
+template <bool DGRAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_conv_tc64(const __grid_constant__ TcSegs sg, long long in_sstride, float scale, const bf16* __restrict__ relu_src,
+            long long out_sstride, TcGeom g) {
+    constexpr int CH = 4, KS = 2, TM = kTcSub * 128;
+    constexpr uint32_t TMEM_COLS = kAccStages * kTcSub * 64;      // 512
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_full = s_base, s_empty = s_base + 64, s_tfull = s_base + 128, s_tempty = s_base + 192;
+    const uint32_t s_tptr = s_base + 576;
+    const uint32_t s_w = s_base + kSmemHdr64;
+    const uint32_t PS = (uint32_t)g.plane_bytes;
+    const uint32_t slab_bytes = CH * PS;
+    const uint32_t s_slab0 = s_w + (uint32_t)sg.nw * kW64Bytes;
+    const int stages = g.stages;
+    const long long plane = (long long)g.S * 8;
+    const int tile_shift = DGRAD ? -1 : 0;                    // position of a tile's row 0: t * 255 + tile_shift
+
+    if (tid == 0) {
+        for (int i = 0; i < kRing; ++i) reinterpret_cast<volatile uint32_t*>(smem + 512)[i] = 0xFFFFFFFFu;
+        for (int i = 0; i < 32; ++i) reinterpret_cast<volatile int*>(smem + 640)[i] = 1;
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(s_full + 8 * i, 1);
+            mbar_init(s_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(s_tfull + 8 * i, 1);
+            mbar_init(s_tempty + 8 * i, kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 576);
+    pdl_grid_sync();
+    constexpr int kStageThreads = kTcThreads - 32;
+    if (warp != kEpiAll + kMmaWarps) {
+        // weights per dy: B1[n = dx*32 + (co | ci)][k] for dx = 0, 1 and B2[n][k] for dx = 2, K-major [k chunk][n][8 k]
+        for (int ws = 0; ws < sg.nw; ++ws) {
+            const bf16* __restrict__ wts = ws ? sg.wts[1] : sg.wts[0];            // global: [tap = dy*3 + dx][co][ci]
+            if (!DGRAD) {
+                for (int i = tid; i < 9 * 32 * CH; i += kStageThreads) {
+                    const int t = i / (32 * CH), rem = i - t * (32 * CH), n = rem / CH, kc = rem - n * CH;
+                    const int dy = t / 3, dx = t - dy * 3;
+                    const uint32_t off = dx < 2 ? (uint32_t)((kc * 64 + dx * 32 + n) * 16) : 4096u + (uint32_t)((kc * 32 + n) * 16);
+                    cp_async16(s_w + ws * kW64Bytes + dy * kW64Dy + off, wts + ((t * 32 + n) * 32 + kc * 8), 16);
+                }
+                if (tid < 32) reinterpret_cast<float*>(smem + 256 + ws * 128)[tid] = (ws ? sg.bias[1] : sg.bias[0])[tid];
+            } else {
+                for (int i = tid; i < 9 * 32 * 32; i += kStageThreads) {
+                    const int t = i / 1024, rem = i - t * 1024, co = rem >> 5, ci = rem & 31;
+                    const int dy = t / 3, dx = t - dy * 3;
+                    const int kc = co >> 3, k8 = co & 7;
+                    const uint32_t off = dx < 2 ? (uint32_t)(((kc * 64 + dx * 32 + ci) * 8 + k8) * 2)
+                                                : 4096u + (uint32_t)(((kc * 32 + ci) * 8 + k8) * 2);
+                    *reinterpret_cast<bf16*>(smem + kSmemHdr64 + ws * kW64Bytes + dy * kW64Dy + off) = wts[i];
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory");
+    }
+
+    if (warp < kEpiAll) {
+        // ================= epilogue
+        const int egroup = warp / kEpiWarps, ew = warp % kEpiWarps;
+        const int sub = ew >> 2, quarter = ew & 3;
+        const int row_in_tile = sub * 128 + quarter * 32 + lane;
+        const bool row_out = DGRAD ? (row_in_tile >= 1) : (row_in_tile < kT64Out);      // rows this tile stores
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sub * 64);
+        float* const xch = reinterpret_cast<float*>(smem + 768);
+        uint32_t acc = (uint32_t)egroup, acc_phase = 0;
+        auto load_mask = [&](int tile_, uint4 (&dst)[4]) {          // dgrad launches have one segment
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(0u, 0u, 0u, 0u);
+            const int b_ = tc_div(tile_, g.inv_tps);
+            const int p_ = (tile_ - b_ * g.tiles_per_sample) * kT64Out + tile_shift + row_in_tile;
+            if (p_ >= 0 && p_ < g.S && row_out) {
+                const int y_ = tc_div(p_, g.inv_pitch), x_ = p_ - y_ * g.pitch;
+                if (y_ < g.Hv && x_ < g.Wv) {
+                    const long long o_ = (long long)b_ * out_sstride + (long long)p_ * 8;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(relu_src + o_ + c * plane);
+                }
+            }
+        };
+        int par = 0;
+        for (int j = egroup;; j += kEpiGroups, par ^= 1) {
+            uint32_t ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1)));
+            if (!ring_ready(ent, j)) {
+                const long long t0 = clock64();
+                while (!ring_ready(ent = (uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))), j))
+                    if (clock64() - t0 > (1ll << 31)) __trap();
+            }
+            const int tile = ring_tile(ent);
+            if (tile < 0) break;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            const int p = tl.t * kT64Out + tile_shift + row_in_tile;
+            const bool inside = p >= 0 && p < g.S && row_out;
+            int y = 0, x = 0;
+            if (inside) { y = tc_div(p, g.inv_pitch); x = p - y * g.pitch; }
+            const bool valid = inside && (y < g.Hv) && (x < g.Wv);
+            bf16* __restrict__ out = tc_pick(sg.out, tl.seg);
+            const long long o = (long long)tl.b * out_sstride + (long long)p * 8;   // + c*plane
+            const float4* bias4 = reinterpret_cast<const float4*>(smem + 256 + (DGRAD ? 0 : tc_pick(sg.wsel, tl.seg)) * 128);
+            uint4 xm[4];
+            if (DGRAD) load_mask(tile, xm);             // requested before the accumulator wait: its latency overlaps this tile's MMAs
+            float* const xw = xch + (size_t)(par * kEpiAll + warp) * kXch64;
+            mbar_wait(s_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = taddr0 + acc * (kTcSub * 64);
+            float av[32];
+            uint32_t r[32];
+            // ---- D[.][32:64]: the row next to this one (forward: p + 1, dgrad: p - 1)
+            tmem_ld32(taddr + 32, r);
+            if (lane == (DGRAD ? 31 : 0)) {             // the neighbouring warp's edge lane needs this row
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(xw + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                av[i] = DGRAD ? __shfl_up_sync(0xffffffffu, __uint_as_float(r[i]), 1) : __shfl_down_sync(0xffffffffu, __uint_as_float(r[i]), 1);
+            // ---- D[.][0:32]
+            tmem_ld32(taddr, r);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tempty + 8 * acc);      // accumulator stage drained by this warp
+            const bool edge = lane == (DGRAD ? 0 : 31);          // its shuffled value is its own row: replaced below
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + egroup), "n"(kEpiWarps * 32) : "memory");
+            if (edge) {
+                const bool has = DGRAD ? (ew > 0) : (ew + 1 < kEpiWarps);       // the tile's outermost row is not stored
+                const float4* xo = reinterpret_cast<const float4*>(xch + (size_t)(par * kEpiAll + warp + (DGRAD ? -1 : 1)) * kXch64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = has ? xo[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    av[i * 4] = v.x; av[i * 4 + 1] = v.y; av[i * 4 + 2] = v.z; av[i * 4 + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) av[i] += __uint_as_float(r[i]);
+            if (inside) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (!DGRAD) { b0 = bias4[c * 2]; b1 = bias4[c * 2 + 1]; }
+                    const float bq[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v0 = av[c * 8 + q * 2], v1 = av[c * 8 + q * 2 + 1];
+                        if (!DGRAD) {
+                            v0 = valid ? fmaxf(fmaf(v0, scale, bq[q * 2]), 0.f) : 0.f;
+                            v1 = valid ? fmaxf(fmaf(v1, scale, bq[q * 2 + 1]), 0.f) : 0.f;
+                        } else {
+                            const uint32_t m = q == 0 ? xm[c].x : (q == 1 ? xm[c].y : (q == 2 ? xm[c].z : xm[c].w));
+                            const float2 xv = unpack_bf16x2(m);
+                            v0 = xv.x > 0.f ? v0 : 0.f;
+                            v1 = xv.y > 0.f ? v1 : 0.f;
+                        }
+                        w[q] = pack_bf16x2(v0, v1);
+                    }
+                    *reinterpret_cast<uint4*>(out + o + c * plane) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            acc += kEpiGroups;
+            if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
+        }
+    } else if (warp < kEpiAll + kMmaWarps) {
+        // ================= MMA issuers: warp mw takes the CTA's local tiles mw, mw + 2, ...
+        const int mw = warp - kEpiAll;
+        uint32_t stage = (uint32_t)mw, phase = 0, acc = (uint32_t)mw, acc_phase = 0;
+        const uint64_t a_hi = make_desc(0, PS, 128), b1_hi = make_desc(0, 64 * 16, 128), b2_hi = make_desc(0, 32 * 16, 128);
+        // A row shifts (relative to the slab start): MMA 1 / MMA 2 per dy
+        uint32_t a1_off[3 * KS], a2_off[3 * KS];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int base = (DGRAD ? 2 - dy : dy) * g.pitch;
+                a1_off[dy * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)(base + (DGRAD ? 2 : 0)) * 16u) >> 4;
+                a2_off[dy * KS + ks] = ((uint32_t)(2 * ks) * PS + (uint32_t)(base + (DGRAD ? 0 : 2)) * 16u) >> 4;
+            }
+        const int valid_pos = g.Hv * g.pitch;
+        for (int j = mw;; j += kMmaWarps) {
+            mbar_wait(s_full + 8 * stage, phase);
+            const int tile = ring_tile((uint32_t)ld_volatile_s32(smem + 512 + 4 * (j & (kRing - 1))));
+            if (tile < 0) break;
+            const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+            const int nsub = (tl.t * kT64Out + tile_shift + 128 >= valid_pos) ? 1 : kTcSub;
+            const uint32_t w16 = (s_w + (uint32_t)tc_pick(sg.wsel, tl.seg) * kW64Bytes) >> 4;
+            const uint32_t slab16 = (s_slab0 + stage * slab_bytes) >> 4;
+            mbar_wait(s_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int s2 = 0; s2 < kTcSub; ++s2) {
+                    if (s2 >= nsub) break;
+                    const uint32_t d = tmem_base + acc * (kTcSub * 64) + (uint32_t)(s2 * 64);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const uint32_t wdy = w16 + (uint32_t)(dy * (kW64Dy >> 4));
+                            const uint64_t ad1 = a_hi | (uint64_t)((slab16 + (uint32_t)(s2 * 128) + a1_off[dy * KS + ks]) & 0x3FFFu);
+                            const uint64_t bd1 = b1_hi | (uint64_t)((wdy + (uint32_t)(2 * ks * 64)) & 0x3FFFu);
+                            umma_bf16_rt(d, ad1, bd1, kIdesc64, (dy | ks) ? 1u : 0u);
+                            const uint64_t ad2 = a_hi | (uint64_t)((slab16 + (uint32_t)(s2 * 128) + a2_off[dy * KS + ks]) & 0x3FFFu);
+                            const uint64_t bd2 = b2_hi | (uint64_t)((wdy + 256u + (uint32_t)(2 * ks * 32)) & 0x3FFFu);
+                            umma_bf16_rt(d, ad2, bd2, kIdesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(s_empty + 8 * stage);
+                umma_commit(s_tfull + 8 * acc);
+            }
+            __syncwarp();
+            stage += (uint32_t)kMmaWarps;
+            if (stage >= (uint32_t)stages) { stage -= (uint32_t)stages; phase ^= 1; }
+            acc += (uint32_t)kMmaWarps;
+            if (acc >= kAccStages) { acc -= kAccStages; acc_phase ^= 1; }
+        }
+    } else {
+        const int one = ld_volatile_s32(smem + 640 + 4 * lane);
+        if (lane == 0) {
+            // ================= producer: k_conv_tc's, tiles 255 positions apart
+            uint32_t stage = 0, phase = 0;
+            const uint32_t bytes = (uint32_t)g.slab_rows * 16u;
+            int* const ctr = g_tc_ctr + 2 * g.ctr_slot;
+            const int G = (int)gridDim.x;
+            int q[4];
+            q[0] = (int)blockIdx.x - 2 * G; q[1] = q[0] + G;
+            q[2] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[1] + G;
+            q[3] = g.dynamic ? atom_add_nonuniform(ctr, one) : q[2] + G;
+            int sentinels = 0, j = 0;
+            while (sentinels < 2) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (sentinels >= 2) break;
+                    const int tile = q[u] + 2 * G;
+                    const bool real = tile < g.total_tiles;
+                    mbar_wait(s_empty + 8 * stage, phase ^ 1);
+                    *reinterpret_cast<volatile uint32_t*>(smem + 512 + 4 * (j & (kRing - 1))) = ring_entry(j, real ? tile : -1);
+                    const uint32_t bar = s_full + 8 * stage;
+                    if (!real) {
+                        mbar_arrive(bar);
+                    } else {
+                        const TileLoc tl = tc_locate(sg, g.tiles_per_sample, g.inv_tps, tile);
+                        const int p0 = tl.t * kT64Out + tile_shift;
+                        const bf16* src = tc_pick(sg.in, tl.seg) + (long long)tl.b * in_sstride + (long long)(p0 + g.min_off) * 8;
+                        const uint32_t dst = s_slab0 + stage * slab_bytes;
+                        mbar_expect_tx(bar, bytes * CH);
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) bulk_g2s(dst + c * PS, src + c * plane, bytes, bar);
+                    }
+                    ++j;
+                    if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+                    if (!real) ++sentinels;
+                    else q[u] = g.dynamic ? atom_add_nonuniform(ctr, one) : tile + 2 * G;
+                }
+            }
+            if (g.dynamic) {
+                __threadfence();
+                if (atomicAdd(ctr + 1, 1) == G - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- layers 2..4 fused: one sample resident in shared memory
 // k_conv_tc96 still writes every layer's activations to HBM and the next layer's launch reads them back: per
 // encoder pass 428 MB of the 616 MB the conv stack moves.  Here a CTA keeps ONE sample's activation map in
@@ -1238,6 +1542,48 @@ static bool use_n96(int pitch, int Wv, bool dgrad) {
     return dgrad || Wv <= pitch - 2;
 }
 
+// N = 64 + 32 variant (k_conv_tc64): layers 2..4 forward and dgrad, CURLA_CONV_N64=1
+static bool use_n64() {
+    const char* e = getenv("CURLA_CONV_N64");
+    return e && e[0] == '1';
+}
+
+template <bool DGRAD>
+static int launch_tc64(const TcSegs& sg, long long in_sstride, float scale, const void* relu_src, long long out_sstride,
+                       TcGeom g, cudaStream_t stream) {
+    const size_t fixed = kSmemHdr64 + (size_t)sg.nw * kW64Bytes;
+    g.debug = 0;
+    g.plane_bytes = g.plane_rows * 16;
+    const size_t slab = (size_t)4 * g.plane_bytes;
+    size_t budget = 200 * 1024;
+    { const char* e = getenv("CURLA_TC_SMEM_KB"); if (e && atoi(e) >= 64 && atoi(e) <= 225) budget = (size_t)atoi(e) * 1024; }
+    int stages = (int)((budget - fixed) / slab);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) { set_last_error("conv_tc64: pitch %d needs %zu B per slab stage", g.pitch, slab); return -1; }
+    stages &= ~1;                                   // even ring depth: see launch_tc
+    g.stages = stages;
+    const size_t smem = fixed + stages * slab;
+    auto kern = k_conv_tc64<DGRAD>;
+    if (tc_set_smem(kern, smem)) return -1;
+    const int cap = sm_count();
+    const int grid = g.total_tiles < cap ? g.total_tiles : cap;
+    {
+        const char* e = getenv("CURLA_TC_STATIC");
+        g.dynamic = (g.total_tiles > 2 * grid && !(e && e[0] == '1')) ? 1 : 0;
+        g.ctr_slot = g.dynamic ? next_ctr_slot(stream) : 0;
+    }
+    launch_k(kern, dim3(grid), dim3(kTcThreads), smem, stream, sg, in_sstride, scale, (const bf16*)relu_src, out_sstride, g);
+    return 0;
+}
+
+static TcGeom make_tc64_geom(int pitch, int S, int Hv, int Wv, bool dgrad) {
+    TcGeom g = make_tc_geom(1, pitch, S, Hv, Wv, 2 * pitch + 2, dgrad ? -(2 * pitch + 2) : 0);
+    g.tiles_per_sample = cdiv((long long)Hv * pitch, kT64Out);
+    g.total_tiles = g.tiles_per_sample;
+    g.inv_tps = 1.0f / (float)g.tiles_per_sample;
+    return g;
+}
+
 template <bool DGRAD>
 static int launch_tc96(const TcSegs& sg, long long in_sstride, float scale, const void* relu_src, long long out_sstride,
                        TcGeom g, cudaStream_t stream) {
@@ -1357,6 +1703,10 @@ extern "C" int curla_conv_fwd_multi(const curla_conv_seg* segs, int nseg, long l
         }
         if (make_segs(segs, nseg, g, sg)) return -1;
         if (launch_tc<48, 4, false>(sg, in_sstride, scale, nullptr, out_sstride, g, taps, stream)) return -1;
+    } else if (use_n64()) {
+        TcGeom g = make_tc64_geom(pitch, S, Hv, Wv, false);
+        if (make_segs(segs, nseg, g, sg)) return -1;
+        if (launch_tc64<false>(sg, in_sstride, scale, nullptr, out_sstride, g, stream)) return -1;
     } else if (use_n96(pitch, Wv, false)) {
         TcGeom g = make_tc96_geom(pitch, S, Hv, Wv, false);
         if (make_segs(segs, nseg, g, sg)) return -1;
@@ -1385,6 +1735,12 @@ extern "C" int curla_conv_dgrad(const void* dy, long long dy_sstride, const void
     TcTaps taps;
     TcSegs sg;
     const curla_conv_seg seg = {dy, wts, nullptr, dx, B};
+    if (use_n64()) {
+        TcGeom g = make_tc64_geom(pitch, S, Hv, Wv, true);
+        if (make_segs(&seg, 1, g, sg)) return -1;
+        if (launch_tc64<true>(sg, dy_sstride, 1.f, x, dx_sstride, g, stream)) return -1;
+        return check_launch("conv_dgrad");
+    }
     if (use_n96(pitch, Wv, true)) {
         TcGeom g = make_tc96_geom(pitch, S, Hv, Wv, true);
         if (make_segs(&seg, 1, g, sg)) return -1;

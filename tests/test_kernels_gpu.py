@@ -151,6 +151,7 @@ def test_conv_stack_fused_equals_layer_by_layer(H, W, Bs, monkeypatch):
     bit-identical outputs; passes that do not keep conv-2 / conv-3 leave those buffers untouched; up to three passes
     with two weight sets per launch; more samples than CTAs (the buffer is refilled slot by slot behind conv-4)."""
     monkeypatch.setenv('CURLA_CONV_N96', '1')
+    monkeypatch.setenv('CURLA_CONV_N64', '0')
     torch.manual_seed(11)
     npass = len(Bs)
     g0 = Geom(H, W, max(Bs))
@@ -216,12 +217,18 @@ def test_conv_stack_fused_equals_layer_by_layer(H, W, Bs, monkeypatch):
                 assert bool((outs[l] == 7.0).all()), (k, l)
 
 
-@pytest.mark.parametrize('n96', ['1', '0'])
+def _conv_mode(monkeypatch, mode):
+    """layers 2..4: '32' = one tap per MMA (default), '64' = two horizontal taps per MMA + the third by K accumulation
+    (one shifted add in the epilogue), '96' = three horizontal taps per MMA (two shifted adds)."""
+    monkeypatch.setenv('CURLA_CONV_N96', '1' if mode == '96' else '0')
+    monkeypatch.setenv('CURLA_CONV_N64', '1' if mode == '64' else '0')
+
+
+@pytest.mark.parametrize('n96', ['96', '64', '32'])
 @pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (64, 64, 5)])
 def test_conv_forward(H, W, B, n96, monkeypatch):
-    """n96 = '1': layers 2..4 run the N = 96 kernel (three horizontal taps per MMA, shuffle epilogue);
-    '0': the N = 32 kernel (one tap per MMA).  Same tolerances for both."""
-    monkeypatch.setenv('CURLA_CONV_N96', n96)
+    """The three formulations of the 32 -> 32 channel layers (see _conv_mode): same tolerances for all."""
+    _conv_mode(monkeypatch, n96)
     g, x, ws, bs = _conv_case(H, W, B)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     # reference on bf16-rounded operands, layer by layer (our activations are stored bf16)
@@ -309,10 +316,10 @@ def test_conv_forward_multi_segment(H, W):
                   g0.Wo[0], 1, stream())
 
 
-@pytest.mark.parametrize('n96', ['1', '0'])
+@pytest.mark.parametrize('n96', ['96', '64', '32'])
 @pytest.mark.parametrize('H,W,B', [(76, 135, 3), (90, 160, 2), (76, 135, 40)])
 def test_conv_backward(H, W, B, n96, monkeypatch):
-    monkeypatch.setenv('CURLA_CONV_N96', n96)
+    _conv_mode(monkeypatch, n96)
     g, x, ws, bs = _conv_case(H, W, B, seed=1)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(2)
