@@ -137,5 +137,8 @@ __device__ __forceinline__ float u01(uint32_t a) { return (float)a * 2.328306436
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+// CTAs of a persistent conv kernel (one per SM): sm_count() minus the SMs set aside for concurrently running
+// collectives (curla_set_reserved_sms / CURLA_RESERVE_SMS; 0 unless data parallel)
+int conv_grid_cap();
 
 }  // namespace curla

@@ -1520,7 +1520,7 @@ static int launch_tc(const TcSegs& sg, long long in_sstride, float scale, const 
     const size_t smem = fixed + stages * slab;
     auto kern = k_conv_tc<CP, NTAPS, DGRAD>;
     if (tc_set_smem(kern, smem)) return -1;
-    const int cap = sm_count();
+    const int cap = conv_grid_cap();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
     {   // dynamic tile hand-out once every CTA has more than its two round-robin tiles
         const char* e = getenv("CURLA_TC_STATIC");
@@ -1565,7 +1565,7 @@ static int launch_tc64(const TcSegs& sg, long long in_sstride, float scale, cons
     const size_t smem = fixed + stages * slab;
     auto kern = k_conv_tc64<DGRAD>;
     if (tc_set_smem(kern, smem)) return -1;
-    const int cap = sm_count();
+    const int cap = conv_grid_cap();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
     {
         const char* e = getenv("CURLA_TC_STATIC");
@@ -1601,7 +1601,7 @@ static int launch_tc96(const TcSegs& sg, long long in_sstride, float scale, cons
     const size_t smem = fixed + stages * slab;
     auto kern = k_conv_tc96<DGRAD>;
     if (tc_set_smem(kern, smem)) return -1;
-    const int cap = sm_count();
+    const int cap = conv_grid_cap();
     const int grid = g.total_tiles < cap ? g.total_tiles : cap;
     {
         const char* e = getenv("CURLA_TC_STATIC");
@@ -1792,7 +1792,7 @@ extern "C" int curla_conv_stack_fwd(const curla_conv_stack_seg* segs, int nseg, 
     for (int s = nseg; s < 3; ++s) sg.item_end[s] = items;
     g.total_items = items;
     if (tc_set_smem(k_conv_stack96, smem)) return -1;
-    const int cap = sm_count();
+    const int cap = conv_grid_cap();
     const int grid = items < cap ? items : cap;
     launch_k(k_conv_stack96, dim3(grid), dim3(kTcThreads), smem, stream, sg, sstride, g);
     return check_launch("conv_stack");

@@ -431,7 +431,7 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     auto kern = k_conv_wgrad_tc<CP, GR, NDX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }
-    const int cap = sm_count();
+    const int cap = conv_grid_cap();
     const int grid = g.total_runs < cap ? g.total_runs : cap;
     launch_k(kern, dim3(grid), dim3(kWgThreads), smem, stream, tmIn, tmDy, (const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride,
              workspace, g);

@@ -270,7 +270,7 @@ __device__ __forceinline__ uint32_t ldg_u32(const bf16* p) { return __ldg(reinte
 // U_j - mean(U), z_j - mean(z): when the keys are nearly equal -- a collapsing CURL head, logits ~ uniform, the
 // gradient a small difference of large terms -- the error stays relative to the differences, not to the common
 // part (measured on the 8-update parity scenario: conv-1 gradient error 81 % uncentred).
-constexpr int kMeanParts = 8;
+constexpr int kMeanParts = 32;
 __global__ void __launch_bounds__(256)
 k_curl_means(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, float* __restrict__ part) {
     pdl_grid_sync();
@@ -279,8 +279,14 @@ k_curl_means(const float* __restrict__ U, const float* __restrict__ z_pos, int B
     const float* src = col < 64 ? U + col : z_pos + (col - 64);
     const int per = (Bg + kMeanParts - 1) / kMeanParts;
     const int j0 = blockIdx.x * per, j1 = min(Bg, j0 + per);
-    float acc = 0.f;
-    for (int j = j0 + half; j < j1; j += 2) acc += src[(long long)j * 64];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;           // four independent chains: the loads pipeline
+    int j = j0 + half;
+    for (; j + 6 < j1; j += 8) {
+        a0 += src[(long long)j * 64]; a1 += src[(long long)(j + 2) * 64];
+        a2 += src[(long long)(j + 4) * 64]; a3 += src[(long long)(j + 6) * 64];
+    }
+    for (; j < j1; j += 2) a0 += src[(long long)j * 64];
+    const float acc = (a0 + a1) + (a2 + a3);
     red[half][col] = acc;
     __syncthreads();
     if (half == 0) part[blockIdx.x * 128 + col] = red[0][col] + red[1][col];

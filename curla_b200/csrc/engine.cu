@@ -96,6 +96,19 @@ int sm_count() {
     return n;
 }
 
+// The conv kernels are persistent with one CTA per SM and nearly all of its shared memory and registers: an NCCL
+// kernel launched beside them finds no SM to run on until a conv kernel ends.  With world > 1 the engine therefore
+// keeps a few SMs out of the conv grids (the all-reduce of a gradient slice then really runs during the conv
+// backward instead of between its launches).
+static int g_reserved_sms = -1;
+int conv_grid_cap() {
+    if (g_reserved_sms < 0) { const char* e = getenv("CURLA_RESERVE_SMS"); g_reserved_sms = e ? atoi(e) : 0; }
+    int r = g_reserved_sms;
+    if (r < 0) r = 0;
+    if (r > sm_count() / 2) r = sm_count() / 2;
+    return sm_count() - r;
+}
+
 enum { DT_F32 = 0, DT_BF16 = 1, DT_F64 = 2, DT_I32 = 3, DT_U8 = 4 };
 static const int kDtSize[] = {4, 2, 8, 4, 1};
 
