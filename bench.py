@@ -235,8 +235,9 @@ def run_ours(args, rank, world, device):
             nm, cnt, tot = line.split()
             prof[nm] = (int(cnt), float(tot))
         step0 += args.prof_steps
+    nparams = {k: int(agent.engine.t['grad.' + k].numel()) for k in ('critic', 'actor', 'cpc')}
     return dict(ms_per_step=ms_per_step, launches=launches, clocks=clocks, e2e_s=e2e_s, h2d=h2d, d2h=d2h,
-                prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last, obs_hw=tuple(aug.output_shape))
+                prof=prof, prof_steps=args.prof_steps, Bg=Bg, last=L.last, obs_hw=tuple(aug.output_shape), nparams=nparams)
 
 
 def fill_host_replay(rb, seed=1):
@@ -528,17 +529,30 @@ def main():
                               bytes=2 * Bb * kfc * 2 + 64 * kfc * 2, flops=2.0 * Bb * 64 * kfc),
         'gemm_fc_wgrad': dict(kernel='k_gemm_tc (tcgen05 + TMA, encoder fc wgrad, swapped operands)', launches=1,
                               bytes=Bb * kfc * 2 + 50 * kfc * 4, flops=2.0 * Bb * 64 * kfc),
-        'adam_f32': dict(kernel='k_adam (fused multi-tensor Adam)', launches=None, bytes=None, flops=0.0),
     }
+    # elementwise optimizer kernels: 28 B per parameter stepped (p, g, m, v read; p, m, v written), 12 B per parameter of
+    # the EMA (target, online read; target written).  The profiled steps start on an even step: the critic and the
+    # encoder+CURL optimizers step every update, the actor's and the EMA every second one (train.py defaults).
+    ps_ = r['prof_steps']
+    np_ = r['nparams']
+    even = (ps_ + 1) // 2
+    if not wl['pixel_sac']:
+        adam_params = ps_ * (np_['critic'] + np_['cpc']) + even * np_['actor']
+    else:
+        adam_params = ps_ * np_['critic'] + even * np_['actor']
+    table['adam_f32'] = dict(kernel='k_adam (fused Adam, one launch per optimizer)', total_bytes=28.0 * adam_params, flops=0.0)
+    table['ema_f32'] = dict(kernel='k_ema (soft target update, encoder + Q1 + Q2 in one launch)', total_bytes=12.0 * even * np_['critic'], flops=0.0)
     traffic_db = {}
     tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')       # per-launch dram bytes from ncu --set full
     if os.path.exists(tp):
         traffic_db = json.load(open(tp))
     roofs = {}
     for name, t_ in table.items():
-        if name not in r['prof'] or not t_['bytes']:
+        if name not in r['prof']:
             continue
         cnt, tot = r['prof'][name]
+        if 'total_bytes' in t_:                                   # bytes of all profiled launches given directly
+            t_ = dict(t_, bytes=t_['total_bytes'] / cnt, launches=1)
         passes = cnt / float(t_['launches'])                      # conv-stack passes in the profiled steps
         if name == 'conv_fwd':
             # independent passes share launches (curla_conv_fwd_multi), so count passes from the update
