@@ -74,6 +74,8 @@ SIGNATURES = {
     'curla_conv_stack_fits': (_i, [_i, _i, c_vp, c_vp]),
     'curla_conv_stack_fwd': (_i, [c_vp, _i, c_ll, _i, _i, c_vp, c_vp, c_vp]),
     'curla_agent_set_keep_acts': (_i, [c_vp, _i]),
+    'curla_agent_set_mailbox': (_i, [c_vp, c_vp]),
+    'curla_publish_metrics': (_i, [c_vp, c_vp, C.c_uint, c_vp, c_vp]),
     'curla_conv_fwd_multi': (_i, [c_vp, _i, c_ll, _f, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_debug_read': (_i, [c_vp, _i]),
     'curla_gemm_tc_debug_read': (_i, [c_vp]),

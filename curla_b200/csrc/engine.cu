@@ -178,6 +178,7 @@ struct curla_agent {
     // whole-update CUDA graphs: one per update variant (step parity, only_cpc, argument pointers); the per-update
     // scalars a replay needs (Adam step counters, Philox offset) live in dev_state (see curla_set_dev_state)
     int keep_acts;                           // 1: every encoder pass stores conv-2 / conv-3 activations (logging taps read them)
+    float* mailbox;                          // mapped pinned host memory for the logged scalars (curla_agent_set_mailbox) or NULL
     int* dev_state;
     cudaStream_t cap_st;                     // private capture stream (the caller's may be the legacy default stream,
                                              // which cannot be captured); replays are launched into the caller's stream
@@ -469,6 +470,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->last_launches = 0;
     a->graph_mode = -1;
     a->keep_acts = 0;
+    a->mailbox = nullptr;
     a->cap_st = nullptr;
     a->nccl_lib = nullptr; a->comm = nullptr;
     a->side = nullptr; a->side_state = 0;
@@ -806,6 +808,15 @@ extern "C" int curla_agent_last_launches(const curla_agent* a) { return (int)a->
 // 1: every encoder pass of the update stores its conv-2 / conv-3 activations (--log_param_hist_imgs reads the
 // target encoder's, encoder.py:118-130); 0 (default): only the passes a backward follows.  Captured update graphs
 // are dropped: the launch arguments change.
+extern "C" int curla_agent_set_mailbox(curla_agent* a, float* mailbox_host_mapped) {
+    if (mailbox_host_mapped != a->mailbox) {         // a launch argument of the captured graphs
+        for (auto& kv : a->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        a->graphs.clear();
+    }
+    a->mailbox = mailbox_host_mapped;
+    return 0;
+}
+
 extern "C" int curla_agent_set_keep_acts(curla_agent* a, int on) {
     if ((on != 0) != (a->keep_acts != 0)) {
         for (auto& kv : a->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -920,6 +931,12 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
     const bool do_actor = do_sac && (u->step % c.actor_update_freq == 0) && (ph & CURLA_PHASE_ACTOR);
     const bool do_ema = do_sac && (u->step % c.critic_target_update_freq == 0) && (ph & CURLA_PHASE_EMA);
     const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0) && (ph & CURLA_PHASE_CPC);
+    // the logged scalars go to the host right after the last kernel of this update that writes one
+    const int last_writer = do_cpc ? CURLA_PHASE_CPC : (do_actor ? CURLA_PHASE_ACTOR : (do_critic ? CURLA_PHASE_CRITIC : 0));
+    auto publish = [&](int phase, Run& rr) {
+        if (a->mailbox && phase == last_writer && ph == CURLA_PHASE_ALL && rr.ok())
+            rr.chk(curla_publish_metrics(a->metrics, a->mailbox, (unsigned)(u->offset + 1), off_dev, rr.st));
+    };
 
     // ---- sample: gather (+crop) straight into the conv stack's input layout
     auto stage = [&](const float* f32, const uint8_t* frames, const int64_t* h1, const int64_t* w1, bf16* dst) {
@@ -1015,6 +1032,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         r.chk(r2.rc);
         if (r.ok()) r.chk(curla_critic_loss(a->tq[0], a->tq[1], a->logpi_next, a->rew_b, a->nd_b, a->log_alpha, (float)c.discount,
                                             a->q3[0], a->q3[1], B, gs, a->target_q, a->dq[0], a->dq[1], a->metrics, st));
+        publish(CURLA_PHASE_CRITIC, r);
         // backward
         float* gC = a->G + a->g_critic;
         r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, gC, a->off_critic,
@@ -1104,6 +1122,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             r.mlp_fwd_n(a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, B);
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
                                                a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
+            publish(CURLA_PHASE_ACTOR, r);
             r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, nullptr, 0,
                         a->dX[0], a->dX[1] - a->dX[0]);
             if (r.ok()) r.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
@@ -1154,6 +1173,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         float* gK = a->G + a->g_cpc;
         if (r.ok()) r.chk(curla_curl_fwd_bwd(a->t_p5.z, zpos, a->P + a->off_W, B, c.global_batch, feat, c.rank * B, gs, a->curl_ws,
                                              a->metrics + 6, a->dz_curl, gK, nullptr, st));
+        publish(CURLA_PHASE_CPC, r);
         // g_cpc mirrors [W | critic.encoder]: encoder grads start at n_W
         // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once (double_from = n_W).
         // Bucket = [W | conv w,b x4 | fc_w fc_b ln_w ln_b]: the fc/ln tail is final after the fc weight gradient

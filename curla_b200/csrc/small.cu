@@ -535,6 +535,29 @@ extern "C" int curla_policy_fwd(const float* t, const float* noise_in, unsigned 
 
 // Same for rows [row0, row0 + B) of a larger (global) batch: the built-in Philox noise of local
 // row b is the noise global row row0 + b would get on a single GPU.
+// The update's logged scalars, published to the host while the rest of the update is still running: 15 floats +
+// a sequence word into mapped pinned host memory (payload, system-scope fence, then the word the host polls).
+__global__ void k_publish_metrics(const float* __restrict__ metrics, float* __restrict__ mailbox, unsigned seq_host,
+                                  const unsigned long long* __restrict__ seq_dev) {
+    pdl_grid_sync();
+    const int t = threadIdx.x;
+    if (t < 15) {
+        reinterpret_cast<volatile float*>(mailbox)[t] = metrics[t];
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0) {
+        const unsigned seq = seq_dev ? (unsigned)((*seq_dev >> 1) + 1ull) : seq_host;     // dev_state holds 2 * update count
+        reinterpret_cast<volatile unsigned*>(mailbox)[15] = seq;
+        __threadfence_system();
+    }
+}
+extern "C" int curla_publish_metrics(const float* metrics, float* mailbox_host_mapped, unsigned seq,
+                                     const unsigned long long* seq_dev, cudaStream_t stream) {
+    launch_k(k_publish_metrics, dim3(1), dim3(32), 0, stream, metrics, mailbox_host_mapped, seq, seq_dev);
+    return check_launch("publish_metrics");
+}
+
 extern "C" int curla_policy_fwd_rows(const float* t, const float* noise_in, unsigned long long seed,
                                      unsigned long long offset, int row0, int B, int A, float ls_min,
                                      float ls_max, int compute_pi, int compute_log_pi, float* mu,

@@ -11,6 +11,7 @@ PyTorch-eager fallback.
 import ctypes as C
 import math
 import os
+import time
 
 import numpy as np
 import torch
@@ -671,6 +672,14 @@ class CurlSacAgent(_Host):
             _lib.check(eng.lib.curla_agent_set_opt_steps(eng.h, steps[0], steps[1], steps[2], steps[3]), 'set_opt_steps')
         self.engine = eng
         self._engine_gen = getattr(self, '_engine_gen', 0) + 1      # invalidates captured action graphs
+        if self.world == 1 and os.environ.get('CURLA_MAILBOX', '1')[:1] != '0':
+            # the logged scalars arrive in 64 bytes of pinned host memory as soon as the update has computed them
+            # (engine.cu: curla_publish_metrics), so logging every step does not wait for the update's tail
+            if getattr(self, '_mailbox', None) is None:
+                self._mailbox = torch.zeros(16, dtype=torch.float32).pin_memory()
+                self._mailbox_f = self._mailbox.numpy()
+                self._mailbox_u = self._mailbox_f.view(np.uint32)
+            _lib.check(eng.lib.curla_agent_set_mailbox(eng.h, C.c_void_p(self._mailbox.data_ptr())), 'set_mailbox')
         if self.world > 1:
             if old is not None and getattr(self, '_comm_ready', False):
                 # same rank, same world: the communicator moves to the new engine (no collective, so a
@@ -830,16 +839,31 @@ class CurlSacAgent(_Host):
         self._update_count += 1
 
         if step % self.log_interval == 0:
-            m = self.engine.t['metrics']
-            if self.world > 1 and torch.distributed.get_backend() == 'nccl':
-                m = m.clone()
-                torch.distributed.all_reduce(m)
-                m /= self.world
-            if self._metrics_host is None:
-                self._metrics_host = torch.empty(m.shape, dtype=m.dtype).pin_memory()
-            self._metrics_host.copy_(m, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            m = self._metrics_host.numpy()
+            published = (not only_cpc) or (not self.pixel_sac and step % self.cpc_update_freq == 0)      # some phase wrote a scalar
+            if getattr(self, '_mailbox', None) is not None and self.world == 1 and not _phases and published \
+                    and self._noise_override is None:
+                # wait for THIS update's sequence word (update count + 1), then read the scalars published with it
+                want, mu, t0 = np.uint32((self._update_count) & 0xFFFFFFFF), self._mailbox_u, None
+                spins = 0
+                while mu[15] != want:
+                    spins += 1
+                    if spins & 0xFFF == 0:
+                        t0 = t0 or time.perf_counter()
+                        if time.perf_counter() - t0 > 30.0:
+                            torch.cuda.current_stream(self.device).synchronize()      # surfaces a launch error, if any
+                            raise _lib.CurlaError('update: the logged scalars of update %d never arrived' % self._update_count)
+                m = self._mailbox_f.copy()
+            else:
+                m = self.engine.t['metrics']
+                if self.world > 1 and torch.distributed.get_backend() == 'nccl':
+                    m = m.clone()
+                    torch.distributed.all_reduce(m)
+                    m /= self.world
+                if self._metrics_host is None:
+                    self._metrics_host = torch.empty(m.shape, dtype=m.dtype).pin_memory()
+                self._metrics_host.copy_(m, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                m = self._metrics_host.numpy()
             L.log('train/batch_reward', float(m[0]) if not only_cpc else float(reward_for_log()), step)
             if not only_cpc:
                 L.log('train_critic/loss', float(m[1]), step)

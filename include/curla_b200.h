@@ -227,6 +227,11 @@ int curla_policy_fwd_rows_dyn(const float* t, const float* noise_in, unsigned lo
                               int row0, int B, int A, float ls_min, float ls_max, int compute_pi,
                               int compute_log_pi, float* mu, float* pi, float* log_pi, float* ls,
                               float* noise_out, curla_stream_t stream);
+/* metrics[0..14] and a sequence word (index 15, uint32: seq, or (*seq_dev / 2) + 1 when seq_dev != NULL) written
+ * into mapped pinned host memory: the host polls word 15 and reads an update's logged scalars while the update's
+ * tail (CURL backward, optimizer steps) is still running */
+int curla_publish_metrics(const float* metrics, float* mailbox_host_mapped, unsigned seq,
+                          const unsigned long long* seq_dev, curla_stream_t stream);
 int curla_policy_bwd(const float* dx1, const float* dx2, int feat, const float* glogpi,
                      const float* t, const float* noise, const float* pi, const float* ls, int B,
                      int A, float ls_min, float ls_max, float* dt, curla_stream_t stream);
@@ -335,6 +340,10 @@ int curla_agent_update(curla_agent* a, const curla_update_args* args, curla_stre
 /* 1: every encoder pass stores its conv-2 / conv-3 activations (the --log_param_hist_imgs taps read them,
  * encoder.py:118-130); 0 (default): only the passes a backward follows (the fused conv kernel keeps the rest on chip) */
 int curla_agent_set_keep_acts(curla_agent* a, int on);
+/* mailbox: 64 bytes of mapped pinned host memory (or NULL: off).  When set, every update publishes its logged
+ * scalars there right after the last kernel that writes one (curla_publish_metrics; sequence word = the update's
+ * args->offset + 1), so a caller that logs every step does not wait for the whole update */
+int curla_agent_set_mailbox(curla_agent* a, float* mailbox_host_mapped);
 /* number of kernel launches issued by the last curla_agent_update */
 int curla_agent_last_launches(const curla_agent* a);
 /* per-optimizer Adam step counters {critic, actor, log_alpha, encoder+cpc} (the reference

@@ -496,3 +496,31 @@ def test_graph_replayed_updates_equal_eager_updates(name, monkeypatch):
         assert torch.equal(p0, p1), (arena, float((p0 - p1).abs().max()))
     assert torch.equal(a0.engine.t['log_alpha'], a1.engine.t['log_alpha'])
     assert torch.equal(a0.engine.t['metrics'], a1.engine.t['metrics'])
+
+
+def test_logged_scalars_through_the_pinned_mailbox_equal_the_synchronised_read(monkeypatch):
+    """With a single GPU the update publishes its logged scalars into pinned host memory right after the last kernel
+    that writes one (curla_publish_metrics) and update() returns once THEY have arrived, the CURL backward and the
+    optimizer steps still in flight.  Every logged value of every step must equal the value read the slow way
+    (metrics D2H after a full stream synchronisation, CURLA_MAILBOX=0), eager and graph-replayed alike."""
+    cfg = dict(S.SCENARIOS['crop90x160'])
+    run = S.OracleRun(cfg)
+    rows = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('CURLA_MAILBOX', mode)
+        agent, rb = T.build_cuda_agent(cfg, run)
+        assert (getattr(agent, '_mailbox', None) is not None) == (mode == '1')
+        agent._noise_seed = 77
+        L = T.NullLogger()
+        st = np.random.get_state()
+        for u in range(9):
+            agent.update(rb, L, u, only_cpc=(u == 5))
+        np.random.set_state(st)
+        torch.cuda.synchronize()
+        rows[mode] = dict(L.rows)
+        if mode == '1':      # the mailbox holds the last update's scalars, bit for bit what the device buffer holds
+            m = agent.engine.t['metrics'].cpu().numpy()
+            assert np.array_equal(agent._mailbox_f[:15], m[:15])
+            assert int(agent._mailbox_u[15]) == 9
+    assert rows['0'].keys() == rows['1'].keys() and len(rows['0']) > 40
+    assert rows['0'] == rows['1']
