@@ -213,9 +213,8 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
 // (curl_sac.py:211-222) and logits of magnitude ~30 sit in an exp(), so every fp32 operand x is split
 // into THREE bf16 pieces  hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid)  (24 mantissa bits: the fp32 value
 // exactly, up to the last rounding) and a product is  hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi  (six MMAs; the
-// dropped mid.lo / lo.mid / lo.lo terms are 2^-24 relative): fp32-equivalent results.  A two-piece split (three MMAs,
-// 2^-17) was measurably not enough once the CURL head collapses (loss -> ln B): the gradient of the early conv
-// layers is then a small difference of large batch sums and amplified that error to tens of percent.
+// dropped mid.lo / lo.mid / lo.lo terms are 2^-24 relative): fp32-equivalent results, like the fp32 FFMA kernel
+// (CURLA_CURL_TC=0) it replaces.
 //
 // Work unit = one warp: 16 local rows x 64 key columns.  A CTA is 8 warps = the same 16 rows x 512
 // columns; grid (B/16 row blocks, Bg/512 column blocks), so a global batch of 4096 keys spreads over
@@ -263,59 +262,19 @@ __device__ __forceinline__ void mma6(float* acc, const uint32_t (&ah)[4], const 
 }
 __device__ __forceinline__ uint32_t ldg_u32(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 
-// Centred operands.  Softmax and its gradient only see DIFFERENCES between keys: logits_ij = z_i . U_j may be
-// shifted by any per-row constant, and  dz_i = sum_j dl_ij U_j,  V_i = sum_j dl_ij z_j  with  sum_j dl_ij = 0  (up to
-// fp32 rounding, as in the reference's own softmax) are unchanged when a constant vector is subtracted from every
-// U_j / z_j.  The split products carry ~2^-17 of their OPERANDS' magnitude, so the contractions run on
-// U_j - mean(U), z_j - mean(z): when the keys are nearly equal -- a collapsing CURL head, logits ~ uniform, the
-// gradient a small difference of large terms -- the error stays relative to the differences, not to the common
-// part (measured on the 8-update parity scenario: conv-1 gradient error 81 % uncentred).
-constexpr int kMeanParts = 32;
-__global__ void __launch_bounds__(256)
-k_curl_means(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, float* __restrict__ part) {
-    pdl_grid_sync();
-    __shared__ float red[2][128];
-    const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const float* src = col < 64 ? U + col : z_pos + (col - 64);
-    const int per = (Bg + kMeanParts - 1) / kMeanParts;
-    const int j0 = blockIdx.x * per, j1 = min(Bg, j0 + per);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;           // four independent chains: the loads pipeline
-    int j = j0 + half;
-    for (; j + 6 < j1; j += 8) {
-        a0 += src[(long long)j * 64]; a1 += src[(long long)(j + 2) * 64];
-        a2 += src[(long long)(j + 4) * 64]; a3 += src[(long long)(j + 6) * 64];
-    }
-    for (; j < j1; j += 2) a0 += src[(long long)j * 64];
-    const float acc = (a0 + a1) + (a2 + a3);
-    red[half][col] = acc;
-    __syncthreads();
-    if (half == 0) part[blockIdx.x * 128 + col] = red[0][col] + red[1][col];
-}
-
 // U, z_pos: fp32 [Bg][64].  Uk_*: bf16 [BgP][64]; UT_*, ZT_*: bf16 [64][BgP]; rows j >= Bg are zero.
 __global__ void __launch_bounds__(256)
-k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, const float* __restrict__ mean_part,
-            float* __restrict__ means, int Bg, int BgP,
+k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, int BgP,
             bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_mid, bf16* __restrict__ Uk_lo,
             bf16* __restrict__ UT_hi, bf16* __restrict__ UT_mid, bf16* __restrict__ UT_lo,
             bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_mid, bf16* __restrict__ ZT_lo) {
     pdl_grid_sync();
     __shared__ float su[32][65], sz[32][65];
-    __shared__ float mu[128];
-    if (threadIdx.x < 128) {
-        float m = 0.f;
-#pragma unroll
-        for (int q = 0; q < kMeanParts; ++q) m += mean_part[q * 128 + threadIdx.x];       // fixed order: deterministic
-        m /= (float)Bg;
-        mu[threadIdx.x] = m;
-        if (blockIdx.x == 0) means[threadIdx.x] = m;
-    }
-    __syncthreads();
     const int j0 = blockIdx.x * 32;
     for (int t = threadIdx.x; t < 2048; t += 256) {
         const int jj = t >> 6, k = t & 63, j = j0 + jj;
-        const float u = j < Bg ? U[(long long)j * 64 + k] - mu[k] : 0.f;
-        const float z = j < Bg ? z_pos[(long long)j * 64 + k] - mu[64 + k] : 0.f;
+        const float u = j < Bg ? U[(long long)j * 64 + k] : 0.f;
+        const float z = j < Bg ? z_pos[(long long)j * 64 + k] : 0.f;
         su[jj][k] = u; sz[jj][k] = z;
         split3_store(u, Uk_hi, Uk_mid, Uk_lo, (long long)j * 64 + k);
     }
@@ -335,7 +294,6 @@ struct CurlTc {
     float* lab_logit;                          // [Bp]
     float* pdz; float* pV;                     // [NCB][Bp][64] column-block partials (NCB > 1), else dz_a / V directly
     float* logits_copy;                        // optional [B][Bg]
-    const float* means;                        // [128]: mean(U) | mean(z_pos): the operands are centred (see k_curl_means)
     int B, Bg, BgP, Bp, NT, label0;
     float grad_scale;
 };
@@ -382,14 +340,6 @@ k_curl_tc(const CurlTc p) {
     const int labA = p.label0 + rowA, labB = p.label0 + rowB;
     if (PASS == 0) {
         if (!active) return;
-        float cA = 0.f, cB = 0.f;                  // the raw logits (tests) = centred logits + z_i . mean(U)
-        if (p.logits_copy) {
-            for (int k = 0; k < 64; ++k) {
-                const float m = __ldg(p.means + k);
-                if (rowA < p.B) cA = fmaf(p.z_a[(long long)rowA * 64 + k], m, cA);
-                if (rowB < p.B) cB = fmaf(p.z_a[(long long)rowB * 64 + k], m, cB);
-            }
-        }
         float mA = -INFINITY, mB = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
@@ -401,8 +351,8 @@ k_curl_tc(const CurlTc p) {
                     if (j == labA && rowA < p.B) p.lab_logit[rowA] = lg[nt][e];
                     if (j == labB && rowB < p.B) p.lab_logit[rowB] = lg[nt][2 + e];
                     if (p.logits_copy) {
-                        if (rowA < p.B) p.logits_copy[(long long)rowA * p.Bg + j] = lg[nt][e] + cA;
-                        if (rowB < p.B) p.logits_copy[(long long)rowB * p.Bg + j] = lg[nt][2 + e] + cB;
+                        if (rowA < p.B) p.logits_copy[(long long)rowA * p.Bg + j] = lg[nt][e];
+                        if (rowB < p.B) p.logits_copy[(long long)rowB * p.Bg + j] = lg[nt][2 + e];
                     }
                 }
             }
@@ -555,7 +505,7 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 using namespace curla;
 
 namespace {
-struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, off_means, total; };
+struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, total; };
 CurlPlan curl_plan(int B, int Bg) {
     CurlPlan c;
     c.BgP = (Bg + 63) / 64 * 64; c.Bp = (B + 15) / 16 * 16;
@@ -567,7 +517,6 @@ CurlPlan curl_plan(int B, int Bg) {
     c.off_lab = o; o += c.Bp;
     c.off_pdz = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
     c.off_pV = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
-    c.off_means = o; o += 128 + kMeanParts * 128;               // mean(U) | mean(z_pos), and their per-slice partial sums
     c.total = o;
     return c;
 }
@@ -605,12 +554,8 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
             t.pV = cp.NCB > 1 ? workspace + cp.off_pV : V;
             t.logits_copy = logits_copy;
             t.B = B; t.Bg = Bg; t.BgP = (int)cp.BgP; t.Bp = (int)cp.Bp; t.NT = (int)cp.NT; t.label0 = label0; t.grad_scale = grad_scale;
-            float* means = workspace + cp.off_means;
-            t.means = means;
-            launch_k(k_curl_means, dim3(kMeanParts), dim3(256), 0, stream, (const float*)U, z_pos, Bg, means + 128);
-            if (check_launch("curl_prep")) return -1;
-            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, (const float*)(means + 128),
-                     means, Bg, (int)cp.BgP, hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n, hb + 6 * n, hb + 7 * n, hb + 8 * n);
+            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, Bg, (int)cp.BgP,
+                     hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n, hb + 6 * n, hb + 7 * n, hb + 8 * n);
             if (check_launch("curl_prep")) return -1;
             const dim3 grid((unsigned)(cp.Bp / 16), (unsigned)cp.NCB);
             launch_k(k_curl_tc<0>, grid, dim3(256), 0, stream, t);
