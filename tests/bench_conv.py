@@ -1,5 +1,5 @@
 """Timing experiment (not a test): one conv layer in isolation at the bench geometry.
-usage: python tests/bench_conv.py [layer(0..3)] [dgrad]"""
+usage: python tests/bench_conv.py [layer(0..3)] [dgrad|wgrad]"""
 import os
 import sys
 
@@ -11,7 +11,8 @@ from curla_b200 import _lib
 from helpers import Geom, pack_conv_w, stream
 
 layer = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-dgrad = len(sys.argv) > 2
+dgrad = len(sys.argv) > 2 and sys.argv[2] == 'dgrad'
+wgrad = len(sys.argv) > 2 and sys.argv[2] == 'wgrad'
 B = 512
 g = Geom(76, 135, B)
 torch.manual_seed(0)
@@ -19,14 +20,25 @@ cin = g.CP1 if layer == 0 else 32
 fin, vin = g.alloc(cin)
 vin.copy_((torch.rand(vin.shape, device='cuda') * 2).to(torch.bfloat16))
 fout, vout = g.alloc(32)
+if wgrad:
+    vout.copy_((torch.rand(vout.shape, device='cuda') - 0.5).to(torch.bfloat16))
 w = torch.randn(32, 9 if layer == 0 else 32, 3, 3) * 0.05
 wsh = pack_conv_w(w, layer == 0)
 bias = torch.zeros(32, device='cuda')
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
 
+ws_buf = torch.zeros(int(max(_lib.load().curla_conv_wgrad_workspace_floats(0), _lib.load().curla_conv_wgrad_workspace_floats(1))),
+                     device='cuda')
+dW = torch.zeros(32, 9 if layer == 0 else 32, 3, 3, device='cuda')
+db = torch.zeros(32, device='cuda')
+
+
 def run():
-    if dgrad:
+    if wgrad:
+        _lib.call('curla_conv_wgrad', _lib.ptr(vin), g.S * cin, _lib.ptr(vout), g.S * 32, _lib.ptr(ws_buf), _lib.ptr(dW), _lib.ptr(db),
+                  1.0, B, g.pitch, g.S, g.Ho[layer], g.Wo[layer], 9 if layer == 0 else 32, 1 if layer == 0 else 0, stream())
+    elif dgrad:
         _lib.call('curla_conv_dgrad', _lib.ptr(vin), g.S * 32, _lib.ptr(wsh), _lib.ptr(vout), _lib.ptr(vout), g.S * 32,
                   B, g.pitch, g.S, g.Ho[layer - 1], g.Wo[layer - 1], stream())
     else:
@@ -46,6 +58,11 @@ for _ in range(10):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 ts.sort()
+if wgrad:
+    print('layer %d wgrad (+ reduce) copies=%s stages=%s rows=%s: median %.1f us  min %.1f us' % (
+        layer, os.environ.get('CURLA_WG_COPIES', 'default'), os.environ.get('CURLA_WG_STAGES', '2'), os.environ.get('CURLA_WG_ROWS', 'max'),
+        ts[len(ts) // 2], ts[0]))
+    sys.exit(0)
 print('layer %d %s debug=%s stages=%s: median %.1f us  min %.1f us' % (
     layer, 'dgrad' if dgrad else 'fwd', os.environ.get('CURLA_TC_DEBUG', '0'), os.environ.get('CURLA_TC_STAGES', 'max'),
     ts[len(ts) // 2], ts[0]))

@@ -371,6 +371,7 @@ def test_conv_wgrad_staging_modes_agree(H, W, B, monkeypatch):
     image row per request, the shifted dy copies zero-filled by the TMA unit) instead of one linear bulk copy per plane
     per row, and can fetch dy from L2 once, making the shifted copies inside shared memory (CURLA_WG_DY1=1).  Same products, fp32 accumulation: the weight / bias gradients agree to 1e-5, conv-1 (2x2 taps on the
     space-to-depth input, 6 planes) and a 3x3 layer."""
+    monkeypatch.setenv('CURLA_WG_RING', '0')           # (the two-stage kernel: CURLA_WG_DY1 exists only there)
     g, x, ws, bs = _conv_case(H, W, B, seed=4)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(5)
@@ -397,6 +398,60 @@ def test_conv_wgrad_staging_modes_agree(H, W, B, monkeypatch):
             assert rel_l2(got[mode][1], got['00'][1]) < 1e-5, (l, mode)
         assert torch.equal(got['01'][0], got['00'][0]) and torch.equal(got['01'][1], got['00'][1])      # same runs, same MMAs
         assert float(got['11'][0].abs().sum()) > 0
+
+
+@pytest.mark.parametrize('H,W,B', [(76, 135, 5), (90, 160, 3), (76, 135, 1), (76, 135, 37)])
+def test_conv_wgrad_variants_agree(H, W, B, monkeypatch):
+    """conv_wgrad_tc.cu: the row-ring kernel (operands stream through a ring of image rows, CURLA_WG_RS rows per
+    pipeline stage, a CTA owns a contiguous range of the (sample, row) sequence; the default) and the two-stage kernel (CURLA_WG_RING=0); the horizontal taps ride in N
+    (one shifted copy of dy per tap, CURLA_WG_COPIES=3) or on the A side (the input's K window starts 1, 2 rows later
+    against ONE staged dy: CURLA_WG_COPIES=1; 2 = one N = 64 and one N = 32 MMA); the dy copies are issued by the
+    producer warp or by up to four helper warps (CURLA_WG_PRODUCERS); operands staged by linear bulk copies or
+    tensor-map boxes (CURLA_WG_TMAP).  Same products, fp32 accumulation: every variant agrees with the torch gradient
+    and with the others to 1e-5, for conv-1 (2x2 taps) and 3x3 layers; B = 1 leaves most CTAs without work, B = 37
+    gives ranges that straddle sample boundaries."""
+    g, x, ws, bs = _conv_case(H, W, B, seed=6)
+    s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
+    torch.manual_seed(7)
+    ws_buf = torch.zeros(int(max(_lib.load().curla_conv_wgrad_workspace_floats(0),
+                                 _lib.load().curla_conv_wgrad_workspace_floats(1))), device=DEV)
+    # (ring, copies, stages | ring rows, producers, tensor-map staging, image rows per ring stage)
+    variants = [('0', '3', '2', '1', '0', ''), ('0', '2', '2', '1', '0', ''), ('0', '1', '3', '1', '0', ''), ('0', '3', '2', '3', '0', ''),
+                ('0', '1', '4', '4', '0', ''), ('0', '3', '3', '1', '1', ''),
+                ('1', '3', '', '5', '0', '2'), ('1', '3', '', '1', '0', '2'), ('1', '3', '', '3', '0', '1'), ('1', '2', '', '5', '0', '3'),
+                ('1', '1', '', '2', '0', '2'), ('1', '3', '6', '5', '0', '2'), ('1', '3', '', '1', '1', '2'), ('1', '1', '7', '1', '1', '1'),
+                ('1', '3', '', '5', '0', '4'), ('1', '3', '8', '4', '0', '1')]
+    for l in (0, 1, 3):
+        dy = torch.randn(B, 32, g.Ho[l], g.Wo[l], device=DEV)
+        dfull, dview = g.to_pitch(bf16r(dy), l)
+        inp = acts[l - 1] if l > 0 else s2d
+        xin = (x.to(DEV) / 255.0) if l == 0 else bf16r(g.from_pitch(acts[l - 1], g.Ho[l - 1], g.Wo[l - 1]))
+        wref = bf16r(ws[l].to(DEV)).requires_grad_(True)
+        bref = bs[l].to(DEV).clone().requires_grad_(True)
+        y = F.conv2d(xin, wref, bref, stride=2 if l == 0 else 1)
+        gw, gb = torch.autograd.grad(y, [wref, bref], bf16r(dy))
+        got = {}
+        for v in variants:
+            ring, copies, depth, prod, tmap, rs = v
+            monkeypatch.setenv('CURLA_WG_RS', rs)
+            monkeypatch.setenv('CURLA_WG_RING', ring)
+            monkeypatch.setenv('CURLA_WG_COPIES', copies)
+            monkeypatch.setenv('CURLA_WG_STAGES', depth if ring == '0' else '2')
+            monkeypatch.setenv('CURLA_WG_NSD', depth if ring == '1' else '')
+            monkeypatch.setenv('CURLA_WG_PRODUCERS', prod)
+            monkeypatch.setenv('CURLA_WG_TMAP', tmap)
+            dW = torch.full(ws[l].shape, float('nan'), device=DEV)
+            db = torch.full((32,), float('nan'), device=DEV)
+            _lib.call('curla_conv_wgrad', _lib.ptr(inp), g.S * (32 if l > 0 else g.CP1), _lib.ptr(dview), g.S * 32,
+                      _lib.ptr(ws_buf), _lib.ptr(dW), _lib.ptr(db), 1.0 / 255.0 if l == 0 else 1.0, B, g.pitch, g.S,
+                      g.Ho[l], g.Wo[l], ws[l].shape[1], 1 if l == 0 else 0, stream())
+            torch.cuda.synchronize()
+            got[v] = (dW, db)
+            assert rel_l2(dW, gw) < 5e-3, ('dW', l, v, rel_l2(dW, gw))
+            assert rel_l2(db, gb) < 5e-3, ('db', l, v)
+        ref = got[variants[0]]
+        for k, v in got.items():
+            assert rel_l2(v[0], ref[0]) < 1e-5 and rel_l2(v[1], ref[1]) < 1e-5, (l, k)
 
 
 # ------------------------------------------------------------------ GEMM
