@@ -25,6 +25,17 @@
 // K windows are 16 positions inside one image row; every staged dy plane has zero rows in front
 // of (k' < dx) and behind (k' >= pitch + dx) the copied row, so out-of-row taps multiply zeros.
 //
+// What paces it (round 2, gpurun r04a-r04i; the experiments are in git history at 3b521f2): a 3x3 layer needs 280 clk
+// of MMAs per image row (5 K windows x 56 clk) and runs at ~700.  Neither the bytes pulled from L2 (taps on the A side,
+// CURLA_WG_COPIES=1: 19 -> 10 KB per row, slower: 15 N = 32 MMAs per row), nor the pipeline shape (a ring of image rows
+// with a CTA walking a contiguous range of rows so that halo rows are fetched once and HBM never idles: 0.51 vs 0.37 ms)
+// nor the number of requests (tensor-map boxes) moves it; per-role cycle counters of the ring variant show the MMA
+// thread itself blocked ~140 clk per N = 96 MMA (profiles/tools/mma_rate_mn.cu: 56 clk with nothing else running): the
+// bulk copies landing in shared memory (19 KB per row, in 1 KB pieces at 16-byte offsets) and the operand reads (35 KB
+// per row) share the shared-memory port.  What did help: more threads issuing the copies (one thread issues a
+// cp.async.bulk every 50-110 clk whatever its size, profiles/tools/stream_rate.cu) -- the four epilogue warps, idle
+// until the end, issue the dy copies: 0.405 -> 0.368 ms per update.
+//
 // One persistent CTA per SM: producer warp (cp.async.bulk, one copy per plane per image row),
 // MMA warp (R rows x kwin windows, one N = 32*NDX MMA each per stage), accumulators stay in TMEM for
 // the CTA's whole share of the batch; 4 epilogue warps write one fp32 partial per CTA and a
@@ -55,7 +66,7 @@ struct WgGeom {
                            //    by the four otherwise idle epilogue warps (L2 -> SM traffic of a 3x3 layer: 96 -> 52 KB per run)
     int nh;                // helper producers (0..4): epilogue warps that issue the dy copies while the producer warp issues the
                            //    input rows -- one thread issues a cp.async.bulk every ~50-110 clk whatever its size
-                           //    (scratch/probe/probe_stream.cu), and a stage is 88 copies of 1 KB
+                           //    (profiles/tools/stream_rate.cu), and a stage is 88 copies of 1 KB
     int nc;                // staged copies of dy (1..NDX).  nc < NDX: the remaining horizontal taps come from the A side --
                            //    a K window of A starts s = nc, 2 nc, .. rows later (the input rows are contiguous in K, so
                            //    any 16-byte start is a legal descriptor), one more MMA of N = 32 * (taps covered) each
@@ -320,307 +331,6 @@ k_conv_wgrad_tc(const __grid_constant__ CUtensorMap tmIn, const __grid_constant_
     }
 }
 
-// ---------------------------------------------------------------- row-ring variant (the default)
-// The kernel above moves its operands in two big stages (R image rows each): a stage cannot be refilled
-// before its last MMA has read it, so with two stages HBM idles while a stage computes, and three or four
-// shorter stages pay more halo rows (R + GR - 1 input rows per R dy rows).  Measured (gpurun r04c/r04e):
-// time per image row = fill + MMA / 2, the fill paced by the DRAM-sourced bytes at ~3.9 TB/s aggregate.
-// Here the operands stream through a ring of IMAGE ROWS:
-//   * a CTA owns a CONTIGUOUS range of the (sample, dy row) sequence, so consecutive dy rows share their
-//     halo: every input row is fetched once (the GR-1 rows at the start of a CTA's range excepted).  The
-//     range is walked as a sequence of "row steps" u = one input row + the dy row whose LAST input row it is
-//     (the first GR-1 input rows of a sample carry no dy row);
-//   * input rows live in a ring of NR = NS*RS row slots, dy rows in a second ring of NR slots; the M = 128
-//     descriptor needs the GR input rows of a dy row back to back in shared memory: ring rows 0 .. GR-2 are
-//     mirrored behind the last one (those rows are copied twice, the second copy an L2 hit);
-//   * a pipeline stage is RS row steps with ONE full and ONE empty mbarrier: a barrier wait costs the MMA thread
-//     100-200 clk and a tcgen05.commit ~90 clk of the MMA queue, against 280 clk of MMAs per image row -- with a
-//     barrier pair per row the issuing thread, not the memory system, set the pace (gpurun r04g/r04h: 915 clk per row);
-//   * the stage of step j is refilled once step j - NS + ceil((GR-1)/RS) has completed (its rows are the last
-//     readers of the halo);
-//   * up to four helper warps (the epilogue warps, idle until the end) issue the dy copies, the producer warp
-//     the input rows: one thread issues a bulk copy every 50-110 clk (scratch/probe/probe_stream.cu).
-// timing experiments (CURLA_WG_DEBUG=1): clocks of CTA 0's roles -- [0..3] MMA warp: wait full, -, issue, loop total;
-// [4..6] producer: wait empty, issue, loop total; [8..10] helper 0: wait empty, issue, loop total; [12] dy rows
-__device__ long long g_wg_dbg[16];
-
-struct WgRing {
-    int pitch, S, Hv, Wv, B;
-    int kwin, dyr, nc, nh, tmap, pss, dbg;
-    int ns, rs;            // pipeline stages, row steps per stage
-    int rows_total;        // B * Hv dy rows
-};
-
-// walks the row steps of a CTA's range [g0, g1) of dy rows: (sample b, input row r, dy row y = r - (GR-1) or none)
-template <int GR>
-struct WgRowIt {
-    int b, r, ys, ye, left, Hv;          // left = dy rows of the range not yet assigned to a segment
-    __device__ void init(int g0, int g1, int Hv_) {
-        Hv = Hv_; b = g0 / Hv; ys = g0 - b * Hv; left = g1 - g0;
-        const int n = Hv - ys < left ? Hv - ys : left;
-        ye = ys + n - 1; left -= n; r = ys;
-    }
-    __device__ bool has_dy() const { return r - (GR - 1) >= ys; }
-    __device__ int y() const { return r - (GR - 1); }
-    __device__ void next() {
-        if (++r > ye + GR - 1) {
-            ++b; ys = 0;
-            const int n = Hv < left ? Hv : left;
-            ye = n - 1; left -= n; r = 0;
-        }
-    }
-};
-
-template <int CP, int GR, int NDX>
-__global__ void __launch_bounds__(kWgThreads, 1)
-k_conv_wgrad_ring(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmDy,
-                  const bf16* __restrict__ in, long long in_sstride, const bf16* __restrict__ dy,
-                  long long dy_sstride, float* __restrict__ partial, WgRing g) {
-    constexpr int CH = CP / 8, CPL = CH + 1;
-    static_assert(GR * CPL <= 16, "M = 128 holds 16 chunks");
-    constexpr uint32_t TMEM_COLS = 128;
-    constexpr int NTAPS = GR * NDX;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s_base = smem_u32(smem);
-    // header: full[16] @0, empty[16] @128, done @256, tmem ptr @264
-    const uint32_t s_full = s_base, s_empty = s_base + 128, s_done = s_base + 256, s_tptr = s_base + 264;
-    constexpr uint32_t kHdr = 512;
-    const uint32_t PS = (uint32_t)g.pss, PG = (uint32_t)g.pitch * 16u;
-    const uint32_t slot_bytes = CPL * PS;
-    const int NS = g.ns, RS = g.rs, NC = g.nc;
-    const int NR = NS * RS;                                             // ring rows
-    const uint32_t a_bytes = (uint32_t)(NR + GR - 1) * slot_bytes;      // + the mirrored rows
-    const uint32_t DYB = (uint32_t)g.dyr * 16u;
-    const uint32_t drow_bytes = (uint32_t)(4 * NC) * DYB;               // one dy row: NC shifted copies of 4 planes
-    const uint32_t s_a0 = s_base + kHdr, s_d0 = s_a0 + a_bytes;
-    const uint32_t total_bytes = (a_bytes + (uint32_t)NR * drow_bytes + 127u) & ~127u;
-    const long long plane = (long long)g.S * 8;
-    const int lag = (GR - 1 + RS - 1) / RS;                             // steps until a step's rows have had their last reader
-
-    if (tid == 0) {
-        for (int i = 0; i < 16; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
-        mbar_init(s_done, 1);
-        fence_mbar_init();
-    }
-    if (warp == 0) {
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tptr), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // every byte the tensor core may touch must be finite (junk rows meet exact zeros of dy)
-    for (uint32_t i = tid; i < total_bytes / 16; i += kWgThreads)
-        reinterpret_cast<uint4*>(smem + kHdr)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    {   // ones-plane of every input-row slot (bf16 1.0): its D rows are the bias gradient
-        const int prow = (int)(PS / 16);
-        for (int i = tid; i < (NR + GR - 1) * prow; i += kWgThreads) {
-            const int r = i / prow, row = i - r * prow;
-            *reinterpret_cast<uint4*>(smem + kHdr + (size_t)r * slot_bytes + (size_t)CH * PS + (size_t)row * 16) =
-                make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-        }
-    }
-    pdl_grid_sync();     // the prologue above touched no global memory
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 264);
-    // this CTA's contiguous range of the (sample, dy row) sequence and its row steps
-    const int g0 = (int)((long long)g.rows_total * blockIdx.x / gridDim.x);
-    const int g1 = (int)((long long)g.rows_total * (blockIdx.x + 1) / gridDim.x);
-    const int Hv = g.Hv;
-    int U = 0;                                                          // row steps: dy rows + GR-1 per (partial) sample
-    if (g1 > g0) U = (g1 - g0) + ((g1 - 1) / Hv - g0 / Hv + 1) * (GR - 1);
-    const int nsteps = (U + RS - 1) / RS;
-    const bool dbg0 = g.dbg && blockIdx.x == 0;
-
-    // a stage may be refilled for step j once step j - NS + lag has completed
-    auto wait_refill = [&](int j) {
-        const int need = j - NS + lag;
-        if (need >= 0) mbar_wait(s_empty + 8 * (uint32_t)(need % NS), (uint32_t)((need / NS) & 1));
-    };
-
-    if (warp == 5) {
-        // ================= producer: arms the stage's barrier with ALL its bytes, issues the input rows (and the dy rows
-        // when there are no helpers)
-        WgRowIt<GR> it;
-        it.init(g0, g1, Hv);
-        long long tw = 0, ti = 0;
-        const long long tl0 = clock64();
-        int u = 0;
-        for (int j = 0; j < nsteps; ++j) {
-            const long long c0 = dbg0 ? clock64() : 0;
-            wait_refill(j);
-            const long long c1 = dbg0 ? clock64() : 0;
-            tw += c1 - c0;
-            const uint32_t bar = s_full + 8 * (uint32_t)(j % NS);
-            if (elect_one()) {
-                // byte count of the stage: its input rows (mirrored ones twice) + its dy rows
-                WgRowIt<GR> t = it;
-                uint32_t bytes = 0;
-                for (int k = 0, uu = u; k < RS && uu < U; ++k, ++uu, t.next()) {
-                    const uint32_t p = (uint32_t)(uu % NR);
-                    bytes += (g.tmap ? (uint32_t)CH * PS : (uint32_t)CH * PG) * (p < (uint32_t)(GR - 1) ? 2u : 1u);
-                    if (t.has_dy()) bytes += g.tmap ? drow_bytes : (uint32_t)(4 * NC) * PG;
-                }
-                mbar_expect_tx(bar, bytes);
-            }
-            __syncwarp();
-            for (int k = 0; k < RS && u < U; ++k, ++u, it.next()) {
-                const uint32_t p = (uint32_t)(u % NR);
-                if (elect_one()) {
-                    const bool mirror = p < (uint32_t)(GR - 1);
-                    const uint32_t dst = s_a0 + p * slot_bytes, dst2 = s_a0 + (p + (uint32_t)NR) * slot_bytes;
-                    if (g.tmap) {
-                        tma_load_4d(dst, &tmIn, 0, it.r, 0, it.b, bar);
-                        if (mirror) tma_load_4d(dst2, &tmIn, 0, it.r, 0, it.b, bar);
-                    } else {
-                        const bf16* src = in + (long long)it.b * in_sstride + (long long)it.r * g.pitch * 8;
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) bulk_g2s(dst + (uint32_t)c * PS, src + c * plane, PG, bar);
-                        if (mirror) {
-#pragma unroll
-                            for (int c = 0; c < CH; ++c) bulk_g2s(dst2 + (uint32_t)c * PS, src + c * plane, PG, bar);
-                        }
-                    }
-                    if (g.nh == 0 && it.has_dy()) {
-                        const uint32_t sd = s_d0 + p * drow_bytes;
-                        if (g.tmap) {
-#pragma unroll
-                            for (int dx = 0; dx < NDX; ++dx)
-                                if (dx < NC) tma_load_4d(sd + (uint32_t)(dx * 4) * DYB, &tmDy, -2 * dx, it.y(), 0, it.b, bar);
-                        } else {
-                            const bf16* src_d = dy + (long long)it.b * dy_sstride + (long long)it.y() * g.pitch * 8;
-#pragma unroll
-                            for (int dx = 0; dx < NDX; ++dx)
-#pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    if (dx < NC) bulk_g2s(sd + (uint32_t)(dx * 4 + c) * DYB + (uint32_t)dx * 16u, src_d + c * plane, PG, bar);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            if (dbg0) ti += clock64() - c1;
-        }
-        if (dbg0 && lane == 0) { g_wg_dbg[4] = tw; g_wg_dbg[5] = ti; g_wg_dbg[6] = clock64() - tl0; }
-    } else if (warp == 4) {
-        // ================= MMA issuer
-        const uint64_t a_hi = make_desc(0, 128, PS), b_hi = make_desc(0, 128, DYB);   // (lbo = K groups, sbo = chunks)
-        const int ng = (NDX + NC - 1) / NC;
-        const uint32_t id0 = idesc_mn(32u * (uint32_t)(NDX < NC ? NDX : NC));
-        const uint32_t id1 = idesc_mn(32u * (uint32_t)(NDX - NC < NC ? (NDX - NC > 0 ? NDX - NC : 1) : NC));
-        const uint32_t id2 = idesc_mn(32u * (uint32_t)(NDX - 2 * NC > 0 ? NDX - 2 * NC : 1));
-        WgRowIt<GR> it;
-        it.init(g0, g1, Hv);
-        long long tw = 0, ti = 0;
-        const long long tl0 = clock64();
-        uint32_t accum = 0;
-        int u = 0;
-        for (int j = 0; j < nsteps; ++j) {
-            const long long c0 = dbg0 ? clock64() : 0;
-            mbar_wait(s_full + 8 * (uint32_t)(j % NS), (uint32_t)((j / NS) & 1));
-            const long long c1 = dbg0 ? clock64() : 0;
-            tc_fence_after();
-            if (elect_one()) {
-                WgRowIt<GR> t = it;
-                for (int k = 0, uu = u; k < RS && uu < U; ++k, ++uu, t.next()) {
-                    if (!t.has_dy()) continue;
-                    int pa = (uu - (GR - 1)) % NR;                       // ring row of input row y (uu >= GR-1 here)
-                    uint32_t a16 = (s_a0 + (uint32_t)pa * slot_bytes) >> 4;
-                    uint32_t b16 = (s_d0 + (uint32_t)(uu % NR) * drow_bytes) >> 4;
-                    for (int kw = 0; kw < g.kwin; ++kw, a16 += 16u, b16 += 16u) {
-                        const uint64_t bd = b_hi | (uint64_t)(b16 & 0x3FFFu);
-                        umma_bf16_rt(tmem_base, a_hi | (uint64_t)(a16 & 0x3FFFu), bd, id0, accum);
-                        if (ng > 1) umma_bf16_rt(tmem_base + (uint32_t)(32 * NC), a_hi | (uint64_t)((a16 + (uint32_t)NC) & 0x3FFFu), bd, id1, accum);
-                        if (ng > 2) umma_bf16_rt(tmem_base + (uint32_t)(64 * NC), a_hi | (uint64_t)((a16 + 2u * (uint32_t)NC) & 0x3FFFu), bd, id2, accum);
-                        accum = 1;
-                    }
-                }
-                umma_commit(s_empty + 8 * (uint32_t)(j % NS));
-            }
-            __syncwarp();
-            for (int k = 0; k < RS && u < U; ++k, ++u) { if (it.has_dy()) accum = 1; it.next(); }
-            if (dbg0) { tw += c1 - c0; ti += clock64() - c1; }
-        }
-        if (elect_one()) umma_commit(s_done);
-        __syncwarp();
-        if (dbg0 && lane == 0) { g_wg_dbg[0] = tw; g_wg_dbg[1] = 0; g_wg_dbg[2] = ti; g_wg_dbg[3] = clock64() - tl0; g_wg_dbg[12] = g1 - g0; }
-    } else {
-        // ================= helper producers: warp h issues the dy rows of steps h, h + nh, ..
-        if (warp < g.nh) {
-            WgRowIt<GR> it;
-            it.init(g0, g1, Hv);
-            const bool dbg = dbg0 && warp == 0;
-            long long tw = 0, ti = 0;
-            const long long tl0 = clock64();
-            int u = 0;
-            for (int j = 0; j < nsteps; ++j) {
-                if (j % g.nh != warp) {
-                    for (int k = 0; k < RS && u < U; ++k, ++u) it.next();
-                    continue;
-                }
-                const long long c0 = dbg ? clock64() : 0;
-                wait_refill(j);
-                const long long c1 = dbg ? clock64() : 0;
-                tw += c1 - c0;
-                const uint32_t bar = s_full + 8 * (uint32_t)(j % NS);
-                for (int k = 0; k < RS && u < U; ++k, ++u, it.next()) {
-                    if (it.has_dy() && elect_one()) {
-                        const uint32_t sd = s_d0 + (uint32_t)(u % NR) * drow_bytes;
-                        const bf16* src_d = dy + (long long)it.b * dy_sstride + (long long)it.y() * g.pitch * 8;
-#pragma unroll
-                        for (int dx = 0; dx < NDX; ++dx)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (dx < NC) bulk_g2s(sd + (uint32_t)(dx * 4 + c) * DYB + (uint32_t)dx * 16u, src_d + c * plane, PG, bar);
-                    }
-                    __syncwarp();
-                }
-                if (dbg) ti += clock64() - c1;
-            }
-            if (dbg && lane == 0) { g_wg_dbg[8] = tw; g_wg_dbg[9] = ti; g_wg_dbg[10] = clock64() - tl0; }
-        }
-        // ================= epilogue (once): TMEM -> this CTA's fp32 partial [tap][ci][co] + bias[co]
-        float* ws = partial + (long long)blockIdx.x * (NTAPS * CP * 32 + 32);
-        const int m = warp * 32 + lane;                     // D row = chunk*8 + e
-        const int chunk = m >> 3, e = m & 7;
-        const int gg = chunk / CPL, c = chunk - gg * CPL;
-        uint32_t r[32];
-        if (g1 > g0) {
-            mbar_wait(s_done, 0);
-            tc_fence_after();
-        }
-#pragma unroll
-        for (int dx = 0; dx < NDX; ++dx) {
-            if (g1 > g0) {
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(dx * 32), r);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = 0u;
-            }
-            if (gg < GR && c < CH) {
-                float* dst = ws + ((long long)(gg * NDX + dx) * CP + c * 8 + e) * 32;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<uint4*>(dst + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
-            } else if (gg == 0 && c == CH && e == 0 && dx == 0) {
-                float* dst = ws + (long long)NTAPS * CP * 32;          // ones-plane row: sum_P dy[P][co]
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<uint4*>(dst + i * 4) = make_uint4(r[i * 4], r[i * 4 + 1], r[i * 4 + 2], r[i * 4 + 3]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // Deterministic second stage: sum CTA partials, write OIHW fp32 grads (+ bias grad).
 //  s2d=0: dW[co][ci][t]      = scale * sum ws[cta][t][ci][co]           (Cin = 32)
 //  s2d=1: dW[co][c][ky][kx]  = scale * sum ws[cta][by*2+bx][c*4+sy*2+sx][co]
@@ -724,79 +434,11 @@ static bool wg_map(CUtensorMap* out, const void* ptr, int pitch, int rows, int p
     return true;
 }
 
-// Row-ring kernel (k_conv_wgrad_ring).  Returns 1 when launched, 0 when the geometry does not fit (the caller falls
-// back to the two-stage kernel), -1 on error.
-template <int CP, int GR, int NDX>
-static int launch_wgrad_ring(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
-                             float* workspace, int B, int pitch, int S, int Hv, int Wv, int* grid_out,
-                             cudaStream_t stream) {
-    constexpr int CPL = CP / 8 + 1;
-    WgRing g;
-    g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv; g.B = B;
-    g.nc = NDX;
-    { const char* e = getenv("CURLA_WG_COPIES"); if (e && e[0] >= '1' && e[0] <= '0' + NDX) g.nc = e[0] - '0'; }
-    const int NC = g.nc;
-    g.kwin = cdiv(Wv + NC - 1, 16);
-    g.dyr = g.kwin * 16 > pitch + NC - 1 ? g.kwin * 16 : pitch + NC - 1;
-    g.dyr = (g.dyr + 7) / 8 * 8;
-    g.tmap = 0;
-    { const char* e = getenv("CURLA_WG_TMAP"); if (e && e[0] == '1') g.tmap = 1; }
-    g.nh = 4;
-    { const char* e = getenv("CURLA_WG_PRODUCERS"); if (e && e[0] >= '1' && e[0] <= '5') g.nh = e[0] - '1'; }
-    g.dbg = 0;
-    { const char* e = getenv("CURLA_WG_DEBUG"); if (e && e[0] == '1') g.dbg = 1; }
-    CUtensorMap tmIn, tmDy;
-    memset(&tmIn, 0, sizeof(tmIn));
-    memset(&tmDy, 0, sizeof(tmDy));
-    g.pss = pitch * 16;
-    if (g.tmap) {
-        const int pss = (pitch * 16 + 127) / 128 * 128;
-        const bool ok = S % pitch == 0 &&
-                        wg_map(&tmIn, in, pitch, S / pitch, CP / 8, B, (long long)S * 8, in_sstride, pss / 8) &&
-                        wg_map(&tmDy, dy, pitch, S / pitch, 4, B, (long long)S * 8, dy_sstride, g.dyr * 2);
-        if (ok) g.pss = pss; else g.tmap = 0;
-    }
-    if (g.tmap) g.nh = 0;
-    const size_t slot = (size_t)CPL * g.pss, drow = (size_t)4 * NC * g.dyr * 16;
-    const size_t budget = 225 * 1024 - 256 - 512;
-    // ring rows: as many as fit; CURLA_WG_RS = image rows per pipeline stage (one barrier pair per stage)
-    int nr = 0;
-    for (int r = 2; r <= 32; ++r)
-        if ((size_t)(r + GR - 1) * slot + (size_t)r * drow + 128 <= budget) nr = r;
-    int rs = 2;
-    { const char* e = getenv("CURLA_WG_RS"); if (e && e[0] >= '1' && e[0] <= '4') rs = e[0] - '0'; }
-    { const char* e = getenv("CURLA_WG_NSD"); if (e && atoi(e) >= 2 && atoi(e) <= nr) nr = atoi(e); }     // timing experiments: ring rows
-    int ns = nr / rs;
-    if (ns > 16) ns = 16;
-    const int lag = (GR - 1 + rs - 1) / rs;
-    if (ns < lag + 2) return 0;
-    if (g.nh > ns - lag) g.nh = ns - lag;
-    g.ns = ns; g.rs = rs;
-    g.rows_total = B * Hv;
-    const size_t smem = 512 + (((size_t)(ns * rs + GR - 1) * slot + (size_t)(ns * rs) * drow + 127) & ~(size_t)127);
-    auto kern = k_conv_wgrad_ring<CP, GR, NDX>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -1; }
-    const int cap = conv_grid_cap();
-    const int grid = g.rows_total < cap ? g.rows_total : cap;
-    launch_k(kern, dim3(grid), dim3(kWgThreads), smem, stream, tmIn, tmDy, (const bf16*)in, in_sstride, (const bf16*)dy, dy_sstride,
-             workspace, g);
-    *grid_out = grid;
-    return 1;
-}
-
 template <int CP, int GR, int NDX>
 static int launch_wgrad(const void* in, long long in_sstride, const void* dy, long long dy_sstride,
                         float* workspace, int B, int pitch, int S, int Hv, int Wv, int* grid_out,
                         cudaStream_t stream) {
     constexpr int CPL = CP / 8 + 1;
-    {   // CURLA_WG_RING=0: the two-stage kernel below
-        const char* e = getenv("CURLA_WG_RING");
-        if (!(e && e[0] == '0')) {
-            const int r = launch_wgrad_ring<CP, GR, NDX>(in, in_sstride, dy, dy_sstride, workspace, B, pitch, S, Hv, Wv, grid_out, stream);
-            if (r) return r < 0 ? -1 : 0;
-        }
-    }
     WgGeom g;
     g.pitch = pitch; g.S = S; g.Hv = Hv; g.Wv = Wv; g.B = B;
     // CURLA_WG_COPIES: staged dy copies (horizontal taps carried in N); the remaining taps are A-side shifts
@@ -817,7 +459,8 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
     g.dy1 = 0;
     { const char* e = getenv("CURLA_WG_DY1"); if (e && e[0] == '1' && NC == NDX) g.dy1 = 1; }
     // CURLA_WG_PRODUCERS = 1 + helper warps issuing the dy copies (linear staging only)
-    g.nh = 0;
+    // (default: the producer warp + four helpers -- measured 0.405 -> 0.368 ms per update, gpurun r04e)
+    g.nh = 4;
     { const char* e = getenv("CURLA_WG_PRODUCERS"); if (e && e[0] >= '1' && e[0] <= '5') g.nh = e[0] - '1'; }
     if (g.tmap || g.dy1) g.nh = 0;
     g.pss = pitch * 16;
@@ -863,12 +506,6 @@ static int launch_wgrad(const void* in, long long in_sstride, const void* dy, lo
 }  // namespace curla
 
 using namespace curla;
-
-extern "C" int curla_conv_wgrad_debug_read(long long* out16) {
-    cudaError_t e = cudaMemcpyFromSymbol(out16, curla::g_wg_dbg, sizeof(long long) * 16);
-    CURLA_CHECK(e == cudaSuccess, "conv_wgrad_debug_read: %s", cudaGetErrorString(e));
-    return 0;
-}
 
 extern "C" long long curla_conv_wgrad_workspace_floats(int first_layer) {
     const long long per = first_layer ? (4 * 48 * 32 + 32) : (9 * 32 * 32 + 32);

@@ -159,7 +159,7 @@ struct curla_agent {
     float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch;
     // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
     // there while the main stream already runs the next pass's conv stack
-    cudaStream_t side; cudaEvent_t ev[4]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
+    cudaStream_t side; cudaEvent_t ev[5]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
     // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
     cudaStream_t comm_st; cudaEvent_t cev[6]; int comm_state;
@@ -394,6 +394,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
         int sp = cdiv(4 * sm_count(), mt);
         const int ktiles = cdiv(a->Kfc, 32);
         if (sp > ktiles / 4) sp = ktiles / 4 > 0 ? ktiles / 4 : 1;
+        { const char* e = getenv("CURLA_FC_SPLITS"); if (e && atoi(e) >= 1 && atoi(e) <= sp) sp = atoi(e); }     // timing experiments
         a->fc_splits = curla_gemm_effective_splits(a->Kfc, sp);
     }
     a->fc_partial = b.w<float>("fc_partial", DT_F32, {a->fc_splits, B, 64});
@@ -1090,6 +1091,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         profile_mark("nccl_all_gather");
         keys_gathered = true;
     };
+    auto keys_gathered_or_local = [&]() { return c.world == 1 || keys_gathered; };
     auto side_tail = [&](const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, bool keys) {
         Run r2{a, ss7};
         r2.rc = r.rc;
@@ -1099,6 +1101,19 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         if (keys) gather_keys(ss7);
         if (forked7) { cudaEventRecord(a->ev[2], ss7); join7 = true; }
     };
+    // CURL contraction (logits, cross-entropy, dz_anchor, dW): needs the anchor latents (t_p5) and the gathered keys.
+    // On a step that also runs the actor update it is issued on the side stream right after the actor loss and runs
+    // BESIDE the actor's backward + Adam (both are chains of small latency-bound kernels: the contraction fills 32 of
+    // the 148 SMs at a global batch of 512); CURLA_CURL_OVERLAP=0 keeps it on the main stream after the actor step.
+    bool curl_done = false;
+    auto curl_contract = [&](Run& rr) {
+        const float* zpos = c.world > 1 ? a->z_pos_all : a->t_p7.z;
+        if (rr.ok()) rr.chk(curla_curl_fwd_bwd(a->t_p5.z, zpos, a->P + a->off_W, B, c.global_batch, feat, c.rank * B, gs, a->curl_ws,
+                                               a->metrics + 6, a->dz_curl, a->G + a->g_cpc, nullptr, rr.st));
+        publish(CURLA_PHASE_CPC, rr);
+        curl_done = true;
+    };
+    static const bool curl_overlap = [] { const char* e = getenv("CURLA_CURL_OVERLAP"); return !(e && e[0] == '0'); }();
     if (do_sac) {
         if (do_actor) {
             NvtxRange nv("curla/actor_alpha");
@@ -1123,6 +1138,17 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
                                                a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
             publish(CURLA_PHASE_ACTOR, r);
+            if (key_done && forked7 && curl_overlap && keys_gathered_or_local() && r.ok()) {
+                // fork: the side stream already holds the key tail (+ all-gather); it now waits for the anchor latents
+                // and the actor loss (the logged scalars are published after the contraction) and runs the contraction
+                cudaEventRecord(a->ev[4], st);
+                cudaStreamWaitEvent(ss7, a->ev[4], 0);
+                Run rc{a, ss7};
+                rc.rc = r.rc;
+                curl_contract(rc);
+                r.chk(rc.rc);
+                cudaEventRecord(a->ev[2], ss7);          // re-recorded: the join below now also covers the contraction
+            }
             r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, nullptr, 0,
                         a->dX[0], a->dX[1] - a->dX[0]);
             if (r.ok()) r.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
@@ -1168,12 +1194,11 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
         }
         if (join7) cudaStreamWaitEvent(st, a->ev[2], 0);
-        if (!keys_gathered) gather_keys(st);
-        const float* zpos = c.world > 1 ? a->z_pos_all : a->t_p7.z;
         float* gK = a->G + a->g_cpc;
-        if (r.ok()) r.chk(curla_curl_fwd_bwd(a->t_p5.z, zpos, a->P + a->off_W, B, c.global_batch, feat, c.rank * B, gs, a->curl_ws,
-                                             a->metrics + 6, a->dz_curl, gK, nullptr, st));
-        publish(CURLA_PHASE_CPC, r);
+        if (!curl_done) {
+            if (!keys_gathered) gather_keys(st);
+            curl_contract(r);
+        }
         // g_cpc mirrors [W | critic.encoder]: encoder grads start at n_W
         // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once (double_from = n_W).
         // Bucket = [W | conv w,b x4 | fc_w fc_b ln_w ln_b]: the fc/ln tail is final after the fc weight gradient

@@ -37,9 +37,9 @@ namespace curla {
 
 namespace {
 
-constexpr int TM = 128, TN = 64, TK = 64, kMaxSt = 4;
+constexpr int TM = 128, TN = 64, TK = 64, kMaxSt = 8, kDefSt = 4;
 constexpr uint32_t kABytes = TM * TK * 2, kBBytes = TN * TK * 2, kStageBytesTc = kABytes + kBBytes;   // 16 K + 8 K
-constexpr uint32_t kHdrTc = 1024;             // full[4] @0, empty[4] @32, done @64, tmem ptr @72; keeps the stages 1024-byte aligned
+constexpr uint32_t kHdrTc = 1024;             // full[8] @0, empty[8] @64, done @128, tmem ptr @136; keeps the stages 1024-byte aligned
 constexpr int kTcGemmThreads = 192;
 
 struct TmaPlan {
@@ -77,7 +77,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_full = s_base, s_empty = s_base + 32, s_done = s_base + 64, s_tptr = s_base + 72;
+    const uint32_t s_full = s_base, s_empty = s_base + 64, s_done = s_base + 128, s_tptr = s_base + 136;
     const uint32_t s_stage0 = s_base + kHdrTc;
     const long long t_start = clock64();
     if (tid == 0) {
@@ -93,7 +93,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 72);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + 136);
     if (tid == 0) {               // the tensor maps are kernel parameters: fetch them while waiting for the previous kernel
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -675,7 +675,11 @@ int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t s
                      bstr(p.bsB, (unsigned long long)p.K, p.ldb), TN, TK, 1);
     }
     if (!ta || !tb) return -1;
-    pl.nst = nsteps < kMaxSt ? (nsteps < 1 ? 1 : nsteps) : kMaxSt;
+    // ring depth: 4 stages (two CTAs per SM); the split-K fc forward streams its operands once from HBM and
+    // takes CURLA_FC_STAGES (<= 8: one CTA per SM with twice the bytes in flight per CTA)
+    int st_max = kDefSt;
+    if (pl.a_segk) { const char* e = getenv("CURLA_FC_STAGES"); if (e && e[0] >= '2' && e[0] <= '8') st_max = e[0] - '0'; }
+    pl.nst = nsteps < st_max ? (nsteps < 1 ? 1 : nsteps) : st_max;
     dim3 grid(gx, cdiv(p.M, TM), p.batch > 1 ? p.batch : splits);
     if (grid.y > 65535 || grid.z > 65535) return 0;
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
@@ -733,7 +737,7 @@ static int tc_swapped_wgrad(const GemmArgs& p, cudaStream_t stream) {
                                     (unsigned long long)q.ldb * 2, (unsigned long long)p.K * q.ldb * 2, TN, TK, 1);
     if (!ta || !tb) return -1;
     const int nsteps = cdiv(p.K, TK);
-    pl.nst = nsteps < kMaxSt ? nsteps : kMaxSt;
+    pl.nst = nsteps < kDefSt ? nsteps : kDefSt;
     dim3 grid(1, nseg * pl.per_seg, 1);
     if (grid.y > 65535) return 0;
     return launch_one<false, false, true>(ta, tb, q, pl, grid, stream);

@@ -371,7 +371,6 @@ def test_conv_wgrad_staging_modes_agree(H, W, B, monkeypatch):
     image row per request, the shifted dy copies zero-filled by the TMA unit) instead of one linear bulk copy per plane
     per row, and can fetch dy from L2 once, making the shifted copies inside shared memory (CURLA_WG_DY1=1).  Same products, fp32 accumulation: the weight / bias gradients agree to 1e-5, conv-1 (2x2 taps on the
     space-to-depth input, 6 planes) and a 3x3 layer."""
-    monkeypatch.setenv('CURLA_WG_RING', '0')           # (the two-stage kernel: CURLA_WG_DY1 exists only there)
     g, x, ws, bs = _conv_case(H, W, B, seed=4)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(5)
@@ -402,25 +401,20 @@ def test_conv_wgrad_staging_modes_agree(H, W, B, monkeypatch):
 
 @pytest.mark.parametrize('H,W,B', [(76, 135, 5), (90, 160, 3), (76, 135, 1), (76, 135, 37)])
 def test_conv_wgrad_variants_agree(H, W, B, monkeypatch):
-    """conv_wgrad_tc.cu: the row-ring kernel (operands stream through a ring of image rows, CURLA_WG_RS rows per
-    pipeline stage, a CTA owns a contiguous range of the (sample, row) sequence; the default) and the two-stage kernel (CURLA_WG_RING=0); the horizontal taps ride in N
-    (one shifted copy of dy per tap, CURLA_WG_COPIES=3) or on the A side (the input's K window starts 1, 2 rows later
-    against ONE staged dy: CURLA_WG_COPIES=1; 2 = one N = 64 and one N = 32 MMA); the dy copies are issued by the
-    producer warp or by up to four helper warps (CURLA_WG_PRODUCERS); operands staged by linear bulk copies or
+    """conv_wgrad_tc.cu: the horizontal taps ride in N (one shifted copy of dy per tap, CURLA_WG_COPIES=3, the default)
+    or on the A side (the input's K window starts 1, 2 rows later against ONE staged dy: CURLA_WG_COPIES=1; 2 = one
+    N = 64 and one N = 32 MMA); the dy copies are issued by the producer warp or by up to four helper warps
+    (CURLA_WG_PRODUCERS, default 5 threads issuing); ring depth 2..4; operands staged by linear bulk copies or
     tensor-map boxes (CURLA_WG_TMAP).  Same products, fp32 accumulation: every variant agrees with the torch gradient
-    and with the others to 1e-5, for conv-1 (2x2 taps) and 3x3 layers; B = 1 leaves most CTAs without work, B = 37
-    gives ranges that straddle sample boundaries."""
+    and with the others to 1e-5, for conv-1 (2x2 taps) and 3x3 layers; B = 1 leaves most CTAs without work."""
     g, x, ws, bs = _conv_case(H, W, B, seed=6)
     s2d, acts, keep = _run_conv_stack(g, x, ws, bs)
     torch.manual_seed(7)
     ws_buf = torch.zeros(int(max(_lib.load().curla_conv_wgrad_workspace_floats(0),
                                  _lib.load().curla_conv_wgrad_workspace_floats(1))), device=DEV)
-    # (ring, copies, stages | ring rows, producers, tensor-map staging, image rows per ring stage)
-    variants = [('0', '3', '2', '1', '0', ''), ('0', '2', '2', '1', '0', ''), ('0', '1', '3', '1', '0', ''), ('0', '3', '2', '3', '0', ''),
-                ('0', '1', '4', '4', '0', ''), ('0', '3', '3', '1', '1', ''),
-                ('1', '3', '', '5', '0', '2'), ('1', '3', '', '1', '0', '2'), ('1', '3', '', '3', '0', '1'), ('1', '2', '', '5', '0', '3'),
-                ('1', '1', '', '2', '0', '2'), ('1', '3', '6', '5', '0', '2'), ('1', '3', '', '1', '1', '2'), ('1', '1', '7', '1', '1', '1'),
-                ('1', '3', '', '5', '0', '4'), ('1', '3', '8', '4', '0', '1')]
+    # (copies, stages, producers, tensor-map staging)
+    variants = [('3', '2', '1', '0'), ('3', '2', '5', '0'), ('2', '2', '1', '0'), ('1', '3', '1', '0'), ('3', '2', '3', '0'),
+                ('1', '4', '4', '0'), ('3', '3', '1', '1'), ('2', '2', '5', '0'), ('1', '2', '2', '1')]
     for l in (0, 1, 3):
         dy = torch.randn(B, 32, g.Ho[l], g.Wo[l], device=DEV)
         dfull, dview = g.to_pitch(bf16r(dy), l)
@@ -432,12 +426,9 @@ def test_conv_wgrad_variants_agree(H, W, B, monkeypatch):
         gw, gb = torch.autograd.grad(y, [wref, bref], bf16r(dy))
         got = {}
         for v in variants:
-            ring, copies, depth, prod, tmap, rs = v
-            monkeypatch.setenv('CURLA_WG_RS', rs)
-            monkeypatch.setenv('CURLA_WG_RING', ring)
+            copies, depth, prod, tmap = v
             monkeypatch.setenv('CURLA_WG_COPIES', copies)
-            monkeypatch.setenv('CURLA_WG_STAGES', depth if ring == '0' else '2')
-            monkeypatch.setenv('CURLA_WG_NSD', depth if ring == '1' else '')
+            monkeypatch.setenv('CURLA_WG_STAGES', depth)
             monkeypatch.setenv('CURLA_WG_PRODUCERS', prod)
             monkeypatch.setenv('CURLA_WG_TMAP', tmap)
             dW = torch.full(ws[l].shape, float('nan'), device=DEV)
