@@ -156,10 +156,10 @@ struct curla_agent {
     // workspace pointers
     bf16 *s2d_obs, *s2d_next, *s2d_pos, *actA[4], *actB[4], *actC[4], *dact[4];
     long long act_sstride, s2d_sstride;
-    float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch;
+    float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch, *ln_scratch_b;
     // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
     // there while the main stream already runs the next pass's conv stack
-    cudaStream_t side; cudaEvent_t ev[5]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
+    cudaStream_t side; cudaEvent_t ev[6]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
     // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
     cudaStream_t comm_st; cudaEvent_t cev[6]; int comm_state;
@@ -169,7 +169,7 @@ struct curla_agent {
     float *t_out1, *t_out4, *a_next, *logpi_next, *mu_scratch, *pi4, *logpi4, *ls4, *noise4, *ls1;
     float *tq[2], *q3[2], *q5[2], *target_q, *dq[2], *dt4;
     bf16 *dH2, *dH1;
-    float *dX[2], *dXa, *dz_curl, *dfc_f32; bf16* dfc_bf16;
+    float *dX[2], *dXa, *dz_curl, *dfc_f32, *dfc_f32_b; bf16 *dfc_bf16, *dfc_bf16_b;   // _b: the actor's backward beside the CURL phase
     float *z_pos_all, *act_b, *rew_b, *nd_b, *metrics, *glogpi;
     double *log_alpha, *g_log_alpha, *alpha_state;
     // optimizer step counters (host)
@@ -406,6 +406,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     }
     a->curl_ws = b.w<float>("curl_ws", DT_F32, {curla_curl_workspace_floats(B, Bg)});
     a->ln_scratch = b.w<float>("ln_scratch", DT_F32, {2, B, 64});
+    a->ln_scratch_b = b.w<float>("ln_scratch_b", DT_F32, {2, B, 64});
     auto tail = [&](const char* nm, TailBuf& t) {
         t.fc_out = b.w<float>(std::string(nm) + ".fc_out", DT_F32, {B, 64});
         t.z = b.w<float>(std::string(nm) + ".z", DT_F32, {B, 64});
@@ -444,6 +445,8 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->dz_curl = b.w<float>("dz_curl", DT_F32, {B, 64});
     a->dfc_f32 = b.w<float>("dfc_f32", DT_F32, {B, 64});
     a->dfc_bf16 = b.w<bf16>("dfc_bf16", DT_BF16, {B, 64});
+    a->dfc_f32_b = b.w<float>("dfc_f32_b", DT_F32, {B, 64});
+    a->dfc_bf16_b = b.w<bf16>("dfc_bf16_b", DT_BF16, {B, 64});
     a->z_pos_all = b.w<float>("z_pos_all", DT_F32, {Bg, 64});
     a->act_b = b.w<float>("batch.action", DT_F32, {B, A});
     a->rew_b = b.w<float>("batch.reward", DT_F32, {B});
@@ -520,7 +523,7 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
     auto rb = [&](auto*& p) { p = reinterpret_cast<std::remove_reference_t<decltype(p)>>(base + (uintptr_t)p); };
     rb(a->s2d_obs); rb(a->s2d_next); rb(a->s2d_pos);
     for (int i = 0; i < 4; ++i) { rb(a->actA[i]); rb(a->actB[i]); rb(a->actC[i]); rb(a->dact[i]); }
-    rb(a->fc_partial); rb(a->fc_partial2); rb(a->wgrad_ws); rb(a->curl_ws); rb(a->ln_scratch);
+    rb(a->fc_partial); rb(a->fc_partial2); rb(a->wgrad_ws); rb(a->curl_ws); rb(a->ln_scratch); rb(a->ln_scratch_b);
     TailBuf* tb[] = {&a->t_p1, &a->t_p2, &a->t_p3, &a->t_p4, &a->t_p5, &a->t_p7};
     for (auto t : tb) { rb(t->fc_out); rb(t->z); }
     MlpBuf* mb[] = {&a->m_p1, &a->m_p2q[0], &a->m_p2q[1], &a->m_p3q[0], &a->m_p3q[1], &a->m_p4, &a->m_p5q[0], &a->m_p5q[1]};
@@ -528,7 +531,7 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
     rb(a->t_out1); rb(a->t_out4); rb(a->tq[0]); rb(a->tq[1]); rb(a->q3[0]); rb(a->q3[1]); rb(a->q5[0]); rb(a->q5[1]);
     rb(a->a_next); rb(a->logpi_next); rb(a->ls1); rb(a->mu_scratch); rb(a->pi4); rb(a->logpi4); rb(a->ls4); rb(a->noise4);
     rb(a->target_q); rb(a->dq[0]); rb(a->dq[1]); rb(a->dt4); rb(a->dH2); rb(a->dH1);
-    rb(a->dX[0]); rb(a->dX[1]); rb(a->dXa); rb(a->dz_curl); rb(a->dfc_f32); rb(a->dfc_bf16);
+    rb(a->dX[0]); rb(a->dX[1]); rb(a->dXa); rb(a->dz_curl); rb(a->dfc_f32); rb(a->dfc_bf16); rb(a->dfc_f32_b); rb(a->dfc_bf16_b);
     rb(a->z_pos_all); rb(a->act_b); rb(a->rew_b); rb(a->nd_b); rb(a->metrics); rb(a->glogpi);
     rb(a->log_alpha); rb(a->g_log_alpha); rb(a->alpha_state); rb(a->dev_state);
     a->bound = true;
@@ -674,15 +677,19 @@ struct Run {
     // LayerNorm + fc backward (+ conv stack backward when conv==true)
     void enc_bwd(const float* dz_a, const float* dz_b, const TailBuf& t, const EncP& e, long long fc_shadow,
                  const EncS* convs, bf16* const acts[4], const bf16* s2d, float* gbase, long long pbase, bool conv,
-                 const std::function<void()>& after_fc_wgrad = nullptr) {
+                 const std::function<void()>& after_fc_wgrad = nullptr, bool scratch_b = false) {
         if (!ok()) return;
         const int B = a->cfg.batch, feat = a->cfg.feature_dim;
         auto g = [&](long long poff) { return gbase + (poff - pbase); };
-        chk(curla_ln_bwd(dz_a, dz_b, t.fc_out, P(e.ln_w), B, feat, a->dfc_f32, a->dfc_bf16, a->ln_scratch,
+        // (scratch_b: a second set of the small buffers, for a backward that runs beside another one)
+        float* const dfc_f32 = scratch_b ? a->dfc_f32_b : a->dfc_f32;
+        bf16* const dfc_bf16 = scratch_b ? a->dfc_bf16_b : a->dfc_bf16;
+        float* const ln_scratch = scratch_b ? a->ln_scratch_b : a->ln_scratch;
+        chk(curla_ln_bwd(dz_a, dz_b, t.fc_out, P(e.ln_w), B, feat, dfc_f32, dfc_bf16, ln_scratch,
                          g(e.ln_w), g(e.ln_b), g(e.fc_b), st));
         // dWfc[feat][Kfc] = dfc^T . act4
         set_launch_tag("gemm_fc_wgrad");
-        if (ok()) chk(curla_gemm_bf16_seg(a->dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
+        if (ok()) chk(curla_gemm_bf16_seg(dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
                                           a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f,
                                           a->Kfc / 4, (long long)a->S * 8, 2, st));
         set_launch_tag(nullptr);
@@ -692,7 +699,7 @@ struct Run {
         if (!conv) return;
         // d(act4) = relu'(act4) * dfc . Wfc
         set_launch_tag("gemm_fc_dgrad");
-        if (ok()) chk(curla_gemm_bf16_seg(a->dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
+        if (ok()) chk(curla_gemm_bf16_seg(dfc_bf16, 64, Sh(fc_shadow), a->Kfc, a->dact[3], a->act_sstride, B, a->Kfc, 64, 1,
                                           a->Kfc, 1, nullptr, 0, acts[3], a->act_sstride, 1, 0, 1.f,
                                           a->Kfc / 4, (long long)a->S * 8, 4, st));
         set_launch_tag(nullptr);
@@ -1114,6 +1121,8 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         curl_done = true;
     };
     static const bool curl_overlap = [] { const char* e = getenv("CURLA_CURL_OVERLAP"); return !(e && e[0] == '0'); }();
+    static const bool actor_on_side = [] { const char* e = getenv("CURLA_ACTOR_SIDE"); return !(e && e[0] == '0'); }();
+    bool actor_side_pending = false;
     if (do_sac) {
         if (do_actor) {
             NvtxRange nv("curla/actor_alpha");
@@ -1138,9 +1147,14 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
                                                a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
             publish(CURLA_PHASE_ACTOR, r);
-            if (key_done && forked7 && curl_overlap && keys_gathered_or_local() && r.ok()) {
-                // fork: the side stream already holds the key tail (+ all-gather); it now waits for the anchor latents
-                // and the actor loss (the logged scalars are published after the contraction) and runs the contraction
+            // Two ways to use the side stream from here on (it already holds the key tail + all-gather):
+            //   actor_side (default): the actor's whole backward + optimizer step runs there, beside the CURL contraction
+            //     and the contrastive backward on the main stream -- nothing later in THIS update reads the actor's own
+            //     parameters, its gradients or log_alpha (the CURL phase uses the critic / target encoders);
+            //   CURLA_ACTOR_SIDE=0: the CURL contraction runs there beside the actor's backward (CURLA_CURL_OVERLAP=0: neither).
+            const bool can_fork = key_done && forked7 && r.ok();
+            const bool actor_side = can_fork && actor_on_side;
+            if (can_fork && !actor_side && curl_overlap && keys_gathered_or_local()) {
                 cudaEventRecord(a->ev[4], st);
                 cudaStreamWaitEvent(ss7, a->ev[4], 0);
                 Run rc{a, ss7};
@@ -1149,20 +1163,24 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
                 r.chk(rc.rc);
                 cudaEventRecord(a->ev[2], ss7);          // re-recorded: the join below now also covers the contraction
             }
-            r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, nullptr, 0,
-                        a->dX[0], a->dX[1] - a->dX[0]);
-            if (r.ok()) r.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
-                                               (float)c.log_std_min, (float)c.log_std_max, a->dt4, st));
+            const cudaStream_t bs = actor_side ? ss7 : st;            // the stream of the actor's backward
+            if (actor_side) { cudaEventRecord(a->ev[4], st); cudaStreamWaitEvent(ss7, a->ev[4], 0); }
+            Run rb{a, bs};
+            rb.rc = r.rc;
+            rb.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, nullptr, 0,
+                         a->dX[0], a->dX[1] - a->dX[0]);
+            if (rb.ok()) rb.chk(curla_policy_bwd(a->dX[0], a->dX[1], feat, a->glogpi, a->t_out4, a->noise4, a->pi4, a->ls4, B, A,
+                                                 (float)c.log_std_min, (float)c.log_std_max, a->dt4, bs));
             float* gA = a->G + a->g_actor;
-            r.mlp_bwd_n(a->dt4, 0, a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, gA, a->off_actor, a->dXa, 0);
-            r.enc_bwd(a->dXa, nullptr, a->t_p4, a->enc_actor, a->s_actor_fc, nullptr, a->actA, nullptr, gA, a->off_actor, false);
-            // Nothing later in THIS update reads the actor's own parameters or log_alpha (the CURL phase uses
-            // the critic / target encoders): with world > 1 the whole reduce -> Adam -> shadow pack chain
-            // runs on the communication stream beside the CURL phase and is joined at the end of the update
-            const cudaStream_t as = overlap ? cs : st;
+            rb.mlp_bwd_n(a->dt4, 0, a->m_p4.X, &a->trunk_actor, &a->s_trunk, &a->m_p4, 1, gA, a->off_actor, a->dXa, 0);
+            rb.enc_bwd(a->dXa, nullptr, a->t_p4, a->enc_actor, a->s_actor_fc, nullptr, a->actA, nullptr, gA, a->off_actor, false, nullptr,
+                       actor_side);
+            // with world > 1 the reduce -> Adam -> shadow pack chain runs on the communication stream and is joined at
+            // the end of the update
+            const cudaStream_t as = overlap ? cs : bs;
             Run ra{a, as};
-            ra.rc = r.rc;
-            if (overlap) { cudaEventRecord(a->cev[3], st); cudaStreamWaitEvent(cs, a->cev[3], 0); actor_pending = true; }
+            ra.rc = rb.rc;
+            if (overlap) { cudaEventRecord(a->cev[3], bs); cudaStreamWaitEvent(cs, a->cev[3], 0); actor_pending = true; }
             if (ra.ok()) ra.chk(all_reduce(a, gA, (size_t)a->n_actor, NCCL_F32, as));
             if (ra.ok()) ra.chk(all_reduce(a, a->g_log_alpha, 1, NCCL_F64, as));
             if (ra.ok()) ra.chk(curla_adam_f32(a->P + a->off_actor, gA, a->Ad + a->a_m2, a->Ad + a->a_v2, a->n_actor, a->n_actor,
@@ -1170,6 +1188,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             ra.pack(a->pack_actor);
             if (ra.ok()) ra.chk(curla_adam_f64_scalar(a->log_alpha, a->g_log_alpha, a->alpha_state, c.alpha_lr, c.alpha_beta, 0.999,
                                                       1e-8, ++a->t_alpha, td_alpha, as));
+            if (actor_side && !overlap) { cudaEventRecord(a->ev[5], ss7); actor_side_pending = true; }
             r.chk(ra.rc);
         }
         if (do_ema && !ema_first) ema();
@@ -1226,6 +1245,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         cudaEventRecord(a->cev[2], cs);
         cudaStreamWaitEvent(st, a->cev[2], 0);
     }
+    if (actor_side_pending) cudaStreamWaitEvent(st, a->ev[5], 0);
     a->last_launches = g_launches - launches0;
     return r.rc;
 }
