@@ -159,7 +159,7 @@ struct curla_agent {
     float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch, *ln_scratch_b;
     // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
     // there while the main stream already runs the next pass's conv stack
-    cudaStream_t side; cudaEvent_t ev[6]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
+    cudaStream_t side; cudaEvent_t ev[10]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
     // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
     cudaStream_t comm_st; cudaEvent_t cev[6]; int comm_state;
@@ -650,34 +650,43 @@ struct Run {
     // backward of nb 3-layer MLPs.  gbase = gradient buffer mirroring the parameter segment that
     // starts at float offset pbase, or nullptr for "input gradient only".  dOut / dX: head 0's
     // pointer + stride to head 1.
+    // wr != nullptr: the weight / bias gradients (nothing in the backward chain reads them) are issued on wr's stream,
+    // forked behind the kernels that produce dH2 (event e1) and dH1 (event e2); the caller joins wr before the optimizer
     void mlp_bwd_n(const float* dOut, long long sDOut, const bf16* X, const MlpP* m, const MlpS* s, const MlpBuf* buf,
-                   int nb, float* gbase, long long pbase, float* dX, long long sDX) {
+                   int nb, float* gbase, long long pbase, float* dX, long long sDX, Run* wr = nullptr, cudaEvent_t e1 = nullptr,
+                   cudaEvent_t e2 = nullptr) {
         if (!ok()) return;
         const int B = a->cfg.batch, hid = a->cfg.hidden_dim, No = m[0].out, in_real = m[0].in_real;
         const long long sP = nb > 1 ? m[1].w0 - m[0].w0 : 0, sS = nb > 1 ? s[1].w0 - s[0].w0 : 0;
         const long long sH = nb > 1 ? buf[1].H1 - buf[0].H1 : 0, sD = (long long)B * hid;
         auto g = [&](long long poff) { return gbase + (poff - pbase); };
+        Run& w = (wr && gbase) ? *wr : *this;
+        const bool forked = &w != this;
         chk(curla_head_bwd_batched(dOut, P(m[0].w2), buf[0].H2, B, hid, No, a->dH2, nb, sDOut, sP, sH, sD, st));
-        if (gbase && ok()) chk(curla_head_wgrad_batched(dOut, buf[0].H2, B, hid, No, g(m[0].w2), g(m[0].b2), nb, sDOut, sH, sP, st));
+        if (forked && ok()) { cudaEventRecord(e1, st); cudaStreamWaitEvent(w.st, e1, 0); w.rc = rc; }
+        if (gbase && ok()) w.chk(curla_head_wgrad_batched(dOut, buf[0].H2, B, hid, No, g(m[0].w2), g(m[0].b2), nb, sDOut, sH, sP, w.st));
         if (gbase && ok()) {
-            chk(curla_gemm_bf16_batched(a->dH2, hid, buf[0].H1, hid, g(m[0].w1), hid, hid, hid, B, 0, hid, 0, nullptr, 0,
-                                        nullptr, 0, 1.f, nb, sD, sH, sP, 0, 0, st));
-            if (ok()) chk(curla_colsum_bf16_batched(a->dH2, B, hid, g(m[0].b1), nb, sD, sP, st));
+            w.chk(curla_gemm_bf16_batched(a->dH2, hid, buf[0].H1, hid, g(m[0].w1), hid, hid, hid, B, 0, hid, 0, nullptr, 0,
+                                          nullptr, 0, 1.f, nb, sD, sH, sP, 0, 0, w.st));
+            if (w.ok()) w.chk(curla_colsum_bf16_batched(a->dH2, B, hid, g(m[0].b1), nb, sD, sP, w.st));
         }
         if (ok()) chk(curla_gemm_bf16_batched(a->dH2, hid, Sh(s[0].w1), hid, a->dH1, hid, B, hid, hid, 1, hid, 1, nullptr, 0,
                                               buf[0].H1, hid, 1.f, nb, sD, sS, sD, 0, sH, st));
+        if (forked && ok()) { cudaEventRecord(e2, st); cudaStreamWaitEvent(w.st, e2, 0); }
         if (gbase && ok()) {
-            chk(curla_gemm_bf16_batched(a->dH1, hid, X, 64, g(m[0].w0), in_real, hid, 64, B, 0, in_real, 0, nullptr, 0,
-                                        nullptr, 0, 1.f, nb, sD, 0, sP, 0, 0, st));
-            if (ok()) chk(curla_colsum_bf16_batched(a->dH1, B, hid, g(m[0].b0), nb, sD, sP, st));
+            w.chk(curla_gemm_bf16_batched(a->dH1, hid, X, 64, g(m[0].w0), in_real, hid, 64, B, 0, in_real, 0, nullptr, 0,
+                                          nullptr, 0, 1.f, nb, sD, 0, sP, 0, 0, w.st));
+            if (w.ok()) w.chk(curla_colsum_bf16_batched(a->dH1, B, hid, g(m[0].b0), nb, sD, sP, w.st));
         }
         if (dX && ok()) chk(curla_gemm_bf16_batched(a->dH1, hid, Sh(s[0].w0), 64, dX, 64, B, 64, hid, 1, 64, 0, nullptr, 0,
                                                     nullptr, 0, 1.f, nb, sD, sS, sDX, 0, 0, st));
+        if (forked) chk(w.rc);
     }
     // LayerNorm + fc backward (+ conv stack backward when conv==true)
     void enc_bwd(const float* dz_a, const float* dz_b, const TailBuf& t, const EncP& e, long long fc_shadow,
                  const EncS* convs, bf16* const acts[4], const bf16* s2d, float* gbase, long long pbase, bool conv,
-                 const std::function<void()>& after_fc_wgrad = nullptr, bool scratch_b = false) {
+                 const std::function<void()>& after_fc_wgrad = nullptr, bool scratch_b = false, Run* wr = nullptr,
+                 cudaEvent_t e3 = nullptr) {
         if (!ok()) return;
         const int B = a->cfg.batch, feat = a->cfg.feature_dim;
         auto g = [&](long long poff) { return gbase + (poff - pbase); };
@@ -688,11 +697,15 @@ struct Run {
         chk(curla_ln_bwd(dz_a, dz_b, t.fc_out, P(e.ln_w), B, feat, dfc_f32, dfc_bf16, ln_scratch,
                          g(e.ln_w), g(e.ln_b), g(e.fc_b), st));
         // dWfc[feat][Kfc] = dfc^T . act4
+        // (wr: on wr's stream, forked behind the LayerNorm backward -- the conv backward does not read it)
+        Run& w = wr ? *wr : *this;
+        if (wr && ok()) { cudaEventRecord(e3, st); cudaStreamWaitEvent(w.st, e3, 0); w.rc = rc; }
         set_launch_tag("gemm_fc_wgrad");
-        if (ok()) chk(curla_gemm_bf16_seg(dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
-                                          a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f,
-                                          a->Kfc / 4, (long long)a->S * 8, 2, st));
+        if (ok()) w.chk(curla_gemm_bf16_seg(dfc_bf16, 64, acts[3], a->act_sstride, g(e.fc_w), a->Kfc, feat, a->Kfc, B, 0,
+                                            a->Kfc, 0, nullptr, 0, nullptr, 0, 1, 0, 1.f,
+                                            a->Kfc / 4, (long long)a->S * 8, 2, w.st));
         set_launch_tag(nullptr);
+        if (wr) chk(w.rc);
         // everything of this bucket except the conv-layer gradients is final here (data parallel: its
         // all-reduce + Adam start now, beside the conv backward below)
         if (after_fc_wgrad && ok()) after_fc_wgrad();
@@ -1043,19 +1056,30 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         publish(CURLA_PHASE_CRITIC, r);
         // backward
         float* gC = a->G + a->g_critic;
+        // The weight gradients of the Q heads and of the encoder fc (six small kernels + one HBM-bound GEMM that nothing
+        // in the backward chain reads) go to the side stream, idle since the tails joined: the chain
+        // head -> trunk dgrad -> dX -> LayerNorm -> fc dgrad -> conv backward no longer waits for them.  CURLA_WGRAD_SIDE=0: in line.
+        static const bool wgrad_side = [] { const char* e = getenv("CURLA_WGRAD_SIDE"); return !(e && e[0] == '0'); }();
+        Run rw{a, ss};
+        Run* const wr = (forked && wgrad_side) ? &rw : nullptr;
         r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, gC, a->off_critic,
-                    a->dX[0], a->dX[1] - a->dX[0]);
+                    a->dX[0], a->dX[1] - a->dX[0], wr, a->ev[6], a->ev[7]);
         const int tc_ = ++a->t_critic;
         // critic bucket = [conv w,b x4 | fc_w fc_b ln_w ln_b | Q1 | Q2]: everything from fc_w on (99 % of the
         // bytes) is final after the fc weight gradient, i.e. BEFORE the conv backward (0.7 ms at the
         // default batch) starts: its all-reduce and Adam overlap that
         const long long split1 = a->enc_critic.fc_w - a->off_critic;
         auto early1 = [&]() {
-            if (overlap) reduce_step(0, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, split1, a->n_critic, a->n_critic,
-                                     c.critic_lr, c.critic_beta, tc_, td_critic);
+            if (wr) cudaEventRecord(a->ev[8], ss);                     // the side stream's weight gradients are complete
+            if (overlap) {
+                if (wr) cudaStreamWaitEvent(cs, a->ev[8], 0);
+                reduce_step(0, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, split1, a->n_critic, a->n_critic,
+                            c.critic_lr, c.critic_beta, tc_, td_critic);
+            }
         };
         r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
-                  a->off_critic, !c.detach_encoder, early1);
+                  a->off_critic, !c.detach_encoder, early1, false, wr, a->ev[9]);
+        if (wr) cudaStreamWaitEvent(st, a->ev[8], 0);                  // join (long complete: the conv backward ran meanwhile)
         if (overlap) {
             reduce_step(1, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, 0, split1, a->n_critic,
                         c.critic_lr, c.critic_beta, tc_, td_critic);
