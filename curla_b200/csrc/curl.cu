@@ -179,9 +179,12 @@ k_curl_rows(const float* __restrict__ z_a, const float* __restrict__ U, const fl
 }
 
 // dW[a][b] = sum_i z_a[i][a] * V[i][b] (one CTA per a; 64 columns x 4 row groups, fixed-order
-// tree => deterministic); CTA 0 also writes the mean of the per-row losses.
+// tree => deterministic); CTA 0 also writes the mean of the per-row losses -- read from row_loss, or (pstat != nullptr:
+// the tensor-core path with a single column block, where no reduce kernel runs) formed here from the per-tile softmax
+// statistics:  loss_i = log(sum_t s_t exp(m_t - M)) - (l_i,label - M).
 __global__ void __launch_bounds__(256)
 k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const float* __restrict__ row_loss,
+          const float* __restrict__ pstat, const float* __restrict__ lab_logit, int Bp, int NT,
           int B, int feat, float* __restrict__ dW, float* __restrict__ loss_out) {
     pdl_grid_sync();
     __shared__ float s_red[4][64];
@@ -195,7 +198,16 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
     if (q == 0 && b < feat) dW[a * feat + b] = s_red[0][b] + s_red[1][b] + s_red[2][b] + s_red[3][b];
     if (blockIdx.x == 0) {
         float l = 0.f;
-        for (int i = threadIdx.x; i < B; i += 256) l += row_loss[i];
+        for (int i = threadIdx.x; i < B; i += 256) {
+            if (pstat) {
+                float M = -INFINITY, S = 0.f;
+                for (int st = 0; st < NT; ++st) M = fmaxf(M, pstat[((long long)st * Bp + i) * 2]);
+                for (int st = 0; st < NT; ++st) S += pstat[((long long)st * Bp + i) * 2 + 1] * expf(pstat[((long long)st * Bp + i) * 2] - M);
+                l += logf(S) - (lab_logit[i] - M);
+            } else {
+                l += row_loss[i];
+            }
+        }
         l = warp_sum(l);
         if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = l;
         __syncthreads();
@@ -226,8 +238,8 @@ k_curl_dw(const float* __restrict__ z_a, const float* __restrict__ V, const floa
 //                 m16k16 A fragment of the next MMA -- then dz_a += dl . U, V += dl . z_pos; the 8 warps
 //                 are summed in shared memory in a fixed order and written as per-column-block partials
 //   k_curl_reduce: sums the column-block partials (fixed order: deterministic), per-row loss
-// Operands are prepared once per update by k_curl_prep as bf16 hi/lo arrays in the two orientations
-// the B fragments want: Uk[j][k] (logits) and UT[a][j], ZT[a][j] (gradients).
+// Operands are prepared once per update by k_curl_prep_u (U = z_pos . W^T included) as bf16 hi / mid / lo arrays in the
+// two orientations the B fragments want: Uk[j][k] (logits) and UT[a][j], ZT[a][j] (gradients).
 __device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
     const float2 hf = __bfloat1622float2(h);
@@ -262,28 +274,65 @@ __device__ __forceinline__ void mma6(float* acc, const uint32_t (&ah)[4], const 
 }
 __device__ __forceinline__ uint32_t ldg_u32(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 
-// U, z_pos: fp32 [Bg][64].  Uk_*: bf16 [BgP][64]; UT_*, ZT_*: bf16 [64][BgP]; rows j >= Bg are zero.
+// Uk_*: bf16 [BgP][64]; UT_*, ZT_*: bf16 [64][BgP]; rows j >= Bg are zero.
+// U = z_pos . W^T and the nine bf16 operand arrays in ONE launch (was: a strided fp32 GEMM + k_curl_prep, 28 us of
+// two latency-bound launches for 2 MFLOP).  A CTA owns 16 keys: W (zero padded to 64 x 64) and the 16 key rows sit in
+// shared memory, a thread computes 4 of the 16 x 64 outputs (k = 0..63 in order, one accumulator: the same sums as
+// k_sgemm_strided), then the CTA writes its rows of Uk (4-byte pairs) and its 16 columns of UT / ZT.
 __global__ void __launch_bounds__(256)
-k_curl_prep(const float* __restrict__ U, const float* __restrict__ z_pos, int Bg, int BgP,
-            bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_mid, bf16* __restrict__ Uk_lo,
-            bf16* __restrict__ UT_hi, bf16* __restrict__ UT_mid, bf16* __restrict__ UT_lo,
-            bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_mid, bf16* __restrict__ ZT_lo) {
+k_curl_prep_u(const float* __restrict__ z_pos, const float* __restrict__ W, int Bg, int BgP, int feat,
+              bf16* __restrict__ Uk_hi, bf16* __restrict__ Uk_mid, bf16* __restrict__ Uk_lo,
+              bf16* __restrict__ UT_hi, bf16* __restrict__ UT_mid, bf16* __restrict__ UT_lo,
+              bf16* __restrict__ ZT_hi, bf16* __restrict__ ZT_mid, bf16* __restrict__ ZT_lo) {
     pdl_grid_sync();
-    __shared__ float su[32][65], sz[32][65];
-    const int j0 = blockIdx.x * 32;
-    for (int t = threadIdx.x; t < 2048; t += 256) {
+    __shared__ float sW[64][65];
+    __shared__ float sz[16][65], su[16][65];
+    const int tid = threadIdx.x, j0 = blockIdx.x * 16;
+    for (int t = tid; t < 4096; t += 256) {
+        const int a = t >> 6, b = t & 63;
+        sW[a][b] = (a < feat && b < feat) ? W[a * feat + b] : 0.f;
+    }
+    for (int t = tid; t < 1024; t += 256) {
         const int jj = t >> 6, k = t & 63, j = j0 + jj;
-        const float u = j < Bg ? U[(long long)j * 64 + k] : 0.f;
-        const float z = j < Bg ? z_pos[(long long)j * 64 + k] : 0.f;
-        su[jj][k] = u; sz[jj][k] = z;
-        split3_store(u, Uk_hi, Uk_mid, Uk_lo, (long long)j * 64 + k);
+        sz[jj][k] = j < Bg ? z_pos[(long long)j * 64 + k] : 0.f;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 2048; t += 256) {
-        const int a = t >> 5, jj = t & 31;
-        const long long o = (long long)a * BgP + j0 + jj;
-        split3_store(su[jj][a], UT_hi, UT_mid, UT_lo, o);
-        split3_store(sz[jj][a], ZT_hi, ZT_mid, ZT_lo, o);
+    {
+        const int jj = tid >> 4, a4 = (tid & 15) * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+            const float z = sz[jj][b];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += z * sW[a4 + e][b];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) su[jj][a4 + e] = acc[e];
+    }
+    __syncthreads();
+    for (int t = tid; t < 512; t += 256) {
+        {   // Uk[j][k], k pairs
+            const int jj = t >> 5, k = (t & 31) * 2;
+            uint32_t h, m, l;
+            split3_bf16(su[jj][k], su[jj][k + 1], h, m, l);
+            const long long o = (long long)(j0 + jj) * 64 + k;
+            *reinterpret_cast<uint32_t*>(Uk_hi + o) = h;
+            *reinterpret_cast<uint32_t*>(Uk_mid + o) = m;
+            *reinterpret_cast<uint32_t*>(Uk_lo + o) = l;
+        }
+        {   // UT[a][j], ZT[a][j], j pairs
+            const int a = t >> 3, jj = (t & 7) * 2;
+            const long long o = (long long)a * BgP + j0 + jj;
+            uint32_t h, m, l;
+            split3_bf16(su[jj][a], su[jj + 1][a], h, m, l);
+            *reinterpret_cast<uint32_t*>(UT_hi + o) = h;
+            *reinterpret_cast<uint32_t*>(UT_mid + o) = m;
+            *reinterpret_cast<uint32_t*>(UT_lo + o) = l;
+            split3_bf16(sz[jj][a], sz[jj + 1][a], h, m, l);
+            *reinterpret_cast<uint32_t*>(ZT_hi + o) = h;
+            *reinterpret_cast<uint32_t*>(ZT_mid + o) = m;
+            *reinterpret_cast<uint32_t*>(ZT_lo + o) = l;
+        }
     }
 }
 
@@ -298,18 +347,20 @@ struct CurlTc {
     float grad_scale;
 };
 
-template <int PASS>
+// NTW = 8-column tiles per warp (8: 64 key columns, 4: 32 -- twice the warps for the same work: small global batches)
+template <int PASS, int NTW>
 __global__ void __launch_bounds__(256)
 k_curl_tc(const CurlTc p) {
+    constexpr int CW = NTW * 8;                                // key columns per warp
     pdl_grid_sync();
     extern __shared__ __align__(16) float s_red[];            // PASS 1: [8 warps][2][16][64]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int r0 = blockIdx.x * 16;
-    const int jw = (blockIdx.y * 8 + warp) * 64;              // this warp's 64 key columns
+    const int jw = (blockIdx.y * 8 + warp) * CW;              // this warp's key columns
     const bool active = jw < p.BgP;
     const int rowA = r0 + g, rowB = r0 + g + 8;
-    float lg[8][4];
+    float lg[NTW][4];
     if (active) {
         // ---- A = z_a rows (hi / lo), all of K = 64 in registers
         uint32_t a_hi[4][4], a_mid[4][4], a_lo[4][4];
@@ -323,9 +374,9 @@ k_curl_tc(const CurlTc p) {
                 split3_bf16(v.x, v.y, a_hi[kt][h], a_mid[kt][h], a_lo[kt][h]);
             }
         }
-        // ---- logits[16][64] = z_a . U^T : 8 column tiles of 8
+        // ---- logits[16][CW] = z_a . U^T : NTW column tiles of 8
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < NTW; ++nt) {
             lg[nt][0] = lg[nt][1] = lg[nt][2] = lg[nt][3] = 0.f;
             const long long rowoff = (long long)(jw + nt * 8 + g) * 64 + 2 * t;
 #pragma unroll
@@ -342,7 +393,7 @@ k_curl_tc(const CurlTc p) {
         if (!active) return;
         float mA = -INFINITY, mB = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = jw + nt * 8 + 2 * t + e;
@@ -360,7 +411,7 @@ k_curl_tc(const CurlTc p) {
         mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1)); mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
         float sA = 0.f, sB = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = jw + nt * 8 + 2 * t + e;
@@ -369,7 +420,7 @@ k_curl_tc(const CurlTc p) {
         sA += __shfl_xor_sync(0xffffffffu, sA, 1); sA += __shfl_xor_sync(0xffffffffu, sA, 2);
         sB += __shfl_xor_sync(0xffffffffu, sB, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
         if (t == 0) {
-            float* ps = p.pstat + ((long long)(jw >> 6) * p.Bp) * 2;
+            float* ps = p.pstat + ((long long)(jw / CW) * p.Bp) * 2;
             ps[rowA * 2] = mA; ps[rowA * 2 + 1] = sA;
             ps[rowB * 2] = mB; ps[rowB * 2 + 1] = sB;
         }
@@ -396,7 +447,7 @@ k_curl_tc(const CurlTc p) {
             const float iA = 1.f / SA, iB = 1.f / SB;
             const float gA = rowA < p.B ? p.grad_scale : 0.f, gB = rowB < p.B ? p.grad_scale : 0.f;
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+            for (int nt = 0; nt < NTW; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int j = jw + nt * 8 + 2 * t + e;
@@ -406,7 +457,7 @@ k_curl_tc(const CurlTc p) {
                 }
             // ---- dz_a[16][64] += dl . U ; V[16][64] += dl . z_pos   (k = j: 4 steps of 16 columns)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < NTW / 2; ++m) {
                 uint32_t dh[4], dm[4], dlo[4];
                 split3_bf16(lg[2 * m][0], lg[2 * m][1], dh[0], dm[0], dlo[0]);
                 split3_bf16(lg[2 * m][2], lg[2 * m][3], dh[1], dm[1], dlo[1]);
@@ -505,24 +556,52 @@ static int sgemm(const float* A, long long sam, long long sak, const float* Bm, 
 using namespace curla;
 
 namespace {
-struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, total; };
-CurlPlan curl_plan(int B, int Bg) {
+// ntw = 8-column tiles per warp (k_curl_tc): 4 below a global batch of 2048 (twice the warps, half the serial MMA chain per
+// warp), 8 above (CURLA_CURL_NTW=4|8 overrides).  NT = column tiles of the softmax statistics, NCB = column blocks (CTAs
+// along the keys).  The workspace is sized for the finer split.
+struct CurlPlan { long long BgP, Bp, NT, NCB, off_bf16, off_pstat, off_lab, off_pdz, off_pV, total; int ntw; };
+int curl_ntw(int Bg) {
+    const char* e = getenv("CURLA_CURL_NTW");
+    if (e && (e[0] == '4' || e[0] == '8')) return e[0] - '0';
+    return Bg < 2048 ? 4 : 8;
+}
+CurlPlan curl_plan(int B, int Bg, int ntw) {
     CurlPlan c;
+    c.ntw = ntw;
+    const long long cw = ntw * 8;
     c.BgP = (Bg + 63) / 64 * 64; c.Bp = (B + 15) / 16 * 16;
-    c.NT = c.BgP / 64; c.NCB = (c.NT + 7) / 8;
+    c.NT = c.BgP / cw; c.NCB = (c.NT + 7) / 8;
+    const long long NT4 = c.BgP / 32, NCB4 = (NT4 + 7) / 8;       // sizes under the finer split
     long long o = 2LL * Bg * 64 + (long long)B * 64 + B;       // U, Ut, V, row_loss (the CUDA-core path's layout)
     o = (o + 3) / 4 * 4;
     c.off_bf16 = o; o += 9 * c.BgP * 64 / 2 + 2;               // nine bf16 [BgP x 64] arrays
-    c.off_pstat = o; o += c.NT * c.Bp * 2;
+    c.off_pstat = o; o += NT4 * c.Bp * 2;
     c.off_lab = o; o += c.Bp;
-    c.off_pdz = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
-    c.off_pV = o; o += c.NCB > 1 ? c.NCB * c.Bp * 64 : 0;
+    c.off_pdz = o; o += NCB4 > 1 ? NCB4 * c.Bp * 64 : 0;
+    c.off_pV = o; o += NCB4 > 1 ? NCB4 * c.Bp * 64 : 0;
     c.total = o;
     return c;
 }
+template <int NTW>
+int launch_curl_tc(const CurlTc& t, const CurlPlan& cp, cudaStream_t stream) {
+    const dim3 grid((unsigned)(cp.Bp / 16), (unsigned)cp.NCB);
+    launch_k(k_curl_tc<0, NTW>, grid, dim3(256), 0, stream, t);
+    if (check_launch("curl_rows")) return -1;
+    const size_t smem = sizeof(float) * 8 * 2048;
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr[dev]) {
+        cudaError_t e2 = cudaFuncSetAttribute(k_curl_tc<1, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CURLA_CHECK(e2 == cudaSuccess, "curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e2));
+        attr[dev] = true;
+    }
+    launch_k(k_curl_tc<1, NTW>, grid, dim3(256), smem, stream, t);
+    return check_launch("curl_rows");
+}
 }  // namespace
 
-extern "C" long long curla_curl_workspace_floats(int B, int Bg) { return curl_plan(B, Bg).total; }
+extern "C" long long curla_curl_workspace_floats(int B, int Bg) { return curl_plan(B, Bg, 4).total; }
 
 // z_a [B][64] (local rows), z_pos [Bg][64] (all ranks' keys), W [feat][feat].
 // Outputs: loss_out (mean over the LOCAL rows), dz_a [B][64], dW [feat][feat] (local
@@ -536,13 +615,10 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
     float* Ut = U + (long long)Bg * 64;
     float* V = Ut + (long long)Bg * 64;
     float* row_loss = V + (long long)B * 64;
-    // U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace),
-    // written in both orientations: U for the gradient pass, Ut for the coalesced logits pass
-    if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Ut, Bg, Bg, feat, feat, stream)) return -1;
     {   // tensor-core path (default); CURLA_CURL_TC=0 keeps the CUDA-core rows kernel (A/B, tests)
         const char* e = getenv("CURLA_CURL_TC");
         if (!(e && e[0] == '0')) {
-            const CurlPlan cp = curl_plan(B, Bg);
+            const CurlPlan cp = curl_plan(B, Bg, curl_ntw(Bg));
             bf16* hb = reinterpret_cast<bf16*>(workspace + cp.off_bf16);
             const long long n = cp.BgP * 64;
             CurlTc t;
@@ -554,30 +630,28 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
             t.pV = cp.NCB > 1 ? workspace + cp.off_pV : V;
             t.logits_copy = logits_copy;
             t.B = B; t.Bg = Bg; t.BgP = (int)cp.BgP; t.Bp = (int)cp.Bp; t.NT = (int)cp.NT; t.label0 = label0; t.grad_scale = grad_scale;
-            launch_k(k_curl_prep, dim3((unsigned)(cp.BgP / 32)), dim3(256), 0, stream, (const float*)U, z_pos, Bg, (int)cp.BgP,
+            // U = z_pos . W^T and the bf16 operand arrays (one launch)
+            launch_k(k_curl_prep_u, dim3((unsigned)(cp.BgP / 16)), dim3(256), 0, stream, z_pos, W, Bg, (int)cp.BgP, feat,
                      hb, hb + n, hb + 2 * n, hb + 3 * n, hb + 4 * n, hb + 5 * n, hb + 6 * n, hb + 7 * n, hb + 8 * n);
             if (check_launch("curl_prep")) return -1;
-            const dim3 grid((unsigned)(cp.Bp / 16), (unsigned)cp.NCB);
-            launch_k(k_curl_tc<0>, grid, dim3(256), 0, stream, t);
-            if (check_launch("curl_rows")) return -1;
-            const size_t smem = sizeof(float) * 8 * 2048;
-            static bool attr[64] = {};
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (dev >= 0 && dev < 64 && !attr[dev]) {
-                cudaError_t e2 = cudaFuncSetAttribute(k_curl_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                CURLA_CHECK(e2 == cudaSuccess, "curl: %zu B of shared memory: %s", smem, cudaGetErrorString(e2));
-                attr[dev] = true;
+            if ((cp.ntw == 4 ? launch_curl_tc<4>(t, cp, stream) : launch_curl_tc<8>(t, cp, stream))) return -1;
+            if (cp.NCB > 1) {
+                launch_k(k_curl_reduce, dim3(cdiv(B, 4)), dim3(256), 0, stream, (const float*)t.pstat, (const float*)t.lab_logit,
+                         (const float*)t.pdz, (const float*)t.pV, B, (int)cp.Bp, (int)cp.NT, (int)cp.NCB, row_loss, dz_a, V);
+                if (check_launch("curl_reduce")) return -1;
+                launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, (const float*)V, (const float*)row_loss, (const float*)nullptr,
+                         (const float*)nullptr, 0, 0, B, feat, dW, loss_out);
+            } else {
+                // one column block: dz_a / V are final, the per-row losses are formed in k_curl_dw from the tile statistics
+                launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, (const float*)V, (const float*)nullptr, (const float*)t.pstat,
+                         (const float*)t.lab_logit, (int)cp.Bp, (int)cp.NT, B, feat, dW, loss_out);
             }
-            launch_k(k_curl_tc<1>, grid, dim3(256), smem, stream, t);
-            if (check_launch("curl_rows")) return -1;
-            launch_k(k_curl_reduce, dim3(cdiv(B, 4)), dim3(256), 0, stream, (const float*)t.pstat, (const float*)t.lab_logit,
-                     (const float*)t.pdz, (const float*)t.pV, B, (int)cp.Bp, (int)cp.NT, (int)cp.NCB, row_loss, dz_a, V);
-            if (check_launch("curl_reduce")) return -1;
-            launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, V, row_loss, B, feat, dW, loss_out);
             return check_launch("curl_dw");
         }
     }
+    // CUDA-core path: U[j][a] = sum_b z_pos[j][b] * W[a][b]   (columns >= feat stay zero: zero-initialised workspace),
+    // written in both orientations: U for the gradient pass, Ut for the coalesced logits pass
+    if (sgemm(z_pos, 64, 1, W, 1, feat, U, 64, Ut, Bg, Bg, feat, feat, stream)) return -1;
     // rows per CTA: every CTA streams all of U and z_pos (Bg x 512 B) from L2, so the re-read
     // traffic is (B / R) x that -- at a global batch of 4096 it is what bounds the kernel, and more
     // rows per CTA beat more CTAs; at small Bg the kernel is latency-bound and wants >= ~1 CTA/SM.
@@ -593,6 +667,7 @@ extern "C" int curla_curl_fwd_bwd(const float* z_a, const float* z_pos, const fl
         default: rc = launch_curl_rows<1>(z_a, U, Ut, z_pos, B, Bg, label0, grad_scale, row_loss, dz_a, V, logits_copy, stream); break;
     }
     if (rc) return -1;
-    launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, V, row_loss, B, feat, dW, loss_out);
+    launch_k(k_curl_dw, dim3(feat), dim3(256), 0, stream, z_a, (const float*)V, (const float*)row_loss, (const float*)nullptr,
+             (const float*)nullptr, 0, 0, B, feat, dW, loss_out);
     return check_launch("curl_dw");
 }

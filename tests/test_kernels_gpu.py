@@ -724,8 +724,13 @@ def test_mlp_heads_and_losses():
 
 
 # ------------------------------------------------------------------ CURL
-@pytest.mark.parametrize('B,Bg,label0', [(12, 12, 0), (8, 24, 8), (70, 70, 0)])
-def test_curl_fwd_bwd(B, Bg, label0):
+@pytest.mark.parametrize('ntw', ['', '4', '8'])
+@pytest.mark.parametrize('B,Bg,label0', [(12, 12, 0), (8, 24, 8), (70, 70, 0), (512, 512, 0), (128, 1024, 256), (64, 4096, 1024),
+                                         (100, 300, 150)])
+def test_curl_fwd_bwd(B, Bg, label0, ntw, monkeypatch):
+    """(ntw: key columns per warp of the tensor-core kernels / 8 -- 4 and 8 give other column-block counts, so the
+    single-block path without the reduce kernel and the multi-block path are both covered at every size)"""
+    monkeypatch.setenv('CURLA_CURL_NTW', ntw)
     torch.manual_seed(7)
     feat = 50
     za = torch.zeros((B, 64), device=DEV); za[:, :feat] = torch.randn(B, feat, device=DEV)
