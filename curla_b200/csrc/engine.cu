@@ -162,7 +162,7 @@ struct curla_agent {
     cudaStream_t side; cudaEvent_t ev[10]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
     // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
-    cudaStream_t comm_st; cudaEvent_t cev[6]; int comm_state;
+    cudaStream_t comm_st; cudaEvent_t cev[7]; int comm_state;
     long long wgrad_ws_stride;
     TailBuf t_p1, t_p2, t_p3, t_p4, t_p5, t_p7;
     MlpBuf m_p1, m_p2q[2], m_p3q[2], m_p4, m_p5q[2];
@@ -170,7 +170,7 @@ struct curla_agent {
     float *tq[2], *q3[2], *q5[2], *target_q, *dq[2], *dt4;
     bf16 *dH2, *dH1;
     float *dX[2], *dXa, *dz_curl, *dfc_f32, *dfc_f32_b; bf16 *dfc_bf16, *dfc_bf16_b;   // _b: the actor's backward beside the CURL phase
-    float *z_pos_all, *act_b, *rew_b, *nd_b, *metrics, *glogpi;
+    float *z_pos_all, *act_b, *rew_b, *nd_b, *metrics, *metrics_avg, *glogpi;
     double *log_alpha, *g_log_alpha, *alpha_state;
     // optimizer step counters (host)
     int t_critic, t_actor, t_alpha, t_cpc;
@@ -452,6 +452,7 @@ extern "C" curla_agent* curla_agent_create(const curla_agent_config* cfg) {
     a->rew_b = b.w<float>("batch.reward", DT_F32, {B});
     a->nd_b = b.w<float>("batch.not_done", DT_F32, {B});
     a->metrics = b.w<float>("metrics", DT_F32, {16});
+    a->metrics_avg = b.w<float>("metrics_avg", DT_F32, {16});
     a->glogpi = b.w<float>("glogpi", DT_F32, {4});
     a->log_alpha = b.w<double>("log_alpha", DT_F64, {1});
     a->g_log_alpha = b.w<double>("grad.log_alpha", DT_F64, {1});
@@ -532,7 +533,7 @@ extern "C" int curla_agent_bind(curla_agent* a, void* const* arenas) {
     rb(a->a_next); rb(a->logpi_next); rb(a->ls1); rb(a->mu_scratch); rb(a->pi4); rb(a->logpi4); rb(a->ls4); rb(a->noise4);
     rb(a->target_q); rb(a->dq[0]); rb(a->dq[1]); rb(a->dt4); rb(a->dH2); rb(a->dH1);
     rb(a->dX[0]); rb(a->dX[1]); rb(a->dXa); rb(a->dz_curl); rb(a->dfc_f32); rb(a->dfc_bf16); rb(a->dfc_f32_b); rb(a->dfc_bf16_b);
-    rb(a->z_pos_all); rb(a->act_b); rb(a->rew_b); rb(a->nd_b); rb(a->metrics); rb(a->glogpi);
+    rb(a->z_pos_all); rb(a->act_b); rb(a->rew_b); rb(a->nd_b); rb(a->metrics); rb(a->metrics_avg); rb(a->glogpi);
     rb(a->log_alpha); rb(a->g_log_alpha); rb(a->alpha_state); rb(a->dev_state);
     a->bound = true;
     return 0;
@@ -770,7 +771,7 @@ int load_nccl() {
     CURLA_CHECK(g_nccl.all_reduce && g_nccl.all_gather && g_nccl.get_id && g_nccl.init_rank, "nccl: missing symbols");
     return 0;
 }
-enum { NCCL_F32 = 7, NCCL_F64 = 8, NCCL_SUM = 0 };
+enum { NCCL_F32 = 7, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_AVG = 4 };
 int all_reduce(curla_agent* a, void* buf, size_t n, int dt, cudaStream_t st) {
     if (a->cfg.world == 1) return 0;
     CURLA_CHECK(a->comm, "update: world>1 but no communicator (curla_agent_init_comm)");
@@ -954,9 +955,21 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
     const bool do_cpc = !c.pixel_sac && (u->step % c.cpc_update_freq == 0) && (ph & CURLA_PHASE_CPC);
     // the logged scalars go to the host right after the last kernel of this update that writes one
     const int last_writer = do_cpc ? CURLA_PHASE_CPC : (do_actor ? CURLA_PHASE_ACTOR : (do_critic ? CURLA_PHASE_CRITIC : 0));
+    // (data parallel: the scalars are rank means of local-batch means -- one 64-byte ncclAvg in front of the publish,
+    // on the communication stream when there is one, so the collective's latency stays off the update's critical path)
     auto publish = [&](int phase, Run& rr) {
-        if (a->mailbox && phase == last_writer && ph == CURLA_PHASE_ALL && rr.ok())
+        if (!(a->mailbox && phase == last_writer && ph == CURLA_PHASE_ALL && rr.ok())) return;
+        if (c.world == 1) {
             rr.chk(curla_publish_metrics(a->metrics, a->mailbox, (unsigned)(u->offset + 1), off_dev, rr.st));
+            return;
+        }
+        if (!a->comm) { rr.chk(-1); set_last_error("update: world>1 but no communicator"); return; }
+        cudaStream_t ps = rr.st;
+        if (overlap) { cudaEventRecord(a->cev[6], rr.st); cudaStreamWaitEvent(cs, a->cev[6], 0); ps = cs; actor_pending = true; }
+        const int rc_ = g_nccl.all_reduce(a->metrics, a->metrics_avg, 16, NCCL_F32, NCCL_AVG, a->comm, ps);
+        if (rc_ != 0) { rr.chk(-1); set_last_error("ncclAllReduce(metrics) failed (%d)", rc_); return; }
+        profile_mark("nccl_all_reduce");
+        rr.chk(curla_publish_metrics(a->metrics_avg, a->mailbox, (unsigned)(u->offset + 1), off_dev, ps));
     };
 
     // ---- sample: gather (+crop) straight into the conv stack's input layout

@@ -672,9 +672,10 @@ class CurlSacAgent(_Host):
             _lib.check(eng.lib.curla_agent_set_opt_steps(eng.h, steps[0], steps[1], steps[2], steps[3]), 'set_opt_steps')
         self.engine = eng
         self._engine_gen = getattr(self, '_engine_gen', 0) + 1      # invalidates captured action graphs
-        if self.world == 1 and os.environ.get('CURLA_MAILBOX', '1')[:1] != '0':
+        if os.environ.get('CURLA_MAILBOX', '1')[:1] != '0':
             # the logged scalars arrive in 64 bytes of pinned host memory as soon as the update has computed them
-            # (engine.cu: curla_publish_metrics), so logging every step does not wait for the update's tail
+            # (engine.cu: curla_publish_metrics; data parallel: their mean over the ranks, one 64-byte ncclAvg inside the
+            # update), so logging every step does not wait for the update's tail
             if getattr(self, '_mailbox', None) is None:
                 self._mailbox = torch.zeros(16, dtype=torch.float32).pin_memory()
                 self._mailbox_f = self._mailbox.numpy()
@@ -840,8 +841,7 @@ class CurlSacAgent(_Host):
 
         if step % self.log_interval == 0:
             published = (not only_cpc) or (not self.pixel_sac and step % self.cpc_update_freq == 0)      # some phase wrote a scalar
-            if getattr(self, '_mailbox', None) is not None and self.world == 1 and not _phases and published \
-                    and self._noise_override is None:
+            if getattr(self, '_mailbox', None) is not None and not _phases and published and self._noise_override is None:
                 # wait for THIS update's sequence word (update count + 1), then read the scalars published with it
                 want, mu, t0 = np.uint32((self._update_count) & 0xFFFFFFFF), self._mailbox_u, None
                 spins = 0
