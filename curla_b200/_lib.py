@@ -79,6 +79,7 @@ SIGNATURES = {
     'curla_conv_fwd_multi': (_i, [c_vp, _i, c_ll, _f, c_ll, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_debug_read': (_i, [c_vp, _i]),
     'curla_gemm_tc_debug_read': (_i, [c_vp]),
+    'curla_gemm_tc_stamps_read': (_i, [c_vp, _i]),
     'curla_conv_wgrad_workspace_floats': (c_ll, [_i]),
     'curla_conv_wgrad': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, _f, _i, _i, _i, _i, _i, _i, _i, c_vp]),
     'curla_conv_wgrad_partial': (_i, [c_vp, c_ll, c_vp, c_ll, c_vp, _i, _i, _i, _i, _i, _i, c_vp, c_vp]),

@@ -48,6 +48,7 @@ bool pdl_enabled() {
 // launches are serialised).  Used by bench.py for the live per-kernel roofline numbers.
 struct Profiler {
     bool on = false;
+    bool phases = false;       // phase mode: no per-launch marks, side streams stay on, explicit marks at phase boundaries
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
@@ -69,7 +70,10 @@ struct Profiler {
 // per host thread: an agent is driven by one thread (include/curla_b200.h: thread-compatible), so two
 // engines driven by two threads profile independently
 static thread_local Profiler g_prof;
-void profile_mark(const char* what) { if (g_prof.on) g_prof.mark(what); }
+void profile_mark(const char* what) { if (g_prof.on && !g_prof.phases) g_prof.mark(what); }
+// phase mode (curla_profile_enable(2)): where the MAIN stream's time goes with every side stream running -- an event
+// on the main stream at each phase boundary, waits for joins included
+static void phase_mark(const char* what, cudaStream_t st) { if (g_prof.on && g_prof.phases && st == g_prof.stream) g_prof.mark(what); }
 
 static thread_local const char* g_tag = nullptr;
 void set_launch_tag(const char* tag) { g_tag = tag; }
@@ -82,7 +86,7 @@ int check_launch(const char* what) {
         set_last_error("%s: %s", what, cudaGetErrorString(e));
         return -1;
     }
-    if (g_prof.on) g_prof.mark(what);
+    if (g_prof.on && !g_prof.phases) g_prof.mark(what);
     return 0;
 }
 int sm_count() {
@@ -859,6 +863,7 @@ extern "C" int curla_agent_get_opt_steps(const curla_agent* a, int* out4) {
 
 extern "C" int curla_profile_enable(int on) {
     g_prof.on = on != 0;
+    g_prof.phases = on == 2;
     return 0;
 }
 // Synchronises the recorded events and writes "name count total_ms\n" lines (per launch
@@ -898,7 +903,7 @@ static cudaStream_t side_stream(curla_agent* a, cudaStream_t st) {
             if (okev) a->side_state = 1;
         }
     }
-    return (a->side_state == 1 && !g_prof.on) ? a->side : st;
+    return (a->side_state == 1 && (!g_prof.on || g_prof.phases)) ? a->side : st;
 }
 
 // Communication stream (created lazily, world > 1 only).  CURLA_COMM_OVERLAP=0 keeps the collectives
@@ -914,7 +919,7 @@ static cudaStream_t comm_stream(curla_agent* a, cudaStream_t st) {
             if (okev) a->comm_state = 1;
         }
     }
-    return (a->comm_state == 1 && !g_prof.on) ? a->comm_st : st;
+    return (a->comm_state == 1 && (!g_prof.on || g_prof.phases)) ? a->comm_st : st;
 }
 
 // ================================================================== the update
@@ -1008,6 +1013,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
 
     nvtxRangePop();
     bool have_p5 = false;
+    phase_mark("P01_gather", st);
     if (do_critic) {
         NvtxRange nv("curla/critic");
         // ---------------- update_critic (curl_sac.py:349-371)
@@ -1055,6 +1061,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         } else {
             const Run::Pass ps[3] = {p1, p2, p3};
             r.conv_stack_multi(ps, 3);
+            phase_mark("P02_conv_forward_F1+F2+F3", st);
             fork(0);
             r2.rc = r.rc;
             tail1();
@@ -1068,6 +1075,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
                                             a->q3[0], a->q3[1], B, gs, a->target_q, a->dq[0], a->dq[1], a->metrics, st));
         publish(CURLA_PHASE_CRITIC, r);
         // backward
+        phase_mark("P03_tails_F1_F3_+_critic_loss", st);
         float* gC = a->G + a->g_critic;
         // The weight gradients of the Q heads and of the encoder fc (six small kernels + one HBM-bound GEMM that nothing
         // in the backward chain reads) go to the side stream, idle since the tails joined: the chain
@@ -1077,6 +1085,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         Run* const wr = (forked && wgrad_side) ? &rw : nullptr;
         r.mlp_bwd_n(a->dq[0], a->dq[1] - a->dq[0], a->m_p3q[0].X, a->q_critic, a->sq_critic, a->m_p3q, 2, gC, a->off_critic,
                     a->dX[0], a->dX[1] - a->dX[0], wr, a->ev[6], a->ev[7]);
+        phase_mark("P04_Q_heads_backward_chain", st);
         const int tc_ = ++a->t_critic;
         // critic bucket = [conv w,b x4 | fc_w fc_b ln_w ln_b | Q1 | Q2]: everything from fc_w on (99 % of the
         // bytes) is final after the fc weight gradient, i.e. BEFORE the conv backward (0.7 ms at the
@@ -1092,6 +1101,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         };
         r.enc_bwd(a->dX[0], a->dX[1], a->t_p3, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs, gC,
                   a->off_critic, !c.detach_encoder, early1, false, wr, a->ev[9]);
+        phase_mark("P05_critic_LayerNorm_+_fc_dgrad_+_conv_backward", st);
         if (wr) cudaStreamWaitEvent(st, a->ev[8], 0);                  // join (long complete: the conv backward ran meanwhile)
         if (overlap) {
             reduce_step(1, a->P + a->off_critic, gC, a->Ad + a->a_m1, a->Ad + a->a_v1, 0, split1, a->n_critic,
@@ -1106,6 +1116,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         r.pack(a->pack_critic);
     }
     const int mm = merge_mode();
+    phase_mark("P06_critic_join_+_Adam_+_shadow_pack", st);
     auto ema = [&]() {
         // soft_update_params x3 (curl_sac.py:442-445): encoder tau on [0,n_enc), critic tau on Q1,Q2
         if (r.ok()) r.chk(curla_ema_f32(a->P + a->off_target, a->P + a->off_critic, a->n_critic, a->n_enc, c.encoder_tau,
@@ -1117,6 +1128,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
     // is the same computation -- and lets the post-EMA key pass F7 share conv launches with F4.
     const bool ema_first = mm != 0;
     if (do_sac && do_ema && ema_first) { NvtxRange nv("curla/ema"); ema(); }
+    phase_mark("P07_EMA_+_target_shadow_pack", st);
     const cudaStream_t ss7 = do_cpc ? side_stream(a, st) : st;
     const bool forked7 = ss7 != st;
     const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA, true};    // F4 == F5 == F6 conv part
@@ -1168,6 +1180,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (mm && do_cpc) {
                 const Run::Pass ps[2] = {p_anchor, p_key};
                 r.conv_stack_multi(ps, 2);
+                phase_mark("P08_conv_forward_anchor_+_key", st);
                 side_tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, true);   // keys: beside the actor step
                 key_done = true;
             } else {
@@ -1184,6 +1197,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
                                                a->dq[0], a->dq[1], a->glogpi, a->g_log_alpha, a->metrics, st));
             publish(CURLA_PHASE_ACTOR, r);
+            phase_mark("P09_actor_forward_tails_+_loss", st);
             // Two ways to use the side stream from here on (it already holds the key tail + all-gather):
             //   actor_side (default): the actor's whole backward + optimizer step runs there, beside the CURL contraction
             //     and the contrastive backward on the main stream -- nothing later in THIS update reads the actor's own
@@ -1240,6 +1254,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (mm) {
                 const Run::Pass ps[2] = {p_anchor, p_key};
                 r.conv_stack_multi(ps, 2);
+                phase_mark("P08_conv_forward_anchor_+_key", st);
             } else {
                 r.conv_stack_multi(&p_anchor, 1);
             }
@@ -1249,12 +1264,14 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (!(mm && !have_p5)) r.conv_stack_multi(&p_key, 1);
             r.tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, B);
         }
+        phase_mark("P10_cpc_main_stream_tails", st);
         if (join7) cudaStreamWaitEvent(st, a->ev[2], 0);
         float* gK = a->G + a->g_cpc;
         if (!curl_done) {
             if (!keys_gathered) gather_keys(st);
             curl_contract(r);
         }
+        phase_mark("P11_CURL_contraction_+_wait_for_keys", st);
         // g_cpc mirrors [W | critic.encoder]: encoder grads start at n_W
         // encoder_optimizer.step(); cpc_optimizer.step(): encoder twice, W once (double_from = n_W).
         // Bucket = [W | conv w,b x4 | fc_w fc_b ln_w ln_b]: the fc/ln tail is final after the fc weight gradient
@@ -1266,6 +1283,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         };
         r.enc_bwd(a->dz_curl, nullptr, a->t_p5, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs,
                   gK + a->n_W, a->off_critic, true, early3);
+        phase_mark("P12_cpc_LayerNorm_+_fc_dgrad_+_conv_backward", st);
         if (overlap) {
             reduce_step(5, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, 0, split3, a->n_W, c.encoder_lr, 0.9, tk_, td_cpc);
             cudaEventRecord(a->cev[2], cs);
@@ -1277,12 +1295,14 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
                                              0.999, 1e-8, tk_, td_cpc, st));
         }
         r.pack(a->pack_critic_enc);
+        phase_mark("P13_cpc_Adam_+_shadow_pack", st);
     }
     if (actor_pending) {                           // join: everything of this update is complete when `st` is
         cudaEventRecord(a->cev[2], cs);
         cudaStreamWaitEvent(st, a->cev[2], 0);
     }
     if (actor_side_pending) cudaStreamWaitEvent(st, a->ev[5], 0);
+    phase_mark("P14_join_side_streams", st);
     a->last_launches = g_launches - launches0;
     return r.rc;
 }

@@ -50,6 +50,10 @@ struct TmaPlan {
     int per_seg;           // K steps per segment (a_segk) or N / M tiles per segment (b_segn / a_segm)
     int total_steps;       // a_segk: segments * per_seg
     int nst;               // stages allocated
+    int stamps;            // timing experiments: per-CTA %globaltimer stamps (g_gtc_stamps)
+    int ksub;              // 64-wide K steps per pipeline stage (1 or 2): one full / empty barrier round trip and one commit per
+                           // stage cost the MMA thread ~400 clk against 192 clk of MMAs per 64-wide step (the fc forward with
+                           // its A loads removed still took 19 of its 28 us: gpurun r05b), so long K loops take two steps per stage
 };
 
 constexpr uint32_t idesc_tc(bool a_mn, bool b_mn) {
@@ -70,6 +74,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 
 // timing experiments: clocks of the MMA thread of CTA (0,0,0): [0] waiting for `full`, [1] issuing, [4] K loop, [5] K steps, [6] kernel
 __device__ long long g_gtc_dbg[8];
+// timing experiments (CURLA_GEMM_STAMPS=1): %globaltimer stamps (ns) of every CTA of the last k_gemm_tc launch --
+// [0] kernel entry, [1] after the dependency wait, [2] first stage full (MMA warp), [3] K loop issued, [4] accumulator
+// complete (epilogue warp 2), [5] epilogue stores issued, [6] epilogue: tile in shared memory, [7] SM id
+__device__ long long g_gtc_stamps[1024][8];
+__device__ long long g_gtc_epi_clk[1024][2];        // SM clocks of epilogue phase 1 / phase 2 (warp 2)
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 template <bool A_KMAJOR, bool B_KMAJOR, bool SEG>
 __global__ void __launch_bounds__(kTcGemmThreads)
@@ -80,6 +90,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t s_full = s_base, s_empty = s_base + 64, s_done = s_base + 128, s_tptr = s_base + 136;
     const uint32_t s_stage0 = s_base + kHdrTc;
     const long long t_start = clock64();
+    const int cta_lin = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+    const bool stamp = pl.stamps && cta_lin < 1024;
+    if (stamp && tid == 0) {
+        g_gtc_stamps[cta_lin][0] = gtimer();
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_gtc_stamps[cta_lin][7] = smid;
+    }
     if (tid == 0) {
         for (int i = 0; i < kMaxSt; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 1); }
         mbar_init(s_done, 1);
@@ -99,6 +116,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     pdl_grid_sync();              // everything above is independent of earlier kernels
+    if (stamp && tid == 0) g_gtc_stamps[cta_lin][1] = gtimer();
 
     // ---- tile and K-step ranges
     int m0 = blockIdx.y * TM, mrows = TM, am_c0 = 0, am_c1 = 0;
@@ -132,7 +150,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         s_end = (kend + TK - 1) / TK;
     }
     const int nk = s_end > s_beg ? s_end - s_beg : 0;
-    const int nst = pl.nst;
+    const int nst = pl.nst, ksub = pl.ksub;
+    const int nstg = (nk + ksub - 1) / ksub;                 // pipeline stages this CTA runs through
+    const uint32_t stage_bytes = (uint32_t)ksub * kStageBytesTc;
 
     if (warp == 0) {
         // ================= producer (the whole warp runs the loop, one elected lane issues: a loop confined to
@@ -140,13 +160,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         {
             const int za = p.bsA ? bz : 0, zb = p.bsB ? bz : 0;
             uint32_t stage = 0, phase = 0;
-            for (int kt = 0; kt < nk; ++kt) {
-                const int step = s_beg + kt;
+#pragma unroll 1
+            for (int kt = 0; kt < nstg; ++kt) {
                 mbar_wait(s_empty + 8 * stage, phase ^ 1);
                 const uint32_t bar = s_full + 8 * stage;
-                const uint32_t dA = s_stage0 + stage * kStageBytesTc, dB = dA + kABytes;
+                const int nsub = nk - kt * ksub < ksub ? nk - kt * ksub : ksub;
                 if (elect_one()) {
-                mbar_expect_tx(bar, kStageBytesTc);
+                mbar_expect_tx(bar, (uint32_t)nsub * kStageBytesTc);
+                for (int sub = 0; sub < nsub; ++sub) {
+                const int step = s_beg + kt * ksub + sub;
+                const uint32_t dA = s_stage0 + stage * stage_bytes + (uint32_t)sub * kStageBytesTc, dB = dA + kABytes;
                 int kb = step * TK;                           // B's K coordinate (logical K)
                 if (A_KMAJOR) {
                     if (SEG && pl.a_segk) {
@@ -167,6 +190,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 else if (SEG && pl.b_segn) tma_load_3d(dB, &tmB, bn_c0, bn_c1, step * TK, bar);
                 else tma_load_3d(dB, &tmB, n0, step * TK, zb, bar);
                 }
+                }
                 __syncwarp();
                 if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
             }
@@ -179,19 +203,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             long long d0 = 0, d1 = 0;
             const long long dl0 = clock64();
             uint32_t stage = 0, phase = 0;
-            for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll 1
+            for (int kt = 0; kt < nstg; ++kt) {
                 const long long c0 = dbg ? clock64() : 0;
                 mbar_wait(s_full + 8 * stage, phase);
                 const long long c1 = dbg ? clock64() : 0;
+                if (stamp && kt == 0 && lane == 0) g_gtc_stamps[cta_lin][2] = gtimer();
                 tc_fence_after();
-                const uint32_t sA = s_stage0 + stage * kStageBytesTc, sB = sA + kABytes;
+                const int nsub = nk - kt * ksub < ksub ? nk - kt * ksub : ksub;
                 if (elect_one()) {
+                    for (int sub = 0; sub < nsub; ++sub) {
+                        const uint32_t sA = s_stage0 + stage * stage_bytes + (uint32_t)sub * kStageBytesTc, sB = sA + kABytes;
 #pragma unroll
-                    for (int ks = 0; ks < TK / 16; ++ks) {
-                        // K-major: 16 k = 32 bytes further along the swizzled 128-byte rows; MN-major: 16 k rows = 2048 bytes
-                        const uint64_t ad = A_KMAJOR ? desc_sw128(sA + ks * 32, 16, 1024) : desc_sw128(sA + ks * 2048, kABytes / 2, 1024);
-                        const uint64_t bd = B_KMAJOR ? desc_sw128(sB + ks * 32, 16, 1024) : desc_sw128(sB + ks * 2048, kBBytes, 1024);
-                        umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | ks) != 0));
+                        for (int ks = 0; ks < TK / 16; ++ks) {
+                            // K-major: 16 k = 32 bytes further along the swizzled 128-byte rows; MN-major: 16 k rows = 2048 bytes
+                            const uint64_t ad = A_KMAJOR ? desc_sw128(sA + ks * 32, 16, 1024) : desc_sw128(sA + ks * 2048, kABytes / 2, 1024);
+                            const uint64_t bd = B_KMAJOR ? desc_sw128(sB + ks * 32, 16, 1024) : desc_sw128(sB + ks * 2048, kBBytes, 1024);
+                            umma_bf16_rt(tmem_base, ad, bd, kId, (uint32_t)((kt | sub | ks) != 0));
+                        }
                     }
                     umma_commit(s_empty + 8 * stage);        // slot free once these MMAs have read it
                 }
@@ -201,6 +230,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             if (elect_one()) umma_commit(s_done);
             __syncwarp();
+            if (stamp && lane == 0) g_gtc_stamps[cta_lin][3] = gtimer();
             if (dbg) { g_gtc_dbg[0] = d0; g_gtc_dbg[1] = d1; g_gtc_dbg[4] = clock64() - dl0; g_gtc_dbg[5] = nk; }
         }
     } else {
@@ -214,8 +244,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bf16* __restrict__ maskp = p.mask ? p.mask + bz * p.bsMask : nullptr;
         const bool f4 = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cf) & 15) == 0);
         const bool bias_al = (reinterpret_cast<uintptr_t>(biasp) & 15) == 0;
+        // (Code size matters here: the epilogue's first execution fetches its instructions cold, behind the operand stream
+        // of every SM.  With its row loops fully unrolled -- 50 KB of code per instantiation -- the sixteen shared-memory
+        // reads + stores of the fp32 path took 13,000 clk; as plain loops, 2,900.  Per-CTA %globaltimer stamps,
+        // tests/manual/fc_fwd_roles.py, gpurun r05e-r05n: 28.7 -> 23.5 us for the fc forward alone, 1.908 -> 1.886 ms per
+        // update.  Unrolling by four, or a dry run of the epilogue at kernel start to warm the instruction cache, measured no
+        // further gain.)
         mbar_wait(s_done, 0);
         tc_fence_after();
+        if (stamp && tid == 64) g_gtc_stamps[cta_lin][4] = gtimer();
+        const long long ec0 = clock64();
         if (pl.c_trans) {
             // operands were swapped: this thread's row is a COLUMN of the caller's fp32 matrix, so a
             // warp writes 32 consecutive floats per column (no bias / mask on this path)
@@ -265,13 +303,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
             __syncwarp();
+            const long long ec1 = clock64();
+            if (stamp && tid == 64) { g_gtc_stamps[cta_lin][6] = gtimer(); g_gtc_epi_clk[cta_lin][0] = ec1 - ec0; g_gtc_epi_clk[cta_lin][1] = ec1; }
             if (p.out_bf16) {
                 const int cr = lane >> 3, cc = lane & 7;
                 const int c = cc * 8, n = n0 + c;
                 int lim = p.n_store - n;
                 if (ncols - c < lim) lim = ncols - c;
                 const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
-#pragma unroll
+#pragma unroll 1
                 for (int t = 0; t < 8; ++t) {
                     const int row = t * 4 + cr, mm = m0 + q * 32 + row;
                     float4 a, b;
@@ -307,7 +347,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 int lim = p.n_store - n;
                 if (ncols - c < lim) lim = ncols - c;
                 const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
-#pragma unroll
+#pragma unroll 1
                 for (int t = 0; t < 16; ++t) {
                     const int row = t * 2 + cr, mm = m0 + q * 32 + row;
                     float4 a;
@@ -324,6 +364,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     }
+    if (stamp && tid == 64) { g_gtc_stamps[cta_lin][5] = gtimer(); g_gtc_epi_clk[cta_lin][1] = clock64() - g_gtc_epi_clk[cta_lin][1]; }
     tc_fence_before();
     __syncthreads();
     if (tid == 32 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) g_gtc_dbg[6] = clock64() - t_start;
@@ -587,7 +628,7 @@ int launch_one(const CUtensorMap* ta, const CUtensorMap* tb, const GemmArgs& p, 
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         if (e != cudaSuccess) { set_last_error("gemm_tc: cudaFuncSetAttribute(smem=%d): %s", mx, cudaGetErrorString(e)); return -1; }
     }
-    uint32_t smem = kHdrTc + (uint32_t)pl.nst * kStageBytesTc;
+    uint32_t smem = kHdrTc + (uint32_t)(pl.nst * pl.ksub) * kStageBytesTc;
     if (smem < kHdrTc + 4 * 32 * 272) smem = kHdrTc + 4 * 32 * 272;        // the epilogue's four 32-row fp32 patches reuse the stages
     launch_k(kern, grid, dim3(kTcGemmThreads), smem, stream, *ta, *tb, p, pl);
     return 1;
@@ -678,8 +719,18 @@ int gemm_tc_try_launch(const GemmArgs& p, int layout, int splits, cudaStream_t s
     // ring depth: 4 stages (two CTAs per SM); the split-K fc forward streams its operands once from HBM and
     // takes CURLA_FC_STAGES (<= 8: one CTA per SM with twice the bytes in flight per CTA)
     int st_max = kDefSt;
-    if (pl.a_segk) { const char* e = getenv("CURLA_FC_STAGES"); if (e && e[0] >= '2' && e[0] <= '8') st_max = e[0] - '0'; }
-    pl.nst = nsteps < st_max ? (nsteps < 1 ? 1 : nsteps) : st_max;
+    { const char* e = getenv("CURLA_GEMM_STAMPS"); pl.stamps = (e && e[0] == '1') ? 1 : 0; }
+    pl.ksub = 1;
+    if (pl.a_segk) {
+        // the split-K fc forward: CURLA_FC_KSUB=2 takes two 64-wide steps per stage (four 48 KB stages, one CTA per SM; wants
+        // CURLA_FC_SPLITS=37) -- measured no faster than one (gpurun r05c): the MMA thread's per-stage cost is not what paces it
+        pl.ksub = 1;
+        { const char* e = getenv("CURLA_FC_KSUB"); if (e && (e[0] == '1' || e[0] == '2')) pl.ksub = e[0] - '0'; }
+        { const char* e = getenv("CURLA_FC_STAGES"); if (e && e[0] >= '2' && e[0] <= '8') st_max = e[0] - '0'; }
+        if (st_max * pl.ksub > kMaxSt) st_max = kMaxSt / pl.ksub;
+    }
+    const int nstages = cdiv(nsteps, pl.ksub);
+    pl.nst = nstages < st_max ? (nstages < 1 ? 1 : nstages) : st_max;
     dim3 grid(gx, cdiv(p.M, TM), p.batch > 1 ? p.batch : splits);
     if (grid.y > 65535 || grid.z > 65535) return 0;
     switch ((layout & 3) | (p.seg_mask ? 4 : 0)) {
@@ -737,6 +788,7 @@ static int tc_swapped_wgrad(const GemmArgs& p, cudaStream_t stream) {
                                     (unsigned long long)q.ldb * 2, (unsigned long long)p.K * q.ldb * 2, TN, TK, 1);
     if (!ta || !tb) return -1;
     const int nsteps = cdiv(p.K, TK);
+    pl.ksub = 1;
     pl.nst = nsteps < kDefSt ? nsteps : kDefSt;
     dim3 grid(1, nseg * pl.per_seg, 1);
     if (grid.y > 65535) return 0;
@@ -744,6 +796,20 @@ static int tc_swapped_wgrad(const GemmArgs& p, cudaStream_t stream) {
 }
 
 }  // namespace curla
+
+extern "C" int curla_gemm_tc_stamps_read(long long* out, int nctas) {
+    CURLA_CHECK(nctas >= 1 && nctas <= 1024, "gemm_tc_stamps_read: 1..1024 CTAs");
+    cudaError_t e = cudaMemcpyFromSymbol(out, curla::g_gtc_stamps, sizeof(long long) * 8 * nctas);
+    CURLA_CHECK(e == cudaSuccess, "gemm_tc_stamps_read: %s", cudaGetErrorString(e));
+    // (experiments: the epilogue's SM clock counts replace slots [2] / [3] when CURLA_GEMM_STAMPS_CLK is set)
+    if (getenv("CURLA_GEMM_STAMPS_CLK")) {
+        static long long tmp[1024][2];
+        e = cudaMemcpyFromSymbol(tmp, curla::g_gtc_epi_clk, sizeof(tmp));
+        CURLA_CHECK(e == cudaSuccess, "gemm_tc_stamps_read: %s", cudaGetErrorString(e));
+        for (int i = 0; i < nctas; ++i) { out[i * 8 + 2] = tmp[i][0]; out[i * 8 + 3] = tmp[i][1]; }
+    }
+    return 0;
+}
 
 extern "C" int curla_gemm_tc_debug_read(long long* out8) {
     cudaError_t e = cudaMemcpyFromSymbol(out8, curla::g_gtc_dbg, sizeof(long long) * 8);

@@ -160,6 +160,8 @@ int curla_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, 
                     long long split_stride, float alpha, curla_stream_t stream);
 /* timing experiments: clock counters of one thread of the tcgen05 GEMM (gemm_tc.cu) */
 int curla_gemm_tc_debug_read(long long* out8);
+/* timing experiments (CURLA_GEMM_STAMPS=1): eight %globaltimer stamps (ns) per CTA of the last tcgen05 GEMM launch */
+int curla_gemm_tc_stamps_read(long long* out, int nctas);
 /* same, with the contiguous index of A (seg_mask&1), B (&2) or C+mask columns (&4) split into
  * segments of seg_len elements seg_stride apart (channel-plane activations) */
 int curla_gemm_bf16_seg(const void* A, long long lda, const void* B, long long ldb, void* C,

@@ -4,7 +4,7 @@
 tag=${1:-r03}
 out=gpurun_out
 mkdir -p $out
-SEL='test_conv_forward or test_conv_backward or test_gather or test_curl or test_gemm_layouts or test_conv_wgrad_staging'
+SEL='test_conv_forward or test_conv_backward or test_gather or test_curl or test_gemm_layouts or test_conv_wgrad_staging or test_conv_wgrad_variants'
 for tool in memcheck racecheck; do
   timeout 1500 compute-sanitizer --tool $tool --error-exitcode 66 --print-limit 20 \
       python -m pytest tests/test_kernels_gpu.py -x -q -k "$SEL" > $out/${tag}_sanitizer_${tool}_kernels.txt 2>&1
