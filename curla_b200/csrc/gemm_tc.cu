@@ -434,6 +434,7 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
         uint32_t stage = 0, phase = 0;
+#pragma unroll 1
         for (int i = 0; i < my_tiles; ++i) {
             mbar_wait(s_bempty + 8 * stage, phase ^ 1);
             if (elect_one()) {
@@ -447,6 +448,7 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         constexpr uint32_t kId = idesc_tc(false, true);          // A K-major, B MN-major
         mbar_wait(s_afull, 0);
         uint32_t stage = 0, phase = 0;
+#pragma unroll 1
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
             mbar_wait(s_bfull + 8 * stage, phase);
@@ -485,6 +487,7 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         };
         if (g < my_tiles) load_mask(g);
+#pragma unroll 1
         for (int i = g; i < my_tiles; i += kNlAcc) {
             const uint32_t acc = (uint32_t)(i % kNlAcc), acc_phase = (uint32_t)((i / kNlAcc) & 1);
             mbar_wait(s_tfull + 8 * acc, acc_phase);
@@ -509,21 +512,30 @@ k_gemm_tc_nloop(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) mbar_arrive(s_tempty + 8 * acc);
             const int n = (t_first + i) * TN + cc * 8;
             const long long nc = seg_off(n, p.seg_len, p.seg_stride, p.seg_inv, SEG && (p.seg_mask & 4));
+            // (n, hence the ragged-tail case, does not depend on the row: the per-element tail path lives in its own plain
+            // loop instead of being replicated in each of the eight unrolled row steps)
+            if (n + 8 <= p.n_store) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const int row = t * 4 + cr, m = m0 + q * 32 + row;
-                uint4 v;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(patch + row * 144 + cc * 16));
-                if (m >= p.M || n >= p.n_store) continue;
-                const long long o = (long long)m * p.ldc + nc;
-                if (n + 8 <= p.n_store) {
+                for (int t = 0; t < 8; ++t) {
+                    const int row = t * 4 + cr, m = m0 + q * 32 + row;
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(patch + row * 144 + cc * 16));
+                    if (m >= p.M) continue;
                     auto keep = [](uint32_t val, uint32_t mw) {
                         const float2 mv = unpack_bf16x2(mw);
                         return (mv.x > 0.f ? val & 0x0000FFFFu : 0u) | (mv.y > 0.f ? val & 0xFFFF0000u : 0u);
                     };
                     v.x = keep(v.x, mk[t].x); v.y = keep(v.y, mk[t].y); v.z = keep(v.z, mk[t].z); v.w = keep(v.w, mk[t].w);
-                    *reinterpret_cast<uint4*>(Cb + o) = v;
-                } else {
+                    *reinterpret_cast<uint4*>(Cb + (long long)m * p.ldc + nc) = v;
+                }
+            } else if (n < p.n_store) {
+#pragma unroll 1
+                for (int t = 0; t < 8; ++t) {
+                    const int row = t * 4 + cr, m = m0 + q * 32 + row;
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(patch + row * 144 + cc * 16));
+                    if (m >= p.M) continue;
+                    const long long o = (long long)m * p.ldc + nc;
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                     for (int e = 0; e < p.n_store - n; ++e) {
                         uint16_t x = (uint16_t)(w[e >> 1] >> ((e & 1) * 16));
