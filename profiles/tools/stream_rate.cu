@@ -1,4 +1,6 @@
-// Probe: how fast can one producer thread per SM stream HBM into shared memory with cp.async.bulk / TMA boxes,
+// Probe (profiles/r04d_stream_rate.txt was taken with a 4 GB buffer: its strided bulk-copy cases beyond 4 GB were
+// skipped and the run ended at the first two-CTAs-per-SM tensor-map case; the buffer below covers them all):
+// how fast can one producer thread per SM stream HBM into shared memory with cp.async.bulk / TMA boxes,
 // as a function of the contiguous chunk size, the ring depth and the stage size?  (No compute: the consumer
 // releases a stage as soon as it is full.)
 #include <cuda.h>
@@ -80,7 +82,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int main() {
-    const size_t BYTES = 4ull << 30;
+    const size_t BYTES = 8ull << 30;            // the TMA-box cases walk 148 x 2 x 128 rows of 165,376 B = 6.3 GB
     uint8_t* buf; CK(cudaMalloc(&buf, BYTES)); CK(cudaMemset(buf, 1, BYTES));
     uint8_t* flush; CK(cudaMalloc(&flush, 512ull << 20));
     void* f = nullptr; cudaDriverEntryPointQueryResult q;
