@@ -163,3 +163,30 @@ def test_init_rng_matches_reference(case):
     assert np.array_equal(S.summarize(W), gold['param/W'])
     assert np.array_equal(after, gold['next_rand'])
     assert float(gold['param/log_alpha'][0]) == float(np.log(S.HP['init_temperature']))
+
+
+def test_one_shot_gemm_kernels_stay_small(lib):
+    """Code size is a performance property of the one-shot tcgen05 GEMM kernels ("Instruction
+    fetch"): a CTA executes its epilogue exactly once, every instruction a cold fetch behind the operand stream of all
+    SMs -- with the epilogue's row loops unrolled (6,300 instructions per instantiation, 6,160 for the N-loop kernel)
+    the fc forward spent 7 of its 29 us there.  Guard the plain-loop form: instruction counts from cuobjdump."""
+    import shutil
+    import subprocess
+    from curla_b200 import build
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([exe, '-sass', build.OUT], capture_output=True, text=True).stdout
+    counts, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            name = m.group(1)
+            counts[name] = 0
+        elif name and re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+\S', line):
+            counts[name] += 1
+    gemm = {k: v for k, v in counts.items() if 'k_gemm_tcIL' in k}
+    nloop = {k: v for k, v in counts.items() if 'k_gemm_tc_nloop' in k}
+    assert len(gemm) == 8 and len(nloop) == 2, (sorted(gemm), sorted(nloop))
+    assert max(gemm.values()) < 4500, gemm
+    assert max(nloop.values()) < 3000, nloop
