@@ -163,7 +163,7 @@ struct curla_agent {
     float *fc_partial, *fc_partial2, *wgrad_ws, *curl_ws, *ln_scratch, *ln_scratch_b;
     // side stream: the latency-bound tails (fc + LayerNorm + MLP heads) of one encoder pass run
     // there while the main stream already runs the next pass's conv stack
-    cudaStream_t side; cudaEvent_t ev[10]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
+    cudaStream_t side; cudaEvent_t ev[11]; int side_state;   // 0 = not created, 1 = ready, -1 = disabled
     // communication stream (world > 1): gradient all-reduce + Adam of a bucket slice run there while the
     // main stream is still in the conv backward (critic, CURL) or already in the next phase (actor)
     cudaStream_t comm_st; cudaEvent_t cev[7]; int comm_state;
@@ -617,18 +617,24 @@ struct Run {
         conv_stack_multi(&p, 1, B);
     }
     // fc (split-K) + bias + LayerNorm
-    void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
-              const float* act = nullptr, bf16* X_out = nullptr, float* partial = nullptr) {
+    void tail_fc(const bf16* act4, long long fc_shadow, int B, float* partial) {
         if (!ok()) return;
-        if (!partial) partial = a->fc_partial;
         set_launch_tag("gemm_fc_fwd");
         chk(curla_gemm_bf16_seg(act4, a->act_sstride, Sh(fc_shadow), a->Kfc, partial, 64, B, 64, a->Kfc,
                                 3, 64, 0, nullptr, 0, nullptr, 0, a->fc_splits, (long long)B * 64, 1.f,
                                 a->Kfc / 4, (long long)a->S * 8, 1, st));
         set_launch_tag(nullptr);
+    }
+    void tail_ln(const float* partial, const EncP& e, TailBuf& t, int B, int apply_tanh, const float* act, bf16* X_out) {
         if (!ok()) return;
         chk(curla_ln_fwd_x(partial, a->fc_splits, (long long)B * 64, P(e.fc_b), P(e.ln_w), P(e.ln_b), B,
                            a->cfg.feature_dim, apply_tanh, t.fc_out, t.z, act, act ? a->cfg.action_dim : 0, X_out, st));
+    }
+    void tail(const bf16* act4, long long fc_shadow, const EncP& e, TailBuf& t, int B, int apply_tanh = 0,
+              const float* act = nullptr, bf16* X_out = nullptr, float* partial = nullptr) {
+        if (!partial) partial = a->fc_partial;
+        tail_fc(act4, fc_shadow, B, partial);
+        tail_ln(partial, e, t, B, apply_tanh, act, X_out);
     }
     // nb MLPs of one shape in one launch each (nb = 2: the critic's Q1 || Q2 on the shared input
     // rows X; curl_sac.py:158-169).  m/s/buf point at nb consecutive descriptors; the strides
@@ -1133,7 +1139,7 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
     const bool forked7 = ss7 != st;
     const Run::Pass p_anchor = {a->s2d_obs, &a->enc_critic, &a->s_critic, a->actA, true};    // F4 == F5 == F6 conv part
     const Run::Pass p_key = {s2d_pos, &a->enc_target, &a->s_target, a->actB, false};          // F7
-    bool key_done = false, join7 = false;
+    bool key_done = false, join7 = false, f5_early = false;
     // tail of one pass on the side stream (fc_partial2 is the side stream's split-K buffer)
     // all-gather of the CURL keys (the one real exchange step of the update): issued on the stream that
     // produced them, as early as they exist -- before the actor bucket's all-reduce is queued on the
@@ -1183,6 +1189,18 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
                 phase_mark("P08_conv_forward_anchor_+_key", st);
                 side_tail(a->actB[3], a->s_target.fc, a->enc_target, a->t_p7, true);   // keys: beside the actor step
                 key_done = true;
+                // F5 = critic.encoder(obs) for Q(obs, pi): its fc GEMM depends on the conv stack only (pi enters at the
+                // LayerNorm's concat), so it runs on the side stream behind the key tail while the main stream is in the
+                // actor's fc -> LayerNorm -> trunk -> policy chain (CURLA_F5_EARLY=0: in line)
+                static const bool f5_on = [] { const char* e = getenv("CURLA_F5_EARLY"); return !(e && e[0] == '0'); }();
+                if (f5_on && forked7 && r.ok()) {
+                    Run r5{a, ss7};
+                    r5.rc = r.rc;
+                    r5.tail_fc(a->actA[3], a->s_critic.fc, B, a->fc_partial2);
+                    r.chk(r5.rc);
+                    cudaEventRecord(a->ev[10], ss7);
+                    f5_early = true;
+                }
             } else {
                 r.conv_stack_multi(&p_anchor, 1);
             }
@@ -1191,7 +1209,13 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
             if (r.ok()) r.chk(curla_policy_fwd_rows_dyn(a->t_out4, u->noise_cur, u->seed, off_cur, off_dev, c.rank * B, B, A,
                                                    (float)c.log_std_min, (float)c.log_std_max, 1, 1, a->mu_scratch, a->pi4, a->logpi4,
                                                    a->ls4, a->noise4, st));
-            r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
+            if (f5_early) {
+                // (its fc GEMM ran on the side stream behind the key tail; the LayerNorm needs pi, hence it is here)
+                cudaStreamWaitEvent(st, a->ev[10], 0);
+                r.tail_ln(a->fc_partial2, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
+            } else {
+                r.tail(a->actA[3], a->s_critic.fc, a->enc_critic, a->t_p5, B, 0, a->pi4, a->m_p5q[0].X);
+            }
             have_p5 = true;
             r.mlp_fwd_n(a->m_p5q[0].X, a->q_critic, a->sq_critic, a->m_p5q, 2, B);
             if (r.ok()) r.chk(curla_actor_loss(a->logpi4, a->q5[0], a->q5[1], a->ls4, B, A, a->log_alpha, (float)c.target_entropy, gs,
