@@ -1301,12 +1301,22 @@ static int update_body(curla_agent* a, const curla_update_args* u, cudaStream_t 
         // Bucket = [W | conv w,b x4 | fc_w fc_b ln_w ln_b]: the fc/ln tail is final after the fc weight gradient
         const int tk_ = ++a->t_cpc;
         const long long split3 = a->n_W + (a->enc_critic.fc_w - a->off_critic);
+        // (the fc weight gradient off the backward chain, as in the critic phase: on the side stream -- behind the actor's
+        // backward when that runs there -- joined before the optimizer step)
+        static const bool wgrad_side3 = [] { const char* e = getenv("CURLA_WGRAD_SIDE"); return !(e && e[0] == '0'); }();
+        Run rw3{a, ss7};
+        Run* const wr3 = (forked7 && wgrad_side3) ? &rw3 : nullptr;
         auto early3 = [&]() {
-            if (overlap) reduce_step(4, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, split3, a->n_cpc, a->n_W,
-                                     c.encoder_lr, 0.9, tk_, td_cpc);
+            if (wr3) cudaEventRecord(a->ev[8], ss7);
+            if (overlap) {
+                if (wr3) cudaStreamWaitEvent(cs, a->ev[8], 0);
+                reduce_step(4, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, split3, a->n_cpc, a->n_W,
+                            c.encoder_lr, 0.9, tk_, td_cpc);
+            }
         };
         r.enc_bwd(a->dz_curl, nullptr, a->t_p5, a->enc_critic, a->s_critic.fc, &a->s_critic, a->actA, a->s2d_obs,
-                  gK + a->n_W, a->off_critic, true, early3);
+                  gK + a->n_W, a->off_critic, true, early3, false, wr3, a->ev[9]);
+        if (wr3) cudaStreamWaitEvent(st, a->ev[8], 0);
         phase_mark("P12_cpc_LayerNorm_+_fc_dgrad_+_conv_backward", st);
         if (overlap) {
             reduce_step(5, a->P + a->off_W, gK, a->Ad + a->a_m3, a->Ad + a->a_v3, 0, split3, a->n_W, c.encoder_lr, 0.9, tk_, td_cpc);
