@@ -3,8 +3,13 @@
 //
 // Host-side C++ only (no kernels here).  The caller (curla_b200/curl_sac.py) owns five
 // zero-initialised arenas; this file decides where every tensor lives in them, exposes
-// that table (curla_agent_tensor_info) and issues the kernels of gather.cu / conv.cu /
-// gemm.cu / small.cu / curl.cu / optim.cu in dependency order on one stream.
+// that table (curla_agent_tensor_info) and issues the kernels of gather.cu / conv_tc.cu /
+// conv_wgrad_tc.cu / gemm_tc.cu / gemm.cu / small.cu / curl.cu / optim.cu in dependency order:
+// the big kernels on the caller's stream, the chains of small kernels that feed nothing downstream
+// (pass tails, Q-head / fc weight gradients, the actor's backward + optimizer step) on an
+// engine-owned side stream, the collectives and the optimizer steps they feed on a communication
+// stream (world > 1) -- event fork / join only, no host synchronisation; the whole sequence is
+// captured once per update variant and replayed as a CUDA graph.
 //
 // Distinct-work schedule (numerically identical to the reference's 7 encoder forwards,
 // SURVEY.md 3.4): F1 conv_theta(next), F2 conv_target(next), F3 conv_theta(obs)+bwd,
