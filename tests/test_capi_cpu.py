@@ -190,3 +190,17 @@ def test_one_shot_gemm_kernels_stay_small(lib):
     assert len(gemm) == 8 and len(nloop) == 2, (sorted(gemm), sorted(nloop))
     assert max(gemm.values()) < 4500, gemm
     assert max(nloop.values()) < 3000, nloop
+
+
+def test_scripts_compile():
+    """bench.py, __graft_entry__.py and the manual experiment / profiling scripts at least byte-compile (they only run
+    on the GPU box, where a syntax error costs a GPU call)."""
+    import glob
+    import py_compile
+    files = [os.path.join(ROOT, 'bench.py'), os.path.join(ROOT, '__graft_entry__.py')]
+    files += sorted(glob.glob(os.path.join(ROOT, 'tests', 'manual', '*.py')))
+    files += sorted(glob.glob(os.path.join(ROOT, 'tests', 'bench_*.py')))
+    files += sorted(glob.glob(os.path.join(ROOT, 'profiles', 'tools', '*.py')))
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
