@@ -41,8 +41,10 @@ tensor 1e-1; measured 0.5e-2 .. 2.7e-2 per bucket).  The eight-step B=64 / hidde
 measures 6.9e-2 in the actor bucket -- the output layer of the policy trunk agrees to 0.6e-2, its two
 hidden layers and everything below them to 1.1e-1 each: the signature of ReLU units whose bf16-rounded
 pre-activation falls on the other side of zero than the oracle's fp32 one (a flipped unit adds or removes
-a whole gradient element: for scale, some 50 flipped of 8,000 active units would be sqrt(50/8000) = 8e-2 --
-an estimate, the flips were not counted).
+a whole gradient element).  tests/manual/numerics_relu_flips.py reproduces the signature on the oracle alone
+(profiles/r05_numerics_relu_flips.txt): with only the trunk GEMM operands rounded to bf16, 10 - 36 of the
+~8,500 active units per hidden layer flip and the hidden layers' gradients are off by 1e-2 .. 3.4e-2 while the
+output layer's is off by 1e-3 .. 7e-3.
 Which update lands there depends on the trajectory: the same scenario measured 2.7e-2 at its worst before
 the CURL contraction changed its rounding (fp32 FFMA: 6.2e-2, three-piece bf16: 6.9e-2 at update 6).
 """
