@@ -353,7 +353,9 @@ int curla_agent_last_launches(const curla_agent* a);
  * teacher-forced from another implementation's optimizer state */
 int curla_agent_set_opt_steps(curla_agent* a, int t_critic, int t_actor, int t_alpha, int t_cpc);
 int curla_agent_get_opt_steps(const curla_agent* a, int* out4);
-/* CUDA-event profiler: per-launch device times on the engine stream (measurement only) */
+/* CUDA-event profiler (measurement only).  on = 1: an event after every launch, everything serialised on the engine
+ * stream: per-launch device times.  on = 2: side streams stay on, an event on the main stream at each phase boundary of
+ * the update (joins included): where the main stream's time goes.  Profiled updates are launched eagerly. */
 int curla_profile_enable(int on);
 int curla_profile_read(char* buf, int cap);
 
